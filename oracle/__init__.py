@@ -1,0 +1,321 @@
+"""CPU ORACLE -- test infrastructure, NOT product code.
+
+A CPU restatement of the arithmetic on VideoYOLO's per-frame detection
+post-processing path (anchor decode -> temporal fusion conv -> box_nms).  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package; ``videoyolo_b200`` never does.
+
+PARITY UNPINNED by the reference itself: /root/reference holds no tests or golden
+vectors and its arithmetic runs in un-vendored, un-pinned ``mxnet-cu100`` /
+``gluoncv`` (requirements.txt:1-2), neither of which is installable here.  The
+oracle is pinned instead by:
+  * tests/golden/box_nms_mxnet_doc.json  - known answers from MXNet's public
+    ``box_nms`` documentation / unit test (hand transcribed, provenance flagged);
+  * oracle.box_nms_py - an independently structured python twin;
+  * torchvision.ops.nms per class (same IoU formula);
+  * tests/golden/bbox_iou_ref.npz - outputs of the reference's own
+    utils/bbox.py:bbox_iou, imported in the build container
+    (tests/golden/make_golden.py is the generating script).
+
+Functions and what they follow:
+  decode_numpy        models/definitions/yolo/yolo3.py:151-199 op for op (numpy fp32)
+  decode_c            same, C (oracle/vy_oracle.c), writes the concatenated tensor (yolo3.py:523)
+  box_nms_c/_py       F.contrib.box_nms as called at yolo3.py:525-530
+  yolov3_tail         yolo3.py:523-534 (concat -> box_nms -> slice post_nms -> split)
+  bbox_iou            utils/bbox.py:11-38
+  conv_bn_leaky       models/definitions/layers.py:63-89,135-158 (torch CPU fp32 engine)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# reference constants: models/definitions/yolo/wrappers.py:80-84, used reversed (yolo3.py:416-417)
+ANCHORS = [[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]]
+STRIDES = [8, 16, 32]
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/vy_oracle.c -> oracle/libvy_oracle.so (gcc, seconds)."""
+    so = os.path.join(_HERE, "libvy_oracle.so")
+    src = os.path.join(_HERE, "vy_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return so
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(build())
+        f32p = ctypes.POINTER(ctypes.c_float)
+        L.vy_oracle_decode_f32.argtypes = [f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_float, f32p, ctypes.c_int, f32p,
+                                           ctypes.c_long, ctypes.c_long]
+        L.vy_oracle_decode_f32.restype = None
+        L.vy_oracle_box_nms_f32.argtypes = [f32p, ctypes.c_int, ctypes.c_long, ctypes.c_int,
+                                            ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            f32p, ctypes.POINTER(ctypes.c_int32)]
+        L.vy_oracle_box_nms_f32.restype = ctypes.c_int
+        f64p = ctypes.POINTER(ctypes.c_double)
+        L.vy_oracle_bbox_iou_f64.argtypes = [f64p, ctypes.c_int, f64p, ctypes.c_int, ctypes.c_double, f64p]
+        L.vy_oracle_bbox_iou_f64.restype = None
+        L.vy_oracle_set_threads.argtypes = [ctypes.c_int]
+        L.vy_oracle_get_threads.restype = ctypes.c_int
+        _LIB = L
+    return _LIB
+
+
+def set_threads(n: int) -> None:
+    lib().vy_oracle_set_threads(int(n))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, t=ctypes.c_float):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+# --------------------------------------------------------------------------- decode
+def grid_sizes(size: int):
+    """Head grids in the order the network emits them: strides 32, 16, 8 (yolo3.py:416-417)."""
+    return [size // 32, size // 16, size // 8]
+
+
+def n_boxes(grids: Sequence[int], A: int = 3) -> int:
+    return sum(g * g * A for g in grids)
+
+
+def decode_numpy(pred: np.ndarray, anchors, stride: float, num_class: int, agnostic: bool = False):
+    """Op-for-op numpy fp32 restatement of YOLOOutputV3.hybrid_forward, yolo3.py:151-199.
+
+    pred: (B, A*P, H, W) -- the output of the 1x1 ``prediction`` conv (:157).
+    returns (B, C*H*W*A, 6) rows [cls, score, x1, y1, x2, y2]; agnostic: (B, H*W*A, 6).
+    """
+    pred = _f32(pred)
+    anchors = np.asarray(anchors, dtype=np.float32).reshape(1, 1, -1, 2)            # :46,:64
+    A = anchors.shape[2]
+    P = 5 + num_class
+    B, _, H, W = pred.shape
+    p = pred.reshape(B, A * P, H * W)                                              # :158
+    p = p.transpose(0, 2, 1).reshape(B, H * W, A, P)                               # :160
+    raw_centers, raw_scales = p[..., 0:2], p[..., 2:4]                             # :162-163
+    objness, class_pred = p[..., 4:5], p[..., 5:]                                  # :164-165
+    gx, gy = np.meshgrid(np.arange(W), np.arange(H))                               # :67-69
+    offsets = np.concatenate((gx[:, :, None], gy[:, :, None]), axis=-1)            # :71
+    offsets = offsets.reshape(1, -1, 1, 2).astype(np.float32)                      # :168-170
+    one = np.float32(1.0)
+    sig = lambda v: one / (one + np.exp(-v, dtype=np.float32))                     # mshadow sigmoid
+    box_centers = (sig(raw_centers) + offsets) * np.float32(stride)                # :172
+    box_scales = np.exp(raw_scales, dtype=np.float32) * anchors                    # :173
+    confidence = sig(objness)                                                      # :174
+    class_score = sig(class_pred) * confidence                                     # :175
+    wh = box_scales / np.float32(2.0)                                              # :176
+    bbox = np.concatenate((box_centers - wh, box_centers + wh), axis=-1)           # :177
+    if agnostic:                                                                   # :184-188
+        ids = confidence * 0
+        return np.concatenate((ids, confidence, bbox), axis=-1).reshape(B, -1, 6)
+    bboxes = np.tile(bbox, (num_class, 1, 1, 1, 1))                                # :191
+    scores = class_score.transpose(3, 0, 1, 2)[..., None]                          # :192
+    ids = scores * 0 + np.arange(num_class, dtype=np.float32).reshape(-1, 1, 1, 1, 1)  # :194
+    det = np.concatenate((ids, scores, bboxes), axis=-1)                           # :195
+    return det.transpose(1, 0, 2, 3, 4).reshape(B, -1, 6).astype(np.float32)       # :197
+
+
+def decode_c(heads: Sequence[np.ndarray], num_class: int, strides=None, anchors=None,
+             agnostic: bool = False) -> np.ndarray:
+    """Decode the three head maps (order: stride 32, 16, 8) and concatenate along rows
+    exactly like yolo3.py:523.  Returns (B, R, 6) fp32."""
+    strides = list(strides) if strides is not None else STRIDES[::-1]
+    anchors = list(anchors) if anchors is not None else ANCHORS[::-1]
+    B = heads[0].shape[0]
+    A = len(anchors[0]) // 2
+    C = 1 if agnostic else num_class
+    R = sum(C * h.shape[2] * h.shape[3] * A for h in heads)
+    out = np.empty((B, R, 6), dtype=np.float32)
+    off = 0
+    L = lib()
+    for h, st, an in zip(heads, strides, anchors):
+        h = _f32(h)
+        an = _f32(an)
+        assert h.shape[1] == A * (5 + num_class), (h.shape, A, num_class)
+        L.vy_oracle_decode_f32(_p(h), B, A, num_class, h.shape[2], h.shape[3], float(st), _p(an),
+                               int(agnostic), _p(out), R, off)
+        off += C * h.shape[2] * h.shape[3] * A
+    return out
+
+
+# --------------------------------------------------------------------------- box_nms
+_FMT = {"corner": 0, "center": 1}
+
+
+def box_nms_c(data, overlap_thresh=0.5, valid_thresh=0.0, topk=-1, coord_start=2, score_index=1,
+              id_index=-1, background_id=-1, force_suppress=False, in_format="corner",
+              out_format="corner", return_record=False):
+    """MXNet ``_contrib_box_nms`` semantics (C).  Leading dims are batch (yolo3_temporal.py:545)."""
+    d = _f32(data)
+    shp = d.shape
+    R, W = shp[-2], shp[-1]
+    B = int(np.prod(shp[:-2])) if len(shp) > 2 else 1
+    out = np.empty((B, R, W), dtype=np.float32)
+    rec = np.empty((B, R), dtype=np.int32)
+    rc = lib().vy_oracle_box_nms_f32(_p(d), B, R, W, overlap_thresh, valid_thresh, int(topk),
+                                     coord_start, score_index, id_index, background_id,
+                                     int(bool(force_suppress)), _FMT[in_format], _FMT[out_format],
+                                     _p(out), _p(rec, ctypes.c_int32))
+    if rc != 0:
+        raise ValueError("vy_oracle_box_nms_f32 rc=%d" % rc)
+    out = out.reshape(shp)
+    return (out, rec.reshape(shp[:-1])) if return_record else out
+
+
+def box_nms_py(data, overlap_thresh=0.5, valid_thresh=0.0, topk=-1, coord_start=2, score_index=1,
+               id_index=-1, background_id=-1, force_suppress=False, in_format="corner",
+               out_format="corner", return_record=False):
+    """Independently structured python twin of box_nms_c (numpy fp32 scalars; small inputs only)."""
+    d = _f32(data)
+    shp = d.shape
+    R, W = shp[-2], shp[-1]
+    d3 = d.reshape(-1, R, W)
+    out = np.full_like(d3, -1.0)
+    rec = np.full(d3.shape[:2], -1, dtype=np.int32)
+    f = np.float32
+
+    def corners(b):
+        if in_format == "corner":
+            return b[0], b[1], b[2], b[3]
+        hw, hh = b[2] / f(2), b[3] / f(2)
+        return b[0] - hw, b[1] - hh, b[0] + hw, b[1] + hh
+
+    for bi in range(d3.shape[0]):
+        img = d3[bi]
+        sc = img[:, score_index]
+        valid = sc > f(valid_thresh)
+        if id_index >= 0 and background_id >= 0:
+            valid &= img[:, id_index].astype(np.int64) != background_id
+        rows = np.nonzero(valid)[0]
+        order = rows[np.argsort(-sc[rows], kind="stable")]      # desc, ties -> lower row first
+        k = R if topk < 0 else min(R, topk)
+        order = order[:k]
+        boxes = img[order, coord_start:coord_start + 4]
+        if in_format == "corner":
+            w_, h_ = boxes[:, 2] - boxes[:, 0], boxes[:, 3] - boxes[:, 1]
+        else:
+            w_, h_ = boxes[:, 2], boxes[:, 3]
+        area = np.where((w_ < 0) | (h_ < 0), f(0), w_ * h_).astype(np.float32)
+        ids = img[order, id_index].astype(np.int64) if id_index >= 0 else None
+        alive = np.ones(len(order), dtype=bool)
+        for r in range(len(order)):
+            if not alive[r]:
+                continue
+            rx1, ry1, rx2, ry2 = corners(boxes[r])
+            for t in range(r + 1, len(order)):
+                if not alive[t]:
+                    continue
+                if not force_suppress and ids is not None and ids[r] != ids[t]:
+                    continue
+                tx1, ty1, tx2, ty2 = corners(boxes[t])
+                iw = max(f(0), min(rx2, tx2) - max(rx1, tx1))
+                ih = max(f(0), min(ry2, ty2) - max(ry1, ty1))
+                inter = f(iw * ih)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    iou = inter / f(f(area[r] + area[t]) - inter)
+                if iou > f(overlap_thresh):
+                    alive[t] = False
+        kept = order[alive]
+        out[bi, :len(kept)] = img[kept]
+        rec[bi, :len(kept)] = kept
+        if in_format != out_format:
+            for j in range(len(kept)):
+                c = out[bi, j, coord_start:coord_start + 4]
+                if c[0] < 0:
+                    continue
+                if out_format == "center":
+                    l, t, r2, b2 = c.copy()
+                    c[:] = ((l + r2) / f(2), (t + b2) / f(2), r2 - l, b2 - t)
+                else:
+                    x, y, w2, h2 = c.copy()
+                    c[:] = (x - w2 / f(2), y - h2 / f(2), x + w2 / f(2), y + h2 / f(2))
+    out = out.reshape(shp)
+    return (out, rec.reshape(shp[:-1])) if return_record else out
+
+
+def yolov3_tail(dets: np.ndarray, nms_thresh=0.45, nms_topk=400, post_nms=100,
+                valid_thresh=0.01, force_suppress=False, return_record=False):
+    """yolo3.py:523-534: box_nms on the concatenated detections, slice post_nms, split."""
+    result, rec = dets, None
+    if 0 < nms_thresh < 1:                                                          # :525
+        result, rec = box_nms_c(dets, overlap_thresh=nms_thresh, valid_thresh=valid_thresh,
+                                topk=nms_topk, id_index=0, score_index=1, coord_start=2,
+                                force_suppress=force_suppress, return_record=True)  # :526-528
+        if post_nms > 0:                                                            # :529-530
+            result, rec = result[:, :post_nms], rec[:, :post_nms]
+    ids, scores, bboxes = result[..., 0:1], result[..., 1:2], result[..., 2:6]      # :531-533
+    return (ids, scores, bboxes, rec) if return_record else (ids, scores, bboxes)
+
+
+def yolov3_postprocess(heads, num_class, nms_thresh=0.45, nms_topk=400, post_nms=100,
+                       valid_thresh=0.01, agnostic=False, strides=None, anchors=None,
+                       return_record=False):
+    """heads (stride 32,16,8 order) -> (ids, scores, bboxes): decode + yolo3.py:523-534."""
+    dets = decode_c(heads, num_class, strides=strides, anchors=anchors, agnostic=agnostic)
+    return yolov3_tail(dets, nms_thresh, nms_topk, post_nms, valid_thresh, return_record=return_record)
+
+
+# --------------------------------------------------------------------------- bbox_iou
+def bbox_iou(bbox_a: np.ndarray, bbox_b: np.ndarray, offset=0) -> np.ndarray:
+    """utils/bbox.py:11-38 restated (C, float64 like numpy float64 inputs)."""
+    a = np.ascontiguousarray(bbox_a, dtype=np.float64)
+    b = np.ascontiguousarray(bbox_b, dtype=np.float64)
+    if a.shape[1] < 4 or b.shape[1] < 4:                                            # :29-30
+        raise IndexError("Bounding boxes axis 1 must have at least length 4")
+    a4 = np.ascontiguousarray(a[:, :4])
+    b4 = np.ascontiguousarray(b[:, :4])
+    out = np.empty((a.shape[0], b.shape[0]), dtype=np.float64)
+    f64p = ctypes.POINTER(ctypes.c_double)
+    with np.errstate(all="ignore"):
+        lib().vy_oracle_bbox_iou_f64(a4.ctypes.data_as(f64p), a.shape[0], b4.ctypes.data_as(f64p),
+                                     b.shape[0], float(offset), out.ctypes.data_as(f64p))
+    return out
+
+
+# --------------------------------------------------------------------------- fusion conv
+def conv_bn_leaky(x, w, gamma, beta, mean, var, padding, stride=1, eps=1e-5, slope=0.1):
+    """LeakyReLU_0.1(BN_eps1e-5(ConvND(x))), use_bias=False -- layers.py:63-79.
+
+    x: (B, Cin, [T,] H, W) fp32 (NCHW / NCDHW like the reference), w: (Cout, Cin, [kt,] kh, kw).
+    Arithmetic engine: torch CPU fp32 (the reference's MXNet conv is not installable).
+    """
+    import torch
+    import torch.nn.functional as F
+    x = torch.as_tensor(np.asarray(x), dtype=torch.float32)
+    w = torch.as_tensor(np.asarray(w), dtype=torch.float32)
+    conv = F.conv3d if x.dim() == 5 else F.conv2d
+    y = conv(x, w, bias=None, stride=stride, padding=padding)
+    shape = [1, -1] + [1] * (x.dim() - 2)
+    g, b_, m, v = (torch.as_tensor(np.asarray(t), dtype=torch.float32).reshape(shape)
+                   for t in (gamma, beta, mean, var))
+    y = (y - m) / torch.sqrt(v + eps) * g + b_
+    return F.leaky_relu(y, slope).numpy()
+
+
+def conv21d_bn_leaky(x, w_s, bn_s, w_t, bn_t, padding=1, stride=1):
+    """_conv21d (layers.py:82-89): (1,d,d) conv+BN+LReLU then (t,1,1) conv+BN+LReLU."""
+    y = conv_bn_leaky(x, w_s, *bn_s, padding=(0, padding, padding), stride=stride)
+    return conv_bn_leaky(y, w_t, *bn_t, padding=(padding, 0, 0), stride=stride)
+
+
+def temporal_pool(x: np.ndarray, type: str = "max") -> np.ndarray:
+    """TemporalPooling 'direct' style, layers.py:201-205: reduce axis 1 of (B,K,C,H,W)."""
+    return x.max(axis=1) if type == "max" else x.mean(axis=1)

@@ -1,0 +1,214 @@
+"""CPU tests: the oracle against the golden vectors and against independent restatements.
+
+The oracle (oracle/) is the checker for every GPU parity test, so it is pinned here first:
+MXNet's published box_nms answers, the reference's own bbox_iou outputs, a python twin,
+torchvision's nms, and the closed-form decode identities of SURVEY.md 8(c).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+import oracle
+
+
+# ----------------------------------------------------------------------------- box_nms
+def _cases(golden_dir=os.path.join(os.path.dirname(__file__), "golden")):
+    with open(os.path.join(golden_dir, "box_nms_mxnet_doc.json")) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c["name"])
+@pytest.mark.parametrize("impl", ["c", "py"])
+def test_box_nms_mxnet_known_answers(case, impl):
+    fn = oracle.box_nms_c if impl == "c" else oracle.box_nms_py
+    out, rec = fn(np.array(case["data"], dtype=np.float32), return_record=True, **case["args"])
+    exp = np.array(case["expected"], dtype=np.float32)
+    if case.get("approx"):
+        np.testing.assert_allclose(out, exp, rtol=1e-5, atol=1e-6)
+    else:
+        np.testing.assert_array_equal(out, exp)
+    np.testing.assert_array_equal(rec, np.array(case["kept"]))
+
+
+def _random_dets(rng, B, R, n_cls, quant=None, scale=100.0):
+    xy = rng.uniform(0, scale, size=(B, R, 2))
+    wh = rng.uniform(-0.05 * scale, 0.5 * scale, size=(B, R, 2))     # a few inverted boxes -> area 0
+    sc = rng.uniform(-0.1, 1.0, size=(B, R, 1))
+    if quant:
+        sc = np.round(sc * quant) / quant                            # force score ties
+    ids = rng.randint(0, n_cls, size=(B, R, 1)).astype(np.float64)
+    return np.concatenate([ids, sc, xy, xy + wh], axis=-1).astype(np.float32)
+
+
+@settings(max_examples=60, deadline=None)
+@given(seed=st.integers(0, 2**31 - 1), R=st.integers(1, 70), n_cls=st.integers(1, 4),
+       topk=st.sampled_from([-1, 1, 5, 30, 1000]), force=st.booleans(),
+       thr=st.sampled_from([0.1, 0.45, 0.7]), valid=st.sampled_from([-1.0, 0.0, 0.01, 0.5]),
+       quant=st.sampled_from([None, 8, 64]), id_index=st.sampled_from([0, -1]),
+       fmt=st.sampled_from(["corner", "center"]))
+def test_box_nms_c_equals_python_twin(seed, R, n_cls, topk, force, thr, valid, quant, id_index, fmt):
+    rng = np.random.RandomState(seed)
+    d = _random_dets(rng, 2, R, n_cls, quant)
+    if fmt == "center":
+        c = d.copy()
+        c[..., 2:4] = (d[..., 2:4] + d[..., 4:6]) / 2
+        c[..., 4:6] = d[..., 4:6] - d[..., 2:4]
+        d = c
+    kw = dict(overlap_thresh=thr, valid_thresh=valid, topk=topk, id_index=id_index,
+              force_suppress=force, in_format=fmt, out_format=fmt, return_record=True)
+    oc, rc = oracle.box_nms_c(d, **kw)
+    op, rp = oracle.box_nms_py(d, **kw)
+    np.testing.assert_array_equal(rc, rp)
+    np.testing.assert_array_equal(oc, op)
+
+
+def test_box_nms_against_torchvision_per_class():
+    import torch
+    import torchvision
+    rng = np.random.RandomState(7)
+    d = _random_dets(rng, 1, 400, 5)
+    d[..., 4:6] = np.maximum(d[..., 4:6], d[..., 2:4] + 1.0)         # torchvision needs x2>x1
+    d[..., 1] = rng.permutation(400).reshape(1, 400) / 400.0 + 0.001  # distinct scores
+    out, rec = oracle.box_nms_c(d, overlap_thresh=0.45, valid_thresh=0.0, topk=-1, id_index=0,
+                                return_record=True)
+    keep = []
+    for c in range(5):
+        rows = np.nonzero(d[0, :, 0] == c)[0]
+        k = torchvision.ops.nms(torch.from_numpy(d[0, rows, 2:6]), torch.from_numpy(d[0, rows, 1]), 0.45)
+        keep += list(rows[k.numpy()])
+    keep = sorted(keep, key=lambda r: -d[0, r, 1])
+    assert list(rec[0][rec[0] >= 0]) == keep
+
+
+def test_box_nms_edge_cases():
+    # empty candidate set -> all -1
+    d = _random_dets(np.random.RandomState(0), 2, 9, 3)
+    out, rec = oracle.box_nms_c(d, valid_thresh=5.0, return_record=True)
+    assert (out == -1).all() and (rec == -1).all()
+    # strict '>' on valid_thresh and stable ties (lower row first)
+    d = np.zeros((1, 4, 6), np.float32)
+    d[0, :, 1] = [0.5, 0.7, 0.7, 0.01]
+    d[0, :, 2:6] = [[0, 0, 1, 1], [10, 10, 11, 11], [20, 20, 21, 21], [30, 30, 31, 31]]
+    out, rec = oracle.box_nms_c(d, valid_thresh=0.01, id_index=0, return_record=True)
+    assert list(rec[0]) == [1, 2, 0, -1]
+    # identical boxes, same class: IoU = 1 > thr -> only the first survives; 0-area pair: 0/0 = NaN keeps
+    d = np.zeros((1, 3, 6), np.float32)
+    d[0, :, 1] = [0.9, 0.8, 0.7]
+    d[0, :2, 2:6] = [5, 5, 9, 9]
+    d[0, 2, 2:6] = [3, 3, 3, 3]
+    out, rec = oracle.box_nms_c(d, overlap_thresh=0.45, id_index=0, return_record=True)
+    assert list(rec[0]) == [0, 2, -1]
+    # topk cuts BEFORE suppression, globally across classes
+    d = _random_dets(np.random.RandomState(3), 1, 50, 3)
+    o1, r1 = oracle.box_nms_c(d, topk=7, id_index=0, return_record=True)
+    order = np.argsort(-d[0, :, 1], kind="stable")[:7]
+    assert set(r1[0][r1[0] >= 0]) <= set(order)
+
+
+# ----------------------------------------------------------------------------- decode
+@pytest.mark.parametrize("C,size,agnostic", [(20, 416, False), (3, 96, False), (30, 320, True), (1, 64, False)])
+def test_decode_c_equals_numpy_graph(C, size, agnostic):
+    rng = np.random.RandomState(C + size)
+    grids = oracle.grid_sizes(size)
+    heads = [rng.normal(0, 1.5, size=(2, 3 * (5 + C), g, g)).astype(np.float32) for g in grids]
+    dets = oracle.decode_c(heads, C, agnostic=agnostic)
+    ref = np.concatenate([oracle.decode_numpy(h, a, s, C, agnostic) for h, a, s in
+                          zip(heads, oracle.ANCHORS[::-1], oracle.STRIDES[::-1])], axis=1)
+    assert dets.shape == ref.shape
+    np.testing.assert_array_equal(dets[..., 0], ref[..., 0])
+    # glibc expf vs numpy's SIMD exp differ by <= a few ulp; the centre/half-size cancellation
+    # in x1 = cx - w/2 needs an absolute term scaled by the coordinate magnitude
+    np.testing.assert_allclose(dets[..., 1], ref[..., 1], rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(dets[..., 2:], ref[..., 2:], rtol=2e-6, atol=2e-6 * 4 * size)
+
+
+def test_decode_identities_zero_logits():
+    """zero logits => sigma=0.5, wh=anchor, centre=(x+0.5)*stride, score=0.25."""
+    C, size = 4, 64
+    grids = oracle.grid_sizes(size)
+    heads = [np.zeros((1, 3 * (5 + C), g, g), np.float32) for g in grids]
+    dets = oracle.decode_c(heads, C)
+    off = 0
+    for g, stride, anc in zip(grids, oracle.STRIDES[::-1], oracle.ANCHORS[::-1]):
+        n_s = g * g * 3
+        blk = dets[0, off:off + C * n_s].reshape(C, g, g, 3, 6)
+        for c in range(C):
+            assert (blk[c, ..., 0] == c).all() and (blk[c, ..., 1] == 0.25).all()
+        for a in range(3):
+            w, h = anc[2 * a], anc[2 * a + 1]
+            ys, xs = np.meshgrid(np.arange(g), np.arange(g), indexing="ij")
+            np.testing.assert_allclose(blk[0, :, :, a, 2], (xs + 0.5) * stride - w / 2.0, rtol=1e-6)
+            np.testing.assert_allclose(blk[0, :, :, a, 3], (ys + 0.5) * stride - h / 2.0, rtol=1e-6)
+            np.testing.assert_allclose(blk[0, :, :, a, 4], (xs + 0.5) * stride + w / 2.0, rtol=1e-6)
+            np.testing.assert_allclose(blk[0, :, :, a, 5], (ys + 0.5) * stride + h / 2.0, rtol=1e-6)
+        off += C * n_s
+    assert off == dets.shape[1]
+
+
+def test_row_order_formula():
+    """global row r = C*sum_{s'<s} n_s' + c*n_s + pos*A + a  (yolo3.py:191-197, :523)."""
+    C, size = 3, 64
+    grids = oracle.grid_sizes(size)
+    rng = np.random.RandomState(5)
+    heads = [rng.normal(size=(1, 3 * (5 + C), g, g)).astype(np.float32) for g in grids]
+    dets = oracle.decode_c(heads, C)
+    s, c, y, x, a = 1, 2, 3, 1, 2
+    g = grids[s]
+    r = C * grids[0] ** 2 * 3 + c * g * g * 3 + (y * g + x) * 3 + a
+    t = heads[s][0].reshape(3, 5 + C, g, g)[a, :, y, x]
+    sig = lambda v: 1 / (1 + np.exp(-v))
+    assert dets[0, r, 0] == c
+    np.testing.assert_allclose(dets[0, r, 1], sig(t[5 + c]) * sig(t[4]), rtol=1e-5)
+    cx = (sig(t[0]) + x) * oracle.STRIDES[::-1][s]
+    w = np.exp(t[2]) * oracle.ANCHORS[::-1][s][2 * a]
+    np.testing.assert_allclose(dets[0, r, 2], cx - w / 2, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["voc416_random", "vid320_trained", "coco_small_trained"])
+def test_postproc_regression_fixture(name, golden_dir):
+    z = np.load(os.path.join(golden_dir, "postproc_regress_%s.npz" % name))
+    ids, scores, bboxes, rec = oracle.yolov3_postprocess([z["h0"], z["h1"], z["h2"]], int(z["C"]),
+                                                         return_record=True)
+    np.testing.assert_array_equal(rec, z["kept_rows"])
+    np.testing.assert_array_equal(ids, z["ids"])
+    np.testing.assert_array_equal(scores, z["scores"])
+    np.testing.assert_array_equal(bboxes, z["bboxes"])
+
+
+def test_temporal_leading_dims_are_batch():
+    """yolo3_temporal.py:545: box_nms on (B,T,N,6) treats B*T as images."""
+    d = _random_dets(np.random.RandomState(11), 6, 40, 3).reshape(2, 3, 40, 6)
+    a = oracle.box_nms_c(d, overlap_thresh=0.45, valid_thresh=0.01, topk=10, id_index=0)
+    b = oracle.box_nms_c(d.reshape(6, 40, 6), overlap_thresh=0.45, valid_thresh=0.01, topk=10, id_index=0)
+    np.testing.assert_array_equal(a.reshape(6, 40, 6), b)
+
+
+# ----------------------------------------------------------------------------- bbox_iou
+def test_bbox_iou_against_reference_outputs(golden_dir):
+    z = np.load(os.path.join(golden_dir, "bbox_iou_ref.npz"))
+    names = sorted({k[:-4] for k in z.files if k.endswith("_iou")})
+    assert names
+    for n in names:
+        got = oracle.bbox_iou(z[n + "_a"], z[n + "_b"], float(z[n + "_off"]))
+        np.testing.assert_allclose(got, z[n + "_iou"], rtol=1e-12, atol=0, equal_nan=True)
+    with pytest.raises(IndexError):
+        oracle.bbox_iou(np.zeros((2, 3)), np.zeros((2, 4)))
+
+
+# ----------------------------------------------------------------------------- fusion conv
+def test_conv_inflation_identity():
+    """three_darknet.py:335-347 property: a clip of identical frames through a (kt,3,3) conv whose
+    weights are the 2-D weights / kt ... equals the 2-D conv (interior frames; zero temporal pad)."""
+    rng = np.random.RandomState(2)
+    x2 = rng.normal(size=(1, 8, 6, 6)).astype(np.float32)
+    w2 = rng.uniform(-0.07, 0.07, size=(16, 8, 3, 3)).astype(np.float32)
+    bn = (np.ones(16), np.zeros(16), np.zeros(16), np.ones(16))
+    y2 = oracle.conv_bn_leaky(x2, w2, *bn, padding=1)
+    x3 = np.repeat(x2[:, :, None], 5, axis=2)
+    w3 = np.repeat(w2[:, :, None], 3, axis=2) / 3.0
+    y3 = oracle.conv_bn_leaky(x3, w3, *bn, padding=1)
+    np.testing.assert_allclose(y3[:, :, 2], y2, rtol=1e-4, atol=1e-5)
+    assert oracle.temporal_pool(np.stack([x2, 2 * x2], 1), "max").shape == x2.shape
