@@ -1,0 +1,138 @@
+/*
+ * vyolo.h -- C ABI of the B200-native VideoYOLO detection post-processing path.
+ *
+ * The reference (HaydenFaulkner/VideoYOLO) has no FFI layer of its own: the path sits behind
+ * Gluon HybridBlocks and one MXNet contrib-op call.  Each entry point below names the reference
+ * interface it replaces (file:line under /root/reference).  INTEGRATION.md shows the ctypes stub
+ * a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory unless the name says host_;
+ *     the small shape/anchor arrays (H, W, stride, anchors, head[]) are HOST arrays;
+ *   - no allocation, no ownership transfer, no implicit synchronisation: work is enqueued on
+ *     `stream` (a cudaStream_t passed as void*) and the caller owns ordering;
+ *   - the caller has made the target GPU current (cudaSetDevice) before calling;
+ *   - returns VY_OK (0) or a negative VY_E* code; vy_last_error() gives a thread-local message;
+ *   - sm_100a only.  There is no CPU fallback anywhere in this library.
+ */
+#ifndef VYOLO_H_
+#define VYOLO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VY_ABI_VERSION 1
+
+#define VY_OK            0
+#define VY_EINVAL       -1   /* bad shape / argument                       */
+#define VY_EALIGN       -2   /* pointer not aligned as documented          */
+#define VY_EWORKSPACE   -3   /* workspace missing or too small             */
+#define VY_ECUDA        -4   /* CUDA runtime/driver error, see last_error  */
+#define VY_EUNSUPPORTED -5   /* valid request this build cannot serve      */
+
+#define VY_MAX_SCALES   4
+#define VY_MAX_ANCHORS  8    /* anchors per scale */
+
+#define VY_FMT_CORNER   0    /* MXNet box_nms in_format/out_format 'corner' */
+#define VY_FMT_CENTER   1    /* 'center'                                    */
+
+typedef void *vy_stream_t;   /* cudaStream_t */
+
+int         vy_version(void);
+const char *vy_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Anchor decode of the YOLOv3 output layers into the reference's detection tensor.
+ * Replaces: YOLOOutputV3.hybrid_forward, models/definitions/yolo/yolo3.py:151-199 (dup
+ *           yolo3_temporal.py:137-179) for each scale, plus the scale concat yolo3.py:523.
+ *   host_head[s]  device ptr, (B, A*(5+C), H[s], W[s]) fp32 NCHW = output of the 1x1 `prediction`
+ *                 conv (yolo3.py:157); scales in network order (stride 32, 16, 8: yolo3.py:416-417)
+ *   host_anchors  n_scales*A*2 floats (w,h) in the same scale order
+ *   dets          (B, R, 6) rows [cls, score, x1, y1, x2, y2];  R = Ceff * sum_s H*W*A,
+ *                 Ceff = agnostic ? 1 : C; row = Ceff*sum_{s'<s} n_s' + c*n_s + (y*W+x)*A + a
+ *   agnostic      yolo3.py:184-188 branch: one row per box, id 0, score = objectness
+ */
+int vy_decode_f32(const float *const *host_head, const int *host_H, const int *host_W,
+                  const float *host_stride, const float *host_anchors, int n_scales,
+                  int B, int A, int C, int agnostic, float *dets, vy_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * box_nms on a materialised detection tensor.
+ * Replaces: F.contrib.box_nms(...) at yolo3.py:526-528 (+ :807-809, :1198-1200, :1578-1580,
+ *           :1862-1864, yolo3_temporal.py:545-547) = MXNet `_contrib_box_nms`, and optionally the
+ *           slice_axis(0, post_nms) that follows it (yolo3.py:529-530).
+ *   data       (B, R, W_elem) fp32; B = product of all leading dims
+ *   out_rows   rows written per image: R for the operator's own output shape, or post_nms to
+ *              fuse the slice.  out is (B, out_rows, W_elem), kept_rows (B, out_rows) int32 or NULL.
+ *              Rows after the survivors are filled with -1 (kept_rows too).
+ *   topk<0 means all R rows take part; background_id<0 disables the id filter (MXNet >= 1.5).
+ */
+size_t vy_box_nms_workspace_bytes(int B, long R, int W_elem, int topk);
+int vy_box_nms_f32(const float *data, int B, long R, int W_elem,
+                   float overlap_thresh, float valid_thresh, int topk,
+                   int coord_start, int score_index, int id_index, int background_id,
+                   int force_suppress, int in_format, int out_format,
+                   long out_rows, float *out, int32_t *kept_rows,
+                   void *workspace, size_t workspace_bytes, vy_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused decode + box_nms + post_nms slice: head maps -> (ids, scores, bboxes) without ever
+ * materialising the (B, R, 6) tensor.
+ * Replaces: the inference tail of YOLOV3*.hybrid_forward, yolo3.py:496,523-534 (and the same
+ *           tail in YOLOV3T :1159,1195-1206, YOLOV3TS, YOLOV3TB, YOLOV3_noback :1859-1870,
+ *           YOLOV3Temporal yolo3_temporal.py:542-550).
+ *   out        (B, post_nms, 6) rows [cls, score, x1, y1, x2, y2], -1 padded; the caller's
+ *              ids/scores/bboxes are column slices of it (yolo3.py:531-533)
+ *   kept_rows  (B, post_nms) int32 reference row index of every output row (-1 padded), or NULL
+ *   requires 1 <= min(topk, R) <= 1024 and post_nms >= 1 (else use vy_decode_f32 + vy_box_nms_f32)
+ */
+size_t vy_decode_nms_workspace_bytes(const int *host_H, const int *host_W, int n_scales,
+                                     int B, int A, int C, int agnostic, int topk);
+int vy_decode_nms_f32(const float *const *host_head, const int *host_H, const int *host_W,
+                      const float *host_stride, const float *host_anchors, int n_scales,
+                      int B, int A, int C, int agnostic,
+                      float overlap_thresh, float valid_thresh, int topk, int force_suppress,
+                      int post_nms, float *out, int32_t *kept_rows,
+                      void *workspace, size_t workspace_bytes, vy_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pairwise IoU.  Replaces: utils/bbox.py:11-38 bbox_iou(bbox_a, bbox_b, offset).
+ *   a (N, lda>=4), b (M, ldb>=4) row-major [x1,y1,x2,y2,...]; out (N, M).
+ */
+int vy_bbox_iou_f32(const float *a, int N, int lda, const float *b, int M, int ldb,
+                    float offset, float *out, vy_stream_t stream);
+int vy_bbox_iou_f64(const double *a, int N, int lda, const double *b, int M, int ldb,
+                    double offset, double *out, vy_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Temporal fusion convolution: LeakyReLU(BN(ConvND(x))), use_bias=False, stride 1, groups 1.
+ * Replaces: Conv / _conv2d / _conv3d / _conv21d cells, models/definitions/layers.py:63-89,135-158,
+ *           as used by YOLODetectionBlockV3 (yolo3.py:229-253) -- one call per conv+BN+LReLU cell
+ *           ('21' = two calls).  tcgen05/TMEM implicit GEMM fed by TMA.
+ *   x        (B, T, H, W, Cin)  bf16 channels-last (NDHWC; T=1 for 2-D)
+ *   w        (Cout, kt, kh, kw, Cin) bf16
+ *   scale, shift  per-Cout fp32 folded inference BatchNorm: y = conv*scale + shift
+ *                 (scale = gamma/sqrt(var+eps), shift = beta - mean*scale; layers.py:68,77)
+ *   y        (B, T, H, W, Cout) bf16 (y_is_f32 = 0) or fp32 (1); 'same' padding: p = k/2
+ *   requires Cin % 64 == 0, Cout % 64 == 0, kt,kh,kw in {1,3}
+ */
+size_t vy_fusion_conv_workspace_bytes(int B, int T, int H, int W, int Cin, int Cout,
+                                      int kt, int kh, int kw);
+int vy_fusion_conv_bf16(const void *x, const void *w, const float *scale, const float *shift,
+                        float leaky_slope, int B, int T, int H, int W, int Cin, int Cout,
+                        int kt, int kh, int kw, void *y, int y_is_f32,
+                        void *workspace, size_t workspace_bytes, vy_stream_t stream);
+
+/* TemporalPooling 'direct' style (layers.py:201-205) on channels-last data:
+ * x (B, T, H*W*C) -> y (B, H*W*C), mode 0 = max, 1 = mean.  bf16 in/out. */
+int vy_temporal_pool_bf16(const void *x, int B, int T, long inner, int mode, void *y,
+                          vy_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VYOLO_H_ */

@@ -117,28 +117,7 @@ def ref_bbox_iou():
     np.savez_compressed(os.path.join(HERE, "bbox_iou_ref.npz"), **out)
 
 
-def trained_like_heads(rng, B, C, size, boost_frac=0.004):
-    """SURVEY.md 8(d) regime (T): few confident, clustered detections."""
-    heads = []
-    for g in (size // 32, size // 16, size // 8):
-        h = np.empty((B, 3, 5 + C, g, g), dtype=np.float32)
-        h[:, :, 0:2] = rng.normal(0, 1, size=h[:, :, 0:2].shape)
-        h[:, :, 2:4] = rng.normal(0, 0.5, size=h[:, :, 2:4].shape)
-        h[:, :, 4] = rng.normal(-6, 1.5, size=h[:, :, 4].shape)
-        h[:, :, 5:] = rng.normal(-3, 1.5, size=h[:, :, 5:].shape)
-        n = max(1, int(boost_frac * g * g))
-        for b in range(B):
-            for _ in range(n):
-                y, x, a = rng.randint(g), rng.randint(g), rng.randint(3)
-                c = rng.randint(C)
-                for dy in (0, 1):
-                    for dx in (0, 1, 2):
-                        yy, xx = min(g - 1, y + dy), min(g - 1, x + dx)
-                        h[b, a, 4, yy, xx] += 10
-                        h[b, a, 5 + c, yy, xx] += 6
-                        h[b, :, 4, yy, xx] += 4        # neighbouring anchors fire too -> overlaps
-        heads.append(h.reshape(B, 3 * (5 + C), g, g))
-    return heads
+from videoyolo_b200.synth import trained_like_heads  # noqa: E402
 
 
 def oracle_regress():

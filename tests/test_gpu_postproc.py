@@ -1,0 +1,323 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(videoyolo_b200.ops -> ctypes -> libvyolo.so) and is checked against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  * box_nms keep-sets, output rows and source-row indices: BIT-EXACT vs the oracle on identical input;
+  * fused decode+NMS: BIT-EXACT vs oracle box_nms applied to the GPU-decoded rows;
+  * decode: scores/boxes within 1e-5 relative of the fp32 CPU restatement (+ an absolute term for
+    the cx - w/2 cancellation, proportional to the coordinate range);
+  * bbox_iou: 1e-12 relative (float64) vs the reference's own outputs.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+DEC_RTOL = 1e-5          # north_star: "decoded boxes and scores within 1e-5 relative (fp32)"
+
+
+@pytest.fixture(scope="module")
+def vy():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import videoyolo_b200
+    videoyolo_b200._lib.lib()          # fails loudly when the CUDA library is missing
+    return videoyolo_b200
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def random_heads(rng, B, C, size, std=1.0, quant=None):
+    hs = [rng.normal(0, std, size=(B, 3 * (5 + C), g, g)).astype(np.float32) for g in oracle.grid_sizes(size)]
+    if quant:
+        hs = [np.round(h * quant) / quant for h in hs]      # massive score ties
+    return [h.astype(np.float32) for h in hs]
+
+
+def trained_heads(rng, B, C, size):
+    from videoyolo_b200.synth import trained_like_heads
+    return trained_like_heads(rng, B, C, size)
+
+
+AN, ST = oracle.ANCHORS[::-1], oracle.STRIDES[::-1]
+
+
+# ----------------------------------------------------------------------------------- decode
+@pytest.mark.parametrize("B,C,size,agnostic", [(1, 20, 416, False), (2, 80, 608, False), (3, 30, 320, False),
+                                               (2, 30, 416, True), (1, 1, 64, False), (2, 7, 96, False)])
+def test_decode_matches_oracle(vy, B, C, size, agnostic):
+    rng = np.random.RandomState(B * 1000 + C + size)
+    heads = random_heads(rng, B, C, size, std=1.5)
+    got = vy.yolo3_decode([dev(h) for h in heads], C, AN, ST, agnostic).cpu().numpy()
+    ref = oracle.decode_c(heads, C, agnostic=agnostic)
+    assert got.shape == ref.shape
+    np.testing.assert_array_equal(got[..., 0], ref[..., 0])
+    np.testing.assert_allclose(got[..., 1], ref[..., 1], rtol=DEC_RTOL, atol=1e-12)
+    # corners are differences of O(size) centres and O(anchor*e^t) half-sizes
+    scale = np.maximum(np.abs(ref[..., 2:]).max(), size)
+    np.testing.assert_allclose(got[..., 2:], ref[..., 2:], rtol=DEC_RTOL, atol=DEC_RTOL * scale)
+
+
+def test_yolo_output_block_surface(vy):
+    rng = np.random.RandomState(3)
+    out = vy.YOLOOutputV3(0, 20, AN[0], ST[0], in_channels=32).cuda()
+    x = torch.from_numpy(rng.normal(size=(2, 32, 13, 13)).astype(np.float32)).cuda()
+    with torch.no_grad():
+        dets = out(x)
+        pred = out.prediction(x)
+    assert dets.shape == (2, 20 * 13 * 13 * 3, 6)
+    ref = oracle.decode_numpy(pred.cpu().numpy(), AN[0], ST[0], 20)
+    np.testing.assert_allclose(dets.cpu().numpy()[..., 1], ref[..., 1], rtol=DEC_RTOL, atol=1e-12)
+    with pytest.raises(ValueError):
+        vy.YOLOOutputV3(0, 20, AN[0], ST[0], alloc_size=(8, 8)).decode(torch.zeros(1, 75, 13, 13).cuda())
+
+
+# ----------------------------------------------------------------------------------- box_nms (generic)
+def _check_nms(vy, d, **kw):
+    okw = dict(kw)
+    out_rows = okw.pop("out_rows", None)
+    exp, rec = oracle.box_nms_c(d, return_record=True, **okw)
+    got, kept = vy.box_nms(dev(d), return_kept=True, out_rows=out_rows, **kw)
+    got, kept = got.cpu().numpy(), kept.cpu().numpy()
+    if out_rows is not None:
+        exp, rec = exp[..., :out_rows, :], rec[..., :out_rows]
+    np.testing.assert_array_equal(kept, rec)
+    np.testing.assert_array_equal(got, exp)
+
+
+def test_box_nms_mxnet_known_answers(vy, golden_dir):
+    with open(os.path.join(golden_dir, "box_nms_mxnet_doc.json")) as f:
+        cases = json.load(f)["cases"]
+    for c in cases:
+        d = np.array(c["data"], dtype=np.float32)
+        got, kept = vy.box_nms(dev(d), return_kept=True, **c["args"])
+        exp = np.array(c["expected"], dtype=np.float32)
+        if c.get("approx"):
+            np.testing.assert_allclose(got.cpu().numpy(), exp, rtol=1e-5, atol=1e-6, err_msg=c["name"])
+        else:
+            np.testing.assert_array_equal(got.cpu().numpy(), exp, err_msg=c["name"])
+        np.testing.assert_array_equal(kept.cpu().numpy(), np.array(c["kept"]), err_msg=c["name"])
+
+
+def _rand_dets(rng, B, R, n_cls, quant=None, scale=100.0, W=6, coord_start=2, score_index=1, id_index=0):
+    xy = rng.uniform(0, scale, size=(B, R, 2))
+    wh = rng.uniform(-0.05 * scale, 0.5 * scale, size=(B, R, 2))
+    sc = rng.uniform(-0.1, 1.0, size=(B, R))
+    if quant:
+        sc = np.round(sc * quant) / quant
+    d = rng.uniform(-1, 1, size=(B, R, W))
+    d[..., coord_start:coord_start + 2] = xy
+    d[..., coord_start + 2:coord_start + 4] = xy + wh
+    d[..., score_index] = sc
+    if id_index >= 0:
+        d[..., id_index] = rng.randint(0, n_cls, size=(B, R))
+    return d.astype(np.float32)
+
+
+@pytest.mark.parametrize("R,topk", [(1, 400), (37, 5), (400, 400), (3000, 400), (3000, 1), (5000, 1024), (70000, 400)])
+@pytest.mark.parametrize("force", [False, True])
+def test_box_nms_bit_exact_random(vy, R, topk, force):
+    rng = np.random.RandomState(R + topk)
+    d = _rand_dets(rng, 3, R, 4, quant=(64 if R % 2 else None))
+    _check_nms(vy, d, overlap_thresh=0.45, valid_thresh=0.01, topk=topk, id_index=0, force_suppress=force)
+
+
+def test_box_nms_argument_variants(vy):
+    rng = np.random.RandomState(77)
+    d = _rand_dets(rng, 2, 900, 3)
+    _check_nms(vy, d, overlap_thresh=0.3, valid_thresh=0.0, topk=200, id_index=-1)               # no ids
+    _check_nms(vy, d, overlap_thresh=0.5, valid_thresh=-1.0, topk=300, id_index=0)                # negative scores take part
+    _check_nms(vy, d, overlap_thresh=0.5, valid_thresh=0.2, topk=300, id_index=0, background_id=1)
+    _check_nms(vy, d, overlap_thresh=0.5, valid_thresh=5.0, topk=300, id_index=0)                 # nothing valid
+    _check_nms(vy, d, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, out_rows=100)  # fused slice
+    _check_nms(vy, d, overlap_thresh=0.45, valid_thresh=0.01, topk=50, id_index=0, out_rows=100)   # topk < out_rows
+    # other column layout: [score, x1,y1,x2,y2, pad, id, pad]
+    d8 = _rand_dets(rng, 2, 500, 5, W=8, coord_start=1, score_index=0, id_index=6)
+    _check_nms(vy, d8, overlap_thresh=0.45, valid_thresh=0.0, topk=100, coord_start=1, score_index=0, id_index=6)
+    # center format in and out
+    c = d.copy()
+    c[..., 2:4] = (d[..., 2:4] + d[..., 4:6]) / 2
+    c[..., 4:6] = d[..., 4:6] - d[..., 2:4]
+    _check_nms(vy, c, overlap_thresh=0.45, valid_thresh=0.01, topk=300, id_index=0, in_format="center", out_format="center")
+    _check_nms(vy, c, overlap_thresh=0.45, valid_thresh=0.01, topk=300, id_index=0, in_format="center", out_format="corner")
+    _check_nms(vy, d, overlap_thresh=0.45, valid_thresh=0.01, topk=300, id_index=0, in_format="corner", out_format="center")
+    # temporal model: (B, T, R, 6), leading dims are batch (yolo3_temporal.py:545)
+    d4 = _rand_dets(rng, 6, 300, 3).reshape(2, 3, 300, 6)
+    _check_nms(vy, d4, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0)
+
+
+def test_box_nms_adversarial_orders(vy):
+    """ascending scores (every row beats the running threshold), all-equal scores (pure row-order
+    ties) and duplicates of one box."""
+    R = 40000
+    d = _rand_dets(np.random.RandomState(1), 2, R, 3)
+    d[..., 1] = np.linspace(0.02, 0.99, R, dtype=np.float32)
+    _check_nms(vy, d, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0)
+    d[..., 1] = 0.5
+    _check_nms(vy, d, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0)
+    d[..., 2:6] = [10, 10, 50, 60]
+    _check_nms(vy, d, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0)
+
+
+def test_box_nms_fed_reference_decoded_boxes(vy):
+    """The north-star wording: keep-sets bit-exact when fed the reference's decoded boxes."""
+    for (B, C, size, regime) in [(2, 20, 416, "R"), (2, 30, 320, "T"), (1, 80, 608, "T")]:
+        rng = np.random.RandomState(C)
+        heads = random_heads(rng, B, C, size) if regime == "R" else trained_heads(rng, B, C, size)
+        dets = oracle.decode_c(heads, C)
+        _check_nms(vy, dets, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, out_rows=100)
+
+
+# ----------------------------------------------------------------------------------- fused path
+def _fused_vs_oracle(vy, heads, C, agnostic=False, nms_thresh=0.45, topk=400, post_nms=100, valid=0.01, force=False):
+    hd = [dev(h) for h in heads]
+    out, kept = vy.yolo3_decode_nms(hd, C, AN, ST, nms_thresh, valid, topk, post_nms, force, agnostic)
+    dets = vy.yolo3_decode(hd, C, AN, ST, agnostic).cpu().numpy()
+    exp, rec = oracle.box_nms_c(dets, overlap_thresh=nms_thresh, valid_thresh=valid, topk=topk, id_index=0,
+                                force_suppress=force, return_record=True)
+    np.testing.assert_array_equal(kept.cpu().numpy(), rec[:, :post_nms])
+    np.testing.assert_array_equal(out.cpu().numpy(), exp[:, :post_nms])
+    return out, kept
+
+
+@pytest.mark.parametrize("B,C,size,regime", [(1, 20, 416, "R"), (4, 20, 416, "T"), (3, 80, 608, "R"),
+                                             (2, 80, 608, "T"), (5, 30, 320, "R"), (5, 30, 320, "T"),
+                                             (2, 3, 96, "R"), (1, 1, 64, "R")])
+def test_fused_equals_decode_then_oracle_nms(vy, B, C, size, regime):
+    rng = np.random.RandomState(B + C + size)
+    heads = random_heads(rng, B, C, size) if regime == "R" else trained_heads(rng, B, C, size)
+    _fused_vs_oracle(vy, heads, C)
+
+
+def test_fused_variants(vy):
+    rng = np.random.RandomState(9)
+    heads = random_heads(rng, 2, 20, 416)
+    _fused_vs_oracle(vy, heads, 20, agnostic=True)
+    _fused_vs_oracle(vy, heads, 20, topk=1)
+    _fused_vs_oracle(vy, heads, 20, topk=1024, post_nms=300)
+    _fused_vs_oracle(vy, heads, 20, force=True)
+    _fused_vs_oracle(vy, heads, 20, valid=0.0)
+    _fused_vs_oracle(vy, heads, 20, valid=0.9)                     # almost nothing valid
+    _fused_vs_oracle(vy, [np.full_like(h, -30.0) for h in heads], 20)   # nothing valid at all
+    _fused_vs_oracle(vy, random_heads(rng, 2, 20, 416, quant=2), 20)    # massive exact ties
+    _fused_vs_oracle(vy, [np.zeros_like(h) for h in heads], 20)         # every score == 0.25
+
+
+def test_fused_ascending_plane_order(vy):
+    """class logits increasing with the class index: later planes always beat the running threshold."""
+    rng = np.random.RandomState(4)
+    C = 80
+    heads = random_heads(rng, 2, C, 416)
+    for h in heads:
+        v = h.reshape(h.shape[0], 3, 5 + C, -1)
+        v[:, :, 5:, :] = np.sort(v[:, :, 5:, :], axis=2)
+    _fused_vs_oracle(vy, heads, C)
+
+
+def test_fused_close_to_cpu_end_to_end(vy, golden_dir):
+    """Against the committed oracle fixtures (CPU decode + CPU NMS): identical detections wherever the
+    CPU and GPU scores are not within rounding of each other -- checked as >= 99% identical rows."""
+    for name in ["voc416_random", "vid320_trained", "coco_small_trained"]:
+        z = np.load(os.path.join(golden_dir, "postproc_regress_%s.npz" % name))
+        C = int(z["C"])
+        net = vy.get_yolov3_postprocess(["c"] * C)
+        ids, scores, bboxes = net(*[dev(z[k]) for k in ("h0", "h1", "h2")])
+        kept = net.last_kept_rows.cpu().numpy()
+        same = (kept == z["kept_rows"]).mean()
+        assert same >= 0.99, (name, same)
+        m = kept == z["kept_rows"]
+        np.testing.assert_allclose(scores.cpu().numpy()[..., 0][m], z["scores"][..., 0][m], rtol=DEC_RTOL, atol=1e-12)
+        np.testing.assert_allclose(bboxes.cpu().numpy()[m], z["bboxes"][m], rtol=DEC_RTOL, atol=DEC_RTOL * 640)
+
+
+def test_yolov3_block_surface_and_set_nms(vy):
+    rng = np.random.RandomState(12)
+    C = 20
+    heads = trained_heads(rng, 2, C, 416)
+    net = vy.get_yolov3_postprocess(["c%d" % i for i in range(C)])
+    assert net.classes == ["c%d" % i for i in range(C)]
+    net.set_nms(nms_thresh=0.45, nms_topk=400)                      # detect_yolo3.py:200
+    ids, scores, bboxes = net(*[dev(h) for h in heads])
+    assert ids.shape == (2, 100, 1) and scores.shape == (2, 100, 1) and bboxes.shape == (2, 100, 4)
+    o_ids, o_sc, o_bb = oracle.yolov3_tail(vy.yolo3_decode([dev(h) for h in heads], C, AN, ST).cpu().numpy())
+    np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
+    np.testing.assert_array_equal(bboxes.cpu().numpy(), o_bb)
+    # nms disabled (yolo3.py:525): the unsorted full tensor is split
+    net.set_nms(nms_thresh=1.5)
+    ids2, _, _ = net(*[dev(h) for h in heads])
+    assert ids2.shape == (2, C * 10647, 1)
+    # post_nms = -1: all rows of the operator output are returned
+    net.set_nms(nms_thresh=0.45, nms_topk=400, post_nms=-1)
+    ids3, sc3, _ = net(*[dev(h) for h in heads])
+    assert ids3.shape == (2, C * 10647, 1)
+    np.testing.assert_array_equal(ids3.cpu().numpy()[:, :100], o_ids)
+    assert (ids3.cpu().numpy()[:, 400:] == -1).all()
+    with pytest.raises(RuntimeError):
+        net(*[torch.from_numpy(h) for h in heads])                   # CPU tensors: no fallback
+
+
+# ----------------------------------------------------------------------------------- full-size properties
+def test_full_size_coco608_b64_properties(vy):
+    """BASELINE config 2 at full size: size-independent properties + oracle spot check on 3 frames."""
+    B, C, size = 64, 80, 608
+    g = torch.Generator(device="cuda").manual_seed(1236)
+    heads = [torch.randn((B, 3 * (5 + C), s, s), generator=g, device="cuda") for s in oracle.grid_sizes(size)]
+    out, kept = vy.yolo3_decode_nms(heads, C, AN, ST)
+    out2, kept2 = vy.yolo3_decode_nms(heads, C, AN, ST)
+    assert torch.equal(out, out2) and torch.equal(kept, kept2)                  # deterministic
+    o = out.cpu().numpy()
+    k = kept.cpu().numpy()
+    valid = k >= 0
+    assert ((o[..., 0] >= 0) == valid).all()
+    for b in range(B):
+        n = valid[b].sum()
+        assert (valid[b][:n]).all()                                             # survivors first, padding after
+        assert (np.diff(o[b, :n, 1]) <= 0).all()                                # score order
+        assert len(set(k[b, :n])) == n                                          # unique source rows
+        assert (o[b, n:] == -1).all()
+    # survivors of one class never overlap above the threshold
+    bx = out[..., 2:6]
+    area = (bx[..., 2] - bx[..., 0]).clamp(min=0) * (bx[..., 3] - bx[..., 1]).clamp(min=0)
+    iw = (torch.minimum(bx[:, :, None, 2], bx[:, None, :, 2]) - torch.maximum(bx[:, :, None, 0], bx[:, None, :, 0])).clamp(min=0)
+    ih = (torch.minimum(bx[:, :, None, 3], bx[:, None, :, 3]) - torch.maximum(bx[:, :, None, 1], bx[:, None, :, 1])).clamp(min=0)
+    iou = iw * ih / (area[:, :, None] + area[:, None, :] - iw * ih)
+    same = (out[:, :, None, 0] == out[:, None, :, 0]) & (out[:, :, None, 0] >= 0)
+    same &= ~torch.eye(out.shape[1], dtype=torch.bool, device="cuda")[None]
+    assert not ((iou > 0.45) & same).any()
+    # batch independence (what frame sharding relies on): frames 5..7 alone == the same frames in the batch
+    sub, ksub = vy.yolo3_decode_nms([h[5:8].contiguous() for h in heads], C, AN, ST)
+    assert torch.equal(sub, out[5:8]) and torch.equal(ksub, kept[5:8])
+    # oracle on the GPU-decoded rows of those frames
+    dets = vy.yolo3_decode([h[5:8].contiguous() for h in heads], C, AN, ST).cpu().numpy()
+    exp, rec = oracle.box_nms_c(dets, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, return_record=True)
+    np.testing.assert_array_equal(ksub.cpu().numpy(), rec[:, :100])
+    np.testing.assert_array_equal(sub.cpu().numpy(), exp[:, :100])
+
+
+def test_box_nms_idempotent_full_size(vy):
+    """NMS of an NMS output changes nothing (valid rows stay, -1 padding is dropped by valid_thresh)."""
+    rng = np.random.RandomState(5)
+    d = dev(_rand_dets(rng, 4, 200000, 20))
+    a = vy.box_nms(d, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0)
+    b = vy.box_nms(a, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0)
+    assert torch.equal(a, b)
+
+
+# ----------------------------------------------------------------------------------- bbox_iou
+def test_bbox_iou_against_reference_outputs(vy, golden_dir):
+    z = np.load(os.path.join(golden_dir, "bbox_iou_ref.npz"))
+    for n in sorted({k[:-4] for k in z.files if k.endswith("_iou")}):
+        got = vy.bbox_iou(dev(z[n + "_a"]), dev(z[n + "_b"]), float(z[n + "_off"])).cpu().numpy()
+        np.testing.assert_allclose(got, z[n + "_iou"], rtol=1e-12, atol=0, equal_nan=True, err_msg=n)
+        got32 = vy.bbox_iou(dev(z[n + "_a"].astype(np.float32)), dev(z[n + "_b"].astype(np.float32)),
+                            float(z[n + "_off"])).cpu().numpy()
+        np.testing.assert_allclose(got32, z[n + "_iou"], rtol=2e-4, atol=1e-6, equal_nan=True, err_msg=n)
+    with pytest.raises(IndexError):
+        vy.bbox_iou(torch.zeros(2, 3).cuda(), torch.zeros(2, 4).cuda())

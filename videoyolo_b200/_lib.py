@@ -1,0 +1,79 @@
+"""ctypes binding of libvyolo.so (the C ABI declared in include/vyolo.h).
+
+There is no fallback: if the CUDA library is missing or a tensor is not on a CUDA device the call
+raises.  PyTorch is used for device buffers and streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libvyolo.so")
+_LIB = None
+
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+c_i32p = ctypes.POINTER(ctypes.c_int)
+c_vp = ctypes.c_void_p
+
+# every symbol include/vyolo.h declares, with its signature (tests check the export list against this)
+SIGNATURES = {
+    "vy_version": (ctypes.c_int, []),
+    "vy_last_error": (ctypes.c_char_p, []),
+    "vy_decode_f32": (ctypes.c_int, [ctypes.POINTER(c_vp), c_i32p, c_i32p, c_f32p, c_f32p, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    "vy_box_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int]),
+    "vy_box_nms_f32": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_float,
+                                      ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long,
+                                      c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "vy_decode_nms_workspace_bytes": (ctypes.c_size_t, [c_i32p, c_i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                        ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "vy_decode_nms_f32": (ctypes.c_int, [ctypes.POINTER(c_vp), c_i32p, c_i32p, c_f32p, c_f32p, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "vy_bbox_iou_f32": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_float, c_vp, c_vp]),
+    "vy_bbox_iou_f64": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_double, c_vp, c_vp]),
+    "vy_fusion_conv_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 9),
+    "vy_fusion_conv_bf16": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_float] + [ctypes.c_int] * 9 +
+                            [c_vp, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp]),
+    "vy_temporal_pool_bf16": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_int,
+                                             c_vp, c_vp]),
+}
+
+VY_OK = 0
+ERRORS = {-1: "VY_EINVAL", -2: "VY_EALIGN", -3: "VY_EWORKSPACE", -4: "VY_ECUDA", -5: "VY_EUNSUPPORTED"}
+
+
+class VyoloError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s (%d): %s" % (ERRORS.get(code, "VY_E?"), code, msg))
+        self.code = code
+
+
+def lib() -> ctypes.CDLL:
+    """Load libvyolo.so.  Raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(
+                "videoyolo_b200: %s is missing - build it with `python -m videoyolo_b200.build` "
+                "(or __graft_entry__.build()); there is no CPU fallback" % SO_PATH)
+        L = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)      # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        if L.vy_version() != 1:
+            raise RuntimeError("videoyolo_b200: ABI version mismatch")
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int) -> None:
+    if rc != VY_OK:
+        raise VyoloError(rc, lib().vy_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,43 @@
+// vy_iou.cu -- pairwise IoU, utils/bbox.py:11-38 (same operation order as the numpy source).
+#include "vy_common.cuh"
+
+template <typename T>
+__global__ void vy_bbox_iou_kernel(const T *__restrict__ a, int N, int lda, const T *__restrict__ b, int M,
+                                   int ldb, T offset, T *__restrict__ out) {
+    const long long total = (long long)N * M;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / M), j = (int)(idx % M);
+        const T *pa = a + (size_t)i * lda, *pb = b + (size_t)j * ldb;
+        const T tlx = pa[0] > pb[0] ? pa[0] : pb[0], tly = pa[1] > pb[1] ? pa[1] : pb[1];   // :32
+        const T brx = pa[2] < pb[2] ? pa[2] : pb[2], bry = pa[3] < pb[3] ? pa[3] : pb[3];   // :33
+        const T valid = (tlx < brx && tly < bry) ? (T)1 : (T)0;
+        const T area_i = ((brx - tlx + offset) * (bry - tly + offset)) * valid;            // :35
+        const T area_a = (pa[2] - pa[0] + offset) * (pa[3] - pa[1] + offset);              // :36
+        const T area_b = (pb[2] - pb[0] + offset) * (pb[3] - pb[1] + offset);              // :37
+        out[idx] = area_i / (area_a + area_b - area_i);                                    // :38
+    }
+}
+
+template <typename T>
+static int launch_iou(const T *a, int N, int lda, const T *b, int M, int ldb, T offset, T *out, vy_stream_t st) {
+    if (N < 0 || M < 0 || lda < 4 || ldb < 4) VY_FAIL(VY_EINVAL, "bbox_iou: boxes need >= 4 columns");   // :29-30
+    if (N == 0 || M == 0) return VY_OK;
+    if (!a || !b || !out) VY_FAIL(VY_EINVAL, "bbox_iou: null pointer");
+    const long long total = (long long)N * M;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)vy_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    vy_bbox_iou_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)st>>>(a, N, lda, b, M, ldb, offset, out);
+    VY_LAUNCH_CHECK("vy_bbox_iou_kernel");
+    return VY_OK;
+}
+
+extern "C" int vy_bbox_iou_f32(const float *a, int N, int lda, const float *b, int M, int ldb, float offset,
+                               float *out, vy_stream_t st) {
+    return launch_iou<float>(a, N, lda, b, M, ldb, offset, out, st);
+}
+extern "C" int vy_bbox_iou_f64(const double *a, int N, int lda, const double *b, int M, int ldb, double offset,
+                               double *out, vy_stream_t st) {
+    return launch_iou<double>(a, N, lda, b, M, ldb, offset, out, st);
+}

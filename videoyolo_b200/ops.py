@@ -1,0 +1,166 @@
+"""Operator-level Python surface over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+Names and argument meaning follow what the reference calls:
+  box_nms(...)         mx.nd.contrib.box_nms as called at models/definitions/yolo/yolo3.py:526-528
+  bbox_iou(a, b, off)  utils/bbox.py:11-38
+  yolo3_decode(...)    YOLOOutputV3.hybrid_forward decode, yolo3.py:151-199 (+ concat :523)
+  yolo3_decode_nms()   the fused inference tail, yolo3.py:496,523-534
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+_FMT = {"corner": 0, "center": 1}
+_WS_CACHE = {}
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor on a CUDA device (no CPU fallback)" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s is on %s: videoyolo_b200 has no CPU path, move it to a CUDA device" % (name, t.device))
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Cached per-(device, stream) scratch buffer; grows monotonically."""
+    key = (torch.device(device).index, _stream())
+    buf = _WS_CACHE.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = buf
+    return buf
+
+
+def _head_args(heads: Sequence[torch.Tensor], anchors, strides):
+    n = len(heads)
+    if n < 1 or n > 4 or len(anchors) != n or len(strides) != n:
+        raise ValueError("need 1..4 scales with matching anchors/strides")
+    heads = [_need_cuda(h, "heads[%d]" % i) for i, h in enumerate(heads)]
+    B = heads[0].shape[0]
+    A = len(anchors[0]) // 2
+    for h in heads:
+        if h.dim() != 4 or h.shape[0] != B or h.device != heads[0].device:
+            raise ValueError("heads must be (B, A*(5+C), H, W) on one device")
+    ptrs = (ctypes.c_void_p * n)(*[h.data_ptr() for h in heads])
+    H = (ctypes.c_int * n)(*[h.shape[2] for h in heads])
+    W = (ctypes.c_int * n)(*[h.shape[3] for h in heads])
+    st = (ctypes.c_float * n)(*[float(s) for s in strides])
+    flat = [float(v) for a in anchors for v in a]
+    an = (ctypes.c_float * len(flat))(*flat)
+    return heads, ptrs, H, W, st, an, n, B, A
+
+
+def n_rows(heads: Sequence[torch.Tensor], num_class: int, A: int = 3, agnostic: bool = False) -> int:
+    ceff = 1 if agnostic else num_class
+    return ceff * sum(h.shape[2] * h.shape[3] * A for h in heads)
+
+
+def yolo3_decode(heads, num_class: int, anchors, strides, agnostic: bool = False,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """heads (network order: stride 32,16,8) -> (B, R, 6) detections in the reference's row order."""
+    heads, ptrs, H, W, st, an, n, B, A = _head_args(heads, anchors, strides)
+    for h in heads:
+        if h.shape[1] != A * (5 + num_class):
+            raise ValueError("head has %d channels, expected A*(5+C)=%d" % (h.shape[1], A * (5 + num_class)))
+    R = n_rows(heads, num_class, A, agnostic)
+    if out is None:
+        out = torch.empty((B, R, 6), dtype=torch.float32, device=heads[0].device)
+    else:
+        out = _need_cuda(out, "out")
+        if tuple(out.shape) != (B, R, 6):
+            raise ValueError("out must be (B, R, 6) = %s" % ((B, R, 6),))
+    with torch.cuda.device(heads[0].device):
+        _lib.check(_lib.lib().vy_decode_f32(ptrs, H, W, st, an, n, B, A, num_class, int(agnostic),
+                                            out.data_ptr(), _stream()))
+    return out
+
+
+def box_nms(data: torch.Tensor, overlap_thresh: float = 0.5, valid_thresh: float = 0, topk: int = -1,
+            coord_start: int = 2, score_index: int = 1, id_index: int = -1, background_id: int = -1,
+            force_suppress: bool = False, in_format: str = "corner", out_format: str = "corner",
+            out_rows: Optional[int] = None, return_kept: bool = False):
+    """MXNet ``contrib.box_nms`` on a CUDA tensor; all leading dims are batch.
+
+    Returns a tensor of the same shape as ``data`` (or with ``out_rows`` rows when given, which fuses
+    the ``slice_axis(axis=1, 0, post_nms)`` of yolo3.py:529-530); with ``return_kept`` also the int32
+    source-row index of every output row (MXNet's hidden ``record`` output).
+    """
+    data = _need_cuda(data, "data")
+    if data.dim() < 2:
+        raise ValueError("data must be (..., R, W)")
+    shp = tuple(data.shape)
+    R, Wd = shp[-2], shp[-1]
+    B = 1
+    for d in shp[:-2]:
+        B *= d
+    rows = R if out_rows is None else int(out_rows)
+    out = torch.empty(shp[:-2] + (rows, Wd), dtype=torch.float32, device=data.device)
+    kept = torch.empty(shp[:-2] + (rows,), dtype=torch.int32, device=data.device)
+    if B == 0 or R == 0:
+        return (out, kept) if return_kept else out
+    L = _lib.lib()
+    with torch.cuda.device(data.device):
+        need = L.vy_box_nms_workspace_bytes(B, R, Wd, int(topk))
+        ws = workspace(need, data.device)
+        _lib.check(L.vy_box_nms_f32(data.data_ptr(), B, R, Wd, float(overlap_thresh), float(valid_thresh),
+                                    int(topk), int(coord_start), int(score_index), int(id_index),
+                                    int(background_id), int(bool(force_suppress)), _FMT[in_format],
+                                    _FMT[out_format], rows, out.data_ptr(), kept.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), _stream()))
+    return (out, kept) if return_kept else out
+
+
+def yolo3_decode_nms(heads, num_class: int, anchors, strides, nms_thresh: float = 0.45,
+                     valid_thresh: float = 0.01, topk: int = 400, post_nms: int = 100,
+                     force_suppress: bool = False, agnostic: bool = False,
+                     out: Optional[torch.Tensor] = None, kept: Optional[torch.Tensor] = None):
+    """Fused decode + box_nms + post_nms slice.  Returns (out (B, post_nms, 6), kept (B, post_nms))."""
+    heads, ptrs, H, W, st, an, n, B, A = _head_args(heads, anchors, strides)
+    for h in heads:
+        if h.shape[1] != A * (5 + num_class):
+            raise ValueError("head has %d channels, expected A*(5+C)=%d" % (h.shape[1], A * (5 + num_class)))
+    dev = heads[0].device
+    if out is None:
+        out = torch.empty((B, post_nms, 6), dtype=torch.float32, device=dev)
+    if kept is None:
+        kept = torch.empty((B, post_nms), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        need = L.vy_decode_nms_workspace_bytes(H, W, n, B, A, num_class, int(agnostic), int(topk))
+        if need == 0:
+            raise _lib.VyoloError(-5, L.vy_last_error().decode())
+        ws = workspace(need, dev)
+        _lib.check(L.vy_decode_nms_f32(ptrs, H, W, st, an, n, B, A, num_class, int(agnostic),
+                                       float(nms_thresh), float(valid_thresh), int(topk),
+                                       int(bool(force_suppress)), int(post_nms), out.data_ptr(),
+                                       kept.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return out, kept
+
+
+def bbox_iou(bbox_a: torch.Tensor, bbox_b: torch.Tensor, offset=0) -> torch.Tensor:
+    """utils/bbox.py:11-38 on CUDA tensors (float32 or float64): (N,>=4) x (M,>=4) -> (N, M)."""
+    if not (isinstance(bbox_a, torch.Tensor) and isinstance(bbox_b, torch.Tensor)):
+        raise TypeError("bbox_iou needs torch CUDA tensors (no CPU fallback)")
+    if bbox_a.dim() != 2 or bbox_b.dim() != 2 or bbox_a.shape[1] < 4 or bbox_b.shape[1] < 4:
+        raise IndexError("Bounding boxes axis 1 must have at least length 4")      # utils/bbox.py:29-30
+    dt = torch.float64 if (bbox_a.dtype == torch.float64 or bbox_b.dtype == torch.float64) else torch.float32
+    a = _need_cuda(bbox_a.to(dt), "bbox_a", dt)
+    b = _need_cuda(bbox_b.to(dt), "bbox_b", dt)
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=dt, device=a.device)
+    fn = _lib.lib().vy_bbox_iou_f64 if dt == torch.float64 else _lib.lib().vy_bbox_iou_f32
+    with torch.cuda.device(a.device):
+        _lib.check(fn(a.data_ptr(), a.shape[0], a.shape[1], b.data_ptr(), b.shape[0], b.shape[1],
+                      float(offset), out.data_ptr(), _stream()))
+    return out

@@ -1,0 +1,150 @@
+"""Host-side mirror of the reference's Gluon block surface for the detection post-processing path.
+
+Same names, constructor arguments, return shapes and error behaviour as
+models/definitions/yolo/yolo3.py (YOLOOutputV3 :25-199, YOLOV3_noback :1686-1870, set_nms :536-556);
+the arithmetic runs in the CUDA library behind include/vyolo.h.  Backbone stages, training branches
+and reset_class are out of scope.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+
+# models/definitions/yolo/wrappers.py:80-84
+ANCHORS = [[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]]
+STRIDES = [8, 16, 32]
+CHANNELS = [512, 256, 128]
+
+
+class YOLOOutputV3(torch.nn.Module):
+    """YOLO output layer V3 (yolo3.py:25-199), inference branch.
+
+    ``__call__(x)`` applies the 1x1 ``prediction`` conv (yolo3.py:62,157; a library conv) to the tip
+    feature map and decodes it with the CUDA kernel into ``(B, C*H*W*A, 6)`` detections in the
+    reference's row order.  ``decode(pred)`` skips the conv for an already computed head map.
+    """
+
+    def __init__(self, index, num_class, anchors, stride, alloc_size=(128, 128), agnostic=False,
+                 in_channels: Optional[int] = None, **kwargs):
+        super().__init__()
+        anchors = np.array(anchors).astype("float32")                      # :46
+        self._index = index
+        self._classes = num_class
+        self._num_pred = 1 + 4 + num_class                                  # :48
+        self._num_anchors = anchors.size // 2                               # :49
+        self._stride = stride
+        self._agnostic = agnostic
+        self._alloc_size = tuple(alloc_size)
+        self._anchors = [float(v) for v in anchors.reshape(-1)]
+        all_pred = self._num_pred * self._num_anchors                       # :57
+        self.prediction = (torch.nn.Conv2d(in_channels, all_pred, kernel_size=1, padding=0, stride=1)
+                           if in_channels else None)                        # :62
+
+    def _check(self, pred: torch.Tensor):
+        if pred.shape[2] > self._alloc_size[0] or pred.shape[3] > self._alloc_size[1]:
+            # the reference crops a (128,128) offset map (yolo3.py:67-74,168): larger maps cannot broadcast
+            raise ValueError("feature map %s exceeds alloc_size %s" % (tuple(pred.shape[2:]), self._alloc_size))
+
+    def decode(self, pred: torch.Tensor) -> torch.Tensor:
+        self._check(pred)
+        return ops.yolo3_decode([pred], self._classes, [self._anchors], [self._stride], self._agnostic)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.prediction is None:
+            raise RuntimeError("YOLOOutputV3 built without in_channels: call decode(pred) with the head map")
+        return self.decode(self.prediction(x))
+
+
+class YOLOV3(torch.nn.Module):
+    """Inference tail of the YOLOV3 family (yolo3.py:350-556; head-level like YOLOV3_noback :1686-1870).
+
+    ``net(x1, x2, x3)`` takes the three inputs of the output layers in network order (stride 32, 16, 8:
+    anchors/strides are used reversed, yolo3.py:416-417) and returns
+    ``ids (B, post_nms, 1), scores (B, post_nms, 1), bboxes (B, post_nms, 4)`` like yolo3.py:531-534.
+    With ``in_channels`` given the inputs are tip feature maps and go through the 1x1 prediction convs
+    first; otherwise they are the head maps themselves.
+    """
+
+    def __init__(self, anchors=None, strides=None, classes: Sequence[str] = (), alloc_size=(128, 128),
+                 nms_thresh=0.45, nms_topk=400, post_nms=100, agnostic=False,
+                 in_channels: Optional[Sequence[int]] = None, **kwargs):
+        super().__init__()
+        anchors = ANCHORS if anchors is None else anchors
+        strides = STRIDES if strides is None else strides
+        self._classes = list(classes)
+        self.nms_thresh = nms_thresh
+        self.nms_topk = nms_topk
+        self.post_nms = post_nms
+        self._agnostic = agnostic
+        self.valid_thresh = 0.01                                            # hard-coded at yolo3.py:527
+        self.yolo_outputs = torch.nn.ModuleList()
+        # note that anchors and strides should be used in reverse order (yolo3.py:415-417)
+        for i, (anchor, stride) in enumerate(zip(anchors[::-1], strides[::-1])):
+            ic = in_channels[i] if in_channels is not None else None
+            self.yolo_outputs.append(YOLOOutputV3(i, len(self._classes), anchor, stride,
+                                                  alloc_size=alloc_size, agnostic=agnostic, in_channels=ic))
+        self.last_kept_rows = None
+
+    @property
+    def num_class(self):
+        return len(self._classes)
+
+    @property
+    def classes(self):
+        return self._classes
+
+    def set_nms(self, nms_thresh=0.45, nms_topk=400, post_nms=100):
+        """yolo3.py:536-556."""
+        self.nms_thresh = nms_thresh
+        self.nms_topk = nms_topk
+        self.post_nms = post_nms
+
+    def _heads(self, xs):
+        if len(xs) != len(self.yolo_outputs):
+            raise ValueError("expected %d inputs (stride 32,16,8 order)" % len(self.yolo_outputs))
+        heads = []
+        for x, out in zip(xs, self.yolo_outputs):
+            h = out.prediction(x) if out.prediction is not None else x
+            out._check(h)
+            heads.append(h)
+        return heads
+
+    def forward(self, *xs):
+        heads = self._heads(xs)
+        C = len(self._classes)
+        anchors = [o._anchors for o in self.yolo_outputs]
+        strides = [o._stride for o in self.yolo_outputs]
+        R = ops.n_rows(heads, C, self.yolo_outputs[0]._num_anchors, self._agnostic)
+        nms_on = 0 < self.nms_thresh < 1                                     # yolo3.py:525
+        k_eff = R if self.nms_topk < 0 else min(R, self.nms_topk)
+        if nms_on and self.post_nms > 0 and 1 <= k_eff <= 1024:
+            # fused: the (B, R, 6) tensor of yolo3.py:523 is never materialised
+            result, kept = ops.yolo3_decode_nms(heads, C, anchors, strides, self.nms_thresh, self.valid_thresh,
+                                                self.nms_topk, min(self.post_nms, R), agnostic=self._agnostic)
+            self.last_kept_rows = kept
+        else:
+            result = ops.yolo3_decode(heads, C, anchors, strides, self._agnostic)        # :496,:523
+            self.last_kept_rows = None
+            if nms_on:
+                rows = min(self.post_nms, R) if self.post_nms > 0 else None              # :529-530
+                result, kept = ops.box_nms(result, overlap_thresh=self.nms_thresh, valid_thresh=self.valid_thresh,
+                                           topk=self.nms_topk, id_index=0, score_index=1, coord_start=2,
+                                           force_suppress=False, out_rows=rows, return_kept=True)  # :526-528
+                self.last_kept_rows = kept
+        ids = result[..., 0:1]                                                           # :531
+        scores = result[..., 1:2]                                                        # :532
+        bboxes = result[..., 2:6]                                                        # :533
+        return ids, scores, bboxes
+
+
+# the reference's YOLOV3_noback takes pre-extracted features; at head level the two coincide
+YOLOV3_noback = YOLOV3
+
+
+def get_yolov3_postprocess(classes, agnostic=False, in_channels=None, **kwargs) -> YOLOV3:
+    """Head-level counterpart of wrappers.yolo3_darknet53 (wrappers.py:9-110): reference anchors/strides."""
+    return YOLOV3(ANCHORS, STRIDES, classes=classes, agnostic=agnostic, in_channels=in_channels, **kwargs)
