@@ -84,7 +84,7 @@ def _check_nms(vy, d, **kw):
     okw = dict(kw)
     out_rows = okw.pop("out_rows", None)
     exp, rec = oracle.box_nms_c(d, return_record=True, **okw)
-    got, kept = vy.box_nms(dev(d), return_kept=True, out_rows=out_rows, **kw)
+    got, kept = vy.box_nms(dev(d), return_kept=True, out_rows=out_rows, **okw)
     got, kept = got.cpu().numpy(), kept.cpu().numpy()
     if out_rows is not None:
         exp, rec = exp[..., :out_rows, :], rec[..., :out_rows]

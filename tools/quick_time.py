@@ -20,15 +20,18 @@ def timeit(fn, n=10, warm=3):
     ts.sort()
     return ts[len(ts) // 2], ts[0]
 
+only = sys.argv[1] if len(sys.argv) > 1 else None
 for name, B, C, size, regime in [("coco608_b64_R", 64, 80, 608, "R"), ("coco608_b64_T", 64, 80, 608, "T"),
                                  ("voc416_b1_R", 1, 20, 416, "R"), ("stress416_b128_R", 128, 80, 416, "R"),
                                  ("vid320_b256_R", 256, 30, 320, "R"), ("vid320_b256_T", 256, 30, 320, "T")]:
+    if only and name != only: continue
     heads = random_heads_cuda(B, C, size, 1234, dev, regime=regime)
     nbytes = sum(h.numel() * 4 for h in heads)
     med, best = timeit(lambda: vy.yolo3_decode_nms(heads, C, AN, ST))
     print("%-18s fused decode+nms: median %.3f ms best %.3f ms | %.1f MB in -> %.0f GB/s (best), %.0f frames/s"
           % (name, med, best, nbytes / 1e6, nbytes / best / 1e6, B / med * 1e3), flush=True)
     del heads
+if only: sys.exit(0)
 heads = random_heads_cuda(8, 80, 608, 1, dev)
 med, best = timeit(lambda: vy.yolo3_decode(heads, 80, AN, ST))
 out_b = 8 * 1819440 * 24

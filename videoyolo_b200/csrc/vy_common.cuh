@@ -44,11 +44,13 @@ int vy_fill_heads(VyHeads *h, const float *const *head, const int *H, const int 
                   int agnostic);
 
 // ------------------------------------------------------------------ decode arithmetic
-// mshadow_op::sigmoid, 1/(1+exp(-x)) in fp32 (F.sigmoid at yolo3.py:172,174,175).  Accurate expf
-// and IEEE division: every score the library ever produces goes through this one function, so
-// the fused and the materialising paths order candidates identically.
+// mshadow_op::sigmoid, 1/(1+exp(-x)) in fp32 (F.sigmoid at yolo3.py:172,174,175).  MUFU-based:
+// ex2.approx(-x*log2e) and rcp.approx; relative error <= ~3e-7 + |x|*6e-8 (the rounding of
+// x*log2e), i.e. < 2e-6 for |x| <= 24 -- inside the 1e-5 parity budget.  Every score the library
+// ever produces goes through this one function, so the fused and the materialising paths order
+// candidates identically.
 __device__ __forceinline__ float vy_sigmoid(float x) {
-    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+    return __fdividef(1.0f, __fadd_rn(1.0f, __expf(-x)));
 }
 
 // score = sigmoid(class_pred) * confidence   (yolo3.py:175)
@@ -92,5 +94,17 @@ __device__ __forceinline__ float4 vy_ldg128(const float *p) {
 __device__ __forceinline__ float vy_ldg32(const float *p) {
     float r;
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+// L1-allocating variants: the selection kernel re-reads the rare planes that hold a hit from L1
+__device__ __forceinline__ float4 vy_ldg128_ca(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float vy_ldg32_ca(const float *p) {
+    float r;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }

@@ -13,64 +13,62 @@
 #include <math_constants.h>
 
 // ------------------------------------------------------------------------------------------------
-// tiling plan shared by workspace sizing and launch
+// job plan shared by workspace sizing and launch
+//   An image is split into G equal shares; job (b, g) streams share g of image b from start to end
+//   in ONE CTA, so its candidate buffer and threshold persist for the whole share.
 // ------------------------------------------------------------------------------------------------
+#ifndef SEL_CTAS_PER_SM
+#define SEL_CTAS_PER_SM 4
+#endif
+
 struct SelPlan {
     int K;                      // min(topk, R)
-    int tiles_per_frame;
-    int csplit, cper;           // heads: class range split
-    int tile_begin[VY_MAX_SCALES + 1];
-    int chunks[VY_MAX_SCALES];  // heads: position chunks per (scale, anchor)
-    long long rows_per_tile;    // rows: rows per tile
+    int G, Kq;                  // CTAs per image, ceil(K / G)
+    int n_jobs;                 // B * G
+    // heads: an "item" is 4 consecutive positions of one (scale, anchor) plane set
+    int items_per_plane[VY_MAX_SCALES];     // ceil(HW / 4)
+    int item_begin[VY_MAX_SCALES + 1];      // first item of each scale (A * items_per_plane each)
+    int items_per_frame;
+    long long rows_per_job;     // rows: multiple of SEL_NT
     int list_cap;               // keys per image in the global list
     float valid_thresh;
 };
 
 struct SelGlobal {              // workspace views
-    u64 *thr;                   // [B]
-    int *count;                 // [B]
+    u64 *thr;                   // [B]        best bound per image
+    int *count;                 // [B]        list fill
+    u64 *slots;                 // [B][G]     per-CTA ceil(K/G)-th largest
     u64 *list;                  // [B][list_cap]
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static size_t sel_workspace_layout(int B, int list_cap, SelGlobal *g, void *base) {
+static size_t sel_workspace_layout(int B, int G, int list_cap, SelGlobal *g, void *base, size_t *header) {
     size_t off = 0;
     const size_t o_thr = off;   off = align_up(off + sizeof(u64) * (size_t)B, 256);
     const size_t o_cnt = off;   off = align_up(off + sizeof(int) * (size_t)B, 256);
+    const size_t o_slot = off;  off = align_up(off + sizeof(u64) * (size_t)B * G, 256);
+    if (header) *header = off;  // the part that must be zeroed per call
     const size_t o_list = off;  off = align_up(off + sizeof(u64) * (size_t)B * (size_t)list_cap, 256);
     if (g && base) {
         g->thr = (u64 *)((char *)base + o_thr);
         g->count = (int *)((char *)base + o_cnt);
+        g->slots = (u64 *)((char *)base + o_slot);
         g->list = (u64 *)((char *)base + o_list);
     }
     return off;
 }
-static inline size_t sel_header_bytes(int B) {   // the part that must be zeroed per call
-    return align_up(align_up(sizeof(u64) * (size_t)B, 256) + sizeof(int) * (size_t)B, 256);
-}
 
 // ------------------------------------------------------------------------------------------------
-// device: threshold sharing + flush
+// device: flush a finished job to the image's global list
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
-    u64 v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// Append the CTA's surviving keys to the image's global list and publish its threshold.
-__device__ void sel_flush(SelBuf &S, int K, u64 *g_thr_b, int *g_count_b, u64 *g_list_b, int list_cap) {
+static __device__ __noinline__ void sel_flush(SelBuf &S, const SelJob &jb, int *g_count_b, u64 *g_list_b, int list_cap) {
     const int tid = threadIdx.x, lane = tid & 31;
     __syncthreads();
     int n = S.count;
-    if (n > K + (K >> 2)) n = sel_compact(S, n, K, false);
-    if (tid == 0) {
-        const u64 mine = S.thr;
-        const u64 old = mine ? atomicMax(g_thr_b, mine) : ld_relaxed_u64(g_thr_b);
-        S.thr = old > mine ? old : mine;
-    }
     __syncthreads();
+    n = sel_update(S, n, jb, false);
+    if (n > jb.K + (jb.K >> 2)) n = sel_compact(S, n, jb.K, false);
     const u64 thr = S.thr;
     for (int base = 0; base < n; base += blockDim.x) {
         const int idx = base + tid;
@@ -89,226 +87,280 @@ __device__ void sel_flush(SelBuf &S, int K, u64 *g_thr_b, int *g_count_b, u64 *g
 }
 
 // ------------------------------------------------------------------------------------------------
-// device: generic adaptive block loop
-//   Src provides: int n_iters; int max_push_per_iter;
-//                 void refresh(u64 thr);                       recompute prefilter state
-//                 void run(SelBuf&, int it0, int it1, u64 thr);  stream iterations [it0,it1)
-// Between CTA barriers a block of U iterations is streamed; U adapts to the observed push rate
-// so that the shared buffer cannot overflow in the steady state; if it still does (cold start,
-// adversarial order) the block's pushes are discarded, the buffer is compacted and the block is
-// replayed with a smaller U.  U == 1 always fits: max_push_per_iter + K <= SEL_CAP.
+// device: generic adaptive block loop over one "round" of a source
+//   Src provides: int n_iters;
+//                 void refresh(SelBuf&, u64 thr);                  recompute prefilter state
+//                 void run(SelBuf&, int it0, int it1);             stream [it0,it1): queue prefilter hits
+//                 void eval(SelBuf&, int q0, int q1, u64 thr);     exact keys of queued hits -> sel_push
+// A block of U iterations is streamed between CTA barriers; U adapts to the observed hit rate so
+// that the hit queue cannot overflow in the steady state.  If it still does (cold start, adversarial
+// order) the block is replayed with a smaller U; U == 1 always fits (<= 4*SEL_NT hits).  Queued hits
+// are evaluated in chunks that fit the key buffer, which is compacted exactly when it is full, so
+// every chunk makes progress (K <= SEL_KMAX leaves >= SEL_CAP - SEL_KMAX free slots).
+// `cnt` (CTA-uniform running key count) and `fresh` (keys pushed since the last selection event)
+// persist across rounds of one job.
 // ------------------------------------------------------------------------------------------------
 template <class Src>
-__device__ void sel_stream(SelBuf &S, Src &src, int K, u64 *g_thr_b) {
-    constexpr int UMAX = 16;
+static __device__ __forceinline__ void sel_stream(SelBuf &S, Src &src, const SelJob &jb, int &cnt, int &fresh) {
+    constexpr int UMAX = 128;
     const int tid = threadIdx.x;
-    __syncthreads();
+    const int trigger = max(16, jb.Kq >> 1);
     int it = 0;
-    int cnt0 = S.count;                              // CTA-uniform running count
-    int U = (S.thr == 0ull) ? 1 : 4;
-    u64 thr_seen = ~0ull, published = S.thr;
-    __syncthreads();                                 // nobody pushes before everybody has read
+    int U = (S.thr == 0ull) ? 1 : 8;
+    u64 thr_seen = ~0ull;
     while (it < src.n_iters) {                       // CTA-uniform loop
         const u64 thr = S.thr;
         u64 gthr = 0;
-        if (tid == 0) gthr = ld_relaxed_u64(g_thr_b);          // consumed after the block
-        if (thr != thr_seen) { src.refresh(thr); thr_seen = thr; }
+        if (tid == 0) gthr = ld_relaxed_u64(jb.g_thr_b);       // consumed after the block
+        if (thr != thr_seen) { src.refresh(S, thr); thr_seen = thr; }
         const int Ub = min(U, src.n_iters - it);
-        src.run(S, it, it + Ub, thr);
-        __syncthreads();                              // pushes of this block complete
-        if (tid == 0) {
-            const int c = S.count;
-            S.flag = c > SEL_CAP;
-            if (S.flag) S.count = cnt0;
-            S.snap = S.flag ? cnt0 : c;
-            if (gthr > S.thr) S.thr = gthr;
-        }
-        __syncthreads();
-        if (S.flag) {                                 // overflow: replay with a smaller block
-            cnt0 = sel_compact(S, cnt0, K, true);
+        src.run(S, it, it + Ub);
+        __syncthreads();                              // hits of this block are queued
+        const int nq = S.qcount;                      // not modified before the barriers below
+        if (nq > SEL_QCAP) {                          // queue overflow: replay a smaller block
+            __syncthreads();
+            if (tid == 0) S.qcount = 0;
+            __syncthreads();
             U = max(1, Ub >> 1);
             continue;
         }
-        int cnt = S.snap;
-        const int pushed = cnt - cnt0;
-        it += Ub;
-        if (cnt > K + (K >> 2) && cnt >= SEL_CAP / 2) {
-            cnt = sel_compact(S, cnt, K, false);
-            const u64 nthr = S.thr;                  // stable: thread 0 next writes it after a barrier
-            if (tid == 0 && nthr > published) atomicMax(g_thr_b, nthr);
-            published = nthr;
+        int q0 = 0;
+        for (;;) {                                    // chunks of queued hits that fit the key buffer
+            const int want = nq - q0;
+            if (want > SEL_CAP - cnt) { cnt = sel_update(S, cnt, jb, true); fresh = 0; }
+            const int take = min(want, SEL_CAP - cnt);
+            if (take > 0) src.eval(S, q0, q0 + take, S.thr);
+            q0 += take;
+            __syncthreads();                          // pushes complete
+            if (tid == 0) {
+                S.snap = S.count;
+                if (q0 >= nq) { S.qcount = 0; if (gthr > S.thr) S.thr = gthr; }
+            }
+            __syncthreads();
+            const int now = S.snap;
+            fresh += now - cnt;
+            cnt = now;
+            if (q0 >= nq) break;
         }
-        const int rate = (pushed + Ub - 1) / Ub;
-        U = min(UMAX, max(1, (SEL_CAP - cnt) / (2 * rate + 1)));
-        cnt0 = cnt;
+        it += Ub;
+        if (cnt >= SEL_CAP / 2 || fresh >= trigger) {
+            cnt = sel_update(S, cnt, jb, false);
+            if (cnt >= SEL_CAP / 2) cnt = sel_compact(S, cnt, jb.K, true);
+            fresh = 0;
+        }
+        const int rate = (nq + Ub - 1) / Ub;          // hits per iteration
+        U = min(UMAX, max(1, SEL_QCAP / (2 * rate + 1)));
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// source 1: YOLO head maps (fused decode).  A tile = (image b, scale s, anchor a, a chunk of
-// SEL_NT*VEC positions, a class range).  Each thread owns VEC consecutive positions and walks the
-// class planes with one 128-bit load per plane.  score = sigmoid(t_c)*conf >= smin is tested in
-// the logit domain against a per-box bound (one compare per element); only elements that pass
-// pay for the exact sigmoid.
+// source 1: YOLO head maps (fused decode).  Each thread owns one item = 4 consecutive positions of
+// one (scale, anchor) and walks the class planes with one 128-bit load per plane (four 32-bit loads
+// when the plane size is not a multiple of 4).  score = sigmoid(t_c)*conf >= smin is tested in the
+// logit domain against a per-box bound: one FSETP per element.
 // ------------------------------------------------------------------------------------------------
-// conservative logit bound: score(t) >= smin  ==>  t >= vy_tcmin(smin, conf)
+// conservative logit bound: score(t) >= smin  ==>  t >= vy_tcmin(smin, conf).  The score that is
+// compared later is fl(S(t)*conf) with S within ~2e-6 of the true sigmoid; q is lowered by 1e-3
+// relative and the logit by 2e-3 absolute, which covers those roundings and the error of the
+// fast intrinsics used here (__fdividef 2 ulp, __logf <= 1e-6 abs on [0.5,2], 3 ulp elsewhere).
 __device__ __forceinline__ float vy_tcmin(float smin, float conf) {
     if (!(smin > 0.0f)) return -CUDART_INF_F;
-    const float q = __fmul_rn(__fdiv_rn(smin, conf), 1.0f - 1e-4f);
+    const float q = __fdividef(smin, conf) * (1.0f - 1e-3f);
     if (!(q < 1.0f)) return CUDART_INF_F;            // also conf == 0 / NaN: no class can pass
-    return logf(__fdiv_rn(q, 1.0f - q)) - 1e-4f;
+    return __logf(__fdividef(q, 1.0f - q)) - 2e-3f;
 }
 
-template <int VEC>
+// any of 16 ordered compares t[u][v] >= c[v]: one FSETP per element, chained through the predicate
+__device__ __forceinline__ u32 vy_any_ge16(const float (&t)[4][4], const float (&c)[4]) {
+    u32 r;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.ge.f32 p, %1, %17;\n\t"
+        "setp.ge.or.f32 p, %2, %18, p;\n\t"
+        "setp.ge.or.f32 p, %3, %19, p;\n\t"
+        "setp.ge.or.f32 p, %4, %20, p;\n\t"
+        "setp.ge.or.f32 p, %5, %17, p;\n\t"
+        "setp.ge.or.f32 p, %6, %18, p;\n\t"
+        "setp.ge.or.f32 p, %7, %19, p;\n\t"
+        "setp.ge.or.f32 p, %8, %20, p;\n\t"
+        "setp.ge.or.f32 p, %9, %17, p;\n\t"
+        "setp.ge.or.f32 p, %10, %18, p;\n\t"
+        "setp.ge.or.f32 p, %11, %19, p;\n\t"
+        "setp.ge.or.f32 p, %12, %20, p;\n\t"
+        "setp.ge.or.f32 p, %13, %17, p;\n\t"
+        "setp.ge.or.f32 p, %14, %18, p;\n\t"
+        "setp.ge.or.f32 p, %15, %19, p;\n\t"
+        "setp.ge.or.f32 p, %16, %20, p;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "f"(t[0][0]), "f"(t[0][1]), "f"(t[0][2]), "f"(t[0][3]),
+          "f"(t[1][0]), "f"(t[1][1]), "f"(t[1][2]), "f"(t[1][3]),
+          "f"(t[2][0]), "f"(t[2][1]), "f"(t[2][2]), "f"(t[2][3]),
+          "f"(t[3][0]), "f"(t[3][1]), "f"(t[3][2]), "f"(t[3][3]),
+          "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+    return r;
+}
+
 struct HeadSrc {
-    int n_iters, max_push_per_iter;
-    const float *plane;          // -> channel a*P + 0 at this thread's first position
+    int n_iters;                 // class planes
+    const VyHeads *hd;
+    const float *p5;             // -> class plane 0 (channel a*P + 5) at this thread's first position
     size_t HW;
-    int c0;
-    bool active;
-    float conf[VEC], tcmin[VEC];
-    u32 row0;                    // row_off + pos0*A + a  (add c*n_s + v*A)
-    u32 n_s, A;
+    int nv;                      // valid positions of this item (0: idle thread)
+    int o1, o2, o3;              // element offsets of positions 1..3 (clamped into the plane)
+    bool vec;                    // 128-bit loads allowed
+    float tcmin[4];
     float valid_thresh;
 
-    __device__ void refresh(u64 thr) {
+    __device__ __forceinline__ void refresh(SelBuf &S, u64 thr) {
         const float ts = thr ? vy_key_score(thr) : valid_thresh;
         const float smin = fmaxf(ts, valid_thresh);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) tcmin[v] = active ? vy_tcmin(smin, conf[v]) : CUDART_INF_F;
+        for (int v = 0; v < 4; ++v)
+            tcmin[v] = v < nv ? vy_tcmin(smin, S.it_conf[v][threadIdx.x]) : CUDART_INF_F;
     }
-    __device__ __forceinline__ void hit(SelBuf &S, float t, int v, int c, u64 thr) {
-        const float s = vy_score(t, conf[v]);
-        if (s > valid_thresh) {
-            const u64 key = vy_make_key(s, row0 + (u32)c * n_s + (u32)v * A);
-            if (key >= thr) sel_push(S, key);
+    __device__ __forceinline__ void load(float (&t)[4], const float *p) const {
+        if (vec) {
+            const float4 q = vy_ldg128_ca(p);
+            t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
+        } else {      // positions past the end of the plane re-read the last valid one (tcmin = +inf there)
+            t[0] = vy_ldg32_ca(p); t[1] = vy_ldg32_ca(p + o1); t[2] = vy_ldg32_ca(p + o2); t[3] = vy_ldg32_ca(p + o3);
         }
     }
-    __device__ void run(SelBuf &S, int it0, int it1, u64 thr) {
-        if (!active) return;
+    // planes [c, c+n) of this item into t (n in 1..4); the rest can never hit (tcmin may be -inf)
+    __device__ __forceinline__ void load_group(float (&t)[4][4], const float *p, int n) const {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (u < n) load(t[u], p + (size_t)u * HW);
+            else t[u][0] = t[u][1] = t[u][2] = t[u][3] = CUDART_NAN_F;   // NaN >= x is false for every x
+        }
+    }
+    __device__ __forceinline__ void run(SelBuf &S, int it0, int it1) {
+        if (nv == 0) return;
+        float t[4][4];
+        const float *p = p5 + (size_t)it0 * HW;
+        load_group(t, p, min(4, it1 - it0));
         for (int it = it0; it < it1; it += 4) {
-            if (VEC == 4) {
-                float4 t[4];
+            u32 mask = 0;
+            if (vy_any_ge16(t, tcmin)) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (it + u < it1) t[u] = vy_ldg128(plane + (size_t)(5 + c0 + it + u) * HW);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (it + u < it1) {
-                        const int c = c0 + it + u;
-                        if (t[u].x >= tcmin[0]) hit(S, t[u].x, 0, c, thr);
-                        if (t[u].y >= tcmin[1 % VEC]) hit(S, t[u].y, 1 % VEC, c, thr);
-                        if (t[u].z >= tcmin[2 % VEC]) hit(S, t[u].z, 2 % VEC, c, thr);
-                        if (t[u].w >= tcmin[3 % VEC]) hit(S, t[u].w, 3 % VEC, c, thr);
-                    }
-                }
-            } else {
-                float t[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (it + u < it1) t[u] = vy_ldg32(plane + (size_t)(5 + c0 + it + u) * HW);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (it + u < it1 && t[u] >= tcmin[0]) hit(S, t[u], 0, c0 + it + u, thr);
+                    for (int v = 0; v < 4; ++v) mask |= (t[u][v] >= tcmin[v]) ? (1u << (u * 4 + v)) : 0u;
+            }
+            // the next group's loads go out before the hits of this one are queued
+            p += 4 * HW;
+            const int left = it1 - (it + 4);
+            if (left >= 4) load_group(t, p, 4);
+            else if (left > 0) load_group(t, p, left);
+            while (mask) {
+                const int k = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int slot = atomicAdd(&S.qcount, 1);
+                if (slot < SEL_QCAP) S.queue[slot] = ((u32)(it + (k >> 2)) << 10) | (threadIdx.x << 2) | (u32)(k & 3);
+            }
+        }
+    }
+    __device__ __forceinline__ void eval(SelBuf &S, int q0, int q1, u64 thr) const {
+        for (int q = q0 + threadIdx.x; q < q1; q += SEL_NT) {
+            const u32 code = S.queue[q];
+            const int v = code & 3, owner = (code >> 2) & 255, c = code >> 10;
+            const VyScale &sc = hd->sc[S.it_scale[owner]];
+            const float tv = vy_ldg32_ca(sc.head + S.it_off[owner] + (size_t)(5 + c) * (size_t)sc.HW + v);
+            const float s = vy_score(tv, S.it_conf[v][owner]);
+            if (s > valid_thresh) {
+                const u64 key = vy_make_key(s, S.it_row0[owner] + (u32)c * (u32)sc.n_s + (u32)v * (u32)hd->A);
+                if (key >= thr) sel_push(S, key);
             }
         }
     }
 };
 
-template <int VEC>
-__device__ void head_tile(SelBuf &S, const VyHeads &hd, const VyScale &sc, int b, int a, int chunk,
-                          int c0, int c1, int K, float valid_thresh, u64 *g_thr_b) {
-    const int tid = threadIdx.x;
-    const int pos0 = (chunk * SEL_NT + tid) * VEC;
-    HeadSrc<VEC> src;
-    src.active = pos0 < sc.HW;
-    src.HW = (size_t)sc.HW;
-    src.plane = sc.head + ((size_t)(b * hd.A + a) * hd.P) * src.HW + (src.active ? pos0 : 0);
-    src.c0 = c0;
-    src.n_s = (u32)sc.n_s;
-    src.A = (u32)hd.A;
-    src.row0 = (u32)(sc.row_off + (long long)pos0 * hd.A + a);
-    src.valid_thresh = valid_thresh;
-    src.max_push_per_iter = SEL_NT * VEC;
-    if (VEC == 4) {
-        float4 to = make_float4(0, 0, 0, 0);
-        if (src.active) to = vy_ldg128(src.plane + 4 * src.HW);
-        src.conf[0] = vy_sigmoid(to.x); src.conf[1 % VEC] = vy_sigmoid(to.y);
-        src.conf[2 % VEC] = vy_sigmoid(to.z); src.conf[3 % VEC] = vy_sigmoid(to.w);
-    } else {
-        src.conf[0] = src.active ? vy_sigmoid(vy_ldg32(src.plane + 4 * src.HW)) : 0.0f;
-    }
-    if (hd.agnostic) {
-        // yolo3.py:184-188: one candidate per box, score = objectness, row = off + pos*A + a
-        src.n_iters = 0;
-        __syncthreads();
-        const int cnt = S.count;
-        __syncthreads();
-        if (cnt > SEL_CAP - SEL_NT * VEC) sel_compact(S, cnt, K, true);
-        const u64 thr = S.thr;
-        if (src.active) {
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                const float s = src.conf[v];
-                if (s > valid_thresh) {
-                    const u64 key = vy_make_key(s, src.row0 + (u32)v * src.A);
-                    if (key >= thr) sel_push(S, key);
-                }
-            }
-        }
-        __syncthreads();
-        return;
-    }
-    src.n_iters = c1 - c0;
-    sel_stream(S, src, K, g_thr_b);
-}
-
-__global__ void __launch_bounds__(SEL_NT, 4)
-vy_decode_select_kernel(VyHeads hd, SelPlan pl, SelGlobal g, int total_tiles) {
+__global__ void __launch_bounds__(SEL_NT, SEL_CTAS_PER_SM)
+vy_decode_select_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl, SelGlobal g) {
     __shared__ SelBuf S;
-    int cur_b = -1;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int b = t % hd.B;
-        const int j = t / hd.B;
-        if (b != cur_b) {
-            if (cur_b >= 0)
-                sel_flush(S, pl.K, g.thr + cur_b, g.count + cur_b, g.list + (size_t)cur_b * pl.list_cap, pl.list_cap);
-            __syncthreads();
-            if (threadIdx.x == 0) { S.count = 0; S.thr = ld_relaxed_u64(g.thr + b); }
-            cur_b = b;
-            __syncthreads();
+    const int tid = threadIdx.x;
+    for (int job = blockIdx.x; job < pl.n_jobs; job += gridDim.x) {
+        const int b = job / pl.G;
+        SelJob jb;
+        jb.G = pl.G; jb.g = job % pl.G; jb.K = pl.K; jb.Kq = pl.Kq;
+        jb.g_thr_b = g.thr + b;
+        jb.slots_b = g.slots + (size_t)b * pl.G;
+        __syncthreads();
+        if (tid == 0) { S.count = 0; S.qcount = 0; S.slot_pub = 0; S.thr = ld_relaxed_u64(jb.g_thr_b); }
+        __syncthreads();
+        const long long T = pl.items_per_frame;
+        const int i0 = (int)(T * jb.g / pl.G), i1 = (int)(T * (jb.g + 1) / pl.G);
+        int cnt = 0, fresh = 0;
+        for (int base = i0; base < i1; base += SEL_NT) {
+            const int idx = base + tid;
+            HeadSrc src;
+            src.hd = &hd;
+            src.nv = 0; src.vec = false; src.p5 = nullptr; src.HW = 0; src.o1 = src.o2 = src.o3 = 0;
+            src.valid_thresh = pl.valid_thresh;
+            src.n_iters = hd.agnostic ? 0 : hd.C;
+            float conf[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            u32 row0 = 0, A = (u32)hd.A;
+            if (idx < i1) {
+                int s = 0;
+                while (s + 1 < hd.n_scales && idx >= pl.item_begin[s + 1]) ++s;
+                const VyScale &sc = hd.sc[s];
+                const int rel = idx - pl.item_begin[s];
+                const int a = rel / pl.items_per_plane[s];
+                const int pos0 = (rel % pl.items_per_plane[s]) * 4;
+                src.nv = min(4, sc.HW - pos0);
+                src.o1 = min(1, src.nv - 1); src.o2 = min(2, src.nv - 1); src.o3 = min(3, src.nv - 1);
+                src.vec = sc.vec == 4;
+                src.HW = (size_t)sc.HW;
+                const size_t off = ((size_t)(b * hd.A + a) * hd.P) * src.HW + pos0;
+                src.p5 = sc.head + off + 5 * src.HW;
+                row0 = (u32)(sc.row_off + (long long)pos0 * hd.A + a);
+                float to[4];
+                src.load(to, sc.head + off + 4 * src.HW);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) conf[v] = v < src.nv ? vy_sigmoid(to[v]) : 0.0f;
+                S.it_off[tid] = (u32)off;
+                S.it_row0[tid] = row0;
+                S.it_scale[tid] = (u32)s;
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v) S.it_conf[v][tid] = conf[v];
+            if (hd.agnostic) {
+                // yolo3.py:184-188: one candidate per box, score = objectness, row = off + pos*A + a
+                if (cnt > SEL_CAP - 4 * SEL_NT) { cnt = sel_update(S, cnt, jb, true); fresh = 0; }
+                const u64 thr = S.thr;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float s = conf[v];
+                    if (v < src.nv && s > pl.valid_thresh) {
+                        const u64 key = vy_make_key(s, row0 + (u32)v * A);
+                        if (key >= thr) sel_push(S, key);
+                    }
+                }
+                __syncthreads();
+                cnt = S.count;
+                __syncthreads();
+                continue;
+            }
+            sel_stream(S, src, jb, cnt, fresh);
         }
-        int s = 0;
-        while (s + 1 < hd.n_scales && j >= pl.tile_begin[s + 1]) ++s;
-        int jj = j - pl.tile_begin[s];
-        const int cpart = jj % pl.csplit; jj /= pl.csplit;
-        const int chunk = jj % pl.chunks[s];
-        const int a = jj / pl.chunks[s];
-        const int c0 = cpart * pl.cper;
-        const int c1 = min(hd.C, c0 + pl.cper);
-        if (hd.sc[s].vec == 4)
-            head_tile<4>(S, hd, hd.sc[s], b, a, chunk, c0, c1, pl.K, pl.valid_thresh, g.thr + b);
-        else
-            head_tile<1>(S, hd, hd.sc[s], b, a, chunk, c0, c1, pl.K, pl.valid_thresh, g.thr + b);
+        sel_flush(S, jb, g.count + b, g.list + (size_t)b * pl.list_cap, pl.list_cap);
     }
-    if (cur_b >= 0)
-        sel_flush(S, pl.K, g.thr + cur_b, g.count + cur_b, g.list + (size_t)cur_b * pl.list_cap, pl.list_cap);
 }
 
 // ------------------------------------------------------------------------------------------------
 // source 2: materialised detection rows (generic box_nms).  Iteration = SEL_NT consecutive rows.
 // ------------------------------------------------------------------------------------------------
 struct RowSrc {
-    int n_iters, max_push_per_iter;
+    int n_iters;
     const float *img;            // data + b*R*W
     long long row_begin, row_end;
     int W, score_index, id_index, background_id;
     float valid_thresh, smin;
 
-    __device__ void refresh(u64 thr) {
+    __device__ __forceinline__ void refresh(SelBuf &, u64 thr) {
         smin = thr ? vy_key_score(thr) : -CUDART_INF_F;
     }
-    __device__ void run(SelBuf &S, int it0, int it1, u64 thr) {
+    __device__ __forceinline__ void run(SelBuf &S, int it0, int it1) {
         for (int it = it0; it < it1; it += 4) {
             float sc[4];
             long long r[4];
@@ -321,43 +373,47 @@ struct RowSrc {
             for (int u = 0; u < 4; ++u) {
                 const float s = sc[u];
                 if (s > valid_thresh && s >= smin) {          // NaN fails both
-                    if (id_index >= 0 && background_id >= 0 &&
-                        (int)img[r[u] * W + id_index] == background_id) continue;
-                    const u64 key = vy_make_key(s, (u32)r[u]);
-                    if (key >= thr) sel_push(S, key);
+                    const int slot = atomicAdd(&S.qcount, 1);
+                    if (slot < SEL_QCAP) S.queue[slot] = (u32)(r[u] - row_begin);
                 }
             }
         }
     }
+    __device__ __forceinline__ void eval(SelBuf &S, int q0, int q1, u64 thr) const {
+        for (int q = q0 + threadIdx.x; q < q1; q += SEL_NT) {
+            const long long r = row_begin + S.queue[q];
+            const float s = img[r * W + score_index];
+            if (id_index >= 0 && background_id >= 0 && (int)img[r * W + id_index] == background_id) continue;
+            const u64 key = vy_make_key(s, (u32)r);
+            if (key >= thr) sel_push(S, key);
+        }
+    }
 };
 
-__global__ void __launch_bounds__(SEL_NT, 4)
-vy_rows_select_kernel(RowParams rp, int B, SelPlan pl, SelGlobal g, int total_tiles) {
+__global__ void __launch_bounds__(SEL_NT, SEL_CTAS_PER_SM)
+vy_rows_select_kernel(RowParams rp, SelPlan pl, SelGlobal g) {
     __shared__ SelBuf S;
-    int cur_b = -1;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int b = t % B;
-        const long long j = t / B;
-        if (b != cur_b) {
-            if (cur_b >= 0)
-                sel_flush(S, pl.K, g.thr + cur_b, g.count + cur_b, g.list + (size_t)cur_b * pl.list_cap, pl.list_cap);
-            __syncthreads();
-            if (threadIdx.x == 0) { S.count = 0; S.thr = ld_relaxed_u64(g.thr + b); }
-            cur_b = b;
-            __syncthreads();
-        }
+    const int tid = threadIdx.x;
+    for (int job = blockIdx.x; job < pl.n_jobs; job += gridDim.x) {
+        const int b = job / pl.G;
+        SelJob jb;
+        jb.G = pl.G; jb.g = job % pl.G; jb.K = pl.K; jb.Kq = pl.Kq;
+        jb.g_thr_b = g.thr + b;
+        jb.slots_b = g.slots + (size_t)b * pl.G;
+        __syncthreads();
+        if (tid == 0) { S.count = 0; S.qcount = 0; S.slot_pub = 0; S.thr = ld_relaxed_u64(jb.g_thr_b); }
+        __syncthreads();
         RowSrc src;
         src.img = rp.data + (size_t)b * (size_t)rp.R * rp.W;
-        src.row_begin = j * pl.rows_per_tile;
-        src.row_end = min(rp.R, src.row_begin + pl.rows_per_tile);
+        src.row_begin = jb.g * pl.rows_per_job;
+        src.row_end = min(rp.R, src.row_begin + pl.rows_per_job);
         src.W = rp.W; src.score_index = rp.score_index; src.id_index = rp.id_index;
         src.background_id = rp.background_id; src.valid_thresh = rp.valid_thresh;
-        src.n_iters = (int)((src.row_end - src.row_begin + SEL_NT - 1) / SEL_NT);
-        src.max_push_per_iter = SEL_NT;
-        sel_stream(S, src, pl.K, g.thr + b);
+        src.n_iters = src.row_end > src.row_begin ? (int)((src.row_end - src.row_begin + SEL_NT - 1) / SEL_NT) : 0;
+        int cnt = 0, fresh = 0;
+        sel_stream(S, src, jb, cnt, fresh);
+        sel_flush(S, jb, g.count + b, g.list + (size_t)b * pl.list_cap, pl.list_cap);
     }
-    if (cur_b >= 0)
-        sel_flush(S, pl.K, g.thr + cur_b, g.count + cur_b, g.list + (size_t)cur_b * pl.list_cap, pl.list_cap);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -401,6 +457,42 @@ __device__ __forceinline__ float nms_isect(float a1, float a2, float b1, float b
     return w > 0 ? w : 0.0f;
 }
 
+// source row -> class id (and, for head maps, where its box logits live)
+template <int SRC>
+__device__ __forceinline__ int fin_class(const VyHeads &hd, const RowParams &rp, int b, u32 row) {
+    if (SRC == 0) {
+        if (hd.agnostic) return 0;
+        int s = 0;
+        while (s + 1 < hd.n_scales && (long long)row >= hd.sc[s + 1].row_off) ++s;
+        return (int)((row - (u32)hd.sc[s].row_off) / (u32)hd.sc[s].n_s);
+    } else {
+        if (rp.id_index < 0) return 0;
+        return (int)rp.data[((size_t)b * (size_t)rp.R + row) * rp.W + rp.id_index];
+    }
+}
+
+template <int SRC>
+__device__ __forceinline__ float4 fin_box(const VyHeads &hd, const RowParams &rp, int b, u32 row) {
+    if (SRC == 0) {
+        int s = 0;
+        while (s + 1 < hd.n_scales && (long long)row >= hd.sc[s + 1].row_off) ++s;
+        const VyScale &sc = hd.sc[s];
+        const u32 rem = (row - (u32)sc.row_off) % (u32)sc.n_s;
+        const int pos = (int)(rem / (u32)hd.A), a = (int)(rem % (u32)hd.A);
+        const int y = pos / sc.W, x = pos % sc.W;
+        const size_t HW = (size_t)sc.HW;
+        const float *p = sc.head + ((size_t)(b * hd.A + a) * hd.P) * HW + pos;
+        return vy_box(p[0], p[HW], p[2 * HW], p[3 * HW], x, y, sc.stride, sc.aw[a], sc.ah[a]);
+    } else {
+        const float *p = rp.data + ((size_t)b * (size_t)rp.R + row) * rp.W + rp.coord_start;
+        return make_float4(p[0], p[1], p[2], p[3]);
+    }
+}
+
+// One CTA per image.  Positions: "rank" = place in the global score order (what the operator's
+// output order is); "slot" = place after a stable regrouping by class, in which every class is one
+// contiguous segment still ordered by rank.  Suppression only ever happens inside a segment, so the
+// IoU bitmask and the greedy scan run over slots and touch (segment length)^2 pairs instead of K^2.
 template <int SRC>   // 0: head maps, 1: rows
 __global__ void __launch_bounds__(FIN_NT)
 vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinParams fp) {
@@ -410,13 +502,16 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     const int b = blockIdx.x;
     const int K = pl.K;
     const int nwK = (K + 31) >> 5;
-    float4 *box = (float4 *)dyn;                       // K
-    float *area = (float *)(box + K);                  // K
-    int *cls = (int *)(area + K);                      // K
-    u32 *mask = (u32 *)(cls + K);                      // K * nwK
-    u32 *rowany = mask + (size_t)K * nwK;              // 32
-    u32 *keepw = rowany + 32;                          // 32
+    float4 *box = (float4 *)dyn;                       // K      by slot
+    float *area = (float *)(box + K);                  // K      by slot
+    int *cls = (int *)(area + K);                      // K      by slot
+    int *seg_end = cls + K;                            // K      by slot
+    int *slot_of_rank = seg_end + K;                   // K
+    u32 *mask = (u32 *)(slot_of_rank + K);             // K * nwK, by slot
+    u32 *rowany = mask + (size_t)K * nwK;              // 32     by slot
+    u32 *keepw = rowany + 32;                          // 32     by rank
     int *kprefix = (int *)(keepw + 32);                // 33
+    u64 *key2 = S.keys + SEL_CAP / 2;                  // class-sort scratch (ranks use the lower half)
 
     // ---- 1. exact top-K of the image's candidate list, sorted descending
     if (tid == 0) { S.count = 0; S.thr = g.thr[b]; }
@@ -441,48 +536,53 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     int npow2 = 32;
     while (npow2 < m) npow2 <<= 1;
     for (int i = m + tid; i < npow2; i += FIN_NT) S.keys[i] = 0ull;
+    for (int i = tid; i < m * nwK; i += FIN_NT) mask[i] = 0u;
     if (tid < 32) { rowany[tid] = 0; keepw[tid] = 0; }
     __syncthreads();
-    sel_sort_desc(S, npow2);
+    sel_sort_desc(S.keys, npow2);
 
-    // ---- 2. boxes / classes of the m candidates
-    const int nw = (m + 31) >> 5;
-    for (int i = tid; i < m; i += FIN_NT) {
-        const u32 row = vy_key_row(S.keys[i]);
-        float4 bx; int c;
-        if (SRC == 0) {
-            int s = 0;
-            while (s + 1 < hd.n_scales && (long long)row >= hd.sc[s + 1].row_off) ++s;
-            const VyScale &sc = hd.sc[s];
-            const u32 rel = row - (u32)sc.row_off;
-            c = (int)(rel / (u32)sc.n_s);
-            const u32 rem = rel % (u32)sc.n_s;
-            const int pos = (int)(rem / (u32)hd.A), a = (int)(rem % (u32)hd.A);
-            const int y = pos / sc.W, x = pos % sc.W;
-            const float *p = sc.head + ((size_t)(b * hd.A + a) * hd.P) * (size_t)sc.HW + pos;
-            bx = vy_box(p[0], p[sc.HW], p[2 * (size_t)sc.HW], p[3 * (size_t)sc.HW], x, y,
-                        sc.stride, sc.aw[a], sc.ah[a]);
-            if (hd.agnostic) c = 0;
-        } else {
-            const float *p = rp.data + ((size_t)b * (size_t)rp.R + row) * rp.W;
-            bx = make_float4(p[rp.coord_start], p[rp.coord_start + 1], p[rp.coord_start + 2], p[rp.coord_start + 3]);
-            c = rp.id_index >= 0 ? (int)p[rp.id_index] : 0;
+    // ---- 2. regroup by class (stable in rank): key2 = (class, ~rank), sorted descending
+    const bool all_pairs = fp.force_suppress || (SRC == 1 && rp.id_index < 0) || (SRC == 0 && hd.agnostic);
+    for (int i = tid; i < npow2; i += FIN_NT) {
+        u64 k2 = 0ull;
+        if (i < m) {
+            const int c = all_pairs ? 0 : fin_class<SRC>(hd, rp, b, vy_key_row(S.keys[i]));
+            k2 = ((u64)((u32)c ^ 0x80000000u) << 32) | (u64)(0xffffffffu - (u32)i);
         }
-        box[i] = bx; cls[i] = c; area[i] = nms_area(bx, fp.in_format);
+        key2[i] = k2;
+    }
+    __syncthreads();
+    if (!all_pairs) sel_sort_desc(key2, npow2);
+    for (int j = tid; j < m; j += FIN_NT) {
+        const u64 k2 = key2[j];
+        const int r = (int)(0xffffffffu - (u32)(k2 & 0xffffffffu));
+        slot_of_rank[r] = j;
+        cls[j] = (int)((u32)(k2 >> 32) ^ 0x80000000u);
+        const float4 bx = fin_box<SRC>(hd, rp, b, vy_key_row(S.keys[r]));
+        box[j] = bx;
+        area[j] = nms_area(bx, fp.in_format);
+    }
+    __syncthreads();
+    for (int j = tid; j < m; j += FIN_NT) {
+        int e = j + 1;
+        if (all_pairs) e = m;
+        else { const int c = cls[j]; while (e < m && cls[e] == c) ++e; }
+        seg_end[j] = e;
     }
     __syncthreads();
 
-    // ---- 3. suppression bitmask, one warp per (ref row i, 32-candidate word w >= i/32)
-    const bool all_pairs = fp.force_suppress || (SRC == 1 && rp.id_index < 0);
+    // ---- 3. suppression bitmask, one warp per reference slot, 32 candidate slots per ballot
+    const int nw = (m + 31) >> 5;
     for (int i = warp; i < m; i += nwarps) {
+        const int e = seg_end[i];
+        if (e <= i + 1) continue;                       // alone in its class
         const float4 bi = box[i];
         const float ai = area[i];
-        const int ci = cls[i];
         u32 any = 0;
-        for (int w = i >> 5; w < nw; ++w) {
+        for (int w = i >> 5; w <= (e - 1) >> 5; ++w) {
             const int jx = (w << 5) + lane;
             bool sup = false;
-            if (jx > i && jx < m && (all_pairs || cls[jx] == ci)) {
+            if (jx > i && jx < e) {
                 const float4 bj = box[jx];
                 float inter = nms_isect(bi.x, bi.z, bj.x, bj.z, fp.in_format);
                 inter = __fmul_rn(inter, nms_isect(bi.y, bi.w, bj.y, bj.w, fp.in_format));
@@ -490,14 +590,14 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
                 sup = iou > fp.overlap_thresh;
             }
             const u32 bits = __ballot_sync(0xffffffffu, sup);
-            if (lane == 0) mask[(size_t)i * nwK + w] = bits;
+            if (lane == 0 && bits) mask[(size_t)i * nwK + w] = bits;
             any |= bits;
         }
         if (lane == 0 && any) atomicOr(&rowany[i >> 5], 1u << (i & 31));
     }
     __syncthreads();
 
-    // ---- 4. greedy scan in score order (warp 0).  lane w holds the suppressed-bits of word w.
+    // ---- 4. greedy scan over slots (warp 0).  lane w holds the suppressed-bits of slot word w.
     if (warp == 0) {
         u32 removed = 0;
         for (int blk = 0; blk < nw; ++blk) {
@@ -506,8 +606,7 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
             const u32 ra = rowany[blk] & validm;
             const u32 diag = (r < m && ((ra >> lane) & 1u)) ? mask[(size_t)r * nwK + blk] : 0u;
             u32 rem = __shfl_sync(0xffffffffu, removed, blk);
-            // refs of this block whose row is non-empty, resolved in order
-            u32 pend = ra;
+            u32 pend = ra;                              // references with a non-empty row, in order
             while (pend) {
                 const int i = __ffs(pend) - 1;
                 pend &= pend - 1;
@@ -515,9 +614,12 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
                 if (!((rem >> i) & 1u)) rem |= di;
             }
             const u32 keep = ~rem & validm;
-            if (lane == 0) keepw[blk] = keep;
-            // propagate surviving refs with non-empty rows to the later words
-            u32 act = keep & ra;
+            // survivors by rank
+            if (r < m && ((keep >> lane) & 1u)) {
+                const int rank = (int)(0xffffffffu - (u32)(key2[r] & 0xffffffffu));
+                atomicOr(&keepw[rank >> 5], 1u << (rank & 31));
+            }
+            u32 act = keep & ra;                        // surviving references reach into later words
             if (lane > blk && lane < nw) {
                 u32 acc = 0;
                 while (act) {
@@ -551,8 +653,10 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
         const u32 row = vy_key_row(key);
         float *o = out_b + (size_t)p * W;
         if (SRC == 0) {
-            const float4 bx = box[i];
-            o[0] = (float)cls[i]; o[1] = vy_key_score(key);
+            const int j = slot_of_rank[i];
+            const float4 bx = box[j];
+            o[0] = (float)(all_pairs && !hd.agnostic ? fin_class<SRC>(hd, rp, b, row) : cls[j]);
+            o[1] = vy_key_score(key);
             o[2] = bx.x; o[3] = bx.y; o[4] = bx.z; o[5] = bx.w;
         } else {
             const float *src = rp.data + ((size_t)b * (size_t)rp.R + row) * rp.W;
@@ -595,71 +699,60 @@ __global__ void vy_fill_kernel(float *out, int *kept, size_t n_out, size_t n_kep
 // ------------------------------------------------------------------------------------------------
 static size_t fin_dyn_smem(int K) {
     const int nwK = (K + 31) / 32;
-    return (size_t)K * (16 + 4 + 4) + (size_t)K * nwK * 4 + 32 * 4 + 32 * 4 + 33 * 4 + 16;
+    return (size_t)K * (16 + 4 + 4 + 4 + 4) + (size_t)K * nwK * 4 + 32 * 4 + 32 * 4 + 33 * 4 + 16;
+}
+
+// CTAs that can be resident at once (SEL_CTAS_PER_SM per SM by __launch_bounds__)
+static int resident_ctas() { return SEL_CTAS_PER_SM * vy_sm_count(); }
+
+static void plan_jobs(int B, long long units_per_image, SelPlan *pl) {
+    // G CTAs per image: fill the machine in one wave, at least ~SEL_NT units per job, <= 32 slots
+    long long G = resident_ctas() / B;
+    const long long gmax_units = (units_per_image + SEL_NT - 1) / SEL_NT;
+    if (G > gmax_units) G = gmax_units;
+    if (G > SEL_GMAX) G = SEL_GMAX;
+    if (G < 1) G = 1;
+    pl->G = (int)G;
+    pl->Kq = (pl->K + pl->G - 1) / pl->G;
+    pl->n_jobs = B * pl->G;
+    const long long cap = (long long)pl->G * (pl->K + (pl->K >> 2));
+    pl->list_cap = (int)(cap < 64 ? 64 : cap);
 }
 
 static int plan_heads(const VyHeads &hd, int topk, float valid_thresh, SelPlan *pl) {
+    memset(pl, 0, sizeof(*pl));
     long long K = topk < 0 ? hd.R : (topk < hd.R ? topk : hd.R);
     if (K < 1 || K > SEL_KMAX) return VY_EUNSUPPORTED;
     pl->K = (int)K;
     pl->valid_thresh = valid_thresh;
-    int base_tiles = 0;
+    int items = 0;
     for (int s = 0; s < hd.n_scales; ++s) {
-        const int per = SEL_NT * hd.sc[s].vec;
-        pl->chunks[s] = (hd.sc[s].HW + per - 1) / per;
-        base_tiles += pl->chunks[s] * hd.A;
+        pl->items_per_plane[s] = (hd.sc[s].HW + 3) / 4;
+        pl->item_begin[s] = items;
+        items += pl->items_per_plane[s] * hd.A;
     }
-    // split the class range while the grid is too small to fill the machine, keeping >= 4
-    // class planes per tile so the per-box objectness work stays amortised
-    int csplit = 1;
-    if (!hd.agnostic) {
-        const long long want = 4096;
-        const long long have = (long long)base_tiles * hd.B;
-        csplit = (int)((want + have - 1) / have);
-        const int max_split = hd.C / 4 > 1 ? hd.C / 4 : 1;
-        if (csplit > max_split) csplit = max_split;
-        if (csplit < 1) csplit = 1;
-    }
-    pl->cper = (hd.C + csplit - 1) / csplit;
-    pl->csplit = (hd.C + pl->cper - 1) / pl->cper;
-    int tb = 0;
-    for (int s = 0; s < hd.n_scales; ++s) {
-        pl->tile_begin[s] = tb;
-        tb += pl->chunks[s] * hd.A * pl->csplit;
-    }
-    for (int s = hd.n_scales; s <= VY_MAX_SCALES; ++s) pl->tile_begin[s] = tb;
-    pl->tiles_per_frame = tb;
-    pl->rows_per_tile = 0;
-    const long long cap = (long long)tb * (pl->K + (pl->K >> 2));
-    pl->list_cap = (int)(cap < 64 ? 64 : cap);
+    for (int s = hd.n_scales; s <= VY_MAX_SCALES; ++s) pl->item_begin[s] = items;
+    pl->items_per_frame = items;
+    plan_jobs(hd.B, items, pl);
     return VY_OK;
 }
 
 static int plan_rows(int B, long long R, int topk, float valid_thresh, SelPlan *pl) {
+    memset(pl, 0, sizeof(*pl));
     long long K = topk < 0 ? R : (topk < R ? topk : R);
     if (K < 1 || K > SEL_KMAX) return VY_EUNSUPPORTED;
-    memset(pl, 0, sizeof(*pl));
     pl->K = (int)K;
     pl->valid_thresh = valid_thresh;
-    // ~4096 tiles in flight, each a multiple of SEL_NT rows and at least 16 iterations long
-    long long tiles = (4096 + B - 1) / B;
-    long long rpt = (R + tiles - 1) / tiles;
-    if (rpt < 16 * SEL_NT) rpt = 16 * SEL_NT;
-    rpt = (rpt + SEL_NT - 1) / SEL_NT * SEL_NT;
-    pl->rows_per_tile = rpt;
-    pl->tiles_per_frame = (int)((R + rpt - 1) / rpt);
-    const long long cap = (long long)pl->tiles_per_frame * (pl->K + (pl->K >> 2));
-    pl->list_cap = (int)(cap < 64 ? 64 : cap);
-    pl->csplit = 1; pl->cper = 1;
+    plan_jobs(B, (R + 15) / 16, pl);          // >= 16 iterations of SEL_NT rows per job
+    long long rpj = (R + pl->G - 1) / pl->G;
+    rpj = (rpj + SEL_NT - 1) / SEL_NT * SEL_NT;
+    pl->rows_per_job = rpj;
     return VY_OK;
 }
 
-static int select_grid(const void *kernel, int total_tiles) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SEL_NT, 0) != cudaSuccess || per_sm < 1)
-        per_sm = 4;
-    const long long resident = (long long)per_sm * vy_sm_count();
-    return (int)(total_tiles < resident ? total_tiles : resident);
+static int select_grid(int n_jobs) {
+    const int resident = resident_ctas();
+    return n_jobs < resident ? n_jobs : resident;
 }
 
 template <int SRC>
@@ -682,7 +775,7 @@ extern "C" size_t vy_decode_nms_workspace_bytes(const int *H, const int *W, int 
     if (vy_fill_heads(&hd, fake, H, W, st, an, n_scales, B, A, C, agnostic) != VY_OK) return 0;
     SelPlan pl;
     if (plan_heads(hd, topk, 0.0f, &pl) != VY_OK) { vy_set_error("topk out of range for the fused path"); return 0; }
-    return sel_workspace_layout(B, pl.list_cap, nullptr, nullptr);
+    return sel_workspace_layout(B, pl.G, pl.list_cap, nullptr, nullptr, nullptr);
 }
 
 extern "C" int vy_decode_nms_f32(const float *const *head, const int *H, const int *W, const float *stride,
@@ -700,15 +793,15 @@ extern "C" int vy_decode_nms_f32(const float *const *head, const int *H, const i
     if (rc != VY_OK) VY_FAIL(rc, "vy_decode_nms_f32: min(topk,R)=%d outside [1,%d]; use vy_decode_f32 + vy_box_nms_f32",
                              topk, SEL_KMAX);
     SelGlobal g;
-    const size_t need = sel_workspace_layout(B, pl.list_cap, &g, workspace);
+    size_t header = 0;
+    const size_t need = sel_workspace_layout(B, pl.G, pl.list_cap, &g, workspace, &header);
     if (!workspace || workspace_bytes < need)
         VY_FAIL(VY_EWORKSPACE, "vy_decode_nms_f32: workspace %zu < %zu bytes", workspace_bytes, need);
     if (((uintptr_t)workspace & 255) != 0) VY_FAIL(VY_EALIGN, "workspace must be 256-byte aligned");
-    VY_CUDA_CHECK(cudaMemsetAsync(workspace, 0, sel_header_bytes(B), st));
-    const long long total = (long long)pl.tiles_per_frame * B;
-    if (total > 0x7fffffffLL) VY_FAIL(VY_EINVAL, "too many tiles");
-    const int grid = select_grid((const void *)vy_decode_select_kernel, (int)total);
-    vy_decode_select_kernel<<<grid, SEL_NT, 0, st>>>(hd, pl, g, (int)total);
+    for (int s = 0; s < n_scales; ++s)
+        if (!head[s]) VY_FAIL(VY_EINVAL, "vy_decode_nms_f32: head[%d] is null", s);
+    VY_CUDA_CHECK(cudaMemsetAsync(workspace, 0, header, st));
+    vy_decode_select_kernel<<<select_grid(pl.n_jobs), SEL_NT, 0, st>>>(hd, pl, g);
     VY_LAUNCH_CHECK("vy_decode_select_kernel");
     FinParams fp;
     fp.K = pl.K; fp.post_rows = post_nms; fp.out_stride_rows = post_nms;
@@ -729,7 +822,8 @@ int vy_box_nms_large(const RowParams &rp, int B, long long K, float overlap_thre
 extern "C" size_t vy_box_nms_workspace_bytes(int B, long R, int W_elem, int topk) {
     SelPlan pl;
     if (B < 1 || R < 1) return 0;
-    if (plan_rows(B, R, topk, 0.0f, &pl) == VY_OK) return sel_workspace_layout(B, pl.list_cap, nullptr, nullptr);
+    if (plan_rows(B, R, topk, 0.0f, &pl) == VY_OK)
+        return sel_workspace_layout(B, pl.G, pl.list_cap, nullptr, nullptr, nullptr);
     return vy_box_nms_large_workspace_bytes(B, R, W_elem);
 }
 
@@ -764,15 +858,13 @@ extern "C" int vy_box_nms_f32(const float *data, int B, long R, int W_elem, floa
                                 out, kept_rows, workspace, workspace_bytes, st);
     }
     SelGlobal g;
-    const size_t need = sel_workspace_layout(B, pl.list_cap, &g, workspace);
+    size_t header = 0;
+    const size_t need = sel_workspace_layout(B, pl.G, pl.list_cap, &g, workspace, &header);
     if (!workspace || workspace_bytes < need)
         VY_FAIL(VY_EWORKSPACE, "vy_box_nms_f32: workspace %zu < %zu bytes", workspace_bytes, need);
     if (((uintptr_t)workspace & 255) != 0) VY_FAIL(VY_EALIGN, "workspace must be 256-byte aligned");
-    VY_CUDA_CHECK(cudaMemsetAsync(workspace, 0, sel_header_bytes(B), st));
-    const long long total = (long long)pl.tiles_per_frame * B;
-    if (total > 0x7fffffffLL) VY_FAIL(VY_EINVAL, "too many tiles");
-    const int grid = select_grid((const void *)vy_rows_select_kernel, (int)total);
-    vy_rows_select_kernel<<<grid, SEL_NT, 0, st>>>(rp, B, pl, g, (int)total);
+    VY_CUDA_CHECK(cudaMemsetAsync(workspace, 0, header, st));
+    vy_rows_select_kernel<<<select_grid(pl.n_jobs), SEL_NT, 0, st>>>(rp, pl, g);
     VY_LAUNCH_CHECK("vy_rows_select_kernel");
     FinParams fp;
     fp.K = pl.K; fp.post_rows = (int)(out_rows < pl.K ? out_rows : pl.K); fp.out_stride_rows = out_rows;

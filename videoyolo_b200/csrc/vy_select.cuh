@@ -1,18 +1,24 @@
 // vy_select.cuh -- CTA-level streaming top-K selection over 64-bit keys.
 //
 // A CTA streams candidates past a monotonically rising threshold key.  Candidates that beat the
-// threshold are pushed into a shared-memory buffer; when the buffer fills, an MSB-first radix
-// select finds a (bucket-granular, or exact) K-th largest key, everything below it is dropped
-// and the threshold rises.  Any threshold produced this way is a valid lower bound of the
-// image-wide K-th largest key, so thresholds can be shared between CTAs of one image through a
-// global atomicMax without losing a single top-K candidate.
+// threshold are pushed into a shared-memory buffer.  From time to time the CTA runs an MSB-first
+// radix select over the buffer to (a) bound its own K-th largest key and (b) bound its own
+// ceil(K/G)-th largest key, which it publishes in a per-image slot.  G CTAs share one image:
+//      min over the G slots      -- each CTA holds >= ceil(K/G) candidates at or above its slot, so
+//                                   together they hold >= K candidates at or above the minimum
+//      a CTA's own K-th largest  -- trivially
+// are both valid lower bounds of the image-wide K-th largest key.  Every key below a valid bound
+// can be dropped without losing a single top-K candidate; the best bound known for the image is
+// kept in global memory (atomicMax) and picked up by every CTA working on that image.
 #pragma once
 #include "vy_common.cuh"
 
 constexpr int SEL_NT  = 256;               // threads per selecting CTA
 constexpr int SEL_CAP = 2048;              // candidate keys held in shared memory
-constexpr int SEL_KPT = SEL_CAP / SEL_NT;  // keys per thread during a compaction
+constexpr int SEL_KPT = SEL_CAP / SEL_NT;  // keys per thread during a selection
 constexpr int SEL_KMAX = 1024;             // largest K the small (shared-memory) path serves
+constexpr int SEL_GMAX = 32;               // CTAs sharing one image (one slot per lane of a warp)
+constexpr int SEL_QCAP = 2048;             // prefilter hits queued per streamed block
 
 // a materialised detection tensor (the operand of F.contrib.box_nms, yolo3.py:526)
 struct RowParams {
@@ -25,15 +31,37 @@ struct RowParams {
 struct SelBuf {
     u64 keys[SEL_CAP];
     u32 hist[256];
+    // streaming threads only record WHERE a prefilter hit happened; the exact evaluation is done
+    // afterwards by all threads of the CTA side by side (one queued hit per thread), so a hit costs
+    // a few thread-instructions instead of a divergent warp-long detour
+    u32 queue[SEL_QCAP];
+    float it_conf[4][SEL_NT];   // per streaming thread: objectness of its 4 boxes
+    u32 it_off[SEL_NT];         // element offset of its (b, a, pos0) in the scale's head map
+    u32 it_row0[SEL_NT];        // reference row of (c=0, pos0, a)
+    u32 it_scale[SEL_NT];
+    int qcount;                 // hits queued since the last reset (may exceed SEL_QCAP: overflow)
     u64 thr;            // inclusive lower bound: a candidate is kept iff key >= thr
+    u64 slot_pub;       // what this CTA last published in its slot
     int count;          // number of pushes since the last reset (may exceed SEL_CAP: overflow)
     int sel_digit, sel_above, sel_in;
-    int flag;           // general CTA-uniform scratch
+    int flag;           // CTA-uniform scratch
     int snap;           // count snapshot written by thread 0 between barriers (pushes never touch it)
 };
 
-__device__ __forceinline__ void sel_reset(SelBuf &S) {
-    if (threadIdx.x == 0) { S.count = 0; S.thr = 0; }
+// per-job view of the global sharing state
+struct SelJob {
+    u64 *g_thr_b;       // best valid bound known for the image
+    u64 *slots_b;       // [G] per-CTA ceil(K/G)-th largest keys
+    int G, g, K, Kq;    // Kq = ceil(K / G)
+};
+
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
 // push; keys beyond the capacity are dropped but still counted (the caller detects count > CAP)
@@ -42,14 +70,12 @@ __device__ __forceinline__ void sel_push(SelBuf &S, u64 key) {
     if (slot < SEL_CAP) S.keys[slot] = key;
 }
 
-// Keep (about) the K largest keys of S.keys[0..count).  exact=false stops as soon as at most
-// K + K/4 keys remain (bucket granularity); exact=true keeps exactly K.  Raises S.thr.
-// Preconditions: n == S.count <= SEL_CAP is CTA-uniform, all pushes visible and no push in flight
-// (__syncthreads before the call), called by every thread of a CTA of >= SEL_NT threads.
-// Returns the new count (CTA-uniform).  Ends with a __syncthreads.
-static __device__ int sel_compact(SelBuf &S, int n, int K, bool exact) {
+// Lower bound of the `rank`-th largest key of S.keys[0..n): the returned prefix p satisfies
+// rank <= #{keys >= p} <= rank + slack (slack == 0: p IS the rank-th largest key).
+// Preconditions: 1 <= rank <= n <= SEL_CAP, n CTA-uniform, no push in flight; called by every
+// thread of a CTA of >= SEL_NT threads.  Contains barriers; S.keys is not modified.
+static __device__ __noinline__ u64 sel_rank_bound(SelBuf &S, int n, int rank, int slack) {
     const int tid = threadIdx.x;
-    if (n <= K) return n;                     // CTA-uniform
     u64 my[SEL_KPT];
 #pragma unroll
     for (int i = 0; i < SEL_KPT; ++i) {
@@ -57,9 +83,7 @@ static __device__ int sel_compact(SelBuf &S, int n, int K, bool exact) {
         my[i] = (tid < SEL_NT && idx < n) ? S.keys[idx] : 0ull;
     }
     u64 prefix = 0;
-    int kk = K;                               // looking for the kk-th largest inside the prefix bucket
-    int kept = n;
-    const int slack = exact ? 0 : (K >> 2);
+    int kk = rank;                            // looking for the kk-th largest inside the prefix bucket
     for (int shift = 56; shift >= 0; shift -= 8) {
         if (tid < 256) S.hist[tid] = 0;
         __syncthreads();
@@ -99,31 +123,92 @@ static __device__ int sel_compact(SelBuf &S, int n, int K, bool exact) {
         const int d = S.sel_digit, above = S.sel_above, inb = S.sel_in;
         prefix |= (u64)d << shift;
         kk -= above;                          // 1 <= kk <= inb
-        kept = (K - kk) + inb;                // keys >= prefix (low bits zero)
-        if (kept <= K + slack) break;
+        if (inb - kk <= slack) break;         // #{keys >= prefix} = rank + (inb - kk)
+    }
+    return prefix;
+}
+
+// Drop every key below thr, compacting the survivors to the front.  Returns the new count
+// (CTA-uniform).  Same preconditions as sel_rank_bound; ends with a barrier.
+static __device__ __noinline__ int sel_drop_below(SelBuf &S, int n, u64 thr) {
+    const int tid = threadIdx.x;
+    u64 my[SEL_KPT];
+#pragma unroll
+    for (int i = 0; i < SEL_KPT; ++i) {
+        const int idx = tid + i * SEL_NT;
+        my[i] = (tid < SEL_NT && idx < n) ? S.keys[idx] : 0ull;
     }
     __syncthreads();
-    if (tid == 0) { S.count = 0; if (prefix > S.thr) S.thr = prefix; }
+    if (tid == 0) S.count = 0;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < SEL_KPT; ++i)
-        if (my[i] >= prefix && my[i] != 0ull) { const int slot = atomicAdd(&S.count, 1); S.keys[slot] = my[i]; }
+        if (my[i] >= thr && my[i] != 0ull) { const int slot = atomicAdd(&S.count, 1); S.keys[slot] = my[i]; }
     __syncthreads();
-    return kept;
+    const int m = S.count;
+    __syncthreads();
+    return m;
 }
 
-// In-place descending bitonic sort of S.keys[0..npow2) (npow2 a power of two <= SEL_CAP; the
+// Keep (about) the K largest keys: exact=false leaves at most K + K/4, exact=true exactly K.
+// Raises S.thr.  Returns the new count.
+static __device__ int sel_compact(SelBuf &S, int n, int K, bool exact) {
+    if (n <= K) return n;
+    const u64 p = sel_rank_bound(S, n, K, exact ? 0 : (K >> 2));
+    __syncthreads();
+    if (threadIdx.x == 0 && p > S.thr) S.thr = p;
+    return sel_drop_below(S, n, p);
+}
+
+// Selection event: refresh this CTA's slot, combine every bound known for the image, drop what
+// fell below.  `must_free`: the buffer overflowed, make room (exact local K-th).  Returns count.
+static __device__ __noinline__ int sel_update(SelBuf &S, int n, const SelJob &jb, bool must_free) {
+    const int tid = threadIdx.x;
+    u64 vq = 0, vk = 0;
+    if (n >= jb.Kq) vq = sel_rank_bound(S, n, jb.Kq, jb.Kq >> 2);
+    if (n > jb.K + (jb.K >> 2) || (must_free && n > jb.K))
+        vk = sel_rank_bound(S, n, jb.K, must_free ? 0 : (jb.K >> 2));
+    __syncthreads();
+    if (tid < 32) {
+        const u64 old = S.slot_pub;
+        const u64 mine = vq > old ? vq : old;
+        __syncwarp();
+        if (tid == 0 && mine > old) { S.slot_pub = mine; st_relaxed_u64(jb.slots_b + jb.g, mine); }
+        u64 v = ~0ull;
+        if (tid < jb.G) v = (tid == jb.g) ? mine : ld_relaxed_u64(jb.slots_b + tid);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const u64 o = __shfl_xor_sync(0xffffffffu, v, off);
+            v = o < v ? o : v;
+        }
+        if (tid == 0) {
+            const u64 gthr = ld_relaxed_u64(jb.g_thr_b);
+            u64 t = S.thr;
+            if (vk > t) t = vk;
+            if (v > t) t = v;                 // v == 0 while some CTA has not published yet
+            if (t > gthr) atomicMax(jb.g_thr_b, t);
+            if (gthr > t) t = gthr;
+            S.flag = t > S.thr;
+            S.thr = t;
+        }
+    }
+    __syncthreads();
+    if (S.flag) n = sel_drop_below(S, n, S.thr);
+    return n;
+}
+
+// In-place descending bitonic sort of keys[0..npow2) in shared memory (npow2 a power of two; the
 // caller pads with zeros).  Every thread of the CTA calls it.
-static __device__ void sel_sort_desc(SelBuf &S, int npow2) {
+static __device__ __noinline__ void sel_sort_desc(u64 *keys, int npow2) {
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int k = 2; k <= npow2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int p = tid; p < (npow2 >> 1); p += nt) {
                 const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
                 const int l = i | j;
-                const u64 a = S.keys[i], b = S.keys[l];
+                const u64 a = keys[i], b = keys[l];
                 const bool desc = (i & k) == 0;
-                if ((a < b) == desc) { S.keys[i] = b; S.keys[l] = a; }
+                if ((a < b) == desc) { keys[i] = b; keys[l] = a; }
             }
             __syncthreads();
         }
