@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the detection post-processing hot path (fused decode + box_nms).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config coco608_b64] [--regime R|T]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU restatement of the reference path (oracle/)
+
+A "step" is one pass of the hot path (YOLOv3 head maps -> (ids, scores, bboxes), yolo3.py:496,523-534)
+over one batch of synthetic head maps.  Frames are independent, so N GPUs each take their own batch
+(weak scaling, no collective on the data path); the only collective is the MAX of the per-rank
+elapsed times.  One JSON line is printed by rank 0.
+
+  value         frames/sec with the head maps already resident in HBM (CUDA events, max over ranks)
+  e2e           frames/sec through videoyolo_b200.HostDetector: pinned host head maps -> device ->
+                kernels -> host results, copies inside the timed region
+  roofline      the dominant kernel (candidate selection, the only one that streams the head maps):
+                algorithmic bytes per launch / its average launch duration (CUDA events on the launch
+                stream, recorded by the library: vy_prof_*) against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  oracle/ (C restatement of decode + box_nms) on this box's host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# name -> (BASELINE.json config, classes, input size, frames per GPU)
+CONFIGS = {
+    "voc416_b1": ("configs[0]: YOLOv3 VOC (20 cls) 416x416 batch 1", 20, 416, 1),
+    "coco608_b64": ("configs[1]: YOLOv3 COCO (80 cls) 608x608 batch 64 decode + box_nms (22743 boxes/frame)", 80, 608, 64),
+    "vid416_b32": ("configs[2]: ImageNet-VID (30 cls) 416x416 decode + NMS, batch 32", 30, 416, 32),
+    "stress416_b128": ("configs[3] shape: 80 cls 416x416 (10647 boxes) batch 128, reference NMS arguments", 80, 416, 128),
+    "vid320_b256": ("configs[4]: frame-sharded stream 320x320 batch 256/GPU, VID 30 cls", 30, 320, 256),
+}
+NMS = dict(nms_thresh=0.45, valid_thresh=0.01, topk=400, post_nms=100)      # detect_yolo3.py:200, yolo3.py:527
+FALLBACK_HBM_GBS = 6650.0                                                     # B200_PROFILING.md fallback
+
+
+def grid_sizes(size):
+    return [size // 32, size // 16, size // 8]
+
+
+def frame_bytes(C, size, post_nms=100):
+    """Algorithmic bytes per frame: compulsory fp32 read of the three head maps + the
+    write of the (post_nms, 6) triple and its kept-row indices."""
+    n_box = sum(g * g * 3 for g in grid_sizes(size))
+    return 4 * n_box * (5 + C), 24 * post_nms + 4 * post_nms
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(config_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the selection kernel from the
+    committed `ncu --set full` capture (profiles/roofline_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(config_name, {}).get("vy_decode_select_kernel")
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while `active` is set."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.active = threading.Event()
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            if self.active.is_set():
+                try:
+                    self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+                time.sleep(0.002)
+            else:
+                time.sleep(0.0005)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------- CPU legs
+def cpu_port_fps(C, size, frames, seed, threads, steps=1, warmup=0):
+    """Oracle (C restatement of decode yolo3.py:151-199 + box_nms yolo3.py:523-534) on `frames` frames
+    per step with `threads` host threads.  Returns (frames/sec, seconds per step)."""
+    import numpy as np
+    import oracle
+    oracle.set_threads(threads)
+    rng = np.random.RandomState(seed)
+    heads = [rng.standard_normal(size=(frames, 3 * (5 + C), g, g)).astype(np.float32) for g in grid_sizes(size)]
+    for _ in range(warmup):
+        oracle.yolov3_postprocess(heads, C, NMS["nms_thresh"], NMS["topk"], NMS["post_nms"], NMS["valid_thresh"])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.yolov3_postprocess(heads, C, NMS["nms_thresh"], NMS["topk"], NMS["post_nms"], NMS["valid_thresh"])
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return frames / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  MXNet/GluonCV cannot be installed here (no wheel,
+    no network), so this is the oracle port, all host threads, on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    label, C, size, B = CONFIGS[args.config]
+    cores = os.cpu_count() or 1
+    frames = min(B, max(cores, 8))
+    # calibrate so that K+W steps end within ~2.5 minutes
+    fps1, dt1 = cpu_port_fps(C, size, frames, 1236, cores)
+    budget = 150.0
+    while frames > 1 and dt1 * (args.steps + args.warmup) > budget:
+        frames = max(1, frames // 2)
+        fps1, dt1 = cpu_port_fps(C, size, frames, 1236, cores)
+    fps, dt = cpu_port_fps(C, size, frames, 1236, cores, steps=args.steps, warmup=args.warmup)
+    sample = "%d of %d frames per step, %d threads over frames (oracle/vy_oracle.c)" % (frames, B, cores)
+    line = {"impl": "reference", "metric": "frames/sec decode+NMS", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": label, "classes": C, "input": size, "frames_per_step": frames, "regime": "R",
+                       "nms": NMS},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="coco608_b64", choices=sorted(CONFIGS))
+    ap.add_argument("--regime", default="R", choices=["R", "T"], help="R: N(0,1) logits (random-init); T: trained-like")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import videoyolo_b200 as vy
+    from videoyolo_b200 import _lib
+    from videoyolo_b200.pipeline import HostDetector
+    from videoyolo_b200.synth import random_heads_cuda
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    label, C, size, B = CONFIGS[args.config]
+    AN, ST = vy.ANCHORS[::-1], vy.STRIDES[::-1]
+    heads = random_heads_cuda(B, C, size, 1234 + 2 + rank, dev, regime=args.regime)
+    in_bytes_frame, out_bytes_frame = frame_bytes(C, size, NMS["post_nms"])
+    in_bytes = in_bytes_frame * B
+    out = torch.empty((B, NMS["post_nms"], 6), dtype=torch.float32, device=dev)
+    kept = torch.empty((B, NMS["post_nms"]), dtype=torch.int32, device=dev)
+    # inputs smaller than L2 (126 MB) are evicted between steps by writing a 256 MiB buffer
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if in_bytes < (160 << 20) else None
+
+    def step():
+        vy.yolo3_decode_nms(heads, C, AN, ST, out=out, kept=kept, **NMS)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warmup, sampler=None):
+        """max-over-ranks milliseconds for `steps` calls of fn, device-timed."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if sampler:
+            sampler.active.set()
+        total = 0.0
+        if flush is None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            total = a.elapsed_time(b)
+        else:
+            evs = []
+            for _ in range(steps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            total = sum(a.elapsed_time(b) for a, b in evs)
+        if sampler:
+            sampler.active.clear()
+        barrier()
+        return max_over_ranks(total)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- headline: device-resident
+    c0 = _lib.launch_counts()
+    ms_total = timed(step, args.steps, args.warmup, sampler)
+    c1 = _lib.launch_counts()
+    launches = {k: c1[k] - c0[k] for k in c1 if c1[k] - c0[k]}
+    # warm-up launches are not in the timed region
+    per_step = {k: v // (args.steps + args.warmup) for k, v in launches.items()}
+    gpu_launches = sum(per_step.values()) * args.steps
+    ms_step = ms_total / args.steps
+    fps = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- roofline pass: same steps with the library's per-kernel events switched on
+    _lib.prof_enable(True)
+    _lib.prof_read()
+    ms_prof_total = timed(step, args.steps, 3)
+    prof = _lib.prof_read()
+    _lib.prof_enable(False)
+    peak, peak_src = load_peaks()
+    sel_ms, sel_n = prof.get("vy_decode_select_kernel", (0.0, 0))
+    # the warm-up launches of the profiled pass are in the record too: average over all of them
+    sel_avg_ms = sel_ms / max(sel_n, 1)
+    achieved = in_bytes / (sel_avg_ms * 1e-3) / 1e9 if sel_avg_ms > 0 else 0.0
+    kernel_ms = {k: v[0] / max(v[1], 1) for k, v in prof.items()}
+    roofline = {"bound": "hbm", "kernel": "vy_decode_select_kernel", "achieved": round(achieved, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": load_traffic(args.config),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": in_bytes,
+                "kernel_ms_per_launch": {k: round(v, 5) for k, v in kernel_ms.items()},
+                "kernel_share_of_step": {k: round(v / sum(kernel_ms.values()), 4) for k, v in kernel_ms.items()},
+                "step_frac": round((in_bytes + out_bytes_frame * B) / (ms_step * 1e-3) / 1e9 / peak, 4),
+                "profiled_ms_per_step": round(ms_prof_total / args.steps, 5)}
+
+    # ---- e2e: host buffers through the public host-facing call
+    e2e = None
+    if not args.no_e2e:
+        h_heads = [torch.empty(h.shape, dtype=torch.float32).pin_memory() for h in heads]
+        for hh, h in zip(h_heads, heads):
+            hh.copy_(h)
+        torch.cuda.synchronize()
+        det = HostDetector(C, AN, ST, dev, chunk=max(1, min(8, B)), **{"nms_thresh": NMS["nms_thresh"],
+                           "valid_thresh": NMS["valid_thresh"], "nms_topk": NMS["topk"], "post_nms": NMS["post_nms"]})
+        e2e_steps = args.steps if in_bytes * args.steps < (60 << 30) else max(3, (60 << 30) // in_bytes)
+        last = {}
+
+        def e2e_step():
+            last["r"] = det(h_heads)
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        sampler.active.set()
+        t0 = time.perf_counter()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        b.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        sampler.active.clear()
+        e2e_ms = max_over_ranks(max(a.elapsed_time(b), wall_ms))
+        barrier()
+        # the host results of the last e2e step must be the device-resident results
+        ids_h = last["r"][0]
+        same = bool(torch.equal(ids_h[..., 0], out.cpu()[..., 0]))
+        e2e = {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s",
+               "h2d_bytes_per_step": det.h2d_bytes, "d2h_bytes_per_step": det.d2h_bytes, "steps": e2e_steps,
+               "ms_per_step": e2e_ms / e2e_steps, "api": "videoyolo_b200.pipeline.HostDetector.__call__",
+               "matches_device_path": same}
+        del h_heads
+    sampler.stop()
+
+    # ---- cpu baseline (rank 0, N=1 only): oracle port on a bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle
+        oracle.build()
+        cores = os.cpu_count() or 1
+        frames = min(B, max(cores, 8))
+        v, dt = cpu_port_fps(C, size, frames, 1236, cores)
+        reps = 1
+        while dt * reps < 8.0 and reps < 8:
+            reps += 1
+        if reps > 1:
+            v, dt = cpu_port_fps(C, size, frames, 1236, cores, steps=reps)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "%d of %d frames x %d passes, %d threads over frames (oracle/vy_oracle.c: decode + box_nms)"
+                         % (frames, B, reps, cores)}
+
+    if rank == 0:
+        line = {"metric": "frames/sec decode+NMS", "value": fps, "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": label, "classes": C, "input": size, "frames_per_gpu": B,
+                           "global_frames_per_step": B * world, "boxes_per_frame": in_bytes_frame // (4 * (5 + C)),
+                           "regime": args.regime + (": logits ~ N(0,1) (random-init weights)" if args.regime == "R" else ": trained-like"),
+                           "nms": NMS, "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world,
+                           "l2": ("inputs larger than L2 (%.0f MB per step)" % (in_bytes / 1e6)) if flush is None
+                                 else "L2 flushed between steps (256 MiB write)"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
+                "launches_per_step": per_step, "clocks": sampler.summary()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,28 @@ int         vy_version(void);
 const char *vy_last_error(void);
 
 /* ---------------------------------------------------------------------------------------------
+ * Launch accounting (measurement only; no reference counterpart).  Every kernel the library
+ * launches is counted under one of the ids below.  While vy_prof_enable(1) is in force each launch
+ * is additionally bracketed by cudaEventRecord on the stream it is launched on; vy_prof_read()
+ * synchronises those events, returns summed milliseconds and launch counts per id, and resets.
+ */
+#define VY_K_DECODE        0
+#define VY_K_SELECT_HEADS  1
+#define VY_K_SELECT_ROWS   2
+#define VY_K_FINALIZE      3
+#define VY_K_FILL          4
+#define VY_K_IOU           5
+#define VY_K_FUSION_CONV   6
+#define VY_K_TEMPORAL_POOL 7
+#define VY_K_NMS_LARGE     8
+#define VY_K_LAYOUT        9
+#define VY_K_COUNT        10
+const char *vy_kernel_name(int kernel_id);
+int vy_launch_counts(long long *host_counts, int n);     /* cumulative since load; returns VY_K_COUNT */
+int vy_prof_enable(int on);
+int vy_prof_read(double *host_ms, long long *host_launches, int n);
+
+/* ---------------------------------------------------------------------------------------------
  * Anchor decode of the YOLOv3 output layers into the reference's detection tensor.
  * Replaces: YOLOOutputV3.hybrid_forward, models/definitions/yolo/yolo3.py:151-199 (dup
  *           yolo3_temporal.py:137-179) for each scale, plus the scale concat yolo3.py:523.

@@ -21,6 +21,10 @@ c_vp = ctypes.c_void_p
 SIGNATURES = {
     "vy_version": (ctypes.c_int, []),
     "vy_last_error": (ctypes.c_char_p, []),
+    "vy_kernel_name": (ctypes.c_char_p, [ctypes.c_int]),
+    "vy_launch_counts": (ctypes.c_int, [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]),
+    "vy_prof_enable": (ctypes.c_int, [ctypes.c_int]),
+    "vy_prof_read": (ctypes.c_int, [c_f64p, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]),
     "vy_decode_f32": (ctypes.c_int, [ctypes.POINTER(c_vp), c_i32p, c_i32p, c_f32p, c_f32p, ctypes.c_int,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "vy_box_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int]),
@@ -77,3 +81,25 @@ def lib() -> ctypes.CDLL:
 def check(rc: int) -> None:
     if rc != VY_OK:
         raise VyoloError(rc, lib().vy_last_error().decode("utf-8", "replace"))
+
+
+N_KERNEL_IDS = 10
+
+
+def launch_counts() -> dict:
+    """Cumulative kernel launches of the library per kernel name (include/vyolo.h: vy_launch_counts)."""
+    c = (ctypes.c_longlong * N_KERNEL_IDS)()
+    lib().vy_launch_counts(c, N_KERNEL_IDS)
+    return {lib().vy_kernel_name(i).decode(): int(c[i]) for i in range(N_KERNEL_IDS)}
+
+
+def prof_enable(on: bool) -> None:
+    check(lib().vy_prof_enable(int(bool(on))))
+
+
+def prof_read() -> dict:
+    """{kernel name: (summed ms, launches)} of the launches recorded since the last read."""
+    ms = (ctypes.c_double * N_KERNEL_IDS)()
+    n = (ctypes.c_longlong * N_KERNEL_IDS)()
+    check(lib().vy_prof_read(ms, n, N_KERNEL_IDS))
+    return {lib().vy_kernel_name(i).decode(): (float(ms[i]), int(n[i])) for i in range(N_KERNEL_IDS) if n[i]}

@@ -15,6 +15,63 @@ void vy_set_error(const char *fmt, ...) {
 extern "C" int vy_version(void) { return VY_ABI_VERSION; }
 extern "C" const char *vy_last_error(void) { return g_err; }
 
+// ------------------------------------------------------------------ launch accounting
+#include <atomic>
+#include <mutex>
+#include <vector>
+static const char *const g_kernel_names[VY_K_COUNT] = {
+    "vy_decode_kernel", "vy_decode_select_kernel", "vy_rows_select_kernel", "vy_nms_finalize_kernel",
+    "vy_fill_kernel", "vy_bbox_iou_kernel", "vy_fusion_conv_kernel", "vy_temporal_pool_kernel",
+    "vy_nms_large_kernels", "vy_layout_kernels"};
+static std::atomic<long long> g_launches[VY_K_COUNT];
+static std::atomic<int> g_prof_on{0};
+struct ProfRec { int id; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+static thread_local cudaEvent_t g_prof_open = nullptr;
+
+void vy_prof_pre(int id, cudaStream_t st) {
+    if (id < 0 || id >= VY_K_COUNT) return;
+    g_launches[id].fetch_add(1, std::memory_order_relaxed);
+    g_prof_open = nullptr;
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    cudaEvent_t a = nullptr;
+    if (cudaEventCreate(&a) != cudaSuccess) return;
+    cudaEventRecord(a, st);
+    g_prof_open = a;
+}
+void vy_prof_post(int id, cudaStream_t st) {
+    if (!g_prof_open) return;
+    cudaEvent_t b = nullptr;
+    if (cudaEventCreate(&b) != cudaSuccess) { cudaEventDestroy(g_prof_open); g_prof_open = nullptr; return; }
+    cudaEventRecord(b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back(ProfRec{id, g_prof_open, b});
+    g_prof_open = nullptr;
+}
+extern "C" const char *vy_kernel_name(int id) { return (id >= 0 && id < VY_K_COUNT) ? g_kernel_names[id] : ""; }
+extern "C" int vy_launch_counts(long long *counts, int n) {
+    if (!counts || n < 0) VY_FAIL(VY_EINVAL, "vy_launch_counts: bad arguments");
+    for (int i = 0; i < n; ++i) counts[i] = i < VY_K_COUNT ? g_launches[i].load() : 0;
+    return VY_K_COUNT;
+}
+extern "C" int vy_prof_enable(int on) { g_prof_on.store(on ? 1 : 0); return VY_OK; }
+extern "C" int vy_prof_read(double *ms, long long *launches, int n) {
+    if (!ms || !launches || n < 0) VY_FAIL(VY_EINVAL, "vy_prof_read: bad arguments");
+    for (int i = 0; i < n; ++i) { ms[i] = 0.0; launches[i] = 0; }
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    int rc = VY_OK;
+    for (const ProfRec &r : g_prof_recs) {
+        float t = 0.0f;
+        if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) rc = VY_ECUDA;
+        else if (r.id < n) { ms[r.id] += (double)t; launches[r.id] += 1; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof_recs.clear();
+    if (rc != VY_OK) vy_set_error("vy_prof_read: an event could not be read");
+    return rc;
+}
+
 int vy_sm_count() {
     static int cached[64] = {0};
     int dev = 0;

@@ -19,6 +19,13 @@ void vy_set_error(const char *fmt, ...);
 
 int vy_sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
 
+// ------------------------------------------------------------------ launch accounting (vyolo.h: vy_prof_*)
+// Every kernel launch of the library goes through VY_KERNEL: it is counted always and, while
+// vy_prof_enable(1) is in force, bracketed by cudaEventRecord on the launching stream.
+void vy_prof_pre(int kernel_id, cudaStream_t st);
+void vy_prof_post(int kernel_id, cudaStream_t st);
+#define VY_KERNEL(id, st, ...) do { vy_prof_pre((id), (st)); __VA_ARGS__; vy_prof_post((id), (st)); } while (0)
+
 // ------------------------------------------------------------------ head-map description
 // One YOLO output scale (yolo3.py:43-74): NCHW head map + the constants the decode needs.
 struct VyScale {

@@ -53,7 +53,8 @@ extern "C" int vy_decode_f32(const float *const *head, const int *H, const int *
         const int bpi = (int)((hd.sc[s].n_s + DEC_NT - 1) / DEC_NT);
         const long long grid = (long long)bpi * B;
         if (grid > 0x7fffffffLL) VY_FAIL(VY_EINVAL, "vy_decode_f32: grid too large");
-        vy_decode_kernel<<<(unsigned)grid, DEC_NT, 0, (cudaStream_t)stream>>>(hd, dets, s, bpi);
+        VY_KERNEL(VY_K_DECODE, (cudaStream_t)stream,
+                  vy_decode_kernel<<<(unsigned)grid, DEC_NT, 0, (cudaStream_t)stream>>>(hd, dets, s, bpi));
         VY_LAUNCH_CHECK("vy_decode_kernel");
     }
     return VY_OK;

@@ -28,7 +28,8 @@ static int launch_iou(const T *a, int N, int lda, const T *b, int M, int ldb, T 
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)vy_sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    vy_bbox_iou_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)st>>>(a, N, lda, b, M, ldb, offset, out);
+    VY_KERNEL(VY_K_IOU, (cudaStream_t)st,
+              (vy_bbox_iou_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)st>>>(a, N, lda, b, M, ldb, offset, out)));
     VY_LAUNCH_CHECK("vy_bbox_iou_kernel");
     return VY_OK;
 }

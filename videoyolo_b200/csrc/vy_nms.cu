@@ -761,7 +761,7 @@ static int launch_finalize(const VyHeads &hd, const RowParams &rp, const SelPlan
     const size_t dyn = fin_dyn_smem(pl.K);
     VY_CUDA_CHECK(cudaFuncSetAttribute(vy_nms_finalize_kernel<SRC>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    vy_nms_finalize_kernel<SRC><<<B, FIN_NT, dyn, st>>>(hd, rp, pl, g, fp);
+    VY_KERNEL(VY_K_FINALIZE, st, (vy_nms_finalize_kernel<SRC><<<B, FIN_NT, dyn, st>>>(hd, rp, pl, g, fp)));
     VY_LAUNCH_CHECK("vy_nms_finalize_kernel");
     return VY_OK;
 }
@@ -801,7 +801,7 @@ extern "C" int vy_decode_nms_f32(const float *const *head, const int *H, const i
     for (int s = 0; s < n_scales; ++s)
         if (!head[s]) VY_FAIL(VY_EINVAL, "vy_decode_nms_f32: head[%d] is null", s);
     VY_CUDA_CHECK(cudaMemsetAsync(workspace, 0, header, st));
-    vy_decode_select_kernel<<<select_grid(pl.n_jobs), SEL_NT, 0, st>>>(hd, pl, g);
+    VY_KERNEL(VY_K_SELECT_HEADS, st, (vy_decode_select_kernel<<<select_grid(pl.n_jobs), SEL_NT, 0, st>>>(hd, pl, g)));
     VY_LAUNCH_CHECK("vy_decode_select_kernel");
     FinParams fp;
     fp.K = pl.K; fp.post_rows = post_nms; fp.out_stride_rows = post_nms;
@@ -849,8 +849,8 @@ extern "C" int vy_box_nms_f32(const float *data, int B, long R, int W_elem, floa
     if (plan_rows(B, R, topk, valid_thresh, &pl) != VY_OK) {
         const long long K = topk < 0 ? R : (topk < R ? topk : R);
         if (K < 1) {      // topk == 0: nothing takes part
-            vy_fill_kernel<<<vy_sm_count() * 4, 256, 0, st>>>(out, kept_rows, (size_t)B * out_rows * W_elem,
-                                                               (size_t)B * out_rows);
+            VY_KERNEL(VY_K_FILL, st, (vy_fill_kernel<<<vy_sm_count() * 4, 256, 0, st>>>(
+                out, kept_rows, (size_t)B * out_rows * W_elem, (size_t)B * out_rows)));
             VY_LAUNCH_CHECK("vy_fill_kernel");
             return VY_OK;
         }
@@ -864,7 +864,7 @@ extern "C" int vy_box_nms_f32(const float *data, int B, long R, int W_elem, floa
         VY_FAIL(VY_EWORKSPACE, "vy_box_nms_f32: workspace %zu < %zu bytes", workspace_bytes, need);
     if (((uintptr_t)workspace & 255) != 0) VY_FAIL(VY_EALIGN, "workspace must be 256-byte aligned");
     VY_CUDA_CHECK(cudaMemsetAsync(workspace, 0, header, st));
-    vy_rows_select_kernel<<<select_grid(pl.n_jobs), SEL_NT, 0, st>>>(rp, pl, g);
+    VY_KERNEL(VY_K_SELECT_ROWS, st, (vy_rows_select_kernel<<<select_grid(pl.n_jobs), SEL_NT, 0, st>>>(rp, pl, g)));
     VY_LAUNCH_CHECK("vy_rows_select_kernel");
     FinParams fp;
     fp.K = pl.K; fp.post_rows = (int)(out_rows < pl.K ? out_rows : pl.K); fp.out_stride_rows = out_rows;
@@ -873,8 +873,8 @@ extern "C" int vy_box_nms_f32(const float *data, int B, long R, int W_elem, floa
     fp.out = out; fp.kept_rows = kept_rows;
     if (out_rows > pl.K) {
         // at most K rows can survive: pad everything first, survivors overwrite the front
-        vy_fill_kernel<<<vy_sm_count() * 8, 256, 0, st>>>(out, kept_rows, (size_t)B * out_rows * W_elem,
-                                                           (size_t)B * out_rows);
+        VY_KERNEL(VY_K_FILL, st, (vy_fill_kernel<<<vy_sm_count() * 8, 256, 0, st>>>(
+            out, kept_rows, (size_t)B * out_rows * W_elem, (size_t)B * out_rows)));
         VY_LAUNCH_CHECK("vy_fill_kernel");
         fp.fill_rest = 0;
     } else {

@@ -1,0 +1,90 @@
+"""Host-facing detection call: pinned host head maps in, host (ids, scores, bboxes) out.
+
+This is the call a user of the reference makes around ``net(x)``: ``split_and_load`` (host -> device,
+detect_yolo3.py:211-213), the forward tail, and ``as_numpy`` (device -> host, utils/general.py:6-18,
+detect_yolo3.py:233).  The batch is cut into chunks that travel through a small ring of device
+buffers: the copy engine brings chunk i+1 in on one stream while the decode+NMS kernels of chunk i
+run on another, and the (chunk, post_nms, 6) results leave on the compute stream.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+
+
+class HostDetector:
+    """Fused decode + box_nms for head maps that live in (pinned) host memory."""
+
+    def __init__(self, num_class: int, anchors, strides, device, chunk: int = 8, ring: int = 3,
+                 nms_thresh: float = 0.45, valid_thresh: float = 0.01, nms_topk: int = 400,
+                 post_nms: int = 100, agnostic: bool = False):
+        self.C = num_class
+        self.anchors, self.strides = anchors, strides
+        self.device = torch.device(device)
+        self.chunk, self.ring = int(chunk), int(ring)
+        self.nms = dict(nms_thresh=nms_thresh, valid_thresh=valid_thresh, topk=nms_topk,
+                        post_nms=post_nms, agnostic=agnostic)
+        self.post_nms = post_nms
+        self._copy = torch.cuda.Stream(self.device)
+        self._compute = torch.cuda.Stream(self.device)
+        self._bufs: Optional[List[List[torch.Tensor]]] = None
+        self._shapes = None
+        self._out_dev = self._kept_dev = self._out_host = self._kept_host = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _prepare(self, heads: Sequence[torch.Tensor]):
+        shapes = [tuple(h.shape) for h in heads]
+        if shapes == self._shapes:
+            return
+        B = shapes[0][0]
+        self._bufs = [[torch.empty((self.chunk,) + s[1:], dtype=torch.float32, device=self.device) for s in shapes]
+                      for _ in range(self.ring)]
+        self._free = [torch.cuda.Event() for _ in range(self.ring)]      # chunk buffer consumed
+        self._ready = [torch.cuda.Event() for _ in range(self.ring)]     # chunk buffer filled
+        self._out_dev = torch.empty((B, self.post_nms, 6), dtype=torch.float32, device=self.device)
+        self._kept_dev = torch.empty((B, self.post_nms), dtype=torch.int32, device=self.device)
+        self._out_host = torch.empty((B, self.post_nms, 6), dtype=torch.float32).pin_memory()
+        self._kept_host = torch.empty((B, self.post_nms), dtype=torch.int32).pin_memory()
+        self._shapes = shapes
+        self.h2d_bytes = sum(h.numel() * 4 for h in heads)
+        self.d2h_bytes = self._out_host.numel() * 4 + self._kept_host.numel() * 4
+
+    def __call__(self, heads: Sequence[torch.Tensor]):
+        """heads: host tensors (B, A*(5+C), H, W) fp32 in network order (stride 32, 16, 8); pinned memory
+        makes the copies asynchronous.  Returns host tensors ids (B,post,1), scores (B,post,1),
+        bboxes (B,post,4) and leaves the kept source rows in ``self.kept_rows`` (host, int32)."""
+        for h in heads:
+            if h.is_cuda or h.dtype != torch.float32 or not h.is_contiguous():
+                raise TypeError("HostDetector takes contiguous fp32 host tensors; device tensors go through YOLOV3")
+        self._prepare(heads)
+        B = heads[0].shape[0]
+        start = torch.cuda.current_stream(self.device)
+        self._copy.wait_stream(start)
+        self._compute.wait_stream(start)
+        n_chunks = (B + self.chunk - 1) // self.chunk
+        for i in range(n_chunks):
+            s, e = i * self.chunk, min(B, (i + 1) * self.chunk)
+            slot = i % self.ring
+            with torch.cuda.stream(self._copy):
+                if i >= self.ring:
+                    self._copy.wait_event(self._free[slot])
+                for buf, h in zip(self._bufs[slot], heads):
+                    buf[: e - s].copy_(h[s:e], non_blocking=True)
+                self._ready[slot].record(self._copy)
+            with torch.cuda.stream(self._compute):
+                self._compute.wait_event(self._ready[slot])
+                ops.yolo3_decode_nms([b[: e - s] for b in self._bufs[slot]], self.C, self.anchors, self.strides,
+                                     out=self._out_dev[s:e], kept=self._kept_dev[s:e], **self.nms)
+                self._free[slot].record(self._compute)
+        with torch.cuda.stream(self._compute):
+            self._out_host.copy_(self._out_dev, non_blocking=True)
+            self._kept_host.copy_(self._kept_dev, non_blocking=True)
+        self._compute.synchronize()                                     # as_numpy: the host needs the values
+        start.wait_stream(self._compute)
+        self.kept_rows = self._kept_host
+        r = self._out_host
+        return r[..., 0:1], r[..., 1:2], r[..., 2:6]
