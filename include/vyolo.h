@@ -61,7 +61,9 @@ const char *vy_last_error(void);
 #define VY_K_TEMPORAL_POOL 7
 #define VY_K_NMS_LARGE     8
 #define VY_K_LAYOUT        9
-#define VY_K_COUNT        10
+#define VY_K_SAMPLE       10
+#define VY_K_STREAM       11
+#define VY_K_COUNT        12
 const char *vy_kernel_name(int kernel_id);
 int vy_launch_counts(long long *host_counts, int n);     /* cumulative since load; returns VY_K_COUNT */
 int vy_prof_enable(int on);
@@ -134,14 +136,21 @@ int vy_bbox_iou_f64(const double *a, int N, int lda, const double *b, int M, int
  * Temporal fusion convolution: LeakyReLU(BN(ConvND(x))), use_bias=False, stride 1, groups 1.
  * Replaces: Conv / _conv2d / _conv3d / _conv21d cells, models/definitions/layers.py:63-89,135-158,
  *           as used by YOLODetectionBlockV3 (yolo3.py:229-253) -- one call per conv+BN+LReLU cell
- *           ('21' = two calls).  tcgen05/TMEM implicit GEMM fed by TMA.
- *   x        (B, T, H, W, Cin)  bf16 channels-last (NDHWC; T=1 for 2-D)
- *   w        (Cout, kt, kh, kw, Cin) bf16
+ *           ('21' = two calls: (1,3,3) then (3,1,1), layers.py:82-89).  tcgen05/TMEM implicit GEMM
+ *           fed by TMA.
+ *
+ * Activations use the library's "P layout": [T][B][H+2][W+2][C] bf16 (fp32 allowed for the last
+ * output), time outermost, channels innermost, with a one-pixel ZERO spatial border.  The conv
+ * writes a valid P-layout tensor (border included), so cells chain without repacking.  2-D convs
+ * are T = 1; the 'cat' join (yolo3.py:1135-1136) is T = 1 with C = K*C channels.
+ *   x        P layout, Cin channels
+ *   w        (Cout, kt, kh, kw, Cin) bf16  (the reference's (Cout, Cin, kt, kh, kw) permuted)
  *   scale, shift  per-Cout fp32 folded inference BatchNorm: y = conv*scale + shift
  *                 (scale = gamma/sqrt(var+eps), shift = beta - mean*scale; layers.py:68,77)
- *   y        (B, T, H, W, Cout) bf16 (y_is_f32 = 0) or fp32 (1); 'same' padding: p = k/2
- *   requires Cin % 64 == 0, Cout % 64 == 0, kt,kh,kw in {1,3}
+ *   y        P layout, Cout channels, bf16 (y_is_f32 = 0) or fp32 (1); 'same' padding p = k/2
+ *   requires Cin % 64 == 0, Cout % 64 == 0, kt,kh,kw in {1,3}; needs no workspace.
  */
+size_t vy_p_layout_elems(int B, int T, int H, int W, int C);
 size_t vy_fusion_conv_workspace_bytes(int B, int T, int H, int W, int Cin, int Cout,
                                       int kt, int kh, int kw);
 int vy_fusion_conv_bf16(const void *x, const void *w, const float *scale, const float *shift,
@@ -149,10 +158,17 @@ int vy_fusion_conv_bf16(const void *x, const void *w, const float *scale, const 
                         int kt, int kh, int kw, void *y, int y_is_f32,
                         void *workspace, size_t workspace_bytes, vy_stream_t stream);
 
-/* TemporalPooling 'direct' style (layers.py:201-205) on channels-last data:
- * x (B, T, H*W*C) -> y (B, H*W*C), mode 0 = max, 1 = mean.  bf16 in/out. */
-int vy_temporal_pool_bf16(const void *x, int B, int T, long inner, int mode, void *y,
-                          vy_stream_t stream);
+/* Layout conversion between the reference's fp32 tensors and the P layout.  Element (b, c, t, h, w)
+ * of the fp32 tensor lives at x[b*stride_b + c*stride_c + t*stride_t + h*W + w], which covers both
+ * NCDHW (after the swapaxes of yolo3.py:256-262) and (B, K, C, H, W) (before it), and T = 1 NCHW. */
+int vy_pack_f32_to_p_bf16(const float *x, long long stride_b, long long stride_c, long long stride_t,
+                          int B, int C, int T, int H, int W, void *y_p, vy_stream_t stream);
+int vy_unpack_p_to_f32(const void *y_p, int p_is_f32, int B, int C, int T, int H, int W, float *x,
+                       long long stride_b, long long stride_c, long long stride_t, vy_stream_t stream);
+
+/* TemporalPooling 'direct' style (layers.py:201-205) on P-layout data: x (T, inner) -> y (inner),
+ * inner = B*(H+2)*(W+2)*C, mode 0 = max, 1 = mean.  bf16 in/out. */
+int vy_temporal_pool_bf16(const void *x, int T, long inner, int mode, void *y, vy_stream_t stream);
 
 #ifdef __cplusplus
 }

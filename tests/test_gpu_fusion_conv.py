@@ -1,0 +1,134 @@
+"""GPU parity of the temporal fusion conv (tcgen05 implicit GEMM) against the CPU oracle
+(oracle.conv_bn_leaky: torch CPU fp32 restatement of layers.py:63-89).
+
+Tolerance: operands are bf16, accumulation fp32; the oracle gets the SAME
+bf16-rounded inputs and weights, so the only differences are the summation order and the final
+rounding of the output to bf16 (2^-9 relative): |d| <= 1e-2 * max|y| and rtol 2e-2 elementwise.
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vy():
+    assert torch.cuda.is_available()
+    import videoyolo_b200
+    videoyolo_b200._lib.lib()
+    return videoyolo_b200
+
+
+def bf16_round(a):
+    return torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+
+
+def make_cell(rng, B, T, H, W, Cin, Cout, k3):
+    x = bf16_round(rng.normal(0, 1, size=(B, Cin, T, H, W)).astype(np.float32))
+    w = bf16_round(rng.uniform(-0.07, 0.07, size=(Cout, Cin) + k3).astype(np.float32))   # MXNet Uniform(0.07)
+    gamma = rng.uniform(0.5, 1.5, Cout).astype(np.float32)
+    beta = rng.normal(0, 0.2, Cout).astype(np.float32)
+    mean = rng.normal(0, 0.2, Cout).astype(np.float32)
+    var = rng.uniform(0.5, 2.0, Cout).astype(np.float32)
+    return x, w, (gamma, beta, mean, var)
+
+
+def run_cell(vy, x, w, bn, out_f32=False):
+    ops = vy.ops
+    dev = "cuda"
+    xp = ops.pack_p(torch.from_numpy(x).to(dev), "NCDHW")
+    wt = ops.conv_weight(torch.from_numpy(w).to(dev))
+    scale, shift = ops.fold_bn(*[torch.from_numpy(v).to(dev) for v in bn])
+    y = ops.fusion_conv(xp, wt, scale, shift, 0.1, out_f32=out_f32)
+    # the border of the output must be zero again (cells chain without repacking)
+    d = y.data.float()
+    assert float(d[:, :, 0].abs().max()) == 0 and float(d[:, :, -1].abs().max()) == 0
+    assert float(d[:, :, :, 0].abs().max()) == 0 and float(d[:, :, :, -1].abs().max()) == 0
+    return y, ops.unpack_p(y, "NCDHW").cpu().numpy()
+
+
+def check(got, ref, name):
+    scale = np.abs(ref).max()
+    err = np.abs(got - ref)
+    assert err.max() <= 1e-2 * scale, (name, err.max(), scale)
+    np.testing.assert_allclose(got, ref, rtol=2e-2, atol=1e-2 * scale, err_msg=name)
+
+
+@pytest.mark.parametrize("B,T,H,W,Cin,Cout,k3", [
+    (2, 3, 13, 13, 64, 64, (3, 3, 3)),        # smallest shape, BN=64
+    (2, 3, 13, 13, 128, 256, (3, 3, 3)),      # BN=256
+    (1, 3, 26, 26, 64, 128, (1, 3, 3)),       # '21' spatial half (layers.py:86), BN=128
+    (1, 3, 26, 26, 128, 128, (3, 1, 1)),      # '21' temporal half (layers.py:87)
+    (3, 3, 13, 13, 256, 128, (1, 1, 1)),      # the 1x1x1 cells (yolo3.py:229-230)
+    (2, 1, 20, 20, 192, 64, (1, 3, 3)),       # 2-D conv after the 'cat' join: T=1, K*C channels
+    (1, 5, 10, 10, 64, 64, (3, 3, 3)),        # window of 5
+])
+def test_fusion_conv_matches_oracle(vy, B, T, H, W, Cin, Cout, k3):
+    rng = np.random.RandomState(B * 100 + T + H + Cin)
+    x, w, bn = make_cell(rng, B, T, H, W, Cin, Cout, k3)
+    _, got = run_cell(vy, x, w, bn)
+    ref = oracle.conv_bn_leaky(x, w, *bn, padding=tuple(k // 2 for k in k3))
+    check(got, ref, str((B, T, H, W, Cin, Cout, k3)))
+
+
+def test_fusion_conv_fp32_output_and_chain(vy):
+    """conv21d = two chained cells without repacking (layers.py:82-89); last output in fp32."""
+    rng = np.random.RandomState(5)
+    B, T, H, W, C = 2, 3, 13, 13, 64
+    x, w1, bn1 = make_cell(rng, B, T, H, W, C, 128, (1, 3, 3))
+    _, w2, bn2 = make_cell(rng, B, T, H, W, 128, 128, (3, 1, 1))
+    ops = vy.ops
+    xp = ops.pack_p(torch.from_numpy(x).cuda(), "NCDHW")
+    s1, h1 = ops.fold_bn(*[torch.from_numpy(v).cuda() for v in bn1])
+    s2, h2 = ops.fold_bn(*[torch.from_numpy(v).cuda() for v in bn2])
+    y1 = ops.fusion_conv(xp, ops.conv_weight(torch.from_numpy(w1).cuda()), s1, h1)
+    y2 = ops.fusion_conv(y1, ops.conv_weight(torch.from_numpy(w2).cuda()), s2, h2, out_f32=True)
+    got = ops.unpack_p(y2, "NCDHW").cpu().numpy()
+    # oracle: the intermediate is rounded to bf16 like the GPU's
+    r1 = bf16_round(oracle.conv_bn_leaky(x, w1, *bn1, padding=(0, 1, 1)))
+    ref = oracle.conv_bn_leaky(r1, w2, *bn2, padding=(1, 0, 0))
+    check(got, ref, "conv21d")
+
+
+def test_inflated_weights_identity(vy):
+    """three_darknet.py:335-347: a clip of identical frames through a 3x3x3 conv whose weights are the
+    2-D weights / kt in every temporal tap equals the 2-D conv (interior frames)."""
+    rng = np.random.RandomState(8)
+    B, T, H, W, Cin, Cout = 1, 3, 13, 13, 64, 64
+    x2, w2, bn = make_cell(rng, B, 1, H, W, Cin, Cout, (1, 3, 3))
+    x3 = np.repeat(x2, T, axis=2)
+    w3 = bf16_round(np.repeat(w2, 3, axis=2) / 4.0)          # /4 is exact in bf16; 3 taps -> 3/4 of the 2-D sum
+    _, got3 = run_cell(vy, x3, w3, bn)
+    ref = oracle.conv_bn_leaky(x3, w3, *bn, padding=(1, 1, 1))
+    check(got3, ref, "inflated")
+    # middle frame sees all three taps: conv3d = 0.75 * conv2d before BN
+    g2, b2, m2, v2 = bn
+    ref2 = oracle.conv_bn_leaky(x2, bf16_round(w2 * 0.75), g2, b2, m2, v2, padding=(0, 1, 1))
+    check(got3[:, :, 1:2], ref2, "inflated-vs-2d")
+
+
+def test_pack_unpack_roundtrip_and_pool(vy):
+    rng = np.random.RandomState(2)
+    ops = vy.ops
+    x = bf16_round(rng.normal(size=(2, 3, 64, 7, 9)).astype(np.float32))     # (B, K, C, H, W)
+    xp = ops.pack_p(torch.from_numpy(x).cuda(), "NTCHW")
+    assert xp.shape == (2, 64, 3, 7, 9)
+    back = ops.unpack_p(xp, "NTCHW").cpu().numpy()
+    np.testing.assert_array_equal(back, x)
+    back2 = ops.unpack_p(xp, "NCDHW").cpu().numpy()
+    np.testing.assert_array_equal(back2, x.transpose(0, 2, 1, 3, 4))
+    for typ in ("max", "mean"):
+        got = ops.unpack_p(ops.temporal_pool(xp, typ), "NCHW").cpu().numpy()
+        ref = bf16_round(oracle.temporal_pool(x, typ).astype(np.float32))
+        np.testing.assert_allclose(got, ref, rtol=1e-2, atol=1e-2)
+
+
+def test_fusion_conv_rejects_bad_shapes(vy):
+    ops = vy.ops
+    xp = ops.pack_p(torch.zeros(1, 48, 3, 5, 5).cuda(), "NCDHW")
+    w = torch.zeros(64, 3, 3, 3, 48, dtype=torch.bfloat16).cuda()
+    with pytest.raises(vy._lib.VyoloError):
+        ops.fusion_conv(xp, w, torch.ones(64).cuda(), torch.zeros(64).cuda())

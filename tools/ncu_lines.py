@@ -15,14 +15,17 @@ for ln in dis.splitlines():
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*)", ln)
     if m and cur_fn and kern in cur_fn:
         addr2line[int(m.group(1), 16)] = cur_line
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 h = rows[1]; ix = {n: i for i, n in enumerate(h)}
 base = None
 agg = {}
 tot = [0, 0]
+seen_kernels = 0
 for r in rows[2:]:
-    if len(r) < len(h): continue
+    if r and r[0] == "Kernel Name":
+        break                      # only the first matching launch
+    if len(r) < len(h) or r[ix["Address"]] == "Address": continue
     a = int(r[ix["Address"]], 16) if r[ix["Address"]].startswith("0x") else int(r[ix["Address"]])
     if base is None: base = a
     line = addr2line.get(a - base)

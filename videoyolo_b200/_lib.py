@@ -45,8 +45,12 @@ SIGNATURES = {
     "vy_fusion_conv_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 9),
     "vy_fusion_conv_bf16": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_float] + [ctypes.c_int] * 9 +
                             [c_vp, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp]),
-    "vy_temporal_pool_bf16": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_int,
-                                             c_vp, c_vp]),
+    "vy_temporal_pool_bf16": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_long, ctypes.c_int, c_vp, c_vp]),
+    "vy_p_layout_elems": (ctypes.c_size_t, [ctypes.c_int] * 5),
+    "vy_pack_f32_to_p_bf16": (ctypes.c_int, [c_vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong] +
+                              [ctypes.c_int] * 5 + [c_vp, c_vp]),
+    "vy_unpack_p_to_f32": (ctypes.c_int, [c_vp] + [ctypes.c_int] * 6 + [c_vp, ctypes.c_longlong, ctypes.c_longlong,
+                                                                        ctypes.c_longlong, c_vp]),
 }
 
 VY_OK = 0
@@ -83,7 +87,7 @@ def check(rc: int) -> None:
         raise VyoloError(rc, lib().vy_last_error().decode("utf-8", "replace"))
 
 
-N_KERNEL_IDS = 10
+N_KERNEL_IDS = 12
 
 
 def launch_counts() -> dict:

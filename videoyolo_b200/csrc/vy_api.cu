@@ -22,7 +22,7 @@ extern "C" const char *vy_last_error(void) { return g_err; }
 static const char *const g_kernel_names[VY_K_COUNT] = {
     "vy_decode_kernel", "vy_decode_select_kernel", "vy_rows_select_kernel", "vy_nms_finalize_kernel",
     "vy_fill_kernel", "vy_bbox_iou_kernel", "vy_fusion_conv_kernel", "vy_temporal_pool_kernel",
-    "vy_nms_large_kernels", "vy_layout_kernels"};
+    "vy_nms_large_kernels", "vy_layout_kernels", "vy_decode_sample_kernel", "vy_decode_stream_kernel"};
 static std::atomic<long long> g_launches[VY_K_COUNT];
 static std::atomic<int> g_prof_on{0};
 struct ProfRec { int id; cudaEvent_t a, b; };

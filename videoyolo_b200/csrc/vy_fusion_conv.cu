@@ -1,22 +1,475 @@
-// vy_fusion_conv.cu -- temporal fusion convolution (placeholder entry points until the tcgen05 kernel lands).
+// vy_fusion_conv.cu -- temporal fusion convolution: LeakyReLU(BN(ConvND(x))) as a tcgen05/TMEM implicit
+// GEMM fed by TMA.  Replaces the Conv / _conv2d / _conv3d / _conv21d cells of
+// models/definitions/layers.py:63-89,135-158 as used by YOLODetectionBlockV3 (yolo3.py:229-253).
+//
+// Activation layout ("P layout", the library's own; vy_pack_* / vy_unpack_* convert from and to the
+// reference's NCDHW fp32):   [T][B][Hp = H+2][Wp = W+2][C]  bf16, the one-pixel spatial border is zero.
+//   * time is the OUTERMOST axis, so all frames of the batch form one matrix X_t[rows = B*Hp*Wp][C];
+//   * with the border materialised, the input of filter tap (dt, dh, dw) for 128 consecutive output
+//     rows r0.. is simply the 128 consecutive rows r0 + dh*Wp + dw .. of X_{t+dt}: a plain TMA tile.
+//     Frames t+dt outside [0, T) and rows outside the matrix are zero-filled by TMA itself
+//     (the (kt/2) temporal 'same' padding of layers.py:76,86 costs nothing: those taps are skipped).
+//   => the convolution is   Y_t[r0:r0+128, n0:n0+BN] = sum_{taps, Cin blocks} A_tap(128 x 64) * W_tap(BN x 64)^T
+//      with every operand tile fetched by one cp.async.bulk.tensor, and no im2col buffer anywhere.
+//   Outputs are produced for border rows too (garbage) and overwritten with zeros in the epilogue, so
+//   the result is again a valid P-layout tensor and conv cells chain without repacking.
+//
+// Kernel: persistent, one CTA per SM, 192 threads = warp 0 TMA producer (one lane), warp 1 MMA issuer
+// (one lane; owns TMEM), warps 2-5 epilogue.  4-stage smem ring (A 16 KB + B BN*128 B per stage,
+// 128-byte swizzle), accumulators double-buffered in TMEM (2 x BN columns) so the epilogue of tile i
+// overlaps the MMAs of tile i+1.  Epilogue: tcgen05.ld -> scale/shift (folded BN) -> LeakyReLU ->
+// border zeroing -> bf16 (or fp32) -> global.
 #include "vy_common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <string.h>
+
+namespace {
+
+constexpr int CV_BM = 128;            // output rows per tile (UMMA M)
+constexpr int CV_BK = 64;             // channels per k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int CV_STAGES = 4;
+constexpr int CV_NT = 192;
+constexpr int CV_MAX_TAPS = 27;
+
+struct ConvParams {
+    int T, rows, Hp, Wp, Cin, Cout;
+    int kt, kh, kw;
+    int m_tiles, n_tiles, cin_blocks;
+    long long n_tiles_total;
+    float slope;
+    const float *scale, *shift;
+    void *y;
+    int y_is_f32;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64 *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u64 *bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u64 *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(u64 *bar) {      // arrives on bar when all MMAs issued so far are done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, one 128 x N x 16 step
+__device__ __forceinline__ void tc_mma(u32 d_tmem, u64 desc_a, u64 desc_b, u32 idesc, u32 accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane = output row)
+__device__ __forceinline__ void tc_ld32(u32 taddr, u32 (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor of a K-major tile stored as rows of 128 bytes with the 128-byte
+// swizzle (what TMA SWIZZLE_128B writes): 8-row groups 1024 B apart (SBO), descriptor version 1,
+// layout type 2 (SWIZZLE_128B).  Stepping K by 16 bf16 (32 B) inside the row adds 2 to the address field.
+__device__ __forceinline__ u64 umma_desc(u32 smem_addr) {
+    return (u64)((smem_addr >> 4) & 0x3fffu) | ((u64)1 << 16) | ((u64)(1024 >> 4) << 32) | ((u64)1 << 46) | ((u64)2 << 61);
+}
+// instruction descriptor: D fp32 (bit 4), A/B bf16 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr u32 umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(N >> 3) << 17) | ((u32)(M >> 4) << 24);
+}
+
+// taps (dt, dh, dw) of a tile at frame t, temporal taps that leave [0, T) dropped
+struct TapIter {
+    int kt, kh, kw, T, t;
+    __device__ __forceinline__ int count() const {
+        int n = 0;
+        for (int a = 0; a < kt; ++a) { const int tt = t + a - kt / 2; n += (tt >= 0 && tt < T); }
+        return n * kh * kw;
+    }
+};
+
+template <int BN>
+__global__ void __launch_bounds__(CV_NT, 1)
+vy_fusion_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                      const __grid_constant__ ConvParams cp) {
+    constexpr u32 A_BYTES = CV_BM * CV_BK * 2, B_BYTES = BN * CV_BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr u32 TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) u64 bar_full[CV_STAGES], bar_empty[CV_STAGES], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ u32 tmem_base_sh;
+    unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < CV_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(&tmem_base_sh)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const u32 tmem_base = tmem_base_sh;
+
+    const int khw = cp.kh * cp.kw;
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; u32 phase = 0;
+            for (long long tile = blockIdx.x; tile < cp.n_tiles_total; tile += gridDim.x) {
+                const int n_t = (int)(tile % cp.n_tiles);
+                const long long rest = tile / cp.n_tiles;
+                const int m_t = (int)(rest % cp.m_tiles), t = (int)(rest / cp.m_tiles);
+                const int r0 = m_t * CV_BM, n0 = n_t * BN;
+                for (int a = 0; a < cp.kt; ++a) {
+                    const int tt = t + a - cp.kt / 2;
+                    if (tt < 0 || tt >= cp.T) continue;
+                    for (int hw = 0; hw < khw; ++hw) {
+                        const int dh = hw / cp.kw - cp.kh / 2, dw = hw % cp.kw - cp.kw / 2;
+                        const int row = r0 + dh * cp.Wp + dw;
+                        const int kbase = (a * khw + hw) * cp.Cin;
+                        for (int cb = 0; cb < cp.cin_blocks; ++cb) {
+                            mbar_wait(&bar_empty[stage], phase ^ 1u);
+                            unsigned char *sa = tiles + (size_t)stage * STAGE_BYTES, *sb = sa + A_BYTES;
+                            mbar_expect_tx(&bar_full[stage], STAGE_BYTES);
+                            tma_load_3d(sa, &map_x, &bar_full[stage], cb * CV_BK, row, tt);
+                            tma_load_2d(sb, &map_w, &bar_full[stage], kbase + cb * CV_BK, n0);
+                            if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr u32 idesc = umma_idesc(CV_BM, BN);
+            int stage = 0; u32 phase = 0;
+            int acc = 0; u32 acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < cp.n_tiles_total; tile += gridDim.x) {
+                const int t = (int)((tile / cp.n_tiles) / cp.m_tiles);
+                TapIter ti{cp.kt, cp.kh, cp.kw, cp.T, t};
+                const int n_kb = ti.count() * cp.cin_blocks;
+                mbar_wait(&bar_acc_empty[acc], acc_phase ^ 1u);       // epilogue has drained this accumulator
+                tc_fence_after();
+                const u32 d_tmem = tmem_base + (u32)(acc * BN);
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&bar_full[stage], phase);
+                    tc_fence_after();
+                    const u32 sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES), sb = sa + A_BYTES;
+                    const u64 da = umma_desc(sa), db = umma_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < CV_BK / 16; ++k)
+                        tc_mma(d_tmem, da + (u64)(2 * k), db + (u64)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(&bar_empty[stage]);                     // smem slot free once these MMAs retire
+                    if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit(&bar_acc_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;                                  // TMEM lanes 32*quarter .. +31
+        const int plane = cp.Hp * cp.Wp;
+        int acc = 0; u32 acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < cp.n_tiles_total; tile += gridDim.x) {
+            const int n_t = (int)(tile % cp.n_tiles);
+            const long long rest = tile / cp.n_tiles;
+            const int m_t = (int)(rest % cp.m_tiles), t = (int)(rest / cp.m_tiles);
+            const int r = m_t * CV_BM + quarter * 32 + lane, n0 = n_t * BN;
+            const bool in_range = r < cp.rows;
+            const int rr = r % plane, hp = rr / cp.Wp, wp = rr % cp.Wp;
+            const bool interior = hp > 0 && hp < cp.Hp - 1 && wp > 0 && wp < cp.Wp - 1;
+            mbar_wait(&bar_acc_full[acc], acc_phase);
+            tc_fence_after();
+            const size_t out_off = ((size_t)t * cp.rows + (size_t)r) * cp.Cout + n0;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                u32 v[32];
+                tc_ld32(tmem_base + ((u32)(quarter * 32) << 16) + (u32)(acc * BN + ch * 32), v);
+                if (in_range) {
+                    float o[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int n = n0 + ch * 32 + i;
+                        float x = fmaf(__uint_as_float(v[i]), __ldg(cp.scale + n), __ldg(cp.shift + n));   // layers.py:68,77
+                        x = x > 0.0f ? x : x * cp.slope;                                                   // layers.py:69,78
+                        o[i] = interior ? x : 0.0f;
+                    }
+                    if (cp.y_is_f32) {
+                        float4 *dst = (float4 *)((float *)cp.y + out_off + ch * 32);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    } else {
+                        uint4 *dst = (uint4 *)((__nv_bfloat16 *)cp.y + out_off + ch * 32);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[8 * i], o[8 * i + 1]);
+                            __nv_bfloat162 p1 = __floats2bfloat162_rn(o[8 * i + 2], o[8 * i + 3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(o[8 * i + 4], o[8 * i + 5]);
+                            __nv_bfloat162 p3 = __floats2bfloat162_rn(o[8 * i + 6], o[8 * i + 7]);
+                            dst[i] = make_uint4(*(u32 *)&p0, *(u32 *)&p1, *(u32 *)&p2, *(u32 *)&p3);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bar_acc_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ layout kernels
+// (B, C, T, H, W)-strided fp32 (the reference's NCDHW after swapaxes, or (B, K, C, H, W) before it: the
+// strides say which) -> P layout bf16.  One CTA per (t, b, h): reads C rows of W floats, writes W*C bf16.
+__global__ void vy_pack_kernel(const float *__restrict__ x, long long sb, long long sc, long long st, int B, int C,
+                               int T, int H, int W, __nv_bfloat16 *__restrict__ y) {
+    extern __shared__ float tile[];                 // [C][W + 1]
+    const int h = blockIdx.x % H, b = (blockIdx.x / H) % B, t = blockIdx.x / (H * B);
+    const float *src = x + (size_t)b * sb + (size_t)t * st + (size_t)h * W;
+    for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
+        const int c = i / W, w = i % W;
+        tile[c * (W + 1) + w] = src[(size_t)c * sc + w];
+    }
+    __syncthreads();
+    const int Hp = H + 2, Wp = W + 2;
+    __nv_bfloat16 *dst = y + ((((size_t)t * B + b) * Hp + (h + 1)) * Wp + 1) * C;
+    for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
+        const int w = i / C, c = i % C;
+        dst[(size_t)w * C + c] = __float2bfloat16_rn(tile[c * (W + 1) + w]);
+    }
+}
+
+// P layout (bf16 or fp32) -> (B, C, T, H, W)-strided fp32
+template <typename TIn>
+__global__ void vy_unpack_kernel(const TIn *__restrict__ y, int B, int C, int T, int H, int W, float *__restrict__ x,
+                                 long long sb, long long sc, long long st) {
+    extern __shared__ float tile[];
+    const int h = blockIdx.x % H, b = (blockIdx.x / H) % B, t = blockIdx.x / (H * B);
+    const int Hp = H + 2, Wp = W + 2;
+    const TIn *src = y + ((((size_t)t * B + b) * Hp + (h + 1)) * Wp + 1) * C;
+    for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
+        const int w = i / C, c = i % C;
+        tile[c * (W + 1) + w] = (float)src[(size_t)w * C + c];
+    }
+    __syncthreads();
+    float *dst = x + (size_t)b * sb + (size_t)t * st + (size_t)h * W;
+    for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
+        const int c = i / W, w = i % W;
+        dst[(size_t)c * sc + w] = tile[c * (W + 1) + w];
+    }
+}
+
+// TemporalPooling 'direct' (layers.py:201-205) on P layout: y[i] = max / mean over t of x[t][i]
+__global__ void vy_temporal_pool_kernel(const uint4 *__restrict__ x, int T, long long inner8, int mode, uint4 *__restrict__ y) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < inner8; i += stride) {
+        float acc[8];
+        for (int t = 0; t < T; ++t) {
+            const uint4 q = x[(size_t)t * inner8 + i];
+            const __nv_bfloat162 *h = (const __nv_bfloat162 *)&q;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __bfloat1622float2(h[k]);
+                if (t == 0) { acc[2 * k] = f.x; acc[2 * k + 1] = f.y; }
+                else if (mode == 0) { acc[2 * k] = fmaxf(acc[2 * k], f.x); acc[2 * k + 1] = fmaxf(acc[2 * k + 1], f.y); }
+                else { acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+            }
+        }
+        uint4 o;
+        __nv_bfloat162 *oh = (__nv_bfloat162 *)&o;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a = mode == 0 ? acc[2 * k] : acc[2 * k] / (float)T;
+            const float b = mode == 0 ? acc[2 * k + 1] : acc[2 * k + 1] / (float)T;
+            oh[k] = __floats2bfloat162_rn(a, b);
+        }
+        y[i] = o;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+template <int BN>
+int launch_conv(const CUtensorMap &mx, const CUtensorMap &mw, const ConvParams &cp, cudaStream_t st) {
+    const size_t smem = (size_t)CV_STAGES * (CV_BM * CV_BK * 2 + BN * CV_BK * 2) + 1024;
+    VY_CUDA_CHECK(cudaFuncSetAttribute(vy_fusion_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = cp.n_tiles_total < vy_sm_count() ? cp.n_tiles_total : vy_sm_count();
+    VY_KERNEL(VY_K_FUSION_CONV, st, (vy_fusion_conv_kernel<BN><<<(unsigned)grid, CV_NT, smem, st>>>(mx, mw, cp)));
+    VY_LAUNCH_CHECK("vy_fusion_conv_kernel");
+    return VY_OK;
+}
+
+}  // namespace
+
+extern "C" size_t vy_p_layout_elems(int B, int T, int H, int W, int C) {
+    return (size_t)T * B * (H + 2) * (W + 2) * C;
+}
+
+extern "C" int vy_pack_f32_to_p_bf16(const float *x, long long stride_b, long long stride_c, long long stride_t,
+                                     int B, int C, int T, int H, int W, void *y_p, vy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x || !y_p || B < 1 || C < 1 || T < 1 || H < 1 || W < 1) VY_FAIL(VY_EINVAL, "vy_pack_f32_to_p_bf16: bad arguments");
+    const size_t smem = (size_t)C * (W + 1) * 4;
+    if (smem > 200 * 1024) VY_FAIL(VY_EUNSUPPORTED, "vy_pack_f32_to_p_bf16: C*(W+1) too large for one row tile");
+    VY_CUDA_CHECK(cudaMemsetAsync(y_p, 0, vy_p_layout_elems(B, T, H, W, C) * 2, st));
+    VY_CUDA_CHECK(cudaFuncSetAttribute(vy_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VY_KERNEL(VY_K_LAYOUT, st, (vy_pack_kernel<<<T * B * H, 256, smem, st>>>(x, stride_b, stride_c, stride_t, B, C, T, H, W,
+                                                                            (__nv_bfloat16 *)y_p)));
+    VY_LAUNCH_CHECK("vy_pack_kernel");
+    return VY_OK;
+}
+
+extern "C" int vy_unpack_p_to_f32(const void *y_p, int p_is_f32, int B, int C, int T, int H, int W, float *x,
+                                  long long stride_b, long long stride_c, long long stride_t, vy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x || !y_p || B < 1 || C < 1 || T < 1 || H < 1 || W < 1) VY_FAIL(VY_EINVAL, "vy_unpack_p_to_f32: bad arguments");
+    const size_t smem = (size_t)C * (W + 1) * 4;
+    if (smem > 200 * 1024) VY_FAIL(VY_EUNSUPPORTED, "vy_unpack_p_to_f32: C*(W+1) too large for one row tile");
+    if (p_is_f32) {
+        VY_CUDA_CHECK(cudaFuncSetAttribute(vy_unpack_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VY_KERNEL(VY_K_LAYOUT, st, (vy_unpack_kernel<float><<<T * B * H, 256, smem, st>>>((const float *)y_p, B, C, T, H, W, x,
+                                                                                         stride_b, stride_c, stride_t)));
+    } else {
+        VY_CUDA_CHECK(cudaFuncSetAttribute(vy_unpack_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VY_KERNEL(VY_K_LAYOUT, st, (vy_unpack_kernel<__nv_bfloat16><<<T * B * H, 256, smem, st>>>(
+            (const __nv_bfloat16 *)y_p, B, C, T, H, W, x, stride_b, stride_c, stride_t)));
+    }
+    VY_LAUNCH_CHECK("vy_unpack_kernel");
+    return VY_OK;
+}
 
 extern "C" size_t vy_fusion_conv_workspace_bytes(int B, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw) {
     (void)B; (void)T; (void)H; (void)W; (void)Cin; (void)Cout; (void)kt; (void)kh; (void)kw;
-    return 256;
+    return 0;      // operands are read in place through TMA; nothing is staged in global memory
 }
 
 extern "C" int vy_fusion_conv_bf16(const void *x, const void *w, const float *scale, const float *shift,
                                    float leaky_slope, int B, int T, int H, int W, int Cin, int Cout,
                                    int kt, int kh, int kw, void *y, int y_is_f32, void *workspace,
                                    size_t workspace_bytes, vy_stream_t stream) {
-    (void)x; (void)w; (void)scale; (void)shift; (void)leaky_slope; (void)B; (void)T; (void)H; (void)W;
-    (void)Cin; (void)Cout; (void)kt; (void)kh; (void)kw; (void)y; (void)y_is_f32; (void)workspace;
-    (void)workspace_bytes; (void)stream;
-    VY_FAIL(VY_EUNSUPPORTED, "vy_fusion_conv_bf16: kernel not built yet");
+    (void)workspace; (void)workspace_bytes;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x || !w || !scale || !shift || !y) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16: null pointer");
+    if (B < 1 || T < 1 || H < 1 || W < 1) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16: bad shape");
+    if (Cin % 64 != 0 || Cout % 64 != 0 || Cin < 64 || Cout < 64)
+        VY_FAIL(VY_EUNSUPPORTED, "vy_fusion_conv_bf16: Cin and Cout must be multiples of 64 (got %d, %d)", Cin, Cout);
+    if ((kt != 1 && kt != 3) || (kh != 1 && kh != 3) || (kw != 1 && kw != 3))
+        VY_FAIL(VY_EUNSUPPORTED, "vy_fusion_conv_bf16: kernel extents must be 1 or 3");
+    if (kt > 1 && T < 2) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16: temporal kernel needs T > 1 (yolo3.py:979-985)");
+    if ((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) != 0) VY_FAIL(VY_EALIGN, "vy_fusion_conv_bf16: x, w, y must be 16-byte aligned");
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) VY_FAIL(VY_ECUDA, "vy_fusion_conv_bf16: cuTensorMapEncodeTiled is not available from this driver");
+
+    const int Hp = H + 2, Wp = W + 2;
+    const long long rows = (long long)B * Hp * Wp;
+    if (rows > 0x7fffff00LL) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16: B*Hp*Wp too large");
+    const int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    const long long Ktot = (long long)kt * kh * kw * Cin;
+
+    CUtensorMap mx, mw;
+    {   // X: (C, rows, T) bf16, box (64, 128, 1)
+        cuuint64_t dim[3] = {(cuuint64_t)Cin, (cuuint64_t)rows, (cuuint64_t)T};
+        cuuint64_t str[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)rows * Cin * 2};
+        cuuint32_t box[3] = {CV_BK, CV_BM, 1}, es[3] = {1, 1, 1};
+        const CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(x), dim, str, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) VY_FAIL(VY_ECUDA, "cuTensorMapEncodeTiled(x) failed: %d", (int)r);
+    }
+    {   // W: (Ktot, Cout) bf16, box (64, BN)
+        cuuint64_t dim[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+        cuuint64_t str[1] = {(cuuint64_t)Ktot * 2};
+        cuuint32_t box[2] = {CV_BK, (cuuint32_t)BN}, es[2] = {1, 1};
+        const CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(w), dim, str, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) VY_FAIL(VY_ECUDA, "cuTensorMapEncodeTiled(w) failed: %d", (int)r);
+    }
+    ConvParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.T = T; cp.rows = (int)rows; cp.Hp = Hp; cp.Wp = Wp; cp.Cin = Cin; cp.Cout = Cout;
+    cp.kt = kt; cp.kh = kh; cp.kw = kw;
+    cp.m_tiles = (int)((rows + CV_BM - 1) / CV_BM);
+    cp.n_tiles = Cout / BN;
+    cp.cin_blocks = Cin / CV_BK;
+    cp.n_tiles_total = (long long)T * cp.m_tiles * cp.n_tiles;
+    cp.slope = leaky_slope; cp.scale = scale; cp.shift = shift; cp.y = y; cp.y_is_f32 = y_is_f32;
+    if (BN == 256) return launch_conv<256>(mx, mw, cp, st);
+    if (BN == 128) return launch_conv<128>(mx, mw, cp, st);
+    return launch_conv<64>(mx, mw, cp, st);
 }
 
-extern "C" int vy_temporal_pool_bf16(const void *x, int B, int T, long inner, int mode, void *y, vy_stream_t stream) {
-    (void)x; (void)B; (void)T; (void)inner; (void)mode; (void)y; (void)stream;
-    VY_FAIL(VY_EUNSUPPORTED, "vy_temporal_pool_bf16: kernel not built yet");
+extern "C" int vy_temporal_pool_bf16(const void *x, int T, long inner, int mode, void *y, vy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x || !y || T < 1 || inner < 1 || (mode != 0 && mode != 1)) VY_FAIL(VY_EINVAL, "vy_temporal_pool_bf16: bad arguments");
+    if (inner % 8 != 0 || (((uintptr_t)x | (uintptr_t)y) & 15) != 0)
+        VY_FAIL(VY_EALIGN, "vy_temporal_pool_bf16: inner must be a multiple of 8 elements and pointers 16-byte aligned");
+    const long long n8 = inner / 8;
+    long long blocks = (n8 + 255) / 256;
+    const long long cap = (long long)vy_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    VY_KERNEL(VY_K_TEMPORAL_POOL, st, (vy_temporal_pool_kernel<<<(unsigned)blocks, 256, 0, st>>>((const uint4 *)x, T, n8, mode, (uint4 *)y)));
+    VY_LAUNCH_CHECK("vy_temporal_pool_kernel");
+    return VY_OK;
 }

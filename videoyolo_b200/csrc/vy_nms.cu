@@ -32,6 +32,18 @@ struct SelPlan {
     long long rows_per_job;     // rows: multiple of SEL_NT
     int list_cap;               // keys per image in the global list
     float valid_thresh;
+    // ---- streaming path (heads only; stream == 0: not used)
+    int stream;
+    int samp_stride;            // every samp_stride-th PAIR of items is sampled
+    int samp_items;             // sampled items per image (even)
+    int Gs, Ksq;                // sample CTAs per image (= samp_ib * plane blocks), ceil(K / Gs)
+    int samp_ib, samp_ipj;      // item blocks per image, sampled items per job (<= SAMP_NT)
+    int samp_ppj, samp_pls;     // class planes per job, plane lanes per item (threads sharing an item)
+    int n_groups, PU;           // class planes are cut into n_groups groups of PU planes
+    int chunks[VY_MAX_SCALES];  // 128-position chunks per plane
+    int unit_begin[VY_MAX_SCALES + 1];
+    int units_per_image;
+    long long n_units;
 };
 
 struct SelGlobal {              // workspace views
@@ -39,22 +51,39 @@ struct SelGlobal {              // workspace views
     int *count;                 // [B]        list fill
     u64 *slots;                 // [B][G]     per-CTA ceil(K/G)-th largest
     u64 *list;                  // [B][list_cap]
+    // streaming path only (see "sample + stream" below); null otherwise
+    int *scount;                // [B]        fill of the streamed candidate list
+    int *sdone;                 // [B]        sample jobs finished
+    u64 *sslots;                // [B][Gs]    per-sample-job bounds
+    u64 *slist;                 // [B][slist_cap]
+    int slist_cap;
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static size_t sel_workspace_layout(int B, int G, int list_cap, SelGlobal *g, void *base, size_t *header) {
+// Gs == 0: no streaming-path arrays
+static size_t sel_workspace_layout(int B, int G, int list_cap, SelGlobal *g, void *base, size_t *header,
+                                   int Gs = 0, int slist_cap = 0) {
     size_t off = 0;
     const size_t o_thr = off;   off = align_up(off + sizeof(u64) * (size_t)B, 256);
     const size_t o_cnt = off;   off = align_up(off + sizeof(int) * (size_t)B, 256);
     const size_t o_slot = off;  off = align_up(off + sizeof(u64) * (size_t)B * G, 256);
+    const size_t o_scnt = off;  off = align_up(off + sizeof(int) * (size_t)B * (Gs ? 1 : 0), 256);
+    const size_t o_sdone = off; off = align_up(off + sizeof(int) * (size_t)B * (Gs ? 1 : 0), 256);
+    const size_t o_sslot = off; off = align_up(off + sizeof(u64) * (size_t)B * Gs, 256);
     if (header) *header = off;  // the part that must be zeroed per call
     const size_t o_list = off;  off = align_up(off + sizeof(u64) * (size_t)B * (size_t)list_cap, 256);
+    const size_t o_slist = off; off = align_up(off + sizeof(u64) * (size_t)B * (size_t)slist_cap, 256);
     if (g && base) {
         g->thr = (u64 *)((char *)base + o_thr);
         g->count = (int *)((char *)base + o_cnt);
         g->slots = (u64 *)((char *)base + o_slot);
         g->list = (u64 *)((char *)base + o_list);
+        g->scount = Gs ? (int *)((char *)base + o_scnt) : nullptr;
+        g->sdone = Gs ? (int *)((char *)base + o_sdone) : nullptr;
+        g->sslots = Gs ? (u64 *)((char *)base + o_sslot) : nullptr;
+        g->slist = Gs ? (u64 *)((char *)base + o_slist) : nullptr;
+        g->slist_cap = slist_cap;
     }
     return off;
 }
@@ -281,6 +310,9 @@ vy_decode_select_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
     const int tid = threadIdx.x;
     for (int job = blockIdx.x; job < pl.n_jobs; job += gridDim.x) {
         const int b = job / pl.G;
+        // streaming path: this kernel is the rescue pass and only serves images whose streamed
+        // candidate list overflowed (the sample misjudged the score distribution)
+        if (g.scount && g.scount[b] <= g.slist_cap) continue;
         SelJob jb;
         jb.G = pl.G; jb.g = job % pl.G; jb.K = pl.K; jb.Kq = pl.Kq;
         jb.g_thr_b = g.thr + b;
@@ -344,6 +376,306 @@ vy_decode_select_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
             sel_stream(S, src, jb, cnt, fresh);
         }
         sel_flush(S, jb, g.count + b, g.list + (size_t)b * pl.list_cap, pl.list_cap);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sample + stream: the bandwidth path for head maps.
+//
+//   vy_decode_sample_kernel   looks at 1/samp_stride of every image (pairs of adjacent items = 32-byte
+//                             sectors, all class planes) and bounds the image's K-th largest score from
+//                             below: ANY subset's K-th largest is <= the full set's.  Gs CTAs share an
+//                             image; CTA g publishes its ceil(K/Gs)-th largest, the minimum over the
+//                             Gs CTAs is the bound (disjoint subsets: >= K sampled scores lie above it).
+//   vy_decode_stream_kernel   one pass over the head maps with that FIXED bound: no shared state, no
+//                             CTA barrier; a warp owns a unit = 128 positions x one group of class
+//                             planes, tests 16 bytes per lane and plane against a per-box logit bound
+//                             and appends the few survivors (about K * samp_stride per image, whatever
+//                             the score distribution) to the image's list through a warp-private buffer.
+//   vy_decode_select_kernel   (above) runs afterwards for images whose list overflowed -- a sample
+//                             that misjudged the distribution -- and normally exits at once.
+// ------------------------------------------------------------------------------------------------
+constexpr int SAMP_NT = 512;
+constexpr int SAMP_MAXK = 8;       // class planes per thread
+constexpr int SAMP_RUN = 8;        // adjacent items sampled together: 8 x 16 B = one 128-byte line per plane
+
+// sampled item j of image b -> where it lives (item = 4 consecutive positions of one (scale, anchor))
+struct ItemRef { const float *p; int HW, nv, o1, o2, o3; bool vec; };
+__device__ __forceinline__ bool item_ref(const VyHeads &hd, const SelPlan &pl, int b, int idx, ItemRef &r) {
+    if (idx >= pl.items_per_frame) return false;
+    int s = 0;
+    while (s + 1 < hd.n_scales && idx >= pl.item_begin[s + 1]) ++s;
+    const VyScale &sc = hd.sc[s];
+    const int rel = idx - pl.item_begin[s];
+    const int a = rel / pl.items_per_plane[s];
+    const int pos0 = (rel - a * pl.items_per_plane[s]) * 4;
+    r.HW = sc.HW;
+    r.nv = min(4, sc.HW - pos0);
+    r.o1 = min(1, r.nv - 1); r.o2 = min(2, r.nv - 1); r.o3 = min(3, r.nv - 1);
+    r.vec = sc.vec == 4;
+    r.p = sc.head + ((size_t)(b * hd.A + a) * hd.P) * (size_t)sc.HW + pos0;
+    return true;
+}
+__device__ __forceinline__ void item_load(const ItemRef &r, const float *p, float (&t)[4]) {
+    if (r.vec) { const float4 q = vy_ldg128_ca(p); t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w; }
+    else { t[0] = vy_ldg32_ca(p); t[1] = vy_ldg32_ca(p + r.o1); t[2] = vy_ldg32_ca(p + r.o2); t[3] = vy_ldg32_ca(p + r.o3); }
+}
+
+// Job (b, g): item block ib = g % samp_ib, plane block pb = g / samp_ib.  Thread t owns sampled item
+// (ib * samp_ipj + t % samp_ipj) and every samp_pls-th plane of the block, starting at t / samp_ipj:
+// one objectness load and <= SAMP_MAXK class-plane loads, all in flight together.
+__global__ void __launch_bounds__(SAMP_NT, 2)
+vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl, SelGlobal g) {
+    __shared__ u32 hist[256];
+    __shared__ int sh_n, sh_digit, sh_above, sh_in;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x / pl.Gs, gj = blockIdx.x % pl.Gs;
+    const int ib = gj % pl.samp_ib, pb = gj / pl.samp_ib;
+    const int jl = tid % pl.samp_ipj, lanep = tid / pl.samp_ipj;
+    const int j = ib * pl.samp_ipj + jl;
+    const int c_lo = pb * pl.samp_ppj, c_hi = min(hd.C, c_lo + pl.samp_ppj);
+    u32 key[SAMP_MAXK];
+#pragma unroll
+    for (int k = 0; k < SAMP_MAXK; ++k) key[k] = 0u;
+    int n_mine = 0;
+    ItemRef r;
+    if (lanep < pl.samp_pls && j < pl.samp_items &&
+        item_ref(hd, pl, b, (j / SAMP_RUN) * (SAMP_RUN * pl.samp_stride) + (j % SAMP_RUN), r)) {
+        float to[4], tc[SAMP_MAXK][4];
+        item_load(r, r.p + 4 * (size_t)r.HW, to);
+#pragma unroll
+        for (int k = 0; k < SAMP_MAXK; ++k) {
+            const int c = c_lo + lanep + k * pl.samp_pls;
+            if (c < c_hi) item_load(r, r.p + (size_t)(5 + c) * (size_t)r.HW, tc[k]);
+        }
+        // one 32-bit key per (item, plane): the plane's best logit decides (sigmoid is monotonic, the
+        // objectness differs per position, so all <= 4 candidates are scored only where it matters:
+        // score(best of 4) is a score of the image, and any subset of an image's scores bounds it)
+        float cf[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) cf[v] = v < r.nv ? vy_sigmoid(to[v]) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < SAMP_MAXK; ++k) {
+            const int c = c_lo + lanep + k * pl.samp_pls;
+            if (c < c_hi) {
+                float best = 0.0f;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) if (v < r.nv) best = fmaxf(best, vy_score(tc[k][v], cf[v]));
+                if (best > pl.valid_thresh) { key[k] = vy_f2ord(best); ++n_mine; }
+            }
+        }
+    }
+    // ---- CTA-wide: Ksq-th largest of the keys (MSB-first radix select, keys stay in registers)
+    if (tid == 0) sh_n = 0;
+    __syncthreads();
+    if (n_mine) atomicAdd(&sh_n, n_mine);
+    __syncthreads();
+    u32 bound = 0;
+    if (sh_n >= pl.Ksq) {                          // CTA-uniform
+        u32 prefix = 0;
+        int kk = pl.Ksq;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (tid < 256) hist[tid] = 0;
+            __syncthreads();
+            // run-length aggregation: neighbouring keys of a thread mostly share the leading digits
+            u32 cur = 0xffffffffu, run = 0;
+#pragma unroll
+            for (int i = 0; i < SAMP_MAXK; ++i) {
+                const u32 k = key[i];
+                if (k != 0u && (shift == 24 || ((k ^ prefix) >> (shift + 8)) == 0u)) {
+                    const u32 d = (k >> shift) & 255u;
+                    if (d != cur) { if (run) atomicAdd(&hist[cur], run); cur = d; run = 0; }
+                    ++run;
+                }
+            }
+            if (run) atomicAdd(&hist[cur], run);
+            __syncthreads();
+            if (tid < 32) {
+                u32 c[8], sum = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) { c[t] = hist[255 - 8 * tid - t]; sum += c[t]; }
+                u32 inc = sum;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const u32 v = __shfl_up_sync(0xffffffffu, inc, off);
+                    if (tid >= off) inc += v;
+                }
+                const u32 exc = inc - sum;
+                if (exc < (u32)kk && (u32)kk <= inc) {
+                    u32 run2 = exc;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        if (run2 + c[t] >= (u32)kk) { sh_digit = 255 - 8 * tid - t; sh_above = (int)run2; sh_in = (int)c[t]; break; }
+                        run2 += c[t];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix |= (u32)sh_digit << shift;
+            kk -= sh_above;
+            const int inb = sh_in;
+            __syncthreads();
+            if (inb - kk <= (pl.Ksq >> 3)) break;      // #{keys >= prefix} is within Ksq/8 of Ksq
+        }
+        bound = prefix;
+    }
+    // ---- publish; the last job of the image combines
+    if (tid == 0) {
+        st_relaxed_u64(g.sslots + (size_t)b * pl.Gs + gj, (u64)bound << 32);
+        __threadfence();
+        const int ticket = atomicAdd(g.sdone + b, 1);
+        if (ticket == pl.Gs - 1) {
+            __threadfence();
+            u64 m = ~0ull;
+            for (int i = 0; i < pl.Gs; ++i) { const u64 v = ld_relaxed_u64(g.sslots + (size_t)b * pl.Gs + i); m = v < m ? v : m; }
+            if (m != 0ull) atomicMax(g.thr + b, m);
+        }
+    }
+}
+
+constexpr int STR_NT = 256;
+#ifndef STR_CTAS_PER_SM
+#define STR_CTAS_PER_SM 4
+#endif
+#ifndef STR_UN
+#define STR_UN 4
+#endif
+
+struct StrUnit {                 // what one warp streams: 128 positions x planes [c0, c1) of one (b, s, a)
+    const float *pc;             // class plane 0 at this lane's first position
+    size_t HW;
+    int c0, c1, o1, o2, o3;
+    u32 row0, n_s, A;
+    u64 thr;
+    float conf[4], tcmin[4];
+    float valid_thresh;
+};
+
+template <bool VEC>
+__device__ __forceinline__ void str_load(const StrUnit &un, const float *q, float (&t)[4]) {
+    if (VEC) { const float4 w = vy_ldg128_ca(q); t[0] = w.x; t[1] = w.y; t[2] = w.z; t[3] = w.w; }
+    else { t[0] = vy_ldg32_ca(q); t[1] = vy_ldg32_ca(q + un.o1); t[2] = vy_ldg32_ca(q + un.o2); t[3] = vy_ldg32_ca(q + un.o3); }
+}
+
+// rare path, warp-synchronous: every lane evaluates at most one hit per round; survivors go to the
+// warp's buffer, which leaves as one atomic + one 256-byte store per 32 keys
+template <bool VEC>
+__device__ __forceinline__ void str_hits(const StrUnit &un, u32 mask, int c, u64 *wbuf, int &cnt, int b,
+                                         const SelGlobal &g, int lane, u32 lt_mask) {
+    while (__any_sync(0xffffffffu, mask != 0u)) {
+        bool ok = false;
+        u64 key = 0;
+        if (mask) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int u = k >> 2, v = k & 3;
+            const int ov = VEC ? v : (v == 0 ? 0 : (v == 1 ? un.o1 : (v == 2 ? un.o2 : un.o3)));
+            const float cf = v == 0 ? un.conf[0] : (v == 1 ? un.conf[1] : (v == 2 ? un.conf[2] : un.conf[3]));
+            const float tv = vy_ldg32_ca(un.pc + (size_t)(c + u) * un.HW + ov);
+            const float sv = vy_score(tv, cf);
+            if (sv > un.valid_thresh) {
+                key = vy_make_key(sv, un.row0 + (u32)(c + u) * un.n_s + (u32)v * un.A);
+                ok = key >= un.thr;
+            }
+        }
+        const u32 bal = __ballot_sync(0xffffffffu, ok);
+        if (bal) {
+            if (ok) wbuf[cnt + __popc(bal & lt_mask)] = key;
+            cnt += __popc(bal);
+            __syncwarp();
+            if (cnt >= 32) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(g.scount + b, 32);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const u64 k0 = wbuf[lane], k1 = wbuf[32 + lane];
+                if (base + lane < g.slist_cap) g.slist[(size_t)b * g.slist_cap + base + lane] = k0;
+                __syncwarp();
+                wbuf[lane] = k1;
+                cnt -= 32;
+                __syncwarp();
+            }
+        }
+    }
+}
+
+template <bool VEC>
+__device__ __forceinline__ void str_unit(const StrUnit &un, u64 *wbuf, int &cnt, int b, const SelGlobal &g,
+                                         int lane, u32 lt_mask) {
+    int c = un.c0;
+    const float *q = un.pc + (size_t)c * un.HW;
+    for (; c + STR_UN <= un.c1; c += STR_UN, q += (size_t)STR_UN * un.HW) {
+        float t[STR_UN][4];
+#pragma unroll
+        for (int u = 0; u < STR_UN; ++u) str_load<VEC>(un, q + (size_t)u * un.HW, t[u]);
+        u32 mask = 0;
+#pragma unroll
+        for (int u = 0; u < STR_UN; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) mask |= (t[u][v] >= un.tcmin[v]) ? (1u << (u * 4 + v)) : 0u;
+        str_hits<VEC>(un, mask, c, wbuf, cnt, b, g, lane, lt_mask);
+    }
+    for (; c < un.c1; ++c, q += un.HW) {               // < STR_UN planes left
+        float t[4];
+        str_load<VEC>(un, q, t);
+        u32 mask = 0;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) mask |= (t[v] >= un.tcmin[v]) ? (1u << v) : 0u;
+        str_hits<VEC>(un, mask, c, wbuf, cnt, b, g, lane, lt_mask);
+    }
+}
+
+__global__ void __launch_bounds__(STR_NT, STR_CTAS_PER_SM)
+vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl, SelGlobal g) {
+    __shared__ u64 wbuf_all[STR_NT / 32][64];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u64 *wbuf = wbuf_all[wid];
+    const u32 lt_mask = (1u << lane) - 1u;
+    const long long n_warps = (long long)gridDim.x * (STR_NT / 32);
+    for (long long unit = (long long)blockIdx.x * (STR_NT / 32) + wid; unit < pl.n_units; unit += n_warps) {
+        const int b = (int)(unit / pl.units_per_image);
+        int r = (int)(unit - (long long)b * pl.units_per_image);
+        int s = 0;
+        while (s + 1 < hd.n_scales && r >= pl.unit_begin[s + 1]) ++s;
+        r -= pl.unit_begin[s];
+        const VyScale &sc = hd.sc[s];
+        const int chunks = pl.chunks[s];
+        const int q1 = r / chunks, chunk = r - q1 * chunks;
+        const int a = q1 / pl.n_groups, grp = q1 - a * pl.n_groups;
+        StrUnit un;
+        un.c0 = grp * pl.PU;
+        un.c1 = min(hd.C, un.c0 + pl.PU);
+        un.HW = (size_t)sc.HW;
+        int pos0 = (chunk * 32 + lane) * 4;
+        int nv = min(4, sc.HW - pos0);
+        if (nv <= 0) { nv = 0; pos0 = 0; }                 // idle lane: reads position 0, can never hit
+        un.o1 = min(1, max(nv - 1, 0)); un.o2 = min(2, max(nv - 1, 0)); un.o3 = min(3, max(nv - 1, 0));
+        const float *p = sc.head + ((size_t)(b * hd.A + a) * hd.P) * un.HW + pos0;
+        un.pc = p + 5 * un.HW;
+        un.row0 = (u32)(sc.row_off + (long long)pos0 * hd.A + a);
+        un.n_s = (u32)sc.n_s; un.A = (u32)hd.A;
+        un.valid_thresh = pl.valid_thresh;
+        un.thr = g.thr[b];
+        const float smin = fmaxf(un.thr ? vy_key_score(un.thr) : pl.valid_thresh, pl.valid_thresh);
+        const bool vec = sc.vec == 4;
+        {
+            float to[4];
+            if (vec) str_load<true>(un, p + 4 * un.HW, to); else str_load<false>(un, p + 4 * un.HW, to);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                un.conf[v] = vy_sigmoid(to[v]);
+                un.tcmin[v] = v < nv ? vy_tcmin(smin, un.conf[v]) : CUDART_INF_F;
+            }
+        }
+        int cnt = 0;                                       // keys waiting in wbuf (warp-uniform)
+        if (vec) str_unit<true>(un, wbuf, cnt, b, g, lane, lt_mask);
+        else str_unit<false>(un, wbuf, cnt, b, g, lane, lt_mask);
+        if (cnt > 0) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(g.scount + b, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lane < cnt && base + lane < g.slist_cap) g.slist[(size_t)b * g.slist_cap + base + lane] = wbuf[lane];
+            __syncwarp();
+        }
     }
 }
 
@@ -420,6 +752,7 @@ vy_rows_select_kernel(RowParams rp, SelPlan pl, SelGlobal g) {
 // finalize: one CTA per image
 // ------------------------------------------------------------------------------------------------
 constexpr int FIN_NT = 512;
+constexpr int FIN_SLACK = 512;       // candidates beyond K that may reach the all-pairs ranking
 
 struct FinParams {
     int K, post_rows;            // rows written per image
@@ -489,6 +822,58 @@ __device__ __forceinline__ float4 fin_box(const VyHeads &hd, const RowParams &rp
     }
 }
 
+// Lower bound p of the K-th largest key of a list in global memory, with K <= #{keys >= p} <= K + slack
+// (MSB-first radix select, one coalesced sweep of the list per 8-bit digit).  n >= K, slack >= 0.
+static __device__ __noinline__ u64 fin_list_bound(SelBuf &S, const u64 *list, int n, int K, int slack) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    u64 prefix = 0;
+    int kk = K;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        if (tid < 256) S.hist[tid] = 0;
+        __syncthreads();
+        // run-length aggregation: in the leading digits nearly all keys of a list agree, and
+        // same-address shared-memory atomics would serialise
+        u32 cur = 0xffffffffu, run = 0;
+        for (int i = tid; i < n; i += nt) {
+            const u64 k = list[i];
+            if (shift == 56 || ((k ^ prefix) >> (shift + 8)) == 0ull) {
+                const u32 d = (u32)(k >> shift) & 255u;
+                if (d != cur) { if (run) atomicAdd(&S.hist[cur], run); cur = d; run = 0; }
+                ++run;
+            }
+        }
+        if (run) atomicAdd(&S.hist[cur], run);
+        __syncthreads();
+        if (tid < 32) {
+            u32 c[8], sum = 0;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { c[t] = S.hist[255 - 8 * tid - t]; sum += c[t]; }
+            u32 inc = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const u32 v = __shfl_up_sync(0xffffffffu, inc, off);
+                if (tid >= off) inc += v;
+            }
+            const u32 exc = inc - sum;
+            if (exc < (u32)kk && (u32)kk <= inc) {
+                u32 run = exc;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    if (run + c[t] >= (u32)kk) { S.sel_digit = 255 - 8 * tid - t; S.sel_above = (int)run; S.sel_in = (int)c[t]; break; }
+                    run += c[t];
+                }
+            }
+        }
+        __syncthreads();
+        const int d = S.sel_digit, above = S.sel_above, inb = S.sel_in;
+        __syncthreads();
+        prefix |= (u64)d << shift;
+        kk -= above;
+        if (inb - kk <= slack) break;
+    }
+    return prefix;
+}
+
 // One CTA per image.  Positions: "rank" = place in the global score order (what the operator's
 // output order is); "slot" = place after a stable regrouping by class, in which every class is one
 // contiguous segment still ordered by rank.  Suppression only ever happens inside a segment, so the
@@ -502,65 +887,72 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     const int b = blockIdx.x;
     const int K = pl.K;
     const int nwK = (K + 31) >> 5;
-    float4 *box = (float4 *)dyn;                       // K      by slot
+    u64 *cand = (u64 *)dyn;                            // K + FIN_SLACK unordered candidates
+    float4 *box = (float4 *)(dyn + (((size_t)(K + FIN_SLACK) * 8 + 15) & ~(size_t)15));   // K by slot
     float *area = (float *)(box + K);                  // K      by slot
     int *cls = (int *)(area + K);                      // K      by slot
     int *seg_end = cls + K;                            // K      by slot
     int *slot_of_rank = seg_end + K;                   // K
-    u32 *mask = (u32 *)(slot_of_rank + K);             // K * nwK, by slot
+    int *rank_of_slot = slot_of_rank + K;              // K
+    int *cls_r = rank_of_slot + K;                     // K      by rank
+    u32 *mask = (u32 *)(cls_r + K);                    // K * nwK, by slot
     u32 *rowany = mask + (size_t)K * nwK;              // 32     by slot
     u32 *keepw = rowany + 32;                          // 32     by rank
     int *kprefix = (int *)(keepw + 32);                // 33
-    u64 *key2 = S.keys + SEL_CAP / 2;                  // class-sort scratch (ranks use the lower half)
 
     // ---- 1. exact top-K of the image's candidate list, sorted descending
     if (tid == 0) { S.count = 0; S.thr = g.thr[b]; }
     __syncthreads();
-    const int n_list = min(g.count[b], pl.list_cap);
-    const u64 *list = g.list + (size_t)b * pl.list_cap;
-    int cnt = 0;
-    for (int off = 0; off < n_list;) {
-        const int take = min(SEL_CAP - cnt, n_list - off);          // CTA-uniform
-        const u64 thr = S.thr;
-        for (int i = tid; i < take; i += FIN_NT) {
-            const u64 key = list[off + i];
-            if (key >= thr) sel_push(S, key);
-        }
+    // streaming path: the streamed list, unless it overflowed and the rescue pass rebuilt g.list
+    const bool use_s = g.scount != nullptr && g.scount[b] <= g.slist_cap;
+    const int n_list = use_s ? g.scount[b] : min(g.count[b], pl.list_cap);
+    const u64 *list = use_s ? g.slist + (size_t)b * g.slist_cap : g.list + (size_t)b * pl.list_cap;
+    if (n_list > K + FIN_SLACK) {
+        // long list: bound its K-th largest key first, so that one sweep leaves <= K + FIN_SLACK keys
+        const u64 p = fin_list_bound(S, list, n_list, K, FIN_SLACK);
+        if (tid == 0 && p > S.thr) S.thr = p;
         __syncthreads();
-        cnt = S.count;
-        __syncthreads();
-        off += take;
-        if (off < n_list && cnt > K) cnt = sel_compact(S, cnt, K, false);
     }
-    const int m = sel_compact(S, cnt, K, true);         // <= K candidates take part
-    int npow2 = 32;
-    while (npow2 < m) npow2 <<= 1;
-    for (int i = m + tid; i < npow2; i += FIN_NT) S.keys[i] = 0ull;
+    u64 *keyr = S.keys;                                 // the K best by rank (K <= SEL_KMAX <= SEL_CAP)
+    {
+        const u64 thr = S.thr;
+        for (int i = tid; i < n_list; i += FIN_NT) {
+            const u64 key = list[i];
+            if (key >= thr) { const int slot = atomicAdd(&S.count, 1); if (slot < K + FIN_SLACK) cand[slot] = key; }
+        }
+    }
+    __syncthreads();
+    const int m1 = min(S.count, K + FIN_SLACK);
+    const int m = min(m1, K);                           // <= K candidates take part
+    // rank = number of larger keys (keys are unique: the row is part of the key); all pairs, the
+    // compared key is a shared-memory broadcast
+    for (int i = tid; i < m1; i += FIN_NT) {
+        const u64 mine = cand[i];
+        int rank = 0;
+        for (int j = 0; j < m1; ++j) rank += cand[j] > mine;
+        if (rank < K) keyr[rank] = mine;
+    }
     for (int i = tid; i < m * nwK; i += FIN_NT) mask[i] = 0u;
     if (tid < 32) { rowany[tid] = 0; keepw[tid] = 0; }
     __syncthreads();
-    sel_sort_desc(S.keys, npow2);
 
-    // ---- 2. regroup by class (stable in rank): key2 = (class, ~rank), sorted descending
+    // ---- 2. regroup by class, stable in rank: slot = #{(class, rank) pairs below mine}
     const bool all_pairs = fp.force_suppress || (SRC == 1 && rp.id_index < 0) || (SRC == 0 && hd.agnostic);
-    for (int i = tid; i < npow2; i += FIN_NT) {
-        u64 k2 = 0ull;
-        if (i < m) {
-            const int c = all_pairs ? 0 : fin_class<SRC>(hd, rp, b, vy_key_row(S.keys[i]));
-            k2 = ((u64)((u32)c ^ 0x80000000u) << 32) | (u64)(0xffffffffu - (u32)i);
-        }
-        key2[i] = k2;
-    }
+    for (int i = tid; i < m; i += FIN_NT) cls_r[i] = all_pairs ? 0 : fin_class<SRC>(hd, rp, b, vy_key_row(keyr[i]));
     __syncthreads();
-    if (!all_pairs) sel_sort_desc(key2, npow2);
-    for (int j = tid; j < m; j += FIN_NT) {
-        const u64 k2 = key2[j];
-        const int r = (int)(0xffffffffu - (u32)(k2 & 0xffffffffu));
-        slot_of_rank[r] = j;
-        cls[j] = (int)((u32)(k2 >> 32) ^ 0x80000000u);
-        const float4 bx = fin_box<SRC>(hd, rp, b, vy_key_row(S.keys[r]));
-        box[j] = bx;
-        area[j] = nms_area(bx, fp.in_format);
+    for (int i = tid; i < m; i += FIN_NT) {
+        const int c = cls_r[i];
+        int slot = i;
+        if (!all_pairs) {
+            slot = 0;
+            for (int j = 0; j < m; ++j) { const int cj = cls_r[j]; slot += (cj < c) || (cj == c && j < i); }
+        }
+        slot_of_rank[i] = slot;
+        rank_of_slot[slot] = i;
+        cls[slot] = c;
+        const float4 bx = fin_box<SRC>(hd, rp, b, vy_key_row(keyr[i]));
+        box[slot] = bx;
+        area[slot] = nms_area(bx, fp.in_format);
     }
     __syncthreads();
     for (int j = tid; j < m; j += FIN_NT) {
@@ -616,7 +1008,7 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
             const u32 keep = ~rem & validm;
             // survivors by rank
             if (r < m && ((keep >> lane) & 1u)) {
-                const int rank = (int)(0xffffffffu - (u32)(key2[r] & 0xffffffffu));
+                const int rank = rank_of_slot[r];
                 atomicOr(&keepw[rank >> 5], 1u << (rank & 31));
             }
             u32 act = keep & ra;                        // surviving references reach into later words
@@ -649,7 +1041,7 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
         if (!((kw >> (i & 31)) & 1u)) continue;
         const int p = kprefix[i >> 5] + __popc(kw & ((1u << (i & 31)) - 1u));
         if (p >= fp.post_rows) continue;
-        const u64 key = S.keys[i];
+        const u64 key = keyr[i];
         const u32 row = vy_key_row(key);
         float *o = out_b + (size_t)p * W;
         if (SRC == 0) {
@@ -699,7 +1091,8 @@ __global__ void vy_fill_kernel(float *out, int *kept, size_t n_out, size_t n_kep
 // ------------------------------------------------------------------------------------------------
 static size_t fin_dyn_smem(int K) {
     const int nwK = (K + 31) / 32;
-    return (size_t)K * (16 + 4 + 4 + 4 + 4) + (size_t)K * nwK * 4 + 32 * 4 + 32 * 4 + 33 * 4 + 16;
+    return (((size_t)(K + FIN_SLACK) * 8 + 15) & ~(size_t)15) + (size_t)K * (16 + 4 + 4 + 4 + 4 + 4 + 4) +
+           (size_t)K * nwK * 4 + 32 * 4 + 32 * 4 + 33 * 4 + 16;
 }
 
 // CTAs that can be resident at once (SEL_CTAS_PER_SM per SM by __launch_bounds__)
@@ -719,6 +1112,8 @@ static void plan_jobs(int B, long long units_per_image, SelPlan *pl) {
     pl->list_cap = (int)(cap < 64 ? 64 : cap);
 }
 
+static void plan_stream(const VyHeads &hd, SelPlan *pl);
+
 static int plan_heads(const VyHeads &hd, int topk, float valid_thresh, SelPlan *pl) {
     memset(pl, 0, sizeof(*pl));
     long long K = topk < 0 ? hd.R : (topk < hd.R ? topk : hd.R);
@@ -734,7 +1129,61 @@ static int plan_heads(const VyHeads &hd, int topk, float valid_thresh, SelPlan *
     for (int s = hd.n_scales; s <= VY_MAX_SCALES; ++s) pl->item_begin[s] = items;
     pl->items_per_frame = items;
     plan_jobs(hd.B, items, pl);
+    plan_stream(hd, pl);
     return VY_OK;
+}
+
+// streaming path: worthwhile once an image has enough rows for a sample to be cheap AND sharp
+static void plan_stream(const VyHeads &hd, SelPlan *pl) {
+    pl->stream = 0;
+    if (hd.agnostic || hd.R < 131072 || hd.C < 1) return;
+    // sampled fraction 1/S: about K*S candidates per image reach the list (distribution-free)
+    long long S = hd.R / (40LL * pl->K);
+    if (S < 4) return;
+    if (S > 32) S = 32;
+    for (;; S *= 2) {
+        const long long runs = ((long long)pl->items_per_frame + SAMP_RUN * S - 1) / (SAMP_RUN * S);
+        const long long items = runs * SAMP_RUN;
+        // jobs: item blocks of <= SAMP_NT items x plane blocks; a thread owns <= SAMP_MAXK planes
+        long long ib = (items + SAMP_NT - 1) / SAMP_NT;
+        long long ipj = (items + ib - 1) / ib;
+        long long pls = SAMP_NT / ipj;                                  // >= 1
+        long long pbk = (hd.C + pls * 8 - 1) / (pls * 8);               // aim at ~8 planes per thread
+        if (pbk < 1) pbk = 1;
+        if (ib * pbk > SEL_GMAX) pbk = SEL_GMAX / ib;
+        if (pbk < 1) continue;                                          // too many item blocks: sample less
+        long long ppj = (hd.C + pbk - 1) / pbk;
+        pbk = (hd.C + ppj - 1) / ppj;
+        if (ppj > pls * SAMP_MAXK) continue;                            // too many planes per thread
+        if (ib * pbk > pl->K) continue;
+        pl->samp_stride = (int)S;
+        pl->samp_items = (int)items;
+        pl->samp_ib = (int)ib; pl->samp_ipj = (int)ipj;
+        pl->samp_ppj = (int)ppj; pl->samp_pls = (int)pls;
+        pl->Gs = (int)(ib * pbk);
+        break;
+    }
+    pl->Ksq = (pl->K + pl->Gs - 1) / pl->Gs;
+    pl->n_groups = (hd.C + 95) / 96;
+    pl->PU = (hd.C + pl->n_groups - 1) / pl->n_groups;
+    int units = 0;
+    for (int s = 0; s < hd.n_scales; ++s) {
+        pl->chunks[s] = (hd.sc[s].HW + 127) / 128;
+        pl->unit_begin[s] = units;
+        units += pl->chunks[s] * pl->n_groups * hd.A;
+    }
+    for (int s = hd.n_scales; s <= VY_MAX_SCALES; ++s) pl->unit_begin[s] = units;
+    pl->units_per_image = units;
+    pl->n_units = (long long)units * hd.B;
+    pl->stream = 1;
+}
+
+// keys per image in the streamed list: 4x the expected K*S, never more than the image has rows
+static int stream_list_cap(const VyHeads &hd, const SelPlan &pl) {
+    long long cap = 4LL * pl.K * pl.samp_stride;
+    if (cap < 4096) cap = 4096;
+    if (cap > hd.R) cap = hd.R;
+    return (int)cap;
 }
 
 static int plan_rows(int B, long long R, int topk, float valid_thresh, SelPlan *pl) {
@@ -775,7 +1224,8 @@ extern "C" size_t vy_decode_nms_workspace_bytes(const int *H, const int *W, int 
     if (vy_fill_heads(&hd, fake, H, W, st, an, n_scales, B, A, C, agnostic) != VY_OK) return 0;
     SelPlan pl;
     if (plan_heads(hd, topk, 0.0f, &pl) != VY_OK) { vy_set_error("topk out of range for the fused path"); return 0; }
-    return sel_workspace_layout(B, pl.G, pl.list_cap, nullptr, nullptr, nullptr);
+    return sel_workspace_layout(B, pl.G, pl.list_cap, nullptr, nullptr, nullptr, pl.stream ? pl.Gs : 0,
+                                pl.stream ? stream_list_cap(hd, pl) : 0);
 }
 
 extern "C" int vy_decode_nms_f32(const float *const *head, const int *H, const int *W, const float *stride,
@@ -794,13 +1244,23 @@ extern "C" int vy_decode_nms_f32(const float *const *head, const int *H, const i
                              topk, SEL_KMAX);
     SelGlobal g;
     size_t header = 0;
-    const size_t need = sel_workspace_layout(B, pl.G, pl.list_cap, &g, workspace, &header);
+    const size_t need = sel_workspace_layout(B, pl.G, pl.list_cap, &g, workspace, &header, pl.stream ? pl.Gs : 0,
+                                             pl.stream ? stream_list_cap(hd, pl) : 0);
     if (!workspace || workspace_bytes < need)
         VY_FAIL(VY_EWORKSPACE, "vy_decode_nms_f32: workspace %zu < %zu bytes", workspace_bytes, need);
     if (((uintptr_t)workspace & 255) != 0) VY_FAIL(VY_EALIGN, "workspace must be 256-byte aligned");
     for (int s = 0; s < n_scales; ++s)
         if (!head[s]) VY_FAIL(VY_EINVAL, "vy_decode_nms_f32: head[%d] is null", s);
     VY_CUDA_CHECK(cudaMemsetAsync(workspace, 0, header, st));
+    if (pl.stream) {
+        VY_KERNEL(VY_K_SAMPLE, st, (vy_decode_sample_kernel<<<B * pl.Gs, SAMP_NT, 0, st>>>(hd, pl, g)));
+        VY_LAUNCH_CHECK("vy_decode_sample_kernel");
+        long long ctas = (pl.n_units + STR_NT / 32 - 1) / (STR_NT / 32);
+        const long long resident = (long long)STR_CTAS_PER_SM * vy_sm_count();
+        if (ctas > resident) ctas = resident;
+        VY_KERNEL(VY_K_STREAM, st, (vy_decode_stream_kernel<<<(unsigned)ctas, STR_NT, 0, st>>>(hd, pl, g)));
+        VY_LAUNCH_CHECK("vy_decode_stream_kernel");
+    }
     VY_KERNEL(VY_K_SELECT_HEADS, st, (vy_decode_select_kernel<<<select_grid(pl.n_jobs), SEL_NT, 0, st>>>(hd, pl, g)));
     VY_LAUNCH_CHECK("vy_decode_select_kernel");
     FinParams fp;

@@ -164,3 +164,114 @@ def bbox_iou(bbox_a: torch.Tensor, bbox_b: torch.Tensor, offset=0) -> torch.Tens
         _lib.check(fn(a.data_ptr(), a.shape[0], a.shape[1], b.data_ptr(), b.shape[0], b.shape[1],
                       float(offset), out.data_ptr(), _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------------- temporal fusion conv
+class PTensor:
+    """An activation in the library's P layout: ``data`` is a bf16 (or fp32) CUDA tensor of shape
+    (T, B, H+2, W+2, C) whose one-pixel spatial border is zero (include/vyolo.h)."""
+
+    __slots__ = ("data", "B", "T", "H", "W", "C")
+
+    def __init__(self, data, B, T, H, W, C):
+        self.data, self.B, self.T, self.H, self.W, self.C = data, B, T, H, W, C
+
+    @property
+    def shape(self):                       # the reference's NCDHW view of the same tensor
+        return (self.B, self.C, self.T, self.H, self.W)
+
+
+def pack_p(x: torch.Tensor, layout: str = "NCDHW") -> PTensor:
+    """fp32 CUDA tensor in a reference layout -> P layout bf16.  ``layout``: 'NCDHW' (B,C,T,H,W), the
+    block-internal layout after ``swapaxes(1, 2)`` (yolo3.py:256); 'NTCHW' (B,K,C,H,W), what the
+    temporal models carry between blocks; 'NCHW' (B,C,H,W) for 2-D cells."""
+    x = _need_cuda(x, "x")
+    if layout == "NCHW":
+        B, C, H, W = x.shape
+        T, sb, sc, st = 1, C * H * W, H * W, 0
+    elif layout == "NCDHW":
+        B, C, T, H, W = x.shape
+        sb, sc, st = C * T * H * W, T * H * W, H * W
+    elif layout == "NTCHW":
+        B, T, C, H, W = x.shape
+        sb, st, sc = T * C * H * W, C * H * W, H * W
+    else:
+        raise ValueError("layout must be NCHW, NCDHW or NTCHW")
+    out = torch.empty((T, B, H + 2, W + 2, C), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vy_pack_f32_to_p_bf16(x.data_ptr(), sb, sc, st, B, C, T, H, W, out.data_ptr(), _stream()))
+    return PTensor(out, B, T, H, W, C)
+
+
+def unpack_p(p: PTensor, layout: str = "NCDHW") -> torch.Tensor:
+    """P layout (bf16 or fp32) -> fp32 CUDA tensor in a reference layout (see pack_p)."""
+    B, T, H, W, C = p.B, p.T, p.H, p.W, p.C
+    if layout == "NCHW":
+        if T != 1:
+            raise ValueError("NCHW needs T == 1")
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=p.data.device)
+        sb, sc, st = C * H * W, H * W, 0
+    elif layout == "NCDHW":
+        out = torch.empty((B, C, T, H, W), dtype=torch.float32, device=p.data.device)
+        sb, sc, st = C * T * H * W, T * H * W, H * W
+    elif layout == "NTCHW":
+        out = torch.empty((B, T, C, H, W), dtype=torch.float32, device=p.data.device)
+        sb, st, sc = T * C * H * W, C * H * W, H * W
+    else:
+        raise ValueError("layout must be NCHW, NCDHW or NTCHW")
+    with torch.cuda.device(p.data.device):
+        _lib.check(_lib.lib().vy_unpack_p_to_f32(p.data.data_ptr(), int(p.data.dtype == torch.float32), B, C, T, H, W,
+                                                 out.data_ptr(), sb, sc, st, _stream()))
+    return out
+
+
+def fusion_conv(x: PTensor, weight: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
+                slope: float = 0.1, out_f32: bool = False) -> PTensor:
+    """One Conv+BN+LeakyReLU cell (layers.py:63-79) on a P-layout activation.
+
+    weight: (Cout, kt, kh, kw, Cin) bf16 CUDA (see ``conv_weight``); scale/shift: folded inference
+    BatchNorm per output channel, fp32 CUDA.  'same' padding, stride 1."""
+    if not isinstance(x, PTensor):
+        raise TypeError("fusion_conv takes a PTensor (ops.pack_p)")
+    w = _need_cuda(weight, "weight", torch.bfloat16)
+    scale = _need_cuda(scale, "scale")
+    shift = _need_cuda(shift, "shift")
+    Cout, kt, kh, kw, Cin = w.shape
+    if Cin != x.C:
+        raise ValueError("weight has %d input channels, activation has %d" % (Cin, x.C))
+    if scale.numel() != Cout or shift.numel() != Cout:
+        raise ValueError("scale/shift must have Cout elements")
+    y = torch.empty((x.T, x.B, x.H + 2, x.W + 2, Cout), dtype=torch.float32 if out_f32 else torch.bfloat16,
+                    device=x.data.device)
+    with torch.cuda.device(x.data.device):
+        _lib.check(_lib.lib().vy_fusion_conv_bf16(x.data.data_ptr(), w.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                                  float(slope), x.B, x.T, x.H, x.W, Cin, Cout, kt, kh, kw,
+                                                  y.data_ptr(), int(out_f32), None, 0, _stream()))
+    return PTensor(y, x.B, x.T, x.H, x.W, Cout)
+
+
+def conv_weight(w_ref: torch.Tensor) -> torch.Tensor:
+    """The reference's conv weight (Cout, Cin, [kt,] kh, kw) fp32 -> (Cout, kt, kh, kw, Cin) bf16 CUDA."""
+    if w_ref.dim() == 4:
+        w_ref = w_ref[:, :, None]
+    return w_ref.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+
+
+def fold_bn(gamma, beta, mean, var, eps: float = 1e-5):
+    """Inference BatchNorm (layers.py:68,77: epsilon=1e-5) as y = x*scale + shift."""
+    scale = gamma / torch.sqrt(var + eps)
+    return scale.float().contiguous(), (beta - mean * scale).float().contiguous()
+
+
+def temporal_pool(x: PTensor, type: str = "max") -> PTensor:
+    """TemporalPooling 'direct' style (layers.py:201-205): reduce the K frames to one."""
+    if type not in ("max", "mean"):
+        raise ValueError("type must be max or mean")
+    if x.data.dtype != torch.bfloat16:
+        raise TypeError("temporal_pool takes a bf16 P-layout activation")
+    inner = x.B * (x.H + 2) * (x.W + 2) * x.C
+    y = torch.empty((1, x.B, x.H + 2, x.W + 2, x.C), dtype=torch.bfloat16, device=x.data.device)
+    with torch.cuda.device(x.data.device):
+        _lib.check(_lib.lib().vy_temporal_pool_bf16(x.data.data_ptr(), x.T, inner, 0 if type == "max" else 1,
+                                                    y.data_ptr(), _stream()))
+    return PTensor(y, x.B, 1, x.H, x.W, x.C)
