@@ -175,6 +175,86 @@ def test_box_nms_fed_reference_decoded_boxes(vy):
         _check_nms(vy, dets, overlap_thresh=0.45, valid_thresh=0.01, topk=400, id_index=0, out_rows=100)
 
 
+# ----------------------------------------------------------------------------------- box_nms, > 1024 candidates
+def _sparse_dets(rng, B, R, n_cls, extent, box):
+    """small boxes scattered over a large extent: most of them survive, so the kept lists grow long"""
+    d = _rand_dets(rng, B, R, n_cls)
+    xy = rng.uniform(0, extent, size=(B, R, 2))
+    wh = rng.uniform(0.2 * box, box, size=(B, R, 2))
+    d[..., 2:4] = xy
+    d[..., 4:6] = xy + wh
+    return d.astype(np.float32)
+
+
+@pytest.mark.parametrize("R,topk,n_cls", [(1025, -1, 3), (3000, -1, 4), (5000, 2000, 1), (24000, -1, 20), (20000, 15000, 80)])
+@pytest.mark.parametrize("force", [False, True])
+def test_box_nms_large_bit_exact_random(vy, R, topk, n_cls, force):
+    """MXNet's default topk=-1 / topk > 1024 (BASELINE config 4 arguments): sorted-list path."""
+    rng = np.random.RandomState(R + n_cls)
+    d = _rand_dets(rng, 3, R, n_cls, quant=(64 if R % 2 else None))
+    _check_nms(vy, d, overlap_thresh=0.45, valid_thresh=0.001, topk=topk, id_index=0, force_suppress=force)
+
+
+@pytest.mark.parametrize("force", [False, True])
+def test_box_nms_large_long_kept_lists(vy, force):
+    """thousands of survivors per segment: several staged chunks of the kept list, full 1024-wide tiles"""
+    rng = np.random.RandomState(17)
+    d = _sparse_dets(rng, 2, 16000, 3, extent=300.0, box=4.0)
+    exp, rec = oracle.box_nms_c(d, overlap_thresh=0.45, valid_thresh=0.001, topk=-1, id_index=0,
+                                force_suppress=force, return_record=True)
+    assert (rec >= 0).sum(axis=1).min() > 3000
+    got, kept = vy.box_nms(dev(d), overlap_thresh=0.45, valid_thresh=0.001, topk=-1, id_index=0,
+                           force_suppress=force, return_kept=True)
+    np.testing.assert_array_equal(kept.cpu().numpy(), rec)
+    np.testing.assert_array_equal(got.cpu().numpy(), exp)
+
+
+def test_box_nms_large_argument_variants(vy):
+    rng = np.random.RandomState(78)
+    d = _rand_dets(rng, 2, 6000, 5, scale=200.0)
+    _check_nms(vy, d, overlap_thresh=0.3, valid_thresh=0.0, topk=-1, id_index=-1)                  # no ids
+    _check_nms(vy, d, overlap_thresh=0.5, valid_thresh=-1.0, topk=-1, id_index=0)                   # negative scores take part
+    _check_nms(vy, d, overlap_thresh=0.5, valid_thresh=0.2, topk=-1, id_index=0, background_id=1)
+    _check_nms(vy, d, overlap_thresh=0.5, valid_thresh=5.0, topk=-1, id_index=0)                    # nothing valid
+    _check_nms(vy, d, overlap_thresh=0.45, valid_thresh=0.01, topk=-1, id_index=0, out_rows=100)    # fused slice
+    _check_nms(vy, d, overlap_thresh=0.0, valid_thresh=0.01, topk=-1, id_index=0)                   # thr 0: exact-division path
+    _check_nms(vy, d, overlap_thresh=0.999, valid_thresh=0.01, topk=-1, id_index=0)
+    d8 = _rand_dets(rng, 2, 3000, 5, W=8, coord_start=1, score_index=0, id_index=6, scale=150.0)
+    _check_nms(vy, d8, overlap_thresh=0.45, valid_thresh=0.0, topk=-1, coord_start=1, score_index=0, id_index=6)
+    c = d.copy()
+    c[..., 2:4] = (d[..., 2:4] + d[..., 4:6]) / 2
+    c[..., 4:6] = d[..., 4:6] - d[..., 2:4]
+    _check_nms(vy, c, overlap_thresh=0.45, valid_thresh=0.01, topk=-1, id_index=0, in_format="center", out_format="center")
+    _check_nms(vy, c, overlap_thresh=0.45, valid_thresh=0.01, topk=-1, id_index=0, in_format="center", out_format="corner")
+    _check_nms(vy, d, overlap_thresh=0.45, valid_thresh=0.01, topk=-1, id_index=0, in_format="corner", out_format="center")
+    d4 = _rand_dets(rng, 6, 1500, 3).reshape(2, 3, 1500, 6)                                        # (B, T, R, 6)
+    _check_nms(vy, d4, overlap_thresh=0.45, valid_thresh=0.01, topk=-1, id_index=0)
+    # all-equal scores and duplicates of one box (pure row-order ties; a single survivor per class)
+    e = _rand_dets(rng, 2, 5000, 3)
+    e[..., 1] = 0.5
+    _check_nms(vy, e, overlap_thresh=0.45, valid_thresh=0.01, topk=-1, id_index=0)
+    e[..., 2:6] = [10, 10, 50, 60]
+    _check_nms(vy, e, overlap_thresh=0.45, valid_thresh=0.01, topk=-1, id_index=0)
+
+
+def test_box_nms_large_fed_reference_decoded_boxes(vy):
+    """BASELINE config 4 arguments (valid_thresh 0.001, topk -1, force on/off) on decoded YOLO rows."""
+    rng = np.random.RandomState(41)
+    heads = random_heads(rng, 2, 20, 160)
+    dets = oracle.decode_c(heads, 20)                                   # (2, 31500, 6)
+    for force in (False, True):
+        _check_nms(vy, dets, overlap_thresh=0.45, valid_thresh=0.001, topk=-1, id_index=0, force_suppress=force)
+    # through the block surface: set_nms(nms_topk=-1) routes decode -> box_nms (yolo3.py:523-530)
+    net = vy.get_yolov3_postprocess(["c%d" % i for i in range(20)])
+    net.set_nms(nms_thresh=0.45, nms_topk=-1, post_nms=100)
+    ids, scores, bboxes = net(*[dev(h) for h in heads])
+    gd = vy.yolo3_decode([dev(h) for h in heads], 20, AN, ST).cpu().numpy()
+    o_ids, o_sc, o_bb = oracle.yolov3_tail(gd, nms_topk=-1)
+    np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
+    np.testing.assert_array_equal(scores.cpu().numpy(), o_sc)
+    np.testing.assert_array_equal(bboxes.cpu().numpy(), o_bb)
+
+
 # ----------------------------------------------------------------------------------- fused path
 def _fused_vs_oracle(vy, heads, C, agnostic=False, nms_thresh=0.45, topk=400, post_nms=100, valid=0.01, force=False):
     hd = [dev(h) for h in heads]

@@ -10,6 +10,7 @@
 //                         compaction, write of the (post_nms, W) rows + kept source rows.
 // Semantics follow MXNet _contrib_box_nms as called at yolo3.py:525-530.
 #include "vy_select.cuh"
+#include "vy_nms_math.cuh"
 #include <math_constants.h>
 
 // ------------------------------------------------------------------------------------------------
@@ -765,30 +766,7 @@ struct FinParams {
     int *kept_rows;
 };
 
-// upstream BoxArea / Intersect (bounding_box-inl.h), same association order as the oracle
-__device__ __forceinline__ float nms_area(float4 b, int fmt) {
-    float w, h;
-    if (fmt == VY_FMT_CORNER) { w = __fsub_rn(b.z, b.x); h = __fsub_rn(b.w, b.y); }
-    else { w = b.z; h = b.w; }
-    if (w < 0 || h < 0) return 0.0f;
-    return __fmul_rn(w, h);
-}
-__device__ __forceinline__ float nms_isect(float a1, float a2, float b1, float b2, int fmt) {
-    float w;
-    if (fmt == VY_FMT_CORNER) {
-        const float left = a1 > b1 ? a1 : b1;
-        const float right = a2 < b2 ? a2 : b2;
-        w = __fsub_rn(right, left);
-    } else {
-        const float aw = __fdiv_rn(a2, 2.0f), bw = __fdiv_rn(b2, 2.0f);
-        const float al = __fsub_rn(a1, aw), ar = __fadd_rn(a1, aw);
-        const float bl = __fsub_rn(b1, bw), br = __fadd_rn(b1, bw);
-        const float left = bl > al ? bl : al;
-        const float right = br < ar ? br : ar;
-        w = __fsub_rn(right, left);
-    }
-    return w > 0 ? w : 0.0f;
-}
+// BoxArea / Intersect arithmetic: vy_nms_math.cuh
 
 // source row -> class id (and, for head maps, where its box logits live)
 template <int SRC>

@@ -1,15 +1,469 @@
-// vy_nms_large.cu -- box_nms when more than SEL_KMAX candidates take part (topk < 0 or large).
+// vy_nms_large.cu -- box_nms when more than SEL_KMAX candidates take part (topk < 0 or topk > 1024):
+// MXNet's own default (topk = -1) and BASELINE config 4 (80 classes, valid_thresh 0.001, topk -1,
+// force_suppress on/off, up to 851 760 participating rows per image).
+//
+// The small path (vy_nms.cu) keeps K <= 1024 candidates of an image in one CTA's shared memory.  Here
+// every valid row can take part, so the work is organised around global-memory lists:
+//
+//   1. lg_key_kernel      key = (image, orderable score) per row, value = row; counts valid rows
+//   2. radix sort #1      stable, descending  -> per image: rows in MXNet's order (score desc, ties by
+//                         ascending source row), rank = position in that order
+//   3. lg_key2_kernel     (class-aware only) key = (image, takes-part, class id), value = rank
+//      radix sort #2      stable, ascending   -> every (image, class) is one contiguous segment that
+//                         is still in rank order;  lg_seg_kernel lists the segment heads
+//   4. lg_nms_kernel      one CTA per segment (per image when force_suppress / no ids): greedy
+//                         suppression in tiles of 1024 candidates.  A tile is first tested against the
+//                         boxes KEPT by earlier tiles (only survivors can suppress, so the cost is
+//                         candidates x survivors, not candidates^2), then resolved internally with a
+//                         1024 x 1024 suppression bitmask built by ballots and one warp's greedy scan;
+//                         its survivors are appended to the segment's kept list.
+//   5. lg_count / lg_write  survivors compacted to the front of the image in rank order.
+//
+// The two sorts are cub::DeviceRadixSort (CUDA toolkit header library, stable LSD radix sort): a
+// commodity step, not the product; everything that defines the operator's result is in this file.
+// IoU arithmetic: vy_nms_math.cuh (bit-exact with the oracle).
 #include "vy_select.cuh"
+#include "vy_nms_math.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <math.h>
+#include <string.h>
+
+namespace {
+
+constexpr int LG_NT = 1024;          // threads per NMS CTA
+constexpr int LG_TILE = 1024;        // candidates per tile (== LG_NT)
+constexpr int LG_WORDS = LG_TILE / 32;
+constexpr int LG_CHUNK = 2048;       // ranks per compaction chunk
+constexpr int LG_CNT = 256;          // threads per compaction CTA (8 flags each)
+
+struct LgLayout {
+    size_t hdr, keys_a, keys_b, vals_a, vals_b, vals_c, kept_box, kept_area, keep, seg, csum, cub, total;
+    size_t hdr_bytes, cub_bytes;
+};
+
+static size_t lg_align(size_t v) { return (v + 255) / 256 * 256; }
+
+static int lg_bits(int B) { int b = 0; while ((1LL << b) < B) ++b; return b; }
+
+// temp storage of the two sorts (the larger one); 0 on failure
+static size_t lg_cub_bytes(long long N, int bitsB) {
+    size_t t1 = 0, t2 = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(nullptr, t1, (const u64 *)nullptr, (u64 *)nullptr,
+                                                               (const u32 *)nullptr, (u32 *)nullptr, N, 0, 32 + bitsB);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    e = cub::DeviceRadixSort::SortPairs(nullptr, t2, (const u64 *)nullptr, (u64 *)nullptr, (const u32 *)nullptr,
+                                        (u32 *)nullptr, N, 0, 33 + bitsB);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return (t1 > t2 ? t1 : t2) + 256;
+}
+
+static bool lg_layout(int B, long long R, LgLayout *L) {
+    const long long N = (long long)B * R;
+    const int nchunk = (int)((R + LG_CHUNK - 1) / LG_CHUNK);
+    size_t off = 0;
+    L->hdr = off;       L->hdr_bytes = lg_align(sizeof(int) * ((size_t)B + 8)); off += L->hdr_bytes;   // nvalid[B], n_seg
+    L->keys_a = off;    off = lg_align(off + sizeof(u64) * (size_t)N);
+    L->keys_b = off;    off = lg_align(off + sizeof(u64) * (size_t)N);
+    L->vals_a = off;    off = lg_align(off + sizeof(u32) * (size_t)N);
+    L->vals_b = off;    off = lg_align(off + sizeof(u32) * (size_t)N);
+    L->vals_c = off;    off = lg_align(off + sizeof(u32) * (size_t)N);
+    L->kept_box = off;  off = lg_align(off + sizeof(float4) * (size_t)N);
+    L->kept_area = off; off = lg_align(off + sizeof(float) * (size_t)N);
+    L->keep = off;      off = lg_align(off + (size_t)N);
+    L->seg = off;       off = lg_align(off + sizeof(u32) * (size_t)N);
+    L->csum = off;      off = lg_align(off + sizeof(int) * (size_t)B * nchunk);
+    L->cub_bytes = lg_cub_bytes(N, lg_bits(B));
+    if (L->cub_bytes == 0) return false;
+    L->cub = off;       off = lg_align(off + L->cub_bytes);
+    L->total = off;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1. keys of sort #1.  Descending order of ((B-1-b) << 32 | ord(score)) = images ascending, scores
+//    descending; invalid rows carry ord 0 (no valid score maps to 0) and sink to the image's end.
+// ------------------------------------------------------------------------------------------------
+__global__ void lg_key_kernel(RowParams rp, int B, u64 *keys, u32 *vals, int *nvalid) {
+    const long long N = (long long)B * rp.R;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long Nr = (N + 31) / 32 * 32;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < Nr; i += stride) {
+        const bool in = i < N;
+        const int b = in ? (int)(i / rp.R) : -1;
+        bool valid = false;
+        float s = 0.0f;
+        if (in) {
+            const float *row = rp.data + (size_t)i * rp.W;
+            s = vy_ldg32(row + rp.score_index);
+            valid = s > rp.valid_thresh;                                       // strict; NaN fails
+            if (valid && rp.id_index >= 0 && rp.background_id >= 0 && (int)row[rp.id_index] == rp.background_id)
+                valid = false;
+            keys[i] = ((u64)(u32)(B - 1 - b) << 32) | (u64)(valid ? vy_f2ord(s) : 0u);
+            vals[i] = (u32)(i - (long long)b * rp.R);
+        }
+        const u32 peers = __match_any_sync(0xffffffffu, valid ? b : -1);
+        if (valid && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(nvalid + b, __popc(peers));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. keys of sort #2: (image, does-not-take-part, class id + 2^31), value = rank
+// ------------------------------------------------------------------------------------------------
+__global__ void lg_key2_kernel(RowParams rp, int B, long long K, const u32 *row_of, const int *nvalid,
+                               u64 *keys2, u32 *vals2) {
+    const long long N = (long long)B * rp.R;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const int b = (int)(i / rp.R);
+        const long long rank = i - (long long)b * rp.R;
+        const long long nb = min((long long)nvalid[b], K);
+        const bool part = rank < nb;
+        int cls = 0;
+        if (part) cls = (int)rp.data[((size_t)b * (size_t)rp.R + row_of[i]) * rp.W + rp.id_index];
+        keys2[i] = ((u64)(u32)b << 33) | ((u64)(part ? 0u : 1u) << 32) | (u64)((u32)cls ^ 0x80000000u);
+        vals2[i] = (u32)rank;
+    }
+}
+
+__global__ void lg_seg_kernel(const u64 *keys2, long long N, u32 *seg_starts, int *n_seg) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const u64 k = keys2[i];
+        if ((k >> 32) & 1ull) continue;
+        if (i == 0 || keys2[i - 1] != k) seg_starts[atomicAdd(n_seg, 1)] = (u32)i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4. tiled greedy suppression
+// ------------------------------------------------------------------------------------------------
+struct LgNms {
+    RowParams rp;
+    int B;
+    long long K;
+    float thr, thr_lo, thr_hi;
+    int all_pairs;               // one segment per image (force_suppress or no ids)
+    const u32 *row_of;           // [N] source row by (image, rank)            (values of sort #1)
+    const u64 *keys2;            // [N] sorted (image, part, class)            (class-aware only)
+    const u32 *rank_of;          // [N] rank by segment position               (values of sort #2)
+    const u32 *seg_starts;
+    const int *n_seg;
+    const int *nvalid;
+    float4 *kept_box;            // [N] kept boxes of a segment, from the segment's first position
+    float *kept_area;
+    unsigned char *keep;         // [N] by (image, rank)
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant__ LgNms p) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    float4 *tb = (float4 *)dyn;                     // [LG_TILE] live boxes of the tile, in order
+    float4 *sb = tb + LG_TILE;                      // [LG_TILE] staged chunk of the kept list
+    float *ta = (float *)(sb + LG_TILE);            // [LG_TILE]
+    float *sa = ta + LG_TILE;                       // [LG_TILE]
+    u32 *trank = (u32 *)(sa + LG_TILE);             // [LG_TILE]
+    u32 *mask = trank + LG_TILE;                    // [LG_TILE][LG_WORDS]
+    __shared__ u32 rowany[LG_WORDS], keepw[LG_WORDS];
+    __shared__ int wcount[LG_WORDS], woff[LG_WORDS + 1], kpre[LG_WORDS + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 lt_mask = (1u << lane) - 1u;
+    const long long R = p.rp.R, N = (long long)p.B * R;
+    const int n_seg = p.all_pairs ? p.B : *p.n_seg;
+
+    for (int seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
+        long long seg0, len = 0;
+        u64 segkey = 0;
+        int b;
+        if (p.all_pairs) { b = seg; seg0 = (long long)b * R; len = min((long long)p.nvalid[b], p.K); }
+        else { seg0 = p.seg_starts[seg]; segkey = p.keys2[seg0]; b = (int)(segkey >> 33); }
+        const size_t img = (size_t)b * (size_t)R;
+        int m = 0;                                  // boxes kept so far (CTA-uniform)
+        for (long long t0 = 0;; t0 += LG_TILE) {
+            // ---- this thread's candidate
+            bool have;
+            u32 rank = 0;
+            if (p.all_pairs) { have = t0 + tid < len; rank = (u32)(t0 + tid); }
+            else {
+                const long long gi = seg0 + t0 + tid;
+                have = gi < N && p.keys2[gi] == segkey;
+                if (have) rank = p.rank_of[gi];
+            }
+            float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+            float ar = 0.0f;
+            if (have) {
+                const float *q = p.rp.data + (img + p.row_of[img + rank]) * p.rp.W + p.rp.coord_start;
+                bx = make_float4(q[0], q[1], q[2], q[3]);
+                ar = nms_area(bx, FMT);
+            }
+            const int nv = __syncthreads_count(have);
+            if (nv == 0) break;
+            bool alive = have;
+            // ---- a. against the boxes kept by earlier tiles (a suppressed box never suppresses)
+            for (int c0 = 0; c0 < m; c0 += LG_TILE) {
+                const int cnt = min(LG_TILE, m - c0);
+                __syncthreads();
+                if (tid < cnt) { sb[tid] = p.kept_box[seg0 + c0 + tid]; sa[tid] = p.kept_area[seg0 + c0 + tid]; }
+                __syncthreads();
+                if (alive) {
+                    int j = 0;
+                    for (; j + 4 <= cnt; j += 4) {
+                        bool h = nms_suppresses_fast(sb[j], sa[j], bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT);
+                        h |= nms_suppresses_fast(sb[j + 1], sa[j + 1], bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT);
+                        h |= nms_suppresses_fast(sb[j + 2], sa[j + 2], bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT);
+                        h |= nms_suppresses_fast(sb[j + 3], sa[j + 3], bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT);
+                        if (h) { alive = false; break; }
+                    }
+                    if (alive)
+                        for (; j < cnt; ++j)
+                            if (nms_suppresses_fast(sb[j], sa[j], bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT)) { alive = false; break; }
+                }
+            }
+            // ---- b. the tile's live candidates, compacted in order
+            const u32 bal = __ballot_sync(0xffffffffu, alive);
+            if (lane == 0) wcount[warp] = __popc(bal);
+            if (tid < LG_WORDS) rowany[tid] = 0u;
+            __syncthreads();
+            if (warp == 0) {
+                const int c = wcount[lane];
+                int inc = c;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, off);
+                    if (lane >= off) inc += v;
+                }
+                woff[lane + 1] = inc;
+                if (lane == 0) woff[0] = 0;
+            }
+            __syncthreads();
+            const int na = woff[LG_WORDS];
+            if (alive) {
+                const int idx = woff[warp] + __popc(bal & lt_mask);
+                tb[idx] = bx; ta[idx] = ar; trank[idx] = rank;
+            }
+            __syncthreads();
+            if (na > 0) {
+                // suppression bitmask among the live candidates: one warp per reference, 32 later
+                // candidates per ballot; every word from the diagonal on is written
+                const int nw = (na + 31) >> 5;
+                for (int i = warp; i < na; i += LG_NT / 32) {
+                    const float4 bi = tb[i];
+                    const float ai = ta[i];
+                    u32 any = 0;
+                    for (int w = i >> 5; w < nw; ++w) {
+                        const int jx = (w << 5) + lane;
+                        bool sup = false;
+                        if (jx > i && jx < na) sup = nms_suppresses_fast(bi, ai, tb[jx], ta[jx], p.thr, p.thr_lo, p.thr_hi, FMT);
+                        const u32 bits = __ballot_sync(0xffffffffu, sup);
+                        if (lane == 0) mask[(size_t)i * LG_WORDS + w] = bits;
+                        any |= bits;
+                    }
+                    if (lane == 0 && any) atomicOr(&rowany[i >> 5], 1u << (i & 31));
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    nms_greedy_scan_warp(mask, LG_WORDS, rowany, na, keepw, lane);
+                    __syncwarp();
+                    const int c = lane < nw ? __popc(keepw[lane]) : 0;
+                    int inc = c;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, inc, off);
+                        if (lane >= off) inc += v;
+                    }
+                    kpre[lane] = inc - c;
+                    if (lane == 31) kpre[LG_WORDS] = inc;
+                }
+                __syncthreads();
+                if (tid < na) {
+                    const u32 kw = keepw[tid >> 5];
+                    if ((kw >> (tid & 31)) & 1u) {
+                        const int pos = m + kpre[tid >> 5] + __popc(kw & lt_mask);
+                        p.kept_box[seg0 + pos] = tb[tid];
+                        p.kept_area[seg0 + pos] = ta[tid];
+                        p.keep[img + trank[tid]] = 1;
+                    }
+                }
+                m += kpre[LG_WORDS];
+            }
+            if (nv < LG_TILE) break;
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 5. compaction of the survivors, in rank order, to the front of each image
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LG_CNT) lg_count_kernel(const unsigned char *keep, long long R, int nchunk, int *csum) {
+    __shared__ int wsum[LG_CNT / 32];
+    const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    const long long r0 = (long long)chunk * LG_CHUNK + (long long)tid * 8;
+    const unsigned char *kb = keep + (size_t)b * (size_t)R;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (r0 + k < R) s += kb[r0 + k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((tid & 31) == 0) wsum[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < LG_CNT / 32; ++w) t += wsum[w];
+        csum[(size_t)b * nchunk + chunk] = t;
+    }
+}
+
+__global__ void __launch_bounds__(LG_CNT) lg_write_kernel(RowParams rp, const unsigned char *keep, const u32 *row_of,
+                                                          const int *csum, int nchunk, long long out_rows,
+                                                          int in_format, int out_format, float *out, int32_t *kept_rows) {
+    __shared__ int wsum[LG_CNT / 32], sh_base;
+    const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // survivors in the chunks before this one
+    int s = 0;
+    for (int c = tid; c < chunk; c += LG_CNT) s += csum[(size_t)b * nchunk + c];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) wsum[warp] = s;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < LG_CNT / 32; ++w) t += wsum[w]; sh_base = t; }
+    __syncthreads();
+    const long long base = sh_base;
+    if (base >= out_rows) return;
+    __syncthreads();
+    const long long R = rp.R;
+    const size_t img = (size_t)b * (size_t)R;
+    const long long r0 = (long long)chunk * LG_CHUNK + (long long)tid * 8;
+    unsigned char f[8];
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { f[k] = (r0 + k < R) ? keep[img + r0 + k] : 0; mine += f[k]; }
+    int inc = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += v;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += wsum[w];
+    long long pos = base + before + (inc - mine);
+    const int W = rp.W;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (!f[k]) continue;
+        if (pos < out_rows) {
+            const u32 row = row_of[img + r0 + k];
+            const float *src = rp.data + (img + row) * W;
+            float *o = out + ((size_t)b * (size_t)out_rows + (size_t)pos) * W;
+            for (int c = 0; c < W; ++c) o[c] = src[c];
+            if (in_format != out_format) {
+                float *q = o + rp.coord_start;
+                if (!(q[0] < 0)) {
+                    if (out_format == VY_FMT_CENTER) {
+                        const float l = q[0], t = q[1], r2 = q[2], bt = q[3];
+                        q[0] = __fdiv_rn(__fadd_rn(l, r2), 2.0f); q[1] = __fdiv_rn(__fadd_rn(t, bt), 2.0f);
+                        q[2] = __fsub_rn(r2, l); q[3] = __fsub_rn(bt, t);
+                    } else {
+                        const float x = q[0], y = q[1];
+                        const float hw = __fdiv_rn(q[2], 2.0f), hh = __fdiv_rn(q[3], 2.0f);
+                        q[0] = __fsub_rn(x, hw); q[1] = __fsub_rn(y, hh);
+                        q[2] = __fadd_rn(x, hw); q[3] = __fadd_rn(y, hh);
+                    }
+                }
+            }
+            if (kept_rows) kept_rows[(size_t)b * (size_t)out_rows + (size_t)pos] = (int32_t)row;
+        }
+        ++pos;
+    }
+}
+
+__global__ void lg_fill_kernel(float *out, int *kept, size_t n_out, size_t n_kept) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) out[i] = -1.0f;
+    if (kept) for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_kept; i += stride) kept[i] = -1;
+}
+
+}  // namespace
 
 size_t vy_box_nms_large_workspace_bytes(int B, long long R, int W_elem) {
-    (void)B; (void)R; (void)W_elem;
-    return 256;
+    (void)W_elem;
+    if (B < 1 || R < 1 || (long long)B * R > 0x7fffffffLL) { vy_set_error("box_nms (large): B*R must be < 2^31"); return 0; }
+    LgLayout L;
+    if (!lg_layout(B, R, &L)) { vy_set_error("box_nms (large): radix-sort workspace query failed (no CUDA device?)"); return 0; }
+    return L.total;
 }
 
 int vy_box_nms_large(const RowParams &rp, int B, long long K, float overlap_thresh, int force_suppress,
                      int in_format, int out_format, long long out_rows, float *out, int32_t *kept_rows,
                      void *workspace, size_t workspace_bytes, cudaStream_t st) {
-    (void)rp; (void)B; (void)overlap_thresh; (void)force_suppress; (void)in_format; (void)out_format;
-    (void)out_rows; (void)out; (void)kept_rows; (void)workspace; (void)workspace_bytes; (void)st;
-    VY_FAIL(VY_EUNSUPPORTED, "box_nms with %lld > %d participating candidates is not built yet", K, SEL_KMAX);
+    const long long R = rp.R, N = (long long)B * R;
+    if (N > 0x7fffffffLL) VY_FAIL(VY_EUNSUPPORTED, "box_nms with topk > %d needs B*R < 2^31 (got %lld)", SEL_KMAX, N);
+    LgLayout L;
+    if (!lg_layout(B, R, &L)) VY_FAIL(VY_ECUDA, "box_nms (large): radix-sort workspace query failed");
+    if (!workspace || workspace_bytes < L.total)
+        VY_FAIL(VY_EWORKSPACE, "vy_box_nms_f32: workspace %zu < %zu bytes", workspace_bytes, L.total);
+    if (((uintptr_t)workspace & 255) != 0) VY_FAIL(VY_EALIGN, "workspace must be 256-byte aligned");
+    char *ws = (char *)workspace;
+    int *nvalid = (int *)(ws + L.hdr);
+    int *n_seg = nvalid + B;
+    u64 *keys_a = (u64 *)(ws + L.keys_a), *keys_b = (u64 *)(ws + L.keys_b);
+    u32 *vals_a = (u32 *)(ws + L.vals_a), *vals_b = (u32 *)(ws + L.vals_b), *vals_c = (u32 *)(ws + L.vals_c);
+    unsigned char *keep = (unsigned char *)(ws + L.keep);
+    const int sms = vy_sm_count();
+    const int bitsB = lg_bits(B);
+    const bool all_pairs = force_suppress || rp.id_index < 0;
+
+    VY_CUDA_CHECK(cudaMemsetAsync(ws + L.hdr, 0, L.hdr_bytes, st));
+    VY_CUDA_CHECK(cudaMemsetAsync(keep, 0, (size_t)N, st));
+    VY_KERNEL(VY_K_NMS_LARGE, st, (lg_fill_kernel<<<sms * 8, 256, 0, st>>>(out, kept_rows, (size_t)B * out_rows * rp.W,
+                                                                         (size_t)B * out_rows)));
+    VY_LAUNCH_CHECK("lg_fill_kernel");
+    VY_KERNEL(VY_K_NMS_LARGE, st, (lg_key_kernel<<<sms * 8, 256, 0, st>>>(rp, B, keys_a, vals_a, nvalid)));
+    VY_LAUNCH_CHECK("lg_key_kernel");
+    size_t tb = L.cub_bytes;
+    VY_CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(ws + L.cub, tb, (const u64 *)keys_a, keys_b, (const u32 *)vals_a,
+                                                            vals_b, N, 0, 32 + bitsB, st));
+    // vals_b = row_of[(image, rank)]
+    if (!all_pairs) {
+        VY_KERNEL(VY_K_NMS_LARGE, st, (lg_key2_kernel<<<sms * 8, 256, 0, st>>>(rp, B, K, vals_b, nvalid, keys_a, vals_a)));
+        VY_LAUNCH_CHECK("lg_key2_kernel");
+        tb = L.cub_bytes;
+        VY_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ws + L.cub, tb, (const u64 *)keys_a, keys_b, (const u32 *)vals_a, vals_c,
+                                                      N, 0, 33 + bitsB, st));
+        VY_KERNEL(VY_K_NMS_LARGE, st, (lg_seg_kernel<<<sms * 8, 256, 0, st>>>(keys_b, N, (u32 *)(ws + L.seg), n_seg)));
+        VY_LAUNCH_CHECK("lg_seg_kernel");
+    }
+    LgNms p;
+    memset(&p, 0, sizeof(p));
+    p.rp = rp; p.B = B; p.K = K; p.thr = overlap_thresh; p.all_pairs = all_pairs ? 1 : 0;
+    if (overlap_thresh > 0.0f && overlap_thresh < 1e30f) {
+        p.thr_lo = overlap_thresh * (1.0f - 9.5367431640625e-07f);      // 2^-20
+        p.thr_hi = overlap_thresh * (1.0f + 9.5367431640625e-07f);
+    } else {            // thr <= 0 (or absurd): always the exact division
+        p.thr_lo = -INFINITY;
+        p.thr_hi = INFINITY;
+    }
+    p.row_of = vals_b; p.keys2 = keys_b; p.rank_of = vals_c; p.seg_starts = (const u32 *)(ws + L.seg);
+    p.n_seg = n_seg; p.nvalid = nvalid;
+    p.kept_box = (float4 *)(ws + L.kept_box); p.kept_area = (float *)(ws + L.kept_area); p.keep = keep;
+    const size_t dyn = (size_t)LG_TILE * (16 + 16 + 4 + 4 + 4) + (size_t)LG_TILE * LG_WORDS * 4;
+    const int grid = all_pairs ? (B < sms ? B : sms) : sms;
+    if (in_format == VY_FMT_CORNER) {
+        VY_CUDA_CHECK(cudaFuncSetAttribute(lg_nms_kernel<VY_FMT_CORNER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        VY_KERNEL(VY_K_NMS_LARGE, st, (lg_nms_kernel<VY_FMT_CORNER><<<grid, LG_NT, dyn, st>>>(p)));
+    } else {
+        VY_CUDA_CHECK(cudaFuncSetAttribute(lg_nms_kernel<VY_FMT_CENTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        VY_KERNEL(VY_K_NMS_LARGE, st, (lg_nms_kernel<VY_FMT_CENTER><<<grid, LG_NT, dyn, st>>>(p)));
+    }
+    VY_LAUNCH_CHECK("lg_nms_kernel");
+    const int nchunk = (int)((R + LG_CHUNK - 1) / LG_CHUNK);
+    int *csum = (int *)(ws + L.csum);
+    VY_KERNEL(VY_K_NMS_LARGE, st, (lg_count_kernel<<<dim3(nchunk, B), LG_CNT, 0, st>>>(keep, R, nchunk, csum)));
+    VY_LAUNCH_CHECK("lg_count_kernel");
+    VY_KERNEL(VY_K_NMS_LARGE, st, (lg_write_kernel<<<dim3(nchunk, B), LG_CNT, 0, st>>>(rp, keep, vals_b, csum, nchunk, out_rows,
+                                                                                      in_format, out_format, out, kept_rows)));
+    VY_LAUNCH_CHECK("lg_write_kernel");
+    return VY_OK;
 }
