@@ -39,3 +39,13 @@ print("decode full dets B=8 coco608: median %.3f ms, out %.0f MB -> %.0f GB/s" %
 dets = vy.yolo3_decode(heads, 80, AN, ST)
 med, best = timeit(lambda: vy.box_nms(dets, 0.45, 0.01, 400, id_index=0, out_rows=100))
 print("box_nms rows B=8 coco608 (topk 400, out_rows 100): median %.3f ms -> %.0f GB/s read" % (med, out_b / med / 1e6))
+# BASELINE config 4 arguments: 80 cls, valid_thresh 0.001, topk -1, force_suppress on/off, 10647 boxes
+for Bs in (4, 32):
+    heads = random_heads_cuda(Bs, 80, 416, 5, dev)
+    dets = vy.yolo3_decode(heads, 80, AN, ST)
+    for force in (False, True):
+        fn = lambda: vy.box_nms(dets, 0.45, 0.001, -1, id_index=0, force_suppress=force)
+        med, best = timeit(fn, n=3, warm=1)
+        out = fn()
+        print("stress box_nms B=%d R=%d topk=-1 force=%s: median %.2f ms -> %.1f frames/s, survivors/frame %.0f"
+              % (Bs, dets.shape[1], force, med, Bs / med * 1e3, float((out[..., 0] >= 0).sum()) / Bs), flush=True)

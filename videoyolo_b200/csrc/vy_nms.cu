@@ -53,6 +53,7 @@ struct SelGlobal {              // workspace views
     u64 *slots;                 // [B][G]     per-CTA ceil(K/G)-th largest
     u64 *list;                  // [B][list_cap]
     // streaming path only (see "sample + stream" below); null otherwise
+    u64 *sthr;                  // [B]        the sample's bound (stream + finalize; may be optimistic, see below)
     int *scount;                // [B]        fill of the streamed candidate list
     int *sdone;                 // [B]        sample jobs finished
     u64 *sslots;                // [B][Gs]    per-sample-job bounds
@@ -69,6 +70,7 @@ static size_t sel_workspace_layout(int B, int G, int list_cap, SelGlobal *g, voi
     const size_t o_thr = off;   off = align_up(off + sizeof(u64) * (size_t)B, 256);
     const size_t o_cnt = off;   off = align_up(off + sizeof(int) * (size_t)B, 256);
     const size_t o_slot = off;  off = align_up(off + sizeof(u64) * (size_t)B * G, 256);
+    const size_t o_sthr = off;  off = align_up(off + sizeof(u64) * (size_t)B * (Gs ? 1 : 0), 256);
     const size_t o_scnt = off;  off = align_up(off + sizeof(int) * (size_t)B * (Gs ? 1 : 0), 256);
     const size_t o_sdone = off; off = align_up(off + sizeof(int) * (size_t)B * (Gs ? 1 : 0), 256);
     const size_t o_sslot = off; off = align_up(off + sizeof(u64) * (size_t)B * Gs, 256);
@@ -80,6 +82,7 @@ static size_t sel_workspace_layout(int B, int G, int list_cap, SelGlobal *g, voi
         g->count = (int *)((char *)base + o_cnt);
         g->slots = (u64 *)((char *)base + o_slot);
         g->list = (u64 *)((char *)base + o_list);
+        g->sthr = Gs ? (u64 *)((char *)base + o_sthr) : nullptr;
         g->scount = Gs ? (int *)((char *)base + o_scnt) : nullptr;
         g->sdone = Gs ? (int *)((char *)base + o_sdone) : nullptr;
         g->sslots = Gs ? (u64 *)((char *)base + o_sslot) : nullptr;
@@ -87,6 +90,16 @@ static size_t sel_workspace_layout(int B, int G, int list_cap, SelGlobal *g, voi
         g->slist_cap = slist_cap;
     }
     return off;
+}
+
+// Is the streamed candidate list of image b usable?  It is not when it overflowed, or when it holds
+// fewer than K keys although a bound above valid_thresh was in force (the sample's bound is an
+// ESTIMATE of a rank a few times K, not a guaranteed lower bound of the K-th largest score: with
+// probability ~1e-7 per image, or for adversarial layouts, it can be too high).  Those images are
+// redone exactly by vy_decode_select_kernel.
+__device__ __forceinline__ bool stream_list_ok(const SelGlobal &g, int b, int K) {
+    const int n = g.scount[b];
+    return n <= g.slist_cap && (n >= K || g.sthr[b] == 0ull);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -313,7 +326,7 @@ vy_decode_select_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
         const int b = job / pl.G;
         // streaming path: this kernel is the rescue pass and only serves images whose streamed
         // candidate list overflowed (the sample misjudged the score distribution)
-        if (g.scount && g.scount[b] <= g.slist_cap) continue;
+        if (g.scount && stream_list_ok(g, b, pl.K)) continue;
         SelJob jb;
         jb.G = pl.G; jb.g = job % pl.G; jb.K = pl.K; jb.Kq = pl.Kq;
         jb.g_thr_b = g.thr + b;
@@ -397,7 +410,8 @@ vy_decode_select_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
 //                             that misjudged the distribution -- and normally exits at once.
 // ------------------------------------------------------------------------------------------------
 constexpr int SAMP_NT = 512;
-constexpr int SAMP_MAXK = 8;       // class planes per thread
+constexpr int SAMP_MAXK = 16;      // class planes per thread
+constexpr int SAMP_BATCH = 8;      // of which this many are loaded together
 constexpr int SAMP_RUN = 8;        // adjacent items sampled together: 8 x 16 B = one 128-byte line per plane
 
 // sampled item j of image b -> where it lives (item = 4 consecutive positions of one (scale, anchor))
@@ -424,9 +438,12 @@ __device__ __forceinline__ void item_load(const ItemRef &r, const float *p, floa
 
 // Job (b, g): item block ib = g % samp_ib, plane block pb = g / samp_ib.  Thread t owns sampled item
 // (ib * samp_ipj + t % samp_ipj) and every samp_pls-th plane of the block, starting at t / samp_ipj:
-// one objectness load and <= SAMP_MAXK class-plane loads, all in flight together.
+// one objectness load and <= SAMP_MAXK class-plane loads, SAMP_BATCH of them in flight together.
+// One 32-bit key per (item, plane) -- the score of the plane's best of <= 4 positions -- is parked in
+// shared memory; the CTA then radix-selects its Ksq-th largest key.
 __global__ void __launch_bounds__(SAMP_NT, 2)
 vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl, SelGlobal g) {
+    __shared__ u32 skey[SAMP_MAXK][SAMP_NT];
     __shared__ u32 hist[256];
     __shared__ int sh_n, sh_digit, sh_above, sh_in;
     const int tid = threadIdx.x;
@@ -435,38 +452,42 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
     const int jl = tid % pl.samp_ipj, lanep = tid / pl.samp_ipj;
     const int j = ib * pl.samp_ipj + jl;
     const int c_lo = pb * pl.samp_ppj, c_hi = min(hd.C, c_lo + pl.samp_ppj);
-    u32 key[SAMP_MAXK];
 #pragma unroll
-    for (int k = 0; k < SAMP_MAXK; ++k) key[k] = 0u;
+    for (int k = 0; k < SAMP_MAXK; ++k) skey[k][tid] = 0u;
     int n_mine = 0;
     ItemRef r;
     if (lanep < pl.samp_pls && j < pl.samp_items &&
         item_ref(hd, pl, b, (j / SAMP_RUN) * (SAMP_RUN * pl.samp_stride) + (j % SAMP_RUN), r)) {
-        float to[4], tc[SAMP_MAXK][4];
+        float to[4], cf[4];
         item_load(r, r.p + 4 * (size_t)r.HW, to);
 #pragma unroll
-        for (int k = 0; k < SAMP_MAXK; ++k) {
-            const int c = c_lo + lanep + k * pl.samp_pls;
-            if (c < c_hi) item_load(r, r.p + (size_t)(5 + c) * (size_t)r.HW, tc[k]);
-        }
-        // one 32-bit key per (item, plane): the plane's best logit decides (sigmoid is monotonic, the
-        // objectness differs per position, so all <= 4 candidates are scored only where it matters:
-        // score(best of 4) is a score of the image, and any subset of an image's scores bounds it)
-        float cf[4];
+        for (int k0 = 0; k0 < SAMP_MAXK; k0 += SAMP_BATCH) {
+            if (c_lo + lanep + k0 * pl.samp_pls >= c_hi) break;
+            float tc[SAMP_BATCH][4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) cf[v] = v < r.nv ? vy_sigmoid(to[v]) : 0.0f;
+            for (int k = 0; k < SAMP_BATCH; ++k) {
+                const int c = c_lo + lanep + (k0 + k) * pl.samp_pls;
+                if (c < c_hi) item_load(r, r.p + (size_t)(5 + c) * (size_t)r.HW, tc[k]);
+            }
+            if (k0 == 0) {
 #pragma unroll
-        for (int k = 0; k < SAMP_MAXK; ++k) {
-            const int c = c_lo + lanep + k * pl.samp_pls;
-            if (c < c_hi) {
-                float best = 0.0f;
+                for (int v = 0; v < 4; ++v) cf[v] = v < r.nv ? vy_sigmoid(to[v]) : 0.0f;
+            }
+            // sigmoid is monotonic but the objectness differs per position, so all <= 4 candidates are
+            // scored; the best one is a score of the image, and any subset of an image's scores will do
 #pragma unroll
-                for (int v = 0; v < 4; ++v) if (v < r.nv) best = fmaxf(best, vy_score(tc[k][v], cf[v]));
-                if (best > pl.valid_thresh) { key[k] = vy_f2ord(best); ++n_mine; }
+            for (int k = 0; k < SAMP_BATCH; ++k) {
+                const int c = c_lo + lanep + (k0 + k) * pl.samp_pls;
+                if (c < c_hi) {
+                    float best = 0.0f;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) if (v < r.nv) best = fmaxf(best, vy_score(tc[k][v], cf[v]));
+                    if (best > pl.valid_thresh) { skey[k0 + k][tid] = vy_f2ord(best); ++n_mine; }
+                }
             }
         }
     }
-    // ---- CTA-wide: Ksq-th largest of the keys (MSB-first radix select, keys stay in registers)
+    // ---- CTA-wide: Ksq-th largest of the keys (MSB-first radix select over the parked keys)
     if (tid == 0) sh_n = 0;
     __syncthreads();
     if (n_mine) atomicAdd(&sh_n, n_mine);
@@ -480,13 +501,15 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
             __syncthreads();
             // run-length aggregation: neighbouring keys of a thread mostly share the leading digits
             u32 cur = 0xffffffffu, run = 0;
+            if (n_mine) {
 #pragma unroll
-            for (int i = 0; i < SAMP_MAXK; ++i) {
-                const u32 k = key[i];
-                if (k != 0u && (shift == 24 || ((k ^ prefix) >> (shift + 8)) == 0u)) {
-                    const u32 d = (k >> shift) & 255u;
-                    if (d != cur) { if (run) atomicAdd(&hist[cur], run); cur = d; run = 0; }
-                    ++run;
+                for (int i = 0; i < SAMP_MAXK; ++i) {
+                    const u32 k = skey[i][tid];
+                    if (k != 0u && (shift == 24 || ((k ^ prefix) >> (shift + 8)) == 0u)) {
+                        const u32 d = (k >> shift) & 255u;
+                        if (d != cur) { if (run) atomicAdd(&hist[cur], run); cur = d; run = 0; }
+                        ++run;
+                    }
                 }
             }
             if (run) atomicAdd(&hist[cur], run);
@@ -520,7 +543,7 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
         }
         bound = prefix;
     }
-    // ---- publish; the last job of the image combines
+    // ---- publish; the last job of the image combines: the minimum over the jobs
     if (tid == 0) {
         st_relaxed_u64(g.sslots + (size_t)b * pl.Gs + gj, (u64)bound << 32);
         __threadfence();
@@ -529,7 +552,7 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
             __threadfence();
             u64 m = ~0ull;
             for (int i = 0; i < pl.Gs; ++i) { const u64 v = ld_relaxed_u64(g.sslots + (size_t)b * pl.Gs + i); m = v < m ? v : m; }
-            if (m != 0ull) atomicMax(g.thr + b, m);
+            g.sthr[b] = m;
         }
     }
 }
@@ -625,11 +648,69 @@ __device__ __forceinline__ void str_unit(const StrUnit &un, u64 *wbuf, int &cnt,
     }
 }
 
+// ---- the 128-bit path keeps STR_NG groups of STR_UN planes per warp in flight with cp.async: a warp-private
+// ring in shared memory (every lane reads back exactly the 16 bytes it fetched, so a per-thread
+// cp.async.wait_group is all the synchronisation there is), refilled right after a group has been tested.
+#ifndef STR_NG
+#define STR_NG 3
+#endif
+constexpr int STR_RING = STR_NG * STR_UN;          // planes per warp ring
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((u32)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// issue the fetch of plane group gi (planes c0 + gi*STR_UN ...) of the unit into its ring slot; always
+// commits exactly one group (an empty one past the end) so that the wait counts stay uniform
+__device__ __forceinline__ void str_issue(const float *q0, size_t HW, int nplanes, int gi, float4 *ring_lane) {
+    const int slot = (gi % STR_NG) * STR_UN;
+#pragma unroll
+    for (int u = 0; u < STR_UN; ++u) {
+        const int pl_i = gi * STR_UN + u;
+        if (pl_i < nplanes) cp_async16(ring_lane + (slot + u) * 32, q0 + (size_t)pl_i * HW);
+    }
+    cp_async_commit();
+}
+
+// consume: the prologue (groups 0 .. STR_NG-1) has been issued by the caller
+__device__ __forceinline__ void str_unit_async(const StrUnit &un, float4 *ring_lane, u64 *wbuf, int &cnt, int b,
+                                               const SelGlobal &g, int lane, u32 lt_mask) {
+    const int nplanes = un.c1 - un.c0;
+    const int ngroups = (nplanes + STR_UN - 1) / STR_UN;
+    const float *q0 = un.pc + (size_t)un.c0 * un.HW;
+    for (int gi = 0; gi < ngroups; ++gi) {
+        cp_async_wait<STR_NG - 1>();
+        const int slot = (gi % STR_NG) * STR_UN;
+        float t[STR_UN][4];
+#pragma unroll
+        for (int u = 0; u < STR_UN; ++u) {
+            if (gi * STR_UN + u < nplanes) {
+                const float4 w = ring_lane[(slot + u) * 32];
+                t[u][0] = w.x; t[u][1] = w.y; t[u][2] = w.z; t[u][3] = w.w;
+            } else {
+                t[u][0] = t[u][1] = t[u][2] = t[u][3] = CUDART_NAN_F;      // NaN >= x is false for every x
+            }
+        }
+        u32 mask = 0;
+#pragma unroll
+        for (int u = 0; u < STR_UN; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) mask |= (t[u][v] >= un.tcmin[v]) ? (1u << (u * 4 + v)) : 0u;
+        // the slot has been read into registers and tested: refill it
+        str_issue(q0, un.HW, nplanes, gi + STR_NG, ring_lane);
+        str_hits<true>(un, mask, un.c0 + gi * STR_UN, wbuf, cnt, b, g, lane, lt_mask);
+    }
+}
+
 __global__ void __launch_bounds__(STR_NT, STR_CTAS_PER_SM)
 vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl, SelGlobal g) {
     __shared__ u64 wbuf_all[STR_NT / 32][64];
+    extern __shared__ __align__(16) unsigned char str_dyn[];          // [STR_NT/32][STR_RING][32] float4
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     u64 *wbuf = wbuf_all[wid];
+    float4 *ring_lane = (float4 *)str_dyn + (size_t)wid * STR_RING * 32 + lane;
     const u32 lt_mask = (1u << lane) - 1u;
     const long long n_warps = (long long)gridDim.x * (STR_NT / 32);
     for (long long unit = (long long)blockIdx.x * (STR_NT / 32) + wid; unit < pl.n_units; unit += n_warps) {
@@ -652,12 +733,18 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
         un.o1 = min(1, max(nv - 1, 0)); un.o2 = min(2, max(nv - 1, 0)); un.o3 = min(3, max(nv - 1, 0));
         const float *p = sc.head + ((size_t)(b * hd.A + a) * hd.P) * un.HW + pos0;
         un.pc = p + 5 * un.HW;
+        const bool vec = sc.vec == 4;
+        if (vec) {
+            // the class planes do not depend on the bound: get them moving first
+            const float *q0 = un.pc + (size_t)un.c0 * un.HW;
+#pragma unroll
+            for (int gi = 0; gi < STR_NG; ++gi) str_issue(q0, un.HW, un.c1 - un.c0, gi, ring_lane);
+        }
         un.row0 = (u32)(sc.row_off + (long long)pos0 * hd.A + a);
         un.n_s = (u32)sc.n_s; un.A = (u32)hd.A;
         un.valid_thresh = pl.valid_thresh;
-        un.thr = g.thr[b];
+        un.thr = g.sthr[b];
         const float smin = fmaxf(un.thr ? vy_key_score(un.thr) : pl.valid_thresh, pl.valid_thresh);
-        const bool vec = sc.vec == 4;
         {
             float to[4];
             if (vec) str_load<true>(un, p + 4 * un.HW, to); else str_load<false>(un, p + 4 * un.HW, to);
@@ -668,7 +755,7 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
             }
         }
         int cnt = 0;                                       // keys waiting in wbuf (warp-uniform)
-        if (vec) str_unit<true>(un, wbuf, cnt, b, g, lane, lt_mask);
+        if (vec) str_unit_async(un, ring_lane, wbuf, cnt, b, g, lane, lt_mask);
         else str_unit<false>(un, wbuf, cnt, b, g, lane, lt_mask);
         if (cnt > 0) {
             int base = 0;
@@ -753,7 +840,8 @@ vy_rows_select_kernel(RowParams rp, SelPlan pl, SelGlobal g) {
 // finalize: one CTA per image
 // ------------------------------------------------------------------------------------------------
 constexpr int FIN_NT = 512;
-constexpr int FIN_SLACK = 512;       // candidates beyond K that may reach the all-pairs ranking
+constexpr int FIN_SLACK = 512;       // candidates beyond K that may reach the ranking sort
+constexpr int FIN_LCAP = 4096;       // candidate lists up to this length are staged in shared memory
 
 struct FinParams {
     int K, post_rows;            // rows written per image
@@ -762,6 +850,7 @@ struct FinParams {
     int force_suppress, in_format, out_format;
     int W;                       // output row width (6 for heads)
     int fill_rest;               // 1: this kernel writes the -1 padding rows itself
+    int lcap;                    // candidate lists up to this length are staged in shared memory (0: never)
     float *out;
     int *kept_rows;
 };
@@ -865,26 +954,33 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     const int b = blockIdx.x;
     const int K = pl.K;
     const int nwK = (K + 31) >> 5;
-    u64 *cand = (u64 *)dyn;                            // K + FIN_SLACK unordered candidates
-    float4 *box = (float4 *)(dyn + (((size_t)(K + FIN_SLACK) * 8 + 15) & ~(size_t)15));   // K by slot
+    int cp2 = 32;
+    while (cp2 < K + FIN_SLACK) cp2 <<= 1;
+    u64 *cand = (u64 *)dyn;                            // cp2 >= K + FIN_SLACK candidates (sorted in place)
+    float4 *box = (float4 *)(cand + cp2);              // K      by slot
     float *area = (float *)(box + K);                  // K      by slot
     int *cls = (int *)(area + K);                      // K      by slot
     int *seg_end = cls + K;                            // K      by slot
     int *slot_of_rank = seg_end + K;                   // K
     int *rank_of_slot = slot_of_rank + K;              // K
-    int *cls_r = rank_of_slot + K;                     // K      by rank
-    u32 *mask = (u32 *)(cls_r + K);                    // K * nwK, by slot
+    u32 *mask = (u32 *)(rank_of_slot + K);             // K * nwK, by slot
     u32 *rowany = mask + (size_t)K * nwK;              // 32     by slot
     u32 *keepw = rowany + 32;                          // 32     by rank
-    int *kprefix = (int *)(keepw + 32);                // 33
+    int *kprefix = (int *)(keepw + 32);                // 33 (+3 pad)
+    u64 *lbuf = (u64 *)(((uintptr_t)(kprefix + 36) + 15) & ~(uintptr_t)15);   // FIN_LCAP: a short candidate list, staged
 
     // ---- 1. exact top-K of the image's candidate list, sorted descending
-    if (tid == 0) { S.count = 0; S.thr = g.thr[b]; }
-    __syncthreads();
-    // streaming path: the streamed list, unless it overflowed and the rescue pass rebuilt g.list
-    const bool use_s = g.scount != nullptr && g.scount[b] <= g.slist_cap;
+    // streaming path: the streamed list, unless it was unusable and the rescue pass rebuilt g.list
+    const bool use_s = g.scount != nullptr && stream_list_ok(g, b, K);
     const int n_list = use_s ? g.scount[b] : min(g.count[b], pl.list_cap);
     const u64 *list = use_s ? g.slist + (size_t)b * g.slist_cap : g.list + (size_t)b * pl.list_cap;
+    if (tid == 0) { S.count = 0; S.thr = use_s ? g.sthr[b] : g.thr[b]; }
+    if (n_list > K + FIN_SLACK && n_list <= fp.lcap) {
+        // the radix sweeps below then never leave the SM
+        for (int i = tid; i < n_list; i += FIN_NT) lbuf[i] = list[i];
+        list = lbuf;
+    }
+    __syncthreads();
     if (n_list > K + FIN_SLACK) {
         // long list: bound its K-th largest key first, so that one sweep leaves <= K + FIN_SLACK keys
         const u64 p = fin_list_bound(S, list, n_list, K, FIN_SLACK);
@@ -902,32 +998,45 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     __syncthreads();
     const int m1 = min(S.count, K + FIN_SLACK);
     const int m = min(m1, K);                           // <= K candidates take part
-    // rank = number of larger keys (keys are unique: the row is part of the key); all pairs, the
-    // compared key is a shared-memory broadcast
-    for (int i = tid; i < m1; i += FIN_NT) {
-        const u64 mine = cand[i];
-        int rank = 0;
-        for (int j = 0; j < m1; ++j) rank += cand[j] > mine;
-        if (rank < K) keyr[rank] = mine;
+    // rank: keys are unique (the row is part of the key), so a descending sort IS the operator's
+    // stable order; bitonic network over the zero-padded buffer
+    {
+        int np2 = 32;
+        while (np2 < m1) np2 <<= 1;
+        for (int i = m1 + tid; i < np2; i += FIN_NT) cand[i] = 0ull;
+        __syncthreads();
+        sel_sort_desc(cand, np2);
+        for (int i = tid; i < m; i += FIN_NT) keyr[i] = cand[i];
     }
     for (int i = tid; i < m * nwK; i += FIN_NT) mask[i] = 0u;
     if (tid < 32) { rowany[tid] = 0; keepw[tid] = 0; }
     __syncthreads();
 
-    // ---- 2. regroup by class, stable in rank: slot = #{(class, rank) pairs below mine}
+    // ---- 2. regroup by class, stable in rank: ascending sort of (class, rank) pairs
     const bool all_pairs = fp.force_suppress || (SRC == 1 && rp.id_index < 0) || (SRC == 0 && hd.agnostic);
-    for (int i = tid; i < m; i += FIN_NT) cls_r[i] = all_pairs ? 0 : fin_class<SRC>(hd, rp, b, vy_key_row(keyr[i]));
+    if (!all_pairs) {
+        int mp2 = 32;
+        while (mp2 < m) mp2 <<= 1;
+        for (int i = tid; i < mp2; i += FIN_NT) {
+            u64 k = 0ull;                               // padding: ~0 = last in ascending order
+            if (i < m) k = ~(((u64)((u32)fin_class<SRC>(hd, rp, b, vy_key_row(keyr[i])) ^ 0x80000000u) << 32) | (u64)i);
+            cand[i] = k;
+        }
+        __syncthreads();
+        sel_sort_desc(cand, mp2);                       // descending in ~key = ascending in (class, rank)
+        for (int slot = tid; slot < m; slot += FIN_NT) {
+            const u64 k = ~cand[slot];
+            const int rank = (int)(u32)(k & 0xffffffffull);
+            slot_of_rank[rank] = slot;
+            rank_of_slot[slot] = rank;
+            cls[slot] = (int)((u32)(k >> 32) ^ 0x80000000u);
+        }
+    } else {
+        for (int i = tid; i < m; i += FIN_NT) { slot_of_rank[i] = i; rank_of_slot[i] = i; cls[i] = 0; }
+    }
     __syncthreads();
     for (int i = tid; i < m; i += FIN_NT) {
-        const int c = cls_r[i];
-        int slot = i;
-        if (!all_pairs) {
-            slot = 0;
-            for (int j = 0; j < m; ++j) { const int cj = cls_r[j]; slot += (cj < c) || (cj == c && j < i); }
-        }
-        slot_of_rank[i] = slot;
-        rank_of_slot[slot] = i;
-        cls[slot] = c;
+        const int slot = slot_of_rank[i];
         const float4 bx = fin_box<SRC>(hd, rp, b, vy_key_row(keyr[i]));
         box[slot] = bx;
         area[slot] = nms_area(bx, fp.in_format);
@@ -1067,10 +1176,17 @@ __global__ void vy_fill_kernel(float *out, int *kept, size_t n_out, size_t n_kep
 // ------------------------------------------------------------------------------------------------
 // host: planning + launches
 // ------------------------------------------------------------------------------------------------
-static size_t fin_dyn_smem(int K) {
+// shared memory of the finalize kernel; *lcap = how long a staged candidate list may be
+static size_t fin_dyn_smem(int K, int *lcap) {
     const int nwK = (K + 31) / 32;
-    return (((size_t)(K + FIN_SLACK) * 8 + 15) & ~(size_t)15) + (size_t)K * (16 + 4 + 4 + 4 + 4 + 4 + 4) +
-           (size_t)K * nwK * 4 + 32 * 4 + 32 * 4 + 33 * 4 + 16;
+    size_t cp2 = 32;
+    while (cp2 < (size_t)(K + FIN_SLACK)) cp2 <<= 1;
+    const size_t base = cp2 * 8 + (size_t)K * (16 + 4 + 4 + 4 + 4 + 4) + (size_t)K * nwK * 4 + 32 * 4 + 32 * 4 + 36 * 4 + 16;
+    const size_t budget = 227 * 1024 - sizeof(SelBuf) - 2048;        // per-CTA limit minus the static part
+    int cap = FIN_LCAP;
+    if (base + (size_t)cap * 8 > budget) cap = 0;
+    if (lcap) *lcap = cap;
+    return base + (size_t)cap * 8;
 }
 
 // CTAs that can be resident at once (SEL_CTAS_PER_SM per SM by __launch_bounds__)
@@ -1115,22 +1231,28 @@ static int plan_heads(const VyHeads &hd, int topk, float valid_thresh, SelPlan *
 static void plan_stream(const VyHeads &hd, SelPlan *pl) {
     pl->stream = 0;
     if (hd.agnostic || hd.R < 131072 || hd.C < 1) return;
-    // sampled fraction 1/S: about K*S candidates per image reach the list (distribution-free)
+    // sampled fraction 1/S
     long long S = hd.R / (40LL * pl->K);
     if (S < 4) return;
     if (S > 32) S = 32;
+    const long long resident = 2LL * vy_sm_count();                     // __launch_bounds__(SAMP_NT, 2)
     for (;; S *= 2) {
         const long long runs = ((long long)pl->items_per_frame + SAMP_RUN * S - 1) / (SAMP_RUN * S);
         const long long items = runs * SAMP_RUN;
         // jobs: item blocks of <= SAMP_NT items x plane blocks; a thread owns <= SAMP_MAXK planes
-        long long ib = (items + SAMP_NT - 1) / SAMP_NT;
-        long long ipj = (items + ib - 1) / ib;
-        long long pls = SAMP_NT / ipj;                                  // >= 1
-        long long pbk = (hd.C + pls * 8 - 1) / (pls * 8);               // aim at ~8 planes per thread
-        if (pbk < 1) pbk = 1;
+        const long long ib = (items + SAMP_NT - 1) / SAMP_NT;
+        const long long ipj = (items + ib - 1) / ib;
+        const long long pls = SAMP_NT / ipj;                            // >= 1
+        const long long pbk_min = (hd.C + pls * SAMP_MAXK - 1) / (pls * SAMP_MAXK);
+        long long pbk_max = (hd.C + pls * 8 - 1) / (pls * 8);           // no fewer than ~8 planes per thread
+        if (pbk_max < pbk_min) pbk_max = pbk_min;
+        // as many plane blocks as still fit the whole grid in ONE wave of resident CTAs
+        long long pbk = resident / ((long long)hd.B * ib);
+        if (pbk > pbk_max) pbk = pbk_max;
+        if (pbk < pbk_min) pbk = pbk_min;
         if (ib * pbk > SEL_GMAX) pbk = SEL_GMAX / ib;
-        if (pbk < 1) continue;                                          // too many item blocks: sample less
-        long long ppj = (hd.C + pbk - 1) / pbk;
+        if (pbk < pbk_min || pbk < 1) continue;                         // too many item blocks: sample less
+        const long long ppj = (hd.C + pbk - 1) / pbk;
         pbk = (hd.C + ppj - 1) / ppj;
         if (ppj > pls * SAMP_MAXK) continue;                            // too many planes per thread
         if (ib * pbk > pl->K) continue;
@@ -1141,7 +1263,20 @@ static void plan_stream(const VyHeads &hd, SelPlan *pl) {
         pl->Gs = (int)(ib * pbk);
         break;
     }
-    pl->Ksq = (pl->K + pl->Gs - 1) / pl->Gs;
+    // The bound handed to the streaming pass is the minimum over the Gs jobs of each job's Ksq-th largest
+    // sampled score.  With Ksq = ceil(K/Gs) that is a guaranteed lower bound of the image's K-th largest
+    // score (disjoint subsets hold >= K scores above it) but lets ~K*S candidates through.  Aiming the
+    // sample at rank ~4K instead (j = 4K/S sampled scores) cuts the candidate lists ~S/4-fold; the estimate
+    // is below the K-th largest score except with negligible probability (rank std ~ S*sqrt(j) << 3K), and
+    // an image where it is not (fewer than K candidates found under a non-trivial bound) is redone exactly
+    // by the rescue pass (stream_list_ok).
+    long long j = (4LL * pl->K + pl->samp_stride - 1) / pl->samp_stride;
+    if (j > pl->K) j = pl->K;
+    long long ksq = (j + pl->Gs - 1) / pl->Gs;
+    if (ksq < 8) ksq = 8;
+    const long long ksq_sure = ((long long)pl->K + pl->Gs - 1) / pl->Gs;
+    if (ksq > ksq_sure) ksq = ksq_sure;
+    pl->Ksq = (int)ksq;
     pl->n_groups = (hd.C + 95) / 96;
     pl->PU = (hd.C + pl->n_groups - 1) / pl->n_groups;
     int units = 0;
@@ -1185,7 +1320,7 @@ static int select_grid(int n_jobs) {
 template <int SRC>
 static int launch_finalize(const VyHeads &hd, const RowParams &rp, const SelPlan &pl, const SelGlobal &g,
                            FinParams fp, int B, cudaStream_t st) {
-    const size_t dyn = fin_dyn_smem(pl.K);
+    const size_t dyn = fin_dyn_smem(pl.K, &fp.lcap);
     VY_CUDA_CHECK(cudaFuncSetAttribute(vy_nms_finalize_kernel<SRC>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     VY_KERNEL(VY_K_FINALIZE, st, (vy_nms_finalize_kernel<SRC><<<B, FIN_NT, dyn, st>>>(hd, rp, pl, g, fp)));
@@ -1236,7 +1371,9 @@ extern "C" int vy_decode_nms_f32(const float *const *head, const int *H, const i
         long long ctas = (pl.n_units + STR_NT / 32 - 1) / (STR_NT / 32);
         const long long resident = (long long)STR_CTAS_PER_SM * vy_sm_count();
         if (ctas > resident) ctas = resident;
-        VY_KERNEL(VY_K_STREAM, st, (vy_decode_stream_kernel<<<(unsigned)ctas, STR_NT, 0, st>>>(hd, pl, g)));
+        const size_t ring_bytes = (size_t)(STR_NT / 32) * STR_RING * 32 * sizeof(float4);
+        VY_CUDA_CHECK(cudaFuncSetAttribute(vy_decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+        VY_KERNEL(VY_K_STREAM, st, (vy_decode_stream_kernel<<<(unsigned)ctas, STR_NT, ring_bytes, st>>>(hd, pl, g)));
         VY_LAUNCH_CHECK("vy_decode_stream_kernel");
     }
     VY_KERNEL(VY_K_SELECT_HEADS, st, (vy_decode_select_kernel<<<select_grid(pl.n_jobs), SEL_NT, 0, st>>>(hd, pl, g)));
