@@ -12,6 +12,8 @@
 #include "vy_select.cuh"
 #include "vy_nms_math.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
+#include <vector>
 
 // ------------------------------------------------------------------------------------------------
 // job plan shared by workspace sizing and launch
@@ -583,9 +585,12 @@ __device__ __forceinline__ void str_load(const StrUnit &un, const float *q, floa
 
 // rare path, warp-synchronous: every lane evaluates at most one hit per round; survivors go to the
 // warp's buffer, which leaves as one atomic + one 256-byte store per 32 keys
+// ring_group: the 128-bit path passes the ring slot of plane c (the logits are re-read from shared
+// memory, LDS latency instead of an L2 round trip: cp.async.cg leaves nothing in L1); nullptr: re-read
+// from global memory.
 template <bool VEC>
 __device__ __forceinline__ void str_hits(const StrUnit &un, u32 mask, int c, u64 *wbuf, int &cnt, int b,
-                                         const SelGlobal &g, int lane, u32 lt_mask) {
+                                         const SelGlobal &g, int lane, u32 lt_mask, const float4 *ring_group = nullptr) {
     while (__any_sync(0xffffffffu, mask != 0u)) {
         bool ok = false;
         u64 key = 0;
@@ -595,7 +600,8 @@ __device__ __forceinline__ void str_hits(const StrUnit &un, u32 mask, int c, u64
             const int u = k >> 2, v = k & 3;
             const int ov = VEC ? v : (v == 0 ? 0 : (v == 1 ? un.o1 : (v == 2 ? un.o2 : un.o3)));
             const float cf = v == 0 ? un.conf[0] : (v == 1 ? un.conf[1] : (v == 2 ? un.conf[2] : un.conf[3]));
-            const float tv = vy_ldg32_ca(un.pc + (size_t)(c + u) * un.HW + ov);
+            const float tv = ring_group ? ((const float *)(ring_group + u * 32))[v]
+                                        : vy_ldg32_ca(un.pc + (size_t)(c + u) * un.HW + ov);
             const float sv = vy_score(tv, cf);
             if (sv > un.valid_thresh) {
                 key = vy_make_key(sv, un.row0 + (u32)(c + u) * un.n_s + (u32)v * un.A);
@@ -698,9 +704,9 @@ __device__ __forceinline__ void str_unit_async(const StrUnit &un, float4 *ring_l
         for (int u = 0; u < STR_UN; ++u)
 #pragma unroll
             for (int v = 0; v < 4; ++v) mask |= (t[u][v] >= un.tcmin[v]) ? (1u << (u * 4 + v)) : 0u;
-        // the slot has been read into registers and tested: refill it
+        // hits re-read their logit from the ring, so the slot is refilled only afterwards
+        str_hits<true>(un, mask, un.c0 + gi * STR_UN, wbuf, cnt, b, g, lane, lt_mask, ring_lane + slot * 32);
         str_issue(q0, un.HW, nplanes, gi + STR_NG, ring_lane);
-        str_hits<true>(un, mask, un.c0 + gi * STR_UN, wbuf, cnt, b, g, lane, lt_mask);
     }
 }
 
@@ -1005,7 +1011,7 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
         while (np2 < m1) np2 <<= 1;
         for (int i = m1 + tid; i < np2; i += FIN_NT) cand[i] = 0ull;
         __syncthreads();
-        sel_sort_desc(cand, np2);
+        sel_sort_desc_fast(cand, np2);
         for (int i = tid; i < m; i += FIN_NT) keyr[i] = cand[i];
     }
     for (int i = tid; i < m * nwK; i += FIN_NT) mask[i] = 0u;
@@ -1023,7 +1029,7 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
             cand[i] = k;
         }
         __syncthreads();
-        sel_sort_desc(cand, mp2);                       // descending in ~key = ascending in (class, rank)
+        sel_sort_desc_fast(cand, mp2);                  // descending in ~key = ascending in (class, rank)
         for (int slot = tid; slot < m; slot += FIN_NT) {
             const u64 k = ~cand[slot];
             const int rank = (int)(u32)(k & 0xffffffffull);
@@ -1385,7 +1391,24 @@ extern "C" int vy_decode_nms_f32(const float *const *head, const int *H, const i
     fp.out = out; fp.kept_rows = kept_rows;
     RowParams rp;
     memset(&rp, 0, sizeof(rp));
-    return launch_finalize<0>(hd, rp, pl, g, fp, B, st);
+    rc = launch_finalize<0>(hd, rp, pl, g, fp, B, st);
+    // VY_DEBUG_LISTS=1: (debugging aid, synchronises) print the fill of the streamed candidate lists
+    static const bool dbg = getenv("VY_DEBUG_LISTS") != nullptr;
+    if (dbg && pl.stream && rc == VY_OK) {
+        std::vector<int> cnt(B);
+        std::vector<u64> thr(B);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(cnt.data(), g.scount, sizeof(int) * B, cudaMemcpyDeviceToHost);
+        cudaMemcpy(thr.data(), g.sthr, sizeof(u64) * B, cudaMemcpyDeviceToHost);
+        long long sum = 0; int mn = 1 << 30, mx = 0, bad = 0;
+        for (int i = 0; i < B; ++i) {
+            sum += cnt[i]; mn = cnt[i] < mn ? cnt[i] : mn; mx = cnt[i] > mx ? cnt[i] : mx;
+            bad += cnt[i] > g.slist_cap || (cnt[i] < pl.K && thr[i] != 0ull);
+        }
+        fprintf(stderr, "[vyolo] streamed lists: K=%d S=%d Gs=%d Ksq=%d cap=%d | fill mean %.0f min %d max %d | rescued %d of %d\n",
+                pl.K, pl.samp_stride, pl.Gs, pl.Ksq, g.slist_cap, (double)sum / B, mn, mx, bad, B);
+    }
+    return rc;
 }
 
 // implemented in vy_nms_large.cu: topk < 0 or min(topk,R) > SEL_KMAX

@@ -214,3 +214,48 @@ static __device__ __noinline__ void sel_sort_desc(u64 *keys, int npow2) {
         }
     }
 }
+
+// Same result as sel_sort_desc for npow2 <= 2 * blockDim.x, with ~4x fewer CTA barriers: thread t owns the
+// adjacent elements 2t and 2t+1 in registers; compare-exchange distances 1..32 stay inside the thread /
+// the warp (shuffles), only distances >= 64 go through shared memory.
+__device__ __forceinline__ u64 sel_shfl_xor_u64(u64 v, int lane_mask) {
+    const u32 lo = __shfl_xor_sync(0xffffffffu, (u32)v, lane_mask);
+    const u32 hi = __shfl_xor_sync(0xffffffffu, (u32)(v >> 32), lane_mask);
+    return ((u64)hi << 32) | lo;
+}
+static __device__ __noinline__ void sel_sort_desc_fast(u64 *keys, int npow2) {
+    const int tid = threadIdx.x;
+    if (npow2 > 2 * (int)blockDim.x || npow2 < 64) { sel_sort_desc(keys, npow2); return; }
+    const bool act = 2 * tid < npow2;                 // whole warps: npow2 >= 64
+    const int p0 = 2 * tid;
+    for (int k = 2; k <= npow2; k <<= 1) {
+        int j = k >> 1;
+        for (; j >= 64; j >>= 1) {                    // shared-memory stages
+            for (int p = tid; p < (npow2 >> 1); p += blockDim.x) {
+                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                const int l = i | j;
+                const u64 a = keys[i], b = keys[l];
+                const bool desc = (i & k) == 0;
+                if ((a < b) == desc) { keys[i] = b; keys[l] = a; }
+            }
+            __syncthreads();
+        }
+        if (act) {                                    // distances 32 .. 1 in registers
+            u64 a = keys[p0], b = keys[p0 + 1];
+            for (; j >= 2; j >>= 1) {
+                const u64 ya = sel_shfl_xor_u64(a, j >> 1), yb = sel_shfl_xor_u64(b, j >> 1);
+                const bool lower = (p0 & j) == 0;     // both of my elements sit on the same side
+                const bool desc = ((p0 & ~j) & k) == 0;
+                const bool keep_max = lower == desc;
+                a = keep_max ? (a > ya ? a : ya) : (a < ya ? a : ya);
+                b = keep_max ? (b > yb ? b : yb) : (b < yb ? b : yb);
+            }
+            {                                         // distance 1: my own pair
+                const bool desc = (p0 & k) == 0;
+                if ((a < b) == desc) { const u64 t = a; a = b; b = t; }
+            }
+            keys[p0] = a; keys[p0 + 1] = b;
+        }
+        __syncthreads();
+    }
+}
