@@ -65,6 +65,56 @@ def load_peaks():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def load_bf16_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["bf16_tflops"]), "measured burst (MEASURED_PEAKS.json bf16_tflops)"
+    except Exception:
+        return 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def fusion_conv_leg(dev, B=8, T=3, iters=10):
+    """Temporal fusion conv (layers.py:73-79 as used at yolo3.py:250-251): the three K=3 tip convs of
+    BASELINE configs[2] (ImageNet-VID 416^2), 3x3x3, Cin -> 2*Cin, bf16 operands / fp32 accumulation in
+    TMEM.  Kernel timed alone (CUDA events, L2 flushed between launches) against the measured cuBLAS bf16
+    burst peak.  'formula' FLOPs = SURVEY 8d: 2*B*T*H*W*Cout*Cin*27 (counts the zero-padded temporal taps
+    the kernel skips and not the border pixels it computes); 'executed' = what the tensor pipe really did."""
+    import torch
+    from videoyolo_b200 import ops
+    peak, src = load_bf16_peak()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = []
+    for g, cin in ((13, 512), (26, 256), (52, 128)):
+        cout = 2 * cin
+        x = ops.PTensor(torch.zeros((T, B, g + 2, g + 2, cin), dtype=torch.bfloat16, device=dev), B, T, g, g, cin)
+        x.data[:, :, 1:-1, 1:-1] = torch.randn((T, B, g, g, cin), device=dev).to(torch.bfloat16)
+        w = (torch.rand((cout, 3, 3, 3, cin), device=dev) * 0.14 - 0.07).to(torch.bfloat16)      # MXNet Uniform(0.07)
+        sc, sh = torch.ones(cout, device=dev), torch.zeros(cout, device=dev)
+        for _ in range(3):
+            ops.fusion_conv(x, w, sc, sh)
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); ops.fusion_conv(x, w, sc, sh); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = sorted(ts)[len(ts) // 2]
+        f_formula = 2.0 * B * T * g * g * cout * cin * 27
+        rows = -(-(B * (g + 2) * (g + 2)) // 128) * 128
+        taps = sum(sum(1 for dt in (-1, 0, 1) if 0 <= t + dt < T) for t in range(T)) * 9
+        f_exec = 2.0 * rows * cout * cin * taps
+        out.append({"shape": "B%d T%d %dx%d %d->%d k3x3x3" % (B, T, g, g, cin, cout), "ms": round(ms, 4),
+                    "tflops_formula": round(f_formula / ms / 1e9, 1), "tflops_executed": round(f_exec / ms / 1e9, 1),
+                    "frac_formula": round(f_formula / ms / 1e9 / peak, 4), "frac_executed": round(f_exec / ms / 1e9 / peak, 4)})
+    tot_ms = sum(o["ms"] for o in out)
+    return {"workload": "configs[2] fusion conv: K=3 tip convs of YOLODetectionBlockV3 at 416^2, batch %d windows" % B,
+            "bound": "tensor", "unit": "TFLOP/s", "peak": peak, "peak_source": src, "dtype": "bf16 x bf16 -> f32 (TMEM)",
+            "windows_per_s": round(B / (tot_ms * 1e-3), 1), "shapes": out,
+            "l2": "L2 flushed between launches (256 MiB write)"}
+
+
 def load_traffic(config_name, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
     `ncu --set full` capture (profiles/roofline_traffic.json), or None."""
@@ -189,6 +239,7 @@ def main():
     ap.add_argument("--regime", default="R", choices=["R", "T"], help="R: N(0,1) logits (random-init); T: trained-like")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-conv", action="store_true", help="skip the fusion-conv (tensor-pipe) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -344,6 +395,14 @@ def main():
         del h_heads
     sampler.stop()
 
+    # ---- temporal fusion conv: the tensor-core part of the path (rank 0 only; not part of `value`)
+    conv = None
+    if rank == 0 and not args.no_conv:
+        try:
+            conv = fusion_conv_leg(dev)
+        except Exception as e:                     # the headline line must still be printed
+            conv = {"error": str(e)[:200]}
+
     # ---- cpu baseline (rank 0, N=1 only): oracle port on a bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -371,7 +430,7 @@ def main():
                            "nms": NMS, "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world,
                            "l2": ("inputs larger than L2 (%.0f MB per step)" % (in_bytes / 1e6)) if flush is None
                                  else "L2 flushed between steps (256 MiB write)"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fusion_conv": conv, "gpu_launches": gpu_launches,
                 "launches_per_step": per_step, "clocks": sampler.summary()}
         print(json.dumps(line))
     if world > 1:

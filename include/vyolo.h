@@ -170,6 +170,16 @@ int vy_unpack_p_to_f32(const void *y_p, int p_is_f32, int B, int C, int T, int H
  * inner = B*(H+2)*(W+2)*C, mode 0 = max, 1 = mean.  bf16 in/out. */
 int vy_temporal_pool_bf16(const void *x, int T, long inner, int mode, void *y, vy_stream_t stream);
 
+/* Depthwise temporal merge of a window of T frames into one.
+ * Replaces: _conv1d(channels, kernel=T, padding=0, strides=1), models/definitions/layers.py:50-60
+ *           = Conv3D(kernel (T,1,1), groups=channels, use_bias=False) + BatchNorm + LeakyReLU(0.1), as
+ *           applied per window by HDarknet (models/definitions/darknet/h_darknet.py:97-119).
+ *   x      P layout (T, B, H+2, W+2, C) bf16;  w (C, T) fp32 = the reference weight (C, 1, T, 1, 1)
+ *   scale, shift  folded inference BatchNorm per channel;  y P layout (1, B, H+2, W+2, C) bf16
+ *   requires C % 8 == 0.  Accounted under VY_K_TEMPORAL_POOL. */
+int vy_temporal_dwconv_bf16(const void *x, const float *w, const float *scale, const float *shift,
+                            float leaky_slope, int B, int T, int H, int W, int C, void *y, vy_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

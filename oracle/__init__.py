@@ -291,7 +291,7 @@ def bbox_iou(bbox_a: np.ndarray, bbox_b: np.ndarray, offset=0) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------- fusion conv
-def conv_bn_leaky(x, w, gamma, beta, mean, var, padding, stride=1, eps=1e-5, slope=0.1):
+def conv_bn_leaky(x, w, gamma, beta, mean, var, padding, stride=1, eps=1e-5, slope=0.1, groups=1):
     """LeakyReLU_0.1(BN_eps1e-5(ConvND(x))), use_bias=False -- layers.py:63-79.
 
     x: (B, Cin, [T,] H, W) fp32 (NCHW / NCDHW like the reference), w: (Cout, Cin, [kt,] kh, kw).
@@ -302,7 +302,7 @@ def conv_bn_leaky(x, w, gamma, beta, mean, var, padding, stride=1, eps=1e-5, slo
     x = torch.as_tensor(np.asarray(x), dtype=torch.float32)
     w = torch.as_tensor(np.asarray(w), dtype=torch.float32)
     conv = F.conv3d if x.dim() == 5 else F.conv2d
-    y = conv(x, w, bias=None, stride=stride, padding=padding)
+    y = conv(x, w, bias=None, stride=stride, padding=padding, groups=groups)
     shape = [1, -1] + [1] * (x.dim() - 2)
     g, b_, m, v = (torch.as_tensor(np.asarray(t), dtype=torch.float32).reshape(shape)
                    for t in (gamma, beta, mean, var))
@@ -314,6 +314,12 @@ def conv21d_bn_leaky(x, w_s, bn_s, w_t, bn_t, padding=1, stride=1):
     """_conv21d (layers.py:82-89): (1,d,d) conv+BN+LReLU then (t,1,1) conv+BN+LReLU."""
     y = conv_bn_leaky(x, w_s, *bn_s, padding=(0, padding, padding), stride=stride)
     return conv_bn_leaky(y, w_t, *bn_t, padding=(padding, 0, 0), stride=stride)
+
+
+def conv1d_bn_leaky(x, w, gamma, beta, mean, var):
+    """_conv1d (layers.py:50-60) on one window: x (B, C, T, H, W), w (C, 1, T, 1, 1); depthwise
+    Conv3D(kernel (T,1,1), groups=C, padding 0) + BN + LeakyReLU -> (B, C, 1, H, W)."""
+    return conv_bn_leaky(x, w, gamma, beta, mean, var, padding=0, groups=np.asarray(w).shape[0])
 
 
 def temporal_pool(x: np.ndarray, type: str = "max") -> np.ndarray:

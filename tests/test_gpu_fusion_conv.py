@@ -126,6 +126,27 @@ def test_pack_unpack_roundtrip_and_pool(vy):
         np.testing.assert_allclose(got, ref, rtol=1e-2, atol=1e-2)
 
 
+def test_temporal_dwconv_matches_oracle(vy):
+    """_conv1d temporal merge (layers.py:50-60, h_darknet.py:97-119): window of 3 frames, C=32."""
+    rng = np.random.RandomState(21)
+    ops = vy.ops
+    for (B, C, T, H, W) in [(2, 32, 3, 20, 20), (3, 64, 5, 7, 9)]:
+        x = bf16_round(rng.normal(0, 1, size=(B, C, T, H, W)).astype(np.float32))
+        w = rng.uniform(-0.5, 0.5, size=(C, 1, T, 1, 1)).astype(np.float32)
+        gamma = rng.uniform(0.5, 1.5, C).astype(np.float32)
+        beta = rng.normal(0, 0.2, C).astype(np.float32)
+        mean = rng.normal(0, 0.2, C).astype(np.float32)
+        var = rng.uniform(0.5, 2.0, C).astype(np.float32)
+        xp = ops.pack_p(torch.from_numpy(x).cuda(), "NCDHW")
+        scale, shift = ops.fold_bn(*[torch.from_numpy(v).cuda() for v in (gamma, beta, mean, var)])
+        y = ops.temporal_dwconv(xp, torch.from_numpy(w).cuda(), scale, shift, 0.1)
+        d = y.data.float()
+        assert float(d[:, :, 0].abs().max()) == 0 and float(d[:, :, :, -1].abs().max()) == 0     # border stays zero
+        got = ops.unpack_p(y, "NCDHW").cpu().numpy()
+        ref = oracle.conv1d_bn_leaky(x, w, gamma, beta, mean, var)
+        check(got, ref, "conv1d %s" % ((B, C, T, H, W),))
+
+
 def test_fusion_conv_rejects_bad_shapes(vy):
     ops = vy.ops
     xp = ops.pack_p(torch.zeros(1, 48, 3, 5, 5).cuda(), "NCDHW")

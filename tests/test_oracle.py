@@ -212,3 +212,19 @@ def test_conv_inflation_identity():
     y3 = oracle.conv_bn_leaky(x3, w3, *bn, padding=1)
     np.testing.assert_allclose(y3[:, :, 2], y2, rtol=1e-4, atol=1e-5)
     assert oracle.temporal_pool(np.stack([x2, 2 * x2], 1), "max").shape == x2.shape
+
+
+def test_conv1d_temporal_merge_closed_form():
+    """_conv1d (layers.py:50-60): depthwise (T,1,1) conv over a window == per-channel weighted sum of frames."""
+    rng = np.random.RandomState(3)
+    x = rng.normal(size=(2, 8, 3, 4, 5)).astype(np.float32)
+    w = rng.normal(size=(8, 1, 3, 1, 1)).astype(np.float32)
+    g, b, m, v = (rng.uniform(0.5, 1.5, 8).astype(np.float32), rng.normal(size=8).astype(np.float32),
+                  rng.normal(size=8).astype(np.float32), rng.uniform(0.5, 2, 8).astype(np.float32))
+    y = oracle.conv1d_bn_leaky(x, w, g, b, m, v)
+    assert y.shape == (2, 8, 1, 4, 5)
+    s = (x * w.reshape(1, 8, 3, 1, 1)).sum(axis=2, keepdims=True)
+    sh = (1, 8, 1, 1, 1)
+    ref = (s - m.reshape(sh)) / np.sqrt(v.reshape(sh) + 1e-5) * g.reshape(sh) + b.reshape(sh)
+    ref = np.where(ref > 0, ref, 0.1 * ref)
+    np.testing.assert_allclose(y, ref, rtol=1e-5, atol=1e-5)

@@ -46,6 +46,8 @@ SIGNATURES = {
     "vy_fusion_conv_bf16": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_float] + [ctypes.c_int] * 9 +
                             [c_vp, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp]),
     "vy_temporal_pool_bf16": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_long, ctypes.c_int, c_vp, c_vp]),
+    "vy_temporal_dwconv_bf16": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "vy_p_layout_elems": (ctypes.c_size_t, [ctypes.c_int] * 5),
     "vy_pack_f32_to_p_bf16": (ctypes.c_int, [c_vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong] +
                               [ctypes.c_int] * 5 + [c_vp, c_vp]),

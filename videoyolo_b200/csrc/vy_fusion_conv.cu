@@ -333,6 +333,47 @@ __global__ void vy_temporal_pool_kernel(const uint4 *__restrict__ x, int T, long
     }
 }
 
+
+// Depthwise temporal merge (_conv1d, layers.py:50-60, as used by HDarknet h_darknet.py:97-119): a window of
+// exactly T = kernel frames, Conv3D(kernel (T,1,1), groups = C, padding 0) + BN + LeakyReLU -> one frame:
+//   y[i] = LReLU(scale[c] * sum_t w[c][t] * x[t][i] + shift[c]),  c = i % C,  border pixels stay zero.
+// Bandwidth-bound: (T + 1) * inner * 2 bytes; 8 channels (one 16-byte vector) per thread and frame.
+__global__ void vy_temporal_dwconv_kernel(const uint4 *__restrict__ x, int T, long long inner8, int C8, int Hp, int Wp,
+                                          const float *__restrict__ w, const float *__restrict__ scale,
+                                          const float *__restrict__ shift, float slope, uint4 *__restrict__ y) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < inner8; i += stride) {
+        const int c0 = (int)(i % C8) * 8;
+        const long long pix = i / C8;
+        const int wp = (int)(pix % Wp), hp = (int)((pix / Wp) % Hp);
+        const bool interior = hp > 0 && hp < Hp - 1 && wp > 0 && wp < Wp - 1;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+        for (int t = 0; t < T; ++t) {
+            const uint4 q = x[(size_t)t * inner8 + i];
+            const __nv_bfloat162 *h = (const __nv_bfloat162 *)&q;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __bfloat1622float2(h[k]);
+                acc[2 * k] = fmaf(f.x, __ldg(w + (size_t)(c0 + 2 * k) * T + t), acc[2 * k]);
+                acc[2 * k + 1] = fmaf(f.y, __ldg(w + (size_t)(c0 + 2 * k + 1) * T + t), acc[2 * k + 1]);
+            }
+        }
+        uint4 o;
+        __nv_bfloat162 *oh = (__nv_bfloat162 *)&o;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float a = fmaf(acc[2 * k], __ldg(scale + c0 + 2 * k), __ldg(shift + c0 + 2 * k));
+            float b = fmaf(acc[2 * k + 1], __ldg(scale + c0 + 2 * k + 1), __ldg(shift + c0 + 2 * k + 1));
+            a = a > 0.0f ? a : a * slope;
+            b = b > 0.0f ? b : b * slope;
+            oh[k] = __floats2bfloat162_rn(interior ? a : 0.0f, interior ? b : 0.0f);
+        }
+        y[i] = o;
+    }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -471,5 +512,22 @@ extern "C" int vy_temporal_pool_bf16(const void *x, int T, long inner, int mode,
     if (blocks > cap) blocks = cap;
     VY_KERNEL(VY_K_TEMPORAL_POOL, st, (vy_temporal_pool_kernel<<<(unsigned)blocks, 256, 0, st>>>((const uint4 *)x, T, n8, mode, (uint4 *)y)));
     VY_LAUNCH_CHECK("vy_temporal_pool_kernel");
+    return VY_OK;
+}
+
+extern "C" int vy_temporal_dwconv_bf16(const void *x, const float *w, const float *scale, const float *shift,
+                                       float leaky_slope, int B, int T, int H, int W, int C, void *y, vy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x || !w || !scale || !shift || !y || B < 1 || T < 1 || H < 1 || W < 1 || C < 1)
+        VY_FAIL(VY_EINVAL, "vy_temporal_dwconv_bf16: bad arguments");
+    if (C % 8 != 0 || (((uintptr_t)x | (uintptr_t)y) & 15) != 0)
+        VY_FAIL(VY_EALIGN, "vy_temporal_dwconv_bf16: C must be a multiple of 8 and x, y 16-byte aligned");
+    const long long n8 = (long long)B * (H + 2) * (W + 2) * (C / 8);
+    long long blocks = (n8 + 255) / 256;
+    const long long cap = (long long)vy_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    VY_KERNEL(VY_K_TEMPORAL_POOL, st, (vy_temporal_dwconv_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+        (const uint4 *)x, T, n8, C / 8, H + 2, W + 2, w, scale, shift, leaky_slope, (uint4 *)y)));
+    VY_LAUNCH_CHECK("vy_temporal_dwconv_kernel");
     return VY_OK;
 }

@@ -55,7 +55,7 @@ struct SelGlobal {              // workspace views
     u64 *slots;                 // [B][G]     per-CTA ceil(K/G)-th largest
     u64 *list;                  // [B][list_cap]
     // streaming path only (see "sample + stream" below); null otherwise
-    u64 *sthr;                  // [B]        the sample's bound (stream + finalize; may be optimistic, see below)
+    u64 *sthr;                  // [B]        COMPLEMENT of the sample's bound (stream + finalize; may be optimistic, see below)
     int *scount;                // [B]        fill of the streamed candidate list
     int *sdone;                 // [B]        sample jobs finished
     u64 *sslots;                // [B][Gs]    per-sample-job bounds
@@ -101,7 +101,7 @@ static size_t sel_workspace_layout(int B, int G, int list_cap, SelGlobal *g, voi
 // redone exactly by vy_decode_select_kernel.
 __device__ __forceinline__ bool stream_list_ok(const SelGlobal &g, int b, int K) {
     const int n = g.scount[b];
-    return n <= g.slist_cap && (n >= K || g.sthr[b] == 0ull);
+    return n <= g.slist_cap && (n >= K || ~g.sthr[b] == 0ull);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(SAMP_NT, 2)
 vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl, SelGlobal g) {
     __shared__ u32 skey[SAMP_MAXK][SAMP_NT];
     __shared__ u32 hist[256];
-    __shared__ int sh_n, sh_digit, sh_above, sh_in;
+    __shared__ int sh_digit, sh_above, sh_in;
     const int tid = threadIdx.x;
     const int b = blockIdx.x / pl.Gs, gj = blockIdx.x % pl.Gs;
     const int ib = gj % pl.samp_ib, pb = gj / pl.samp_ib;
@@ -462,6 +462,12 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
         item_ref(hd, pl, b, (j / SAMP_RUN) * (SAMP_RUN * pl.samp_stride) + (j % SAMP_RUN), r)) {
         float to[4], cf[4];
         item_load(r, r.p + 4 * (size_t)r.HW, to);
+        // the planes of the second batch: start them towards L2 now
+#pragma unroll
+        for (int k = SAMP_BATCH; k < SAMP_MAXK; ++k) {
+            const int c = c_lo + lanep + k * pl.samp_pls;
+            if (c < c_hi) asm volatile("prefetch.global.L2 [%0];" :: "l"(r.p + (size_t)(5 + c) * (size_t)r.HW));
+        }
 #pragma unroll
         for (int k0 = 0; k0 < SAMP_MAXK; k0 += SAMP_BATCH) {
             if (c_lo + lanep + k0 * pl.samp_pls >= c_hi) break;
@@ -489,13 +495,11 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
             }
         }
     }
-    // ---- CTA-wide: Ksq-th largest of the keys (MSB-first radix select over the parked keys)
-    if (tid == 0) sh_n = 0;
-    __syncthreads();
-    if (n_mine) atomicAdd(&sh_n, n_mine);
-    __syncthreads();
+    // ---- CTA-wide: Ksq-th largest of the keys (MSB-first radix select over the parked keys); fewer than
+    // Ksq keys in all (seen in the first pass: no bin reaches the rank) leave the bound at 0
+    if (tid == 0) sh_digit = -1;
     u32 bound = 0;
-    if (sh_n >= pl.Ksq) {                          // CTA-uniform
+    {
         u32 prefix = 0;
         int kk = pl.Ksq;
         for (int shift = 24; shift >= 0; shift -= 8) {
@@ -537,26 +541,18 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
                 }
             }
             __syncthreads();
-            prefix |= (u32)sh_digit << shift;
+            const int dig = sh_digit, inb = sh_in;
+            if (dig < 0) { prefix = 0; break; }        // CTA-uniform: not enough keys
+            prefix |= (u32)dig << shift;
             kk -= sh_above;
-            const int inb = sh_in;
             __syncthreads();
             if (inb - kk <= (pl.Ksq >> 3)) break;      // #{keys >= prefix} is within Ksq/8 of Ksq
         }
         bound = prefix;
     }
-    // ---- publish; the last job of the image combines: the minimum over the jobs
-    if (tid == 0) {
-        st_relaxed_u64(g.sslots + (size_t)b * pl.Gs + gj, (u64)bound << 32);
-        __threadfence();
-        const int ticket = atomicAdd(g.sdone + b, 1);
-        if (ticket == pl.Gs - 1) {
-            __threadfence();
-            u64 m = ~0ull;
-            for (int i = 0; i < pl.Gs; ++i) { const u64 v = ld_relaxed_u64(g.sslots + (size_t)b * pl.Gs + i); m = v < m ? v : m; }
-            g.sthr[b] = m;
-        }
-    }
+    // ---- publish: the image's bound is the MINIMUM over its jobs, kept as the maximum of the complements
+    // (the workspace header starts at zero = "no job yet" = complement of the largest bound)
+    if (tid == 0) atomicMax(g.sthr + b, ~((u64)bound << 32));
 }
 
 constexpr int STR_NT = 256;
@@ -749,7 +745,7 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
         un.row0 = (u32)(sc.row_off + (long long)pos0 * hd.A + a);
         un.n_s = (u32)sc.n_s; un.A = (u32)hd.A;
         un.valid_thresh = pl.valid_thresh;
-        un.thr = g.sthr[b];
+        un.thr = ~g.sthr[b];
         const float smin = fmaxf(un.thr ? vy_key_score(un.thr) : pl.valid_thresh, pl.valid_thresh);
         {
             float to[4];
@@ -980,7 +976,7 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     const bool use_s = g.scount != nullptr && stream_list_ok(g, b, K);
     const int n_list = use_s ? g.scount[b] : min(g.count[b], pl.list_cap);
     const u64 *list = use_s ? g.slist + (size_t)b * g.slist_cap : g.list + (size_t)b * pl.list_cap;
-    if (tid == 0) { S.count = 0; S.thr = use_s ? g.sthr[b] : g.thr[b]; }
+    if (tid == 0) { S.count = 0; S.thr = use_s ? ~g.sthr[b] : g.thr[b]; }
     if (n_list > K + FIN_SLACK && n_list <= fp.lcap) {
         // the radix sweeps below then never leave the SM
         for (int i = tid; i < n_list; i += FIN_NT) lbuf[i] = list[i];
@@ -1403,7 +1399,7 @@ extern "C" int vy_decode_nms_f32(const float *const *head, const int *H, const i
         long long sum = 0; int mn = 1 << 30, mx = 0, bad = 0;
         for (int i = 0; i < B; ++i) {
             sum += cnt[i]; mn = cnt[i] < mn ? cnt[i] : mn; mx = cnt[i] > mx ? cnt[i] : mx;
-            bad += cnt[i] > g.slist_cap || (cnt[i] < pl.K && thr[i] != 0ull);
+            bad += cnt[i] > g.slist_cap || (cnt[i] < pl.K && ~thr[i] != 0ull);
         }
         fprintf(stderr, "[vyolo] streamed lists: K=%d S=%d Gs=%d Ksq=%d cap=%d | fill mean %.0f min %d max %d | rescued %d of %d\n",
                 pl.K, pl.samp_stride, pl.Gs, pl.Ksq, g.slist_cap, (double)sum / B, mn, mx, bad, B);

@@ -275,3 +275,22 @@ def temporal_pool(x: PTensor, type: str = "max") -> PTensor:
         _lib.check(_lib.lib().vy_temporal_pool_bf16(x.data.data_ptr(), x.T, inner, 0 if type == "max" else 1,
                                                     y.data_ptr(), _stream()))
     return PTensor(y, x.B, 1, x.H, x.W, x.C)
+
+
+def temporal_dwconv(x: PTensor, weight: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
+                    slope: float = 0.1) -> PTensor:
+    """``_conv1d`` (layers.py:50-60) over a window of exactly ``x.T`` frames: depthwise Conv3D with kernel
+    (T,1,1) + BN + LeakyReLU, the temporal merge of HDarknet (h_darknet.py:97-119).
+    weight: the reference's (C, 1, T, 1, 1) (or (C, T)) fp32 CUDA tensor."""
+    if not isinstance(x, PTensor) or x.data.dtype != torch.bfloat16:
+        raise TypeError("temporal_dwconv takes a bf16 PTensor (ops.pack_p)")
+    w = _need_cuda(weight.reshape(weight.shape[0], -1), "weight")
+    if tuple(w.shape) != (x.C, x.T):
+        raise ValueError("weight must be (C, 1, T, 1, 1) with C=%d, T=%d" % (x.C, x.T))
+    scale = _need_cuda(scale, "scale")
+    shift = _need_cuda(shift, "shift")
+    y = torch.empty((1, x.B, x.H + 2, x.W + 2, x.C), dtype=torch.bfloat16, device=x.data.device)
+    with torch.cuda.device(x.data.device):
+        _lib.check(_lib.lib().vy_temporal_dwconv_bf16(x.data.data_ptr(), w.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                                      float(slope), x.B, x.T, x.H, x.W, x.C, y.data_ptr(), _stream()))
+    return PTensor(y, x.B, 1, x.H, x.W, x.C)
