@@ -240,6 +240,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-conv", action="store_true", help="skip the fusion-conv (tensor-pipe) leg")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="CUDA streams the timed steps alternate over (1 = every step waits for the one before)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -274,8 +276,21 @@ def main():
     # inputs smaller than L2 (126 MB) are evicted between steps by writing a 256 MiB buffer
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if in_bytes < (160 << 20) else None
 
-    def step():
-        vy.yolo3_decode_nms(heads, C, AN, ST, out=out, kept=kept, **NMS)
+    # Steps are independent batches, so consecutive steps may overlap: step i runs on stream i % n_streams
+    # with its own output buffers and workspace, which lets the latency-bound head (sample) and tail
+    # (finalize) of one step hide behind the bandwidth-bound streaming pass of its neighbour.  Configs that
+    # need an L2 flush between steps run on one stream.
+    n_streams = max(1, args.streams) if flush is None else 1
+    side = [torch.cuda.Stream(dev) for _ in range(n_streams)]
+    outs = [(out, kept)] + [(torch.empty_like(out), torch.empty_like(kept)) for _ in range(n_streams - 1)]
+
+    def step(i=0, n=1):
+        o, k = outs[i % n]
+        if n == 1:
+            vy.yolo3_decode_nms(heads, C, AN, ST, out=o, kept=k, **NMS)
+        else:
+            with torch.cuda.stream(side[i % n]):
+                vy.yolo3_decode_nms(heads, C, AN, ST, out=o, kept=k, **NMS)
 
     def barrier():
         torch.cuda.synchronize()
@@ -290,28 +305,35 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(fn, steps, warmup, sampler=None):
+    def timed(fn, steps, warmup, sampler=None, n=1):
         """max-over-ranks milliseconds for `steps` calls of fn, device-timed."""
-        for _ in range(warmup):
-            fn()
+        for i in range(warmup):
+            fn(i, n)
         barrier()
         if sampler:
             sampler.active.set()
         total = 0.0
         if flush is None:
+            cur = torch.cuda.current_stream(dev)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(steps):
-                fn()
-            b.record()
+            a.record(cur)
+            if n > 1:
+                for s_ in side[:n]:
+                    s_.wait_event(a)
+            for i in range(steps):
+                fn(i, n)
+            if n > 1:
+                for s_ in side[:n]:
+                    cur.wait_event(s_.record_event())
+            b.record(cur)
             torch.cuda.synchronize()
             total = a.elapsed_time(b)
         else:
             evs = []
-            for _ in range(steps):
+            for i in range(steps):
                 flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); fn(); b.record()
+                a.record(); fn(i, 1); b.record()
                 evs.append((a, b))
             torch.cuda.synchronize()
             total = sum(a.elapsed_time(b) for a, b in evs)
@@ -325,8 +347,10 @@ def main():
 
     # ---- headline: device-resident
     c0 = _lib.launch_counts()
-    ms_total = timed(step, args.steps, args.warmup, sampler)
+    ms_total = timed(step, args.steps, args.warmup, sampler, n_streams)
     c1 = _lib.launch_counts()
+    # the same steps strictly one after the other (reported beside the headline)
+    ms_serial = timed(step, args.steps, 3, None, 1) if n_streams > 1 else ms_total
     launches = {k: c1[k] - c0[k] for k in c1 if c1[k] - c0[k]}
     # warm-up launches are not in the timed region
     per_step = {k: v // (args.steps + args.warmup) for k, v in launches.items()}
@@ -337,7 +361,7 @@ def main():
     # ---- roofline pass: same steps with the library's per-kernel events switched on
     _lib.prof_enable(True)
     _lib.prof_read()
-    ms_prof_total = timed(step, args.steps, 3)
+    ms_prof_total = timed(step, args.steps, 3, None, 1)
     prof = _lib.prof_read()
     _lib.prof_enable(False)
     peak, peak_src = load_peaks()
@@ -353,6 +377,7 @@ def main():
                 "kernel_ms_per_step": {k: round(v, 5) for k, v in kernel_ms.items()},
                 "kernel_share_of_step": {k: round(v / sum(kernel_ms.values()), 4) for k, v in kernel_ms.items()},
                 "step_frac": round((in_bytes + out_bytes_frame * B) / (ms_step * 1e-3) / 1e9 / peak, 4),
+                "step_frac_single_stream": round((in_bytes + out_bytes_frame * B) / (ms_serial / args.steps * 1e-3) / 1e9 / peak, 4),
                 "profiled_ms_per_step": round(ms_prof_total / args.steps, 5)}
 
     # ---- e2e: host buffers through the public host-facing call
@@ -429,7 +454,9 @@ def main():
                            "regime": args.regime + (": logits ~ N(0,1) (random-init weights)" if args.regime == "R" else ": trained-like"),
                            "nms": NMS, "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world,
                            "l2": ("inputs larger than L2 (%.0f MB per step)" % (in_bytes / 1e6)) if flush is None
-                                 else "L2 flushed between steps (256 MiB write)"},
+                                 else "L2 flushed between steps (256 MiB write)",
+                           "streams": n_streams},
+                "value_single_stream": world * B * args.steps / (ms_serial * 1e-3),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fusion_conv": conv, "gpu_launches": gpu_launches,
                 "launches_per_step": per_step, "clocks": sampler.summary()}
         print(json.dumps(line))

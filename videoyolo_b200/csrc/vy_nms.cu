@@ -1279,11 +1279,31 @@ static void plan_stream(const VyHeads &hd, SelPlan *pl) {
     const long long ksq_sure = ((long long)pl->K + pl->Gs - 1) / pl->Gs;
     if (ksq > ksq_sure) ksq = ksq_sure;
     pl->Ksq = (int)ksq;
-    pl->n_groups = (hd.C + 95) / 96;
+    // A unit = 128 positions x one group of class planes, streamed by one warp.  The class planes are cut
+    // into as many groups as make the unit count a near-multiple of the resident warps: every warp walks
+    // ceil(units / warps) units, so 2.47 "waves" cost as much as 3 (each extra group costs a unit prologue).
+    int chunks_total = 0;
+    for (int s = 0; s < hd.n_scales; ++s) {
+        pl->chunks[s] = (hd.sc[s].HW + 127) / 128;
+        chunks_total += pl->chunks[s];
+    }
+    {
+        const double warps = (double)STR_CTAS_PER_SM * vy_sm_count() * (256 / 32);
+        const int g_min = (hd.C + 95) / 96;
+        int best_g = g_min;
+        double best = -1.0;
+        for (int ng = g_min; ng <= g_min + 3; ++ng) {
+            if (ng > g_min && (hd.C + ng - 1) / ng < 16) break;           // groups of fewer than 16 planes are all prologue
+            const double waves = (double)chunks_total * hd.A * ng * hd.B / warps;
+            const double full = waves <= 1.0 ? 1.0 : (double)(long long)(waves + 0.999999);
+            const double score = (waves <= 1.0 ? 1.0 : waves / full) * (1.0 - 0.02 * (ng - g_min));
+            if (score > best) { best = score; best_g = ng; }
+        }
+        pl->n_groups = best_g;
+    }
     pl->PU = (hd.C + pl->n_groups - 1) / pl->n_groups;
     int units = 0;
     for (int s = 0; s < hd.n_scales; ++s) {
-        pl->chunks[s] = (hd.sc[s].HW + 127) / 128;
         pl->unit_begin[s] = units;
         units += pl->chunks[s] * pl->n_groups * hd.A;
     }
