@@ -240,7 +240,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-conv", action="store_true", help="skip the fusion-conv (tensor-pipe) leg")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=4,
                     help="CUDA streams the timed steps alternate over (1 = every step waits for the one before)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
