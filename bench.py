@@ -115,6 +115,37 @@ def fusion_conv_leg(dev, B=8, T=3, iters=10):
             "l2": "L2 flushed between launches (256 MiB write)"}
 
 
+def temporal_tail_leg(dev, B=32, K=3, C=30, size=416, iters=10):
+    """BASELINE configs[2] end to end on the device: ImageNet-VID (30 cls) 416^2, temporal window K=3:
+    (B, K, channel, g, g) fp32 block outputs -> P-layout pack -> 3x3x3 tip conv (tcgen05) -> late 'max' join ->
+    1x1 prediction conv (library conv, fp32) -> fused decode + box_nms -> (ids, scores, bboxes).
+    One window = one detection; CUDA events around the whole call, L2 flushed between calls."""
+    import torch
+    import videoyolo_b200 as vy
+    from videoyolo_b200 import _lib
+    torch.manual_seed(7)
+    net = vy.YOLOV3T(["c%d" % i for i in range(C)], k=K, k_join_type="max", block_conv_type="3").to(dev).eval()
+    xs = [torch.randn((B, K, c, g, g), device=dev) for c, g in zip((512, 256, 128), grid_sizes(size))]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    with torch.no_grad():
+        for _ in range(3):
+            net(*xs)
+        _lib.prof_enable(True); _lib.prof_read()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); net(*xs); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        prof = _lib.prof_read(); _lib.prof_enable(False)
+    ms = sorted(ts)[len(ts) // 2]
+    return {"workload": "configs[2]: ImageNet-VID (30 cls) 416x416, K=3: tip fusion conv + max join + prediction conv + decode + NMS, batch %d windows" % B,
+            "windows_per_s": round(B / (ms * 1e-3), 1), "ms_per_call": round(ms, 4),
+            "library_kernel_ms_per_call": {k: round(v[0] / iters, 4) for k, v in prof.items()},
+            "note": "device-resident fp32 inputs; the 1x1 prediction conv is a library (cuDNN) conv; L2 flushed between calls"}
+
+
 def load_traffic(config_name, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
     `ncu --set full` capture (profiles/roofline_traffic.json), or None."""
@@ -425,6 +456,7 @@ def main():
     if rank == 0 and not args.no_conv:
         try:
             conv = fusion_conv_leg(dev)
+            conv["temporal_tail"] = temporal_tail_leg(dev)
         except Exception as e:                     # the headline line must still be printed
             conv = {"error": str(e)[:200]}
 

@@ -390,6 +390,56 @@ def test_box_nms_idempotent_full_size(vy):
     assert torch.equal(a, b)
 
 
+def test_full_size_stress_config4_properties(vy):
+    """BASELINE config 4 at full row count (80 cls x 10647 boxes = 851760 rows, valid_thresh 0.001, topk -1,
+    force_suppress off/on): size-independent properties of the operator output + idempotence."""
+    B, C, size = 2, 80, 416
+    g = torch.Generator(device="cuda").manual_seed(1238)
+    heads = [torch.randn((B, 3 * (5 + C), s, s), generator=g, device="cuda") for s in oracle.grid_sizes(size)]
+    dets = vy.yolo3_decode(heads, C, AN, ST)
+    R = dets.shape[1]
+    assert R == 851760
+    n_valid = (dets[..., 1] > 0.001).sum(dim=1)
+    for force in (False, True):
+        out, kept = vy.box_nms(dets, overlap_thresh=0.45, valid_thresh=0.001, topk=-1, id_index=0,
+                               force_suppress=force, return_kept=True)
+        out2, kept2 = vy.box_nms(dets, overlap_thresh=0.45, valid_thresh=0.001, topk=-1, id_index=0,
+                                 force_suppress=force, return_kept=True)
+        assert torch.equal(out, out2) and torch.equal(kept, kept2)                       # deterministic
+        valid = kept >= 0
+        n = valid.sum(dim=1)
+        assert (n > 0).all() and (n <= n_valid).all()
+        for b in range(B):
+            nb = int(n[b])
+            assert bool(valid[b, :nb].all()) and not bool(valid[b, nb:].any())            # survivors first
+            assert bool((out[b, nb:] == -1).all())
+            sc = out[b, :nb, 1]
+            assert bool((sc[1:] <= sc[:-1]).all())                                       # score order
+            rows = kept[b, :nb].long()
+            assert int(torch.unique(rows).numel()) == nb                                 # unique source rows
+            assert torch.equal(out[b, :nb], dets[b][rows])                               # rows copied verbatim
+            assert bool((sc > 0.001).all())
+            # the best row always survives; equal-score runs keep ascending source rows
+            top = int(torch.argmax(dets[b, :, 1]))
+            assert int(rows[0]) == top or float(dets[b, top, 1]) == float(sc[0])
+            tie = sc[1:] == sc[:-1]
+            assert bool((rows[1:][tie] > rows[:-1][tie]).all())
+            # survivors do not suppress each other: checked on the 2000 best
+            m = min(nb, 2000)
+            bx, ids = out[b, :m, 2:6], out[b, :m, 0]
+            area = (bx[:, 2] - bx[:, 0]).clamp(min=0) * (bx[:, 3] - bx[:, 1]).clamp(min=0)
+            iw = (torch.minimum(bx[:, None, 2], bx[None, :, 2]) - torch.maximum(bx[:, None, 0], bx[None, :, 0])).clamp(min=0)
+            ih = (torch.minimum(bx[:, None, 3], bx[None, :, 3]) - torch.maximum(bx[:, None, 1], bx[None, :, 1])).clamp(min=0)
+            iou = iw * ih / (area[:, None] + area[None, :] - iw * ih)
+            clash = (iou > 0.45 + 1e-6) & ~torch.eye(m, dtype=torch.bool, device="cuda")   # torch may contract the IoU arithmetic
+            if not force:
+                clash &= ids[:, None] == ids[None, :]
+            assert not bool(clash.any())
+        # idempotence: the survivors survive a second pass unchanged
+        again = vy.box_nms(out, overlap_thresh=0.45, valid_thresh=0.001, topk=-1, id_index=0, force_suppress=force)
+        assert torch.equal(again, out)
+
+
 # ----------------------------------------------------------------------------------- bbox_iou
 def test_bbox_iou_against_reference_outputs(vy, golden_dir):
     z = np.load(os.path.join(golden_dir, "bbox_iou_ref.npz"))

@@ -1,0 +1,117 @@
+"""GPU parity of the temporal detector tail (BASELINE configs[2]: K=3 fusion conv + late join + decode + NMS)
+through the block surface videoyolo_b200.YOLOV3T / layers.Conv / TemporalPooling / TimeDistributed / Conv1D,
+against the CPU oracle chain (oracle.conv_bn_leaky -> temporal_pool -> decode -> box_nms).
+
+Tolerances: the joined tip features within the fusion-conv tolerance (bf16 operands, fp32 accumulation:
+|d| <= 1e-2 * max|y|, rtol 2e-2); the final (ids, scores, bboxes) BIT-EXACT against the oracle tail applied to the
+rows the GPU decoded from its own head maps (the north-star wording: keep-sets bit-exact on identical boxes)."""
+import numpy as np
+import pytest
+
+import oracle
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vy():
+    assert torch.cuda.is_available()
+    import videoyolo_b200
+    videoyolo_b200._lib.lib()
+    return videoyolo_b200
+
+
+def bf16_round(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).float().numpy()
+
+
+def randomize_bn(net, rng):
+    with torch.no_grad():
+        for name, p in list(net.named_parameters()) + list(net.named_buffers()):
+            if name.endswith("gamma"):
+                p.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, p.shape).astype(np.float32)))
+            elif name.endswith("beta") or name.endswith("running_mean"):
+                p.copy_(torch.from_numpy(rng.normal(0, 0.2, p.shape).astype(np.float32)))
+            elif name.endswith("running_var"):
+                p.copy_(torch.from_numpy(rng.uniform(0.5, 2.0, p.shape).astype(np.float32)))
+
+
+def oracle_cell(cell, x_ncdhw):
+    w = bf16_round(cell.weight.detach().cpu().numpy())
+    bn = [t.detach().cpu().numpy() for t in (cell.gamma, cell.beta, cell.running_mean, cell.running_var)]
+    y = oracle.conv_bn_leaky(x_ncdhw, w, *bn, padding=tuple(k // 2 for k in cell.k3))
+    return bf16_round(y)                                  # the kernel stores bf16 activations
+
+
+def check(got, ref, name):
+    scale = np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 1e-2 * scale, (name, np.abs(got - ref).max(), scale)
+    np.testing.assert_allclose(got, ref, rtol=2e-2, atol=1e-2 * scale, err_msg=name)
+
+
+@pytest.mark.parametrize("join,ctype", [("max", "3"), ("mean", "21"), ("cat", "3")])
+def test_yolov3t_tail_matches_oracle_chain(vy, join, ctype):
+    rng = np.random.RandomState(len(join) * 7 + len(ctype))
+    torch.manual_seed(5)
+    B, K, C, size, channels = 2, 3, 20, 160, (128, 64, 64)
+    net = vy.YOLOV3T(["c%d" % i for i in range(C)], k=K, k_join_type=join, block_conv_type=ctype, channels=channels).cuda().eval()
+    randomize_bn(net, rng)
+    xs = [bf16_round(rng.normal(0, 1, size=(B, K, c, g, g))) for c, g in zip(channels, oracle.grid_sizes(size))]
+    with torch.no_grad():
+        feats = net.tip_features(*[torch.from_numpy(x).cuda() for x in xs])
+        ids, scores, bboxes = net(*[torch.from_numpy(x).cuda() for x in xs])
+    # ---- tip conv + late join vs the oracle
+    for i, x in enumerate(xs):
+        y = x.transpose(0, 2, 1, 3, 4)                    # (B, C, K, H, W): swapaxes(1, 2), yolo3.py:256
+        for cell in net.tips[i].cells:
+            y = oracle_cell(cell, y)
+        t = y.transpose(0, 2, 1, 3, 4)                    # back to (B, K, C', H, W)
+        if join == "cat":
+            ref = t.reshape(B, -1, t.shape[3], t.shape[4])                     # yolo3.py:1136
+        else:
+            ref = bf16_round(oracle.temporal_pool(t, join).astype(np.float32))  # layers.py:201-205
+        check(feats[i].cpu().numpy(), ref, "scale %d %s %s" % (i, join, ctype))
+    # ---- output layers + NMS tail: exact against the oracle on the GPU's own decoded rows
+    with torch.no_grad():
+        heads = [o.prediction(f) for o, f in zip(net.tail.yolo_outputs, feats)]
+    AN, ST = oracle.ANCHORS[::-1], oracle.STRIDES[::-1]
+    dets = vy.yolo3_decode(heads, C, AN, ST).cpu().numpy()
+    o_ids, o_sc, o_bb, o_rec = oracle.yolov3_tail(dets, return_record=True)
+    np.testing.assert_array_equal(net.last_kept_rows.cpu().numpy(), o_rec)
+    np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
+    np.testing.assert_array_equal(scores.cpu().numpy(), o_sc)
+    np.testing.assert_array_equal(bboxes.cpu().numpy(), o_bb)
+    # and the decode itself within 1e-5 of the CPU restatement on the same head maps
+    ref = oracle.decode_c([h.cpu().numpy() for h in heads], C)
+    np.testing.assert_allclose(dets[..., 1], ref[..., 1], rtol=1e-5, atol=1e-12)
+
+
+def test_layer_blocks(vy):
+    """Conv('2') under TimeDistributed == the same 2-D conv per frame; Conv1D == oracle _conv1d."""
+    rng = np.random.RandomState(3)
+    B, K, Cin, Cout, g = 2, 3, 64, 64, 9
+    x = bf16_round(rng.normal(size=(B, K, Cin, g, g)))
+    conv2 = vy.Conv("2", Cout, 3, 1, 1, in_channels=Cin).cuda().eval()
+    randomize_bn(conv2, rng)
+    xp = vy.ops.pack_p(torch.from_numpy(x).cuda(), "NTCHW")
+    with pytest.raises(ValueError):
+        conv2(xp)                                          # a 2-D cell needs T == 1
+    with torch.no_grad():
+        y = vy.TimeDistributed(conv2)(xp)
+    got = vy.ops.unpack_p(y, "NTCHW").cpu().numpy()
+    cell = conv2.cells[0]
+    for t in range(K):
+        ref = oracle_cell(cell, x[:, t][:, :, None])[:, :, 0]          # (B, Cout, H, W)
+        check(got[:, t], ref, "frame %d" % t)
+    c1 = vy.Conv1D(Cin, K).cuda().eval()
+    with torch.no_grad():
+        c1.weight.copy_(torch.from_numpy(rng.uniform(-0.5, 0.5, c1.weight.shape).astype(np.float32)))
+    randomize_bn(c1, rng)
+    with torch.no_grad():
+        z = vy.ops.unpack_p(c1(xp), "NCHW").cpu().numpy()
+    ref = oracle.conv1d_bn_leaky(x.transpose(0, 2, 1, 3, 4), c1.weight.detach().cpu().numpy(),
+                                 *[t.detach().cpu().numpy() for t in (c1.gamma, c1.beta, c1.running_mean, c1.running_var)])
+    check(z, ref[:, :, 0], "conv1d")
+    with pytest.raises(ValueError):
+        vy.Conv("3", 64, 3, 1, 2, in_channels=64)          # strided cells are not on this path

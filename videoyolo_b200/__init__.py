@@ -6,7 +6,9 @@ PyTorch supplies device buffers, streams and torch.distributed only.  No CPU fal
 """
 from . import _lib, ops, parallel
 from .ops import bbox_iou, box_nms, yolo3_decode, yolo3_decode_nms
-from .yolo3 import ANCHORS, STRIDES, YOLOOutputV3, YOLOV3, YOLOV3_noback, get_yolov3_postprocess
+from .layers import Conv, Conv1D, TemporalPooling, TimeDistributed
+from .yolo3 import ANCHORS, STRIDES, YOLOOutputV3, YOLOV3, YOLOV3T, YOLOV3_noback, get_yolov3_postprocess
 
 __all__ = ["bbox_iou", "box_nms", "yolo3_decode", "yolo3_decode_nms", "YOLOOutputV3", "YOLOV3",
-           "YOLOV3_noback", "get_yolov3_postprocess", "ANCHORS", "STRIDES", "ops", "parallel"]
+           "YOLOV3_noback", "YOLOV3T", "Conv", "Conv1D", "TemporalPooling", "TimeDistributed", "get_yolov3_postprocess",
+           "ANCHORS", "STRIDES", "ops", "parallel"]

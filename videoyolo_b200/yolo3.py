@@ -145,6 +145,68 @@ class YOLOV3(torch.nn.Module):
 YOLOV3_noback = YOLOV3
 
 
+class YOLOV3T(torch.nn.Module):
+    """Post-backbone tail of the temporal detector YOLOV3T with a late join (yolo3.py:915-1302; the loop
+    :1126-1177 and the NMS tail :1195-1206), i.e. BASELINE configs[2]: per scale
+
+        tip  = Conv(block_conv_type, 2*channel, 3, 1, 1)(x)        the block's tip conv     yolo3.py:250-251,:1132
+        tip  = 'max' | 'mean' TemporalPooling(k) or 'cat' reshape     late join                :1134-1138
+        dets = YOLOOutputV3(tip)                                      1x1 prediction + decode  :1159
+      then concat -> box_nms -> slice -> (ids, scores, bboxes)                                 :1195-1206
+
+    ``net(x32, x16, x8)`` takes the three block-body outputs, each (B, K, channel_i, H_i, W_i) fp32 on a CUDA
+    device (network order, channel_i = 512, 256, 128: wrappers.py:91-103).  The reference asserts that 3-D /
+    2+1-D blocks need k > 1 and a late join (yolo3.py:979-985); so does this class.  The tip convs run in the
+    tcgen05 fusion-conv kernel (bf16 operands, fp32 accumulation); the 1x1 prediction conv is a library conv
+    (fp32) as in YOLOOutputV3; decode + box_nms is the fused kernel path of YOLOV3.
+    """
+
+    def __init__(self, classes: Sequence[str], k: int = 3, k_join_type: str = "max", block_conv_type: str = "3",
+                 channels: Sequence[int] = (512, 256, 128), anchors=None, strides=None,
+                 nms_thresh=0.45, nms_topk=400, post_nms=100, agnostic=False, **kwargs):
+        super().__init__()
+        from .layers import Conv, TemporalPooling
+        assert k > 1, "3-D and 2+1-D convolutions need a temporal window (yolo3.py:981-983)"
+        assert k_join_type in ("max", "mean", "cat")                      # yolo3.py:984
+        assert block_conv_type in ("3", "21")
+        self._k, self._join = k, k_join_type
+        self.tips = torch.nn.ModuleList([Conv(block_conv_type, 2 * c, 3, 1, 1, in_channels=c) for c in channels])
+        self.pools = torch.nn.ModuleList([TemporalPooling(k, k_join_type) for _ in channels]) if k_join_type != "cat" else None
+        mult = k if k_join_type == "cat" else 1
+        self.tail = YOLOV3(anchors, strides, classes=classes, nms_thresh=nms_thresh, nms_topk=nms_topk,
+                           post_nms=post_nms, agnostic=agnostic, in_channels=[2 * c * mult for c in channels])
+
+    @property
+    def classes(self):
+        return self.tail.classes
+
+    def set_nms(self, nms_thresh=0.45, nms_topk=400, post_nms=100):
+        self.tail.set_nms(nms_thresh, nms_topk, post_nms)
+
+    def tip_features(self, *xs):
+        """the three joined tip feature maps (B, C', H, W) fp32 that feed the output layers"""
+        if len(xs) != len(self.tips):
+            raise ValueError("expected %d inputs (stride 32,16,8 order)" % len(self.tips))
+        feats = []
+        for i, x in enumerate(xs):
+            if x.dim() != 5 or x.shape[1] != self._k:
+                raise ValueError("input %d must be (B, K=%d, C, H, W)" % (i, self._k))
+            tip = self.tips[i](ops.pack_p(x, "NTCHW"))
+            if self._join == "cat":
+                t = ops.unpack_p(tip, "NTCHW")                                  # (B, K, C, H, W)
+                feats.append(t.reshape(t.shape[0], -1, t.shape[3], t.shape[4]))  # reshape (0,-3,-2): yolo3.py:1136
+            else:
+                feats.append(ops.unpack_p(self.pools[i](tip), "NCHW"))
+        return feats
+
+    def forward(self, *xs):
+        return self.tail(*self.tip_features(*xs))
+
+    @property
+    def last_kept_rows(self):
+        return self.tail.last_kept_rows
+
+
 def get_yolov3_postprocess(classes, agnostic=False, in_channels=None, **kwargs) -> YOLOV3:
     """Head-level counterpart of wrappers.yolo3_darknet53 (wrappers.py:9-110): reference anchors/strides."""
     return YOLOV3(ANCHORS, STRIDES, classes=classes, agnostic=agnostic, in_channels=in_channels, **kwargs)
