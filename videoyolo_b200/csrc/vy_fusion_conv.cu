@@ -266,42 +266,117 @@ vy_fusion_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 
 // ------------------------------------------------------------------ layout kernels
 // (B, C, T, H, W)-strided fp32 (the reference's NCDHW after swapaxes, or (B, K, C, H, W) before it: the
-// strides say which) -> P layout bf16.  One CTA per (t, b, h): reads C rows of W floats, writes W*C bf16.
-__global__ void vy_pack_kernel(const float *__restrict__ x, long long sb, long long sc, long long st, int B, int C,
-                               int T, int H, int W, __nv_bfloat16 *__restrict__ y) {
-    extern __shared__ float tile[];                 // [C][W + 1]
-    const int h = blockIdx.x % H, b = (blockIdx.x / H) % B, t = blockIdx.x / (H * B);
-    const float *src = x + (size_t)b * sb + (size_t)t * st + (size_t)h * W;
-    for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
-        const int c = i / W, w = i % W;
-        tile[c * (W + 1) + w] = src[(size_t)c * sc + w];
+// strides say which) <-> P layout.  One CTA moves a tile of LY_C channels x LY_P consecutive positions of one
+// (t, b) frame through shared memory: the fp32 side is touched in runs of LY_P consecutive floats of one
+// channel plane, the P side in runs of LY_C consecutive channels of one pixel.
+constexpr int LY_C = 64, LY_P = 128, LY_NT = 256;
+
+__global__ void __launch_bounds__(LY_NT)
+vy_pack_kernel(const float *__restrict__ x, long long sb, long long sc, long long st, int B, int C,
+               int T, int H, int W, __nv_bfloat16 *__restrict__ y) {
+    __shared__ float tile[LY_C][LY_P + 1];
+    const int HW = H * W, Wp = W + 2;
+    const int p0 = blockIdx.x * LY_P, c0 = blockIdx.y * LY_C;
+    const int b = blockIdx.z % B, t = blockIdx.z / B;
+    const float *src = x + (size_t)b * sb + (size_t)t * st;
+    // 8 independent 4-byte loads per thread and round: the fp32 side has no alignment to vectorise on
+    // (H*W is odd at 13x13), so memory-level parallelism comes from unrolling
+    for (int i0 = threadIdx.x; i0 < LY_C * LY_P; i0 += 8 * LY_NT) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * LY_NT, c = i / LY_P, p = i % LY_P;
+            v[u] = (c0 + c < C && p0 + p < HW) ? __ldg(src + (size_t)(c0 + c) * sc + p0 + p) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * LY_NT;
+            tile[i / LY_P][i % LY_P] = v[u];
+        }
     }
     __syncthreads();
+    __nv_bfloat16 *dst = y + ((size_t)t * B + b) * (size_t)(H + 2) * Wp * C;
+    if ((C & 7) == 0) {                                    // 8 channels = one 16-byte store
+        for (int i = threadIdx.x; i < LY_P * (LY_C / 8); i += LY_NT) {
+            const int p = i / (LY_C / 8), c = (i % (LY_C / 8)) * 8;
+            const int pos = p0 + p;
+            if (pos >= HW || c0 + c >= C) continue;
+            const int h = pos / W, w = pos % W;
+            uint4 o;
+            __nv_bfloat162 *oh = (__nv_bfloat162 *)&o;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) oh[k] = __floats2bfloat162_rn(tile[c + 2 * k][p], tile[c + 2 * k + 1][p]);
+            *(uint4 *)(dst + ((size_t)(h + 1) * Wp + (w + 1)) * C + c0 + c) = o;
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < LY_P * LY_C; i += LY_NT) {
+        const int p = i / LY_C, c = i % LY_C;
+        const int pos = p0 + p;
+        if (pos >= HW || c0 + c >= C) continue;
+        const int h = pos / W, w = pos % W;
+        dst[((size_t)(h + 1) * Wp + (w + 1)) * C + c0 + c] = __float2bfloat16_rn(tile[c][p]);
+    }
+}
+
+// the one-pixel zero border of every (t, b) frame of a P-layout tensor (2*Wp + 2*H pixels x C channels)
+__global__ void vy_zero_border_kernel(__nv_bfloat16 *__restrict__ y, int H, int W, int C) {
     const int Hp = H + 2, Wp = W + 2;
-    __nv_bfloat16 *dst = y + ((((size_t)t * B + b) * Hp + (h + 1)) * Wp + 1) * C;
-    for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
-        const int w = i / C, c = i % C;
-        dst[(size_t)w * C + c] = __float2bfloat16_rn(tile[c * (W + 1) + w]);
+    const int nb = 2 * Wp + 2 * H;
+    __nv_bfloat16 *frame = y + (size_t)blockIdx.y * Hp * Wp * C;
+    for (int q = blockIdx.x; q < nb; q += gridDim.x) {
+        int hp, wp;
+        if (q < Wp) { hp = 0; wp = q; }
+        else if (q < 2 * Wp) { hp = Hp - 1; wp = q - Wp; }
+        else { const int r = q - 2 * Wp; hp = 1 + (r >> 1); wp = (r & 1) ? Wp - 1 : 0; }
+        __nv_bfloat16 *o = frame + ((size_t)hp * Wp + wp) * C;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = __float2bfloat16_rn(0.0f);
     }
 }
 
 // P layout (bf16 or fp32) -> (B, C, T, H, W)-strided fp32
 template <typename TIn>
-__global__ void vy_unpack_kernel(const TIn *__restrict__ y, int B, int C, int T, int H, int W, float *__restrict__ x,
-                                 long long sb, long long sc, long long st) {
-    extern __shared__ float tile[];
-    const int h = blockIdx.x % H, b = (blockIdx.x / H) % B, t = blockIdx.x / (H * B);
-    const int Hp = H + 2, Wp = W + 2;
-    const TIn *src = y + ((((size_t)t * B + b) * Hp + (h + 1)) * Wp + 1) * C;
-    for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
-        const int w = i / C, c = i % C;
-        tile[c * (W + 1) + w] = (float)src[(size_t)w * C + c];
+__global__ void __launch_bounds__(LY_NT)
+vy_unpack_kernel(const TIn *__restrict__ y, int B, int C, int T, int H, int W, float *__restrict__ x,
+                 long long sb, long long sc, long long st) {
+    __shared__ float tile[LY_C][LY_P + 1];
+    const int HW = H * W, Wp = W + 2;
+    const int p0 = blockIdx.x * LY_P, c0 = blockIdx.y * LY_C;
+    const int b = blockIdx.z % B, t = blockIdx.z / B;
+    const TIn *src = y + ((size_t)t * B + b) * (size_t)(H + 2) * Wp * C;
+    if (sizeof(TIn) == 2 && (C & 7) == 0) {                // 8 bf16 channels = one 16-byte load, 4 in flight per thread
+        for (int i = threadIdx.x; i < LY_P * (LY_C / 8); i += LY_NT) {
+            const int p = i / (LY_C / 8), c = (i % (LY_C / 8)) * 8;
+            const int pos = p0 + p;
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (pos < HW && c0 + c < C) {
+                const int h = pos / W, w = pos % W;
+                q = *(const uint4 *)((const __nv_bfloat16 *)src + ((size_t)(h + 1) * Wp + (w + 1)) * C + c0 + c);
+            }
+            const __nv_bfloat162 *qh = (const __nv_bfloat162 *)&q;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __bfloat1622float2(qh[k]);
+                tile[c + 2 * k][p] = f.x; tile[c + 2 * k + 1][p] = f.y;
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < LY_P * LY_C; i += LY_NT) {
+            const int p = i / LY_C, c = i % LY_C;
+            const int pos = p0 + p;
+            float v = 0.0f;
+            if (pos < HW && c0 + c < C) {
+                const int h = pos / W, w = pos % W;
+                v = (float)src[((size_t)(h + 1) * Wp + (w + 1)) * C + c0 + c];
+            }
+            tile[c][p] = v;
+        }
     }
     __syncthreads();
-    float *dst = x + (size_t)b * sb + (size_t)t * st + (size_t)h * W;
-    for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
-        const int c = i / W, w = i % W;
-        dst[(size_t)c * sc + w] = tile[c * (W + 1) + w];
+    float *dst = x + (size_t)b * sb + (size_t)t * st;
+    for (int i = threadIdx.x; i < LY_C * LY_P; i += LY_NT) {
+        const int c = i / LY_P, p = i % LY_P;
+        if (c0 + c < C && p0 + p < HW) dst[(size_t)(c0 + c) * sc + p0 + p] = tile[c][p];
     }
 }
 
@@ -411,12 +486,12 @@ extern "C" int vy_pack_f32_to_p_bf16(const float *x, long long stride_b, long lo
                                      int B, int C, int T, int H, int W, void *y_p, vy_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!x || !y_p || B < 1 || C < 1 || T < 1 || H < 1 || W < 1) VY_FAIL(VY_EINVAL, "vy_pack_f32_to_p_bf16: bad arguments");
-    const size_t smem = (size_t)C * (W + 1) * 4;
-    if (smem > 200 * 1024) VY_FAIL(VY_EUNSUPPORTED, "vy_pack_f32_to_p_bf16: C*(W+1) too large for one row tile");
-    VY_CUDA_CHECK(cudaMemsetAsync(y_p, 0, vy_p_layout_elems(B, T, H, W, C) * 2, st));
-    VY_CUDA_CHECK(cudaFuncSetAttribute(vy_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VY_KERNEL(VY_K_LAYOUT, st, (vy_pack_kernel<<<T * B * H, 256, smem, st>>>(x, stride_b, stride_c, stride_t, B, C, T, H, W,
-                                                                            (__nv_bfloat16 *)y_p)));
+    if ((long long)T * B > 65535) VY_FAIL(VY_EUNSUPPORTED, "vy_pack_f32_to_p_bf16: T*B must be <= 65535");
+    VY_KERNEL(VY_K_LAYOUT, st, (vy_zero_border_kernel<<<dim3(64, T * B), 128, 0, st>>>((__nv_bfloat16 *)y_p, H, W, C)));
+    VY_LAUNCH_CHECK("vy_zero_border_kernel");
+    const dim3 grid((H * W + LY_P - 1) / LY_P, (C + LY_C - 1) / LY_C, T * B);
+    VY_KERNEL(VY_K_LAYOUT, st, (vy_pack_kernel<<<grid, LY_NT, 0, st>>>(x, stride_b, stride_c, stride_t, B, C, T, H, W,
+                                                                     (__nv_bfloat16 *)y_p)));
     VY_LAUNCH_CHECK("vy_pack_kernel");
     return VY_OK;
 }
@@ -425,15 +500,13 @@ extern "C" int vy_unpack_p_to_f32(const void *y_p, int p_is_f32, int B, int C, i
                                   long long stride_b, long long stride_c, long long stride_t, vy_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!x || !y_p || B < 1 || C < 1 || T < 1 || H < 1 || W < 1) VY_FAIL(VY_EINVAL, "vy_unpack_p_to_f32: bad arguments");
-    const size_t smem = (size_t)C * (W + 1) * 4;
-    if (smem > 200 * 1024) VY_FAIL(VY_EUNSUPPORTED, "vy_unpack_p_to_f32: C*(W+1) too large for one row tile");
+    if ((long long)T * B > 65535) VY_FAIL(VY_EUNSUPPORTED, "vy_unpack_p_to_f32: T*B must be <= 65535");
+    const dim3 grid((H * W + LY_P - 1) / LY_P, (C + LY_C - 1) / LY_C, T * B);
     if (p_is_f32) {
-        VY_CUDA_CHECK(cudaFuncSetAttribute(vy_unpack_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VY_KERNEL(VY_K_LAYOUT, st, (vy_unpack_kernel<float><<<T * B * H, 256, smem, st>>>((const float *)y_p, B, C, T, H, W, x,
-                                                                                         stride_b, stride_c, stride_t)));
+        VY_KERNEL(VY_K_LAYOUT, st, (vy_unpack_kernel<float><<<grid, LY_NT, 0, st>>>((const float *)y_p, B, C, T, H, W, x,
+                                                                                   stride_b, stride_c, stride_t)));
     } else {
-        VY_CUDA_CHECK(cudaFuncSetAttribute(vy_unpack_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VY_KERNEL(VY_K_LAYOUT, st, (vy_unpack_kernel<__nv_bfloat16><<<T * B * H, 256, smem, st>>>(
+        VY_KERNEL(VY_K_LAYOUT, st, (vy_unpack_kernel<__nv_bfloat16><<<grid, LY_NT, 0, st>>>(
             (const __nv_bfloat16 *)y_p, B, C, T, H, W, x, stride_b, stride_c, stride_t)));
     }
     VY_LAUNCH_CHECK("vy_unpack_kernel");
