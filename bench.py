@@ -447,6 +447,8 @@ def main():
         e2e = {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s",
                "h2d_bytes_per_step": det.h2d_bytes, "d2h_bytes_per_step": det.d2h_bytes, "steps": e2e_steps,
                "ms_per_step": e2e_ms / e2e_steps, "api": "videoyolo_b200.pipeline.HostDetector.__call__",
+               "h2d_gbs": round(det.h2d_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9, 1),
+               "bound": "PCIe host->device copy of the fp32 head maps (the kernels take ~1% of the step)",
                "matches_device_path": same}
         del h_heads
     sampler.stop()

@@ -676,20 +676,53 @@ __device__ __forceinline__ void str_issue(const float *q0, size_t HW, int nplane
     cp_async_commit();
 }
 
-// consume: the prologue (groups 0 .. STR_NG-1) has been issued by the caller
+// consume: the prologue (groups 0 .. STR_NG-1) has been issued by the caller.  The full groups run without
+// any per-plane predicate, with a running ring slot and a running refill pointer (the loop is issue-sensitive:
+// every instruction saved here is a memory request issued earlier); a partial last group takes the general path.
 __device__ __forceinline__ void str_unit_async(const StrUnit &un, float4 *ring_lane, u64 *wbuf, int &cnt, int b,
                                                const SelGlobal &g, int lane, u32 lt_mask) {
     const int nplanes = un.c1 - un.c0;
+    const int nfull = nplanes / STR_UN;                    // groups with all STR_UN planes
     const int ngroups = (nplanes + STR_UN - 1) / STR_UN;
     const float *q0 = un.pc + (size_t)un.c0 * un.HW;
-    for (int gi = 0; gi < ngroups; ++gi) {
+    const size_t plane_bytes = un.HW * sizeof(float);
+    const char *refill = (const char *)q0 + (size_t)(STR_NG * STR_UN) * plane_bytes;      // first plane of group gi + STR_NG
+    int slot = 0;                                          // (gi % STR_NG) * STR_UN
+    int gi = 0;
+    for (; gi < nfull; ++gi) {
         cp_async_wait<STR_NG - 1>();
-        const int slot = (gi % STR_NG) * STR_UN;
+        float4 *rs = ring_lane + slot * 32;
+        float t[STR_UN][4];
+#pragma unroll
+        for (int u = 0; u < STR_UN; ++u) {
+            const float4 w = rs[u * 32];
+            t[u][0] = w.x; t[u][1] = w.y; t[u][2] = w.z; t[u][3] = w.w;
+        }
+        u32 mask = 0;
+#pragma unroll
+        for (int u = 0; u < STR_UN; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) mask |= (t[u][v] >= un.tcmin[v]) ? (1u << (u * 4 + v)) : 0u;
+        // hits re-read their logit from the ring, so the slot is refilled only afterwards
+        str_hits<true>(un, mask, un.c0 + gi * STR_UN, wbuf, cnt, b, g, lane, lt_mask, rs);
+        if (gi + STR_NG < nfull) {
+#pragma unroll
+            for (int u = 0; u < STR_UN; ++u) cp_async16(rs + u * 32, refill + (size_t)u * plane_bytes);
+            cp_async_commit();
+        } else {
+            str_issue(q0, un.HW, nplanes, gi + STR_NG, ring_lane);
+        }
+        refill += (size_t)STR_UN * plane_bytes;
+        slot = slot + STR_UN == STR_RING ? 0 : slot + STR_UN;
+    }
+    for (; gi < ngroups; ++gi) {                           // at most one partial group
+        cp_async_wait<STR_NG - 1>();
+        float4 *rs = ring_lane + slot * 32;
         float t[STR_UN][4];
 #pragma unroll
         for (int u = 0; u < STR_UN; ++u) {
             if (gi * STR_UN + u < nplanes) {
-                const float4 w = ring_lane[(slot + u) * 32];
+                const float4 w = rs[u * 32];
                 t[u][0] = w.x; t[u][1] = w.y; t[u][2] = w.z; t[u][3] = w.w;
             } else {
                 t[u][0] = t[u][1] = t[u][2] = t[u][3] = CUDART_NAN_F;      // NaN >= x is false for every x
@@ -700,9 +733,9 @@ __device__ __forceinline__ void str_unit_async(const StrUnit &un, float4 *ring_l
         for (int u = 0; u < STR_UN; ++u)
 #pragma unroll
             for (int v = 0; v < 4; ++v) mask |= (t[u][v] >= un.tcmin[v]) ? (1u << (u * 4 + v)) : 0u;
-        // hits re-read their logit from the ring, so the slot is refilled only afterwards
-        str_hits<true>(un, mask, un.c0 + gi * STR_UN, wbuf, cnt, b, g, lane, lt_mask, ring_lane + slot * 32);
-        str_issue(q0, un.HW, nplanes, gi + STR_NG, ring_lane);
+        str_hits<true>(un, mask, un.c0 + gi * STR_UN, wbuf, cnt, b, g, lane, lt_mask, rs);
+        cp_async_commit();                                 // keeps the group count uniform
+        slot = slot + STR_UN == STR_RING ? 0 : slot + STR_UN;
     }
 }
 
