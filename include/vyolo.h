@@ -133,6 +133,19 @@ int vy_bbox_iou_f64(const double *a, int N, int lda, const double *b, int M, int
                     double offset, double *out, vy_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * The consumer step that follows net(x) in the reference, on the device.
+ * Replaces: `bboxes.clip(0, W)` (detect_yolo3.py:226, train_yolov3.py:477), `valid_pred = id >= 0` and
+ *           `box / W` (detect_yolo3.py:254-258) -- the part of detect()/validate() between the forward and
+ *           the python lists / metric update.
+ *   dets     (B, P, 6) rows [id, score, x1, y1, x2, y2] as written by vy_decode_nms_f32 / vy_box_nms_f32
+ *   clipped  (B, P, 4) every row's box clipped to [0, clip_hi] (padding rows clip to 0, like NDArray.clip)
+ *   normed   (B, P, 4) clipped / norm for rows with id >= 0, -1 elsewhere
+ *   counts   (B) int32 number of rows with id >= 0 (they are the first rows of each image)
+ *   Accounted under VY_K_IOU. */
+int vy_detect_consume_f32(const float *dets, int B, int P, float clip_hi, float norm, float *clipped,
+                          float *normed, int32_t *counts, vy_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Temporal fusion convolution: LeakyReLU(BN(ConvND(x))), use_bias=False, stride 1, groups 1.
  * Replaces: Conv / _conv2d / _conv3d / _conv21d cells, models/definitions/layers.py:63-89,135-158,
  *           as used by YOLODetectionBlockV3 (yolo3.py:229-253) -- one call per conv+BN+LReLU cell

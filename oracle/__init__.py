@@ -325,3 +325,15 @@ def conv1d_bn_leaky(x, w, gamma, beta, mean, var):
 def temporal_pool(x: np.ndarray, type: str = "max") -> np.ndarray:
     """TemporalPooling 'direct' style, layers.py:201-205: reduce axis 1 of (B,K,C,H,W)."""
     return x.max(axis=1) if type == "max" else x.mean(axis=1)
+
+
+# --------------------------------------------------------------------------- consumer step
+def detect_consume(ids: np.ndarray, bboxes: np.ndarray, size: float):
+    """detect_yolo3.py:226,254-258 restated: clip every box to [0, size]; per image the rows with id >= 0
+    and their boxes / size.  Returns (clipped (B,P,4), list of (valid_rows, normalised boxes))."""
+    clipped = np.clip(bboxes, 0, size).astype(np.float32)                  # :226
+    per_image = []
+    for i in range(ids.shape[0]):
+        valid = np.where(ids[i].flat >= 0)[0]                              # :256
+        per_image.append((valid, (clipped[i, valid, :] / np.float32(size)).astype(np.float32)))   # :257
+    return clipped, per_image

@@ -440,6 +440,37 @@ def test_full_size_stress_config4_properties(vy):
         assert torch.equal(again, out)
 
 
+def test_cuda_graph_replay_equals_eager(vy):
+    """The fused call captured in a CUDA graph (pipeline.GraphedDetector) gives the eager results, replay after replay."""
+    from videoyolo_b200.pipeline import GraphedDetector
+    rng = np.random.RandomState(8)
+    for (B, C, size) in [(1, 20, 416), (4, 80, 320)]:
+        shapes = [(B, 3 * (5 + C), g, g) for g in oracle.grid_sizes(size)]
+        det = GraphedDetector(C, AN, ST, shapes, "cuda")
+        for trial in range(3):
+            heads = [dev(h) for h in (random_heads(rng, B, C, size) if trial != 1 else trained_heads(rng, B, C, size))]
+            out, kept = det(heads)
+            torch.cuda.synchronize()
+            e_out, e_kept = vy.yolo3_decode_nms(heads, C, AN, ST)
+            assert torch.equal(out, e_out) and torch.equal(kept, e_kept)
+
+
+def test_detect_consume_matches_reference_consumer(vy):
+    """clip / valid rows / normalise on the device == the numpy steps of detect() (detect_yolo3.py:226,254-258)."""
+    rng = np.random.RandomState(31)
+    heads = trained_heads(rng, 3, 20, 416)
+    out, _ = vy.yolo3_decode_nms([dev(h) for h in heads], 20, AN, ST)
+    clipped, normed, counts = vy.ops.detect_consume(out, 416)
+    o = out.cpu().numpy()
+    ref_clip, per_image = oracle.detect_consume(o[..., 0:1], o[..., 2:6], 416)
+    np.testing.assert_array_equal(clipped.cpu().numpy(), ref_clip)
+    for i, (valid, boxes) in enumerate(per_image):
+        assert int(counts[i]) == len(valid)
+        np.testing.assert_array_equal(valid, np.arange(len(valid)))              # survivors are the first rows
+        np.testing.assert_array_equal(normed[i, : len(valid)].cpu().numpy(), boxes)
+        assert bool((normed[i, len(valid):] == -1).all())
+
+
 # ----------------------------------------------------------------------------------- bbox_iou
 def test_bbox_iou_against_reference_outputs(vy, golden_dir):
     z = np.load(os.path.join(golden_dir, "bbox_iou_ref.npz"))

@@ -42,3 +42,46 @@ extern "C" int vy_bbox_iou_f64(const double *a, int N, int lda, const double *b,
                                double *out, vy_stream_t st) {
     return launch_iou<double>(a, N, lda, b, M, ldb, offset, out, st);
 }
+
+// ------------------------------------------------------------------------------------------------
+// The consumer step of detect() / validate() on the device (detect_yolo3.py:226,254-265,
+// train_yolov3.py:477): bboxes.clip(0, W) for every row, then per image the rows with id >= 0 and their
+// boxes divided by the input size.  dets: (B, P, 6) rows [id, score, x1, y1, x2, y2] as written by
+// vy_decode_nms_f32 (survivors first, -1 padding).  One warp per image.
+__global__ void vy_detect_consume_kernel(const float *__restrict__ dets, int B, int P, float clip_hi, float norm,
+                                         float *__restrict__ clipped, float *__restrict__ normed,
+                                         int32_t *__restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const int b = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (b >= B) return;
+    int n = 0;
+    for (int r0 = 0; r0 < P; r0 += 32) {
+        const int r = r0 + lane;
+        bool valid = false;
+        if (r < P) {
+            const float *d = dets + ((size_t)b * P + r) * 6;
+            valid = d[0] >= 0.0f;                                            // detect_yolo3.py:256
+            float c[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c[k] = fminf(fmaxf(d[2 + k], 0.0f), clip_hi);      // :226  clip(0, W)
+            float *oc = clipped + ((size_t)b * P + r) * 4;
+            float *on = normed + ((size_t)b * P + r) * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { oc[k] = c[k]; on[k] = valid ? __fdiv_rn(c[k], norm) : -1.0f; }   // :257
+        }
+        n += __popc(__ballot_sync(0xffffffffu, valid));
+    }
+    if (lane == 0) counts[b] = n;
+}
+
+extern "C" int vy_detect_consume_f32(const float *dets, int B, int P, float clip_hi, float norm, float *clipped,
+                                     float *normed, int32_t *counts, vy_stream_t st) {
+    if (!dets || !clipped || !normed || !counts || B < 1 || P < 1) VY_FAIL(VY_EINVAL, "vy_detect_consume_f32: bad arguments");
+    if (!(norm > 0.0f)) VY_FAIL(VY_EINVAL, "vy_detect_consume_f32: norm must be > 0");
+    const int warps_per_cta = 4;
+    const int blocks = (B + warps_per_cta - 1) / warps_per_cta;
+    VY_KERNEL(VY_K_IOU, (cudaStream_t)st, (vy_detect_consume_kernel<<<blocks, warps_per_cta * 32, 0, (cudaStream_t)st>>>(
+        dets, B, P, clip_hi, norm, clipped, normed, counts)));
+    VY_LAUNCH_CHECK("vy_detect_consume_kernel");
+    return VY_OK;
+}

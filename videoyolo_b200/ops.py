@@ -166,6 +166,23 @@ def bbox_iou(bbox_a: torch.Tensor, bbox_b: torch.Tensor, offset=0) -> torch.Tens
     return out
 
 
+def detect_consume(dets: torch.Tensor, size: float):
+    """The device part of what detect()/validate() do with net(x)'s output (detect_yolo3.py:226,254-258):
+    returns (bboxes clipped to [0, size] (B,P,4), normalised boxes of the valid rows (B,P,4; -1 elsewhere),
+    number of valid rows per image (B,) int32).  ``dets`` is the (B, P, 6) tensor of yolo3_decode_nms."""
+    dets = _need_cuda(dets, "dets")
+    if dets.dim() != 3 or dets.shape[2] != 6:
+        raise ValueError("dets must be (B, P, 6)")
+    B, P = dets.shape[0], dets.shape[1]
+    clipped = torch.empty((B, P, 4), dtype=torch.float32, device=dets.device)
+    normed = torch.empty((B, P, 4), dtype=torch.float32, device=dets.device)
+    counts = torch.empty((B,), dtype=torch.int32, device=dets.device)
+    with torch.cuda.device(dets.device):
+        _lib.check(_lib.lib().vy_detect_consume_f32(dets.data_ptr(), B, P, float(size), float(size), clipped.data_ptr(),
+                                                    normed.data_ptr(), counts.data_ptr(), _stream()))
+    return clipped, normed, counts
+
+
 # ----------------------------------------------------------------------------------- temporal fusion conv
 class PTensor:
     """An activation in the library's P layout: ``data`` is a bf16 (or fp32) CUDA tensor of shape

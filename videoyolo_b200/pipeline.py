@@ -88,3 +88,41 @@ class HostDetector:
         self.kept_rows = self._kept_host
         r = self._out_host
         return r[..., 0:1], r[..., 1:2], r[..., 2:6]
+
+
+class GraphedDetector:
+    """Fused decode + box_nms for device-resident head maps of a FIXED shape, captured once in a CUDA graph:
+    a call is one ``cudaGraphLaunch`` instead of a memset and four kernel launches through ctypes.  Meant for
+    the launch-bound end of the path (small batches: BASELINE configs[0] is batch 1, where the kernels take
+    tens of microseconds).  The library needs nothing special for this: it never allocates or synchronises
+    and every launch goes to the stream it is handed, so its calls are capturable as they are.
+
+    ``det(heads)`` copies the heads into the graph's static inputs (device-to-device) and replays;
+    ``det()`` replays on whatever ``det.heads`` currently hold.  Returns ``(out (B, post_nms, 6), kept)``,
+    static tensors that the next replay overwrites.
+    """
+
+    def __init__(self, num_class: int, anchors, strides, shapes: Sequence[Sequence[int]], device,
+                 nms_thresh: float = 0.45, valid_thresh: float = 0.01, nms_topk: int = 400,
+                 post_nms: int = 100, agnostic: bool = False):
+        self.device = torch.device(device)
+        self.heads = [torch.zeros(tuple(s), dtype=torch.float32, device=self.device) for s in shapes]
+        B = self.heads[0].shape[0]
+        self.out = torch.empty((B, post_nms, 6), dtype=torch.float32, device=self.device)
+        self.kept = torch.empty((B, post_nms), dtype=torch.int32, device=self.device)
+        kw = dict(nms_thresh=nms_thresh, valid_thresh=valid_thresh, topk=nms_topk, post_nms=post_nms, agnostic=agnostic)
+        self._stream = torch.cuda.Stream(self.device)
+        self._stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._stream):                 # warm-up: sizes the cached workspace of this stream
+            ops.yolo3_decode_nms(self.heads, num_class, anchors, strides, out=self.out, kept=self.kept, **kw)
+        self._stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self._stream):
+            ops.yolo3_decode_nms(self.heads, num_class, anchors, strides, out=self.out, kept=self.kept, **kw)
+
+    def __call__(self, heads: Optional[Sequence[torch.Tensor]] = None):
+        if heads is not None:
+            for dst, src in zip(self.heads, heads):
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.out, self.kept
