@@ -237,6 +237,59 @@ def test_box_nms_large_argument_variants(vy):
     _check_nms(vy, e, overlap_thresh=0.45, valid_thresh=0.01, topk=-1, id_index=0)
 
 
+def test_box_nms_large_grid_index_equals_exhaustive(vy):
+    """The spatial index over the kept boxes must not change a single keep decision: indexed kernel ==
+    exhaustive kernel (same exact predicate) on awkward geometry, and == the oracle where the oracle is defined."""
+    rng = np.random.RandomState(23)
+    B, R = 2, 12000
+    d = _sparse_dets(rng, B, R, 3, extent=200.0, box=6.0)
+    # a mix of scales (tiny .. huge), far-away coordinates, degenerate and inverted boxes
+    idx = rng.permutation(R)
+    d[:, idx[:1500], 4:6] = d[:, idx[:1500], 2:4] + rng.uniform(20, 400, size=(B, 1500, 2))            # large boxes
+    d[:, idx[1500:2500], 4:6] = d[:, idx[1500:2500], 2:4] + rng.uniform(1e-3, 0.2, size=(B, 1000, 2))  # tiny boxes
+    d[:, idx[2500:2800], 2:6] += 3.0e6                                                                 # far away: coarse fp32 grid
+    d[:, idx[2800:3000], 4] = d[:, idx[2800:3000], 2]                                                  # zero width
+    d[:, idx[3000:3200], 5] = d[:, idx[3000:3200], 3] - 1.0                                            # inverted
+    d[:, idx[3200:3300], 2:6] *= 1.0e12                                                                # enormous
+    d[:, idx[3300:3400], 2:6] *= 1.0e-12                                                               # microscopic
+    d = d.astype(np.float32)
+    for force in (False, True):
+        for fmt in ("corner", "center"):
+            kw = dict(overlap_thresh=0.45, valid_thresh=0.001, topk=-1, id_index=0, force_suppress=force,
+                      in_format=fmt, out_format=fmt, return_kept=True)
+            g_out, g_kept = vy.box_nms(dev(d), **kw)
+            e_out, e_kept = vy.box_nms(dev(d), _exhaustive=True, **kw)
+            assert torch.equal(g_kept, e_kept) and torch.equal(g_out, e_out)
+            if fmt == "corner":
+                exp, rec = oracle.box_nms_c(d, overlap_thresh=0.45, valid_thresh=0.001, topk=-1, id_index=0,
+                                            force_suppress=force, return_record=True)
+                np.testing.assert_array_equal(g_kept.cpu().numpy(), rec)
+    # non-finite coordinates: only GPU against GPU (same predicate code on both sides)
+    d2 = d.copy()
+    d2[:, idx[4000:4050], 2] = np.inf
+    d2[:, idx[4050:4100], 5] = np.nan
+    d2[:, idx[4100:4150], 2:6] = -np.inf
+    for thr in (0.45, 0.1, 0.9):
+        kw = dict(overlap_thresh=thr, valid_thresh=0.001, topk=-1, id_index=0, return_kept=True)
+        g_out, g_kept = vy.box_nms(dev(d2), **kw)
+        e_out, e_kept = vy.box_nms(dev(d2), _exhaustive=True, **kw)
+        assert torch.equal(g_kept, e_kept)
+        assert torch.equal(torch.nan_to_num(g_out, nan=-7.0), torch.nan_to_num(e_out, nan=-7.0))
+
+
+def test_box_nms_large_grid_index_full_size(vy):
+    """BASELINE config 4 rows (851 760 per image): indexed == exhaustive, force_suppress off and on."""
+    B, C, size = 2, 80, 416
+    g = torch.Generator(device="cuda").manual_seed(1239)
+    heads = [torch.randn((B, 3 * (5 + C), s, s), generator=g, device="cuda") for s in oracle.grid_sizes(size)]
+    dets = vy.yolo3_decode(heads, C, AN, ST)
+    for force in (False, True):
+        kw = dict(overlap_thresh=0.45, valid_thresh=0.001, topk=-1, id_index=0, force_suppress=force, return_kept=True)
+        g_out, g_kept = vy.box_nms(dets, **kw)
+        e_out, e_kept = vy.box_nms(dets, _exhaustive=True, **kw)
+        assert torch.equal(g_kept, e_kept) and torch.equal(g_out, e_out)
+
+
 def test_box_nms_large_fed_reference_decoded_boxes(vy):
     """BASELINE config 4 arguments (valid_thresh 0.001, topk -1, force on/off) on decoded YOLO rows."""
     rng = np.random.RandomState(41)

@@ -7,10 +7,11 @@ from videoyolo_b200.synth import random_heads_cuda
 AN, ST = vy.ANCHORS[::-1], vy.STRIDES[::-1]
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+EXH = len(sys.argv) > 2
 heads = random_heads_cuda(B, 80, 416, 5, dev)
 dets = vy.yolo3_decode(heads, 80, AN, ST)
 for force in (False, True):
-    fn = lambda: vy.box_nms(dets, 0.45, 0.001, -1, id_index=0, force_suppress=force)
+    fn = lambda: vy.box_nms(dets, 0.45, 0.001, -1, id_index=0, force_suppress=force, _exhaustive=EXH)
     fn(); torch.cuda.synchronize()
     ts = []
     for _ in range(2):

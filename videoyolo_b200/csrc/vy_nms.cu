@@ -1494,6 +1494,8 @@ extern "C" int vy_box_nms_f32(const float *data, int B, long R, int W_elem, floa
         (out_format != VY_FMT_CORNER && out_format != VY_FMT_CENTER))
         VY_FAIL(VY_EINVAL, "vy_box_nms_f32: bad format");
     if (out_rows < 1 || out_rows > R) VY_FAIL(VY_EINVAL, "vy_box_nms_f32: out_rows must be in [1, R]");
+    const int force_flags = force_suppress;      // bit 0x100: exhaustive large-path kernel (tests)
+    force_suppress = (force_suppress & 0xff) ? 1 : 0;
     RowParams rp;
     rp.data = data; rp.R = R; rp.W = W_elem; rp.coord_start = coord_start; rp.score_index = score_index;
     rp.id_index = id_index; rp.background_id = background_id; rp.valid_thresh = valid_thresh;
@@ -1506,7 +1508,7 @@ extern "C" int vy_box_nms_f32(const float *data, int B, long R, int W_elem, floa
             VY_LAUNCH_CHECK("vy_fill_kernel");
             return VY_OK;
         }
-        return vy_box_nms_large(rp, B, K, overlap_thresh, force_suppress, in_format, out_format, out_rows,
+        return vy_box_nms_large(rp, B, K, overlap_thresh, force_suppress | (force_flags & 0x100), in_format, out_format, out_rows,
                                 out, kept_rows, workspace, workspace_bytes, st);
     }
     SelGlobal g;

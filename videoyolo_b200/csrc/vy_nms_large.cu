@@ -152,9 +152,47 @@ struct LgNms {
     float4 *kept_box;            // [N] kept boxes of a segment, from the segment's first position
     float *kept_area;
     unsigned char *keep;         // [N] by (image, rank)
+    u32 *hash_head;              // [2N] spatial hash of the kept boxes, a power-of-two region per segment (GRID)
+    u32 *next;                   // [N]  chain links of the kept boxes                                    (GRID)
 };
 
+// ---- spatial index over the kept boxes (GRID variant) ------------------------------------------------------
+// A box with IoU > t against a kept box k must overlap it (the fp32 predicate's intersection is positive only if
+// the real intervals overlap: the sign of an fp32 difference is exact) and, from iw*ih > t*w_k*h_k with ih <= h_k
+// and iw <= w_c, has w_k < w_c/t and w_c < w_k/t (same for h): sizes within a factor 1/t per axis.  Kept boxes
+// are therefore registered under (level, cell of the centre), level L = the power of two with
+// 2^(L-1) < max(w,h) <= 2^L and cells of size 2^L, and a candidate only probes the levels its size allows and the
+// cells its extent (+ one cell of the level, the largest a registered box can be) reaches.  Every bound carries
+// a 1e-3 relative slack, orders of magnitude above the 2^-24 roundings of the quantities involved, and the test
+// applied to whatever the probes find is the exact predicate, so the result is the exhaustive kernel's.
+// Boxes that cannot interact (w <= 0, h <= 0 or NaN: zero intersection with everything) are "inert"; boxes the
+// index cannot place (non-finite or absurd magnitudes) are "irregular": kept ones sit on a chain every candidate
+// walks, irregular candidates scan the whole kept list.
+constexpr u32 LG_EMPTY = 0xffffffffu;
+struct LgGeom { float cx, cy, w, h; int kind; };      // kind 0 regular, 1 inert, 2 irregular
 template <int FMT>
+__device__ __forceinline__ LgGeom lg_geom(float4 b) {
+    LgGeom g;
+    if (FMT == VY_FMT_CORNER) {
+        g.w = __fsub_rn(b.z, b.x); g.h = __fsub_rn(b.w, b.y);
+        g.cx = 0.5f * __fadd_rn(b.x, b.z); g.cy = 0.5f * __fadd_rn(b.y, b.w);
+    } else { g.cx = b.x; g.cy = b.y; g.w = b.z; g.h = b.w; }
+    if (!(g.w > 0.0f) || !(g.h > 0.0f)) { g.kind = 1; return g; }
+    const float m = fmaxf(g.w, g.h), mn = fminf(g.w, g.h);
+    const bool ok = m < 1.0e15f && mn > 1.0e-15f && fabsf(g.cx) < 1.0e15f && fabsf(g.cy) < 1.0e15f;   // NaN fails
+    g.kind = ok ? 0 : 2;
+    return g;
+}
+// level of a positive normal float: 2^(L-1) <= m < 2^L
+__device__ __forceinline__ int lg_level(float m) { return (int)((__float_as_uint(m) >> 23) & 0xffu) - 126; }
+__device__ __forceinline__ float lg_pow2(int e) { return __uint_as_float((u32)(e + 127) << 23); }      // e in [-126, 127]
+__device__ __forceinline__ u32 lg_hash(int L, int ix, int iy) {
+    u32 h = (u32)ix * 0x9E3779B1u ^ (u32)iy * 0x85EBCA77u ^ (u32)L * 0xC2B2AE3Du;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    return h;
+}
+
+template <int FMT, bool GRID>
 __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant__ LgNms p) {
     extern __shared__ __align__(16) unsigned char dyn[];
     float4 *tb = (float4 *)dyn;                     // [LG_TILE] live boxes of the tile, in order
@@ -165,6 +203,8 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
     u32 *mask = trank + LG_TILE;                    // [LG_TILE][LG_WORDS]
     __shared__ u32 rowany[LG_WORDS], keepw[LG_WORDS];
     __shared__ int wcount[LG_WORDS], woff[LG_WORDS + 1], kpre[LG_WORDS + 1];
+    __shared__ long long sh_len;
+    __shared__ u32 sh_irr;                           // head of the segment's chain of irregular kept boxes
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 lt_mask = (1u << lane) - 1u;
     const long long R = p.rp.R, N = (long long)p.B * R;
@@ -177,6 +217,29 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
         if (p.all_pairs) { b = seg; seg0 = (long long)b * R; len = min((long long)p.nvalid[b], p.K); }
         else { seg0 = p.seg_starts[seg]; segkey = p.keys2[seg0]; b = (int)(segkey >> 33); }
         const size_t img = (size_t)b * (size_t)R;
+        u32 hmask = 0;
+        u32 *hhead = nullptr;
+        if (GRID) {
+            // the segment's hash region: [2*seg0, 2*seg0 + hsize), hsize the largest power of two <= 2*len
+            if (!p.all_pairs) {
+                if (tid == 0) {                     // end of the segment: first position with another key (sorted)
+                    long long lo = seg0 + 1, hi = N;
+                    while (lo < hi) {
+                        const long long mid = (lo + hi) >> 1;
+                        if (p.keys2[mid] == segkey) lo = mid + 1; else hi = mid;
+                    }
+                    sh_len = lo - seg0;
+                }
+                __syncthreads();
+                len = sh_len;
+            }
+            if (tid == 0) sh_irr = LG_EMPTY;
+            u32 hsize = 2;
+            while ((long long)hsize * 2 <= 2 * len) hsize *= 2;
+            hmask = hsize - 1;
+            hhead = p.hash_head + 2 * (size_t)seg0;
+            __syncthreads();
+        }
         int m = 0;                                  // boxes kept so far (CTA-uniform)
         for (long long t0 = 0;; t0 += LG_TILE) {
             // ---- this thread's candidate
@@ -199,7 +262,7 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
             if (nv == 0) break;
             bool alive = have;
             // ---- a. against the boxes kept by earlier tiles (a suppressed box never suppresses)
-            for (int c0 = 0; c0 < m; c0 += LG_TILE) {
+            for (int c0 = 0; !GRID && c0 < m; c0 += LG_TILE) {
                 const int cnt = min(LG_TILE, m - c0);
                 __syncthreads();
                 if (tid < cnt) { sb[tid] = p.kept_box[seg0 + c0 + tid]; sa[tid] = p.kept_area[seg0 + c0 + tid]; }
@@ -216,6 +279,74 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
                     if (alive)
                         for (; j < cnt; ++j)
                             if (nms_suppresses_fast(sb[j], sa[j], bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT)) { alive = false; break; }
+                }
+            }
+            if (GRID && m > 0) {                         // CTA-uniform; every lane of a warp walks the same loops
+                // The lanes of a warp hold 32 different candidates.  To keep them in step the probe loops run
+                // to the warp's largest trip count and only COLLECT non-empty chain heads; the chains are walked
+                // afterwards, one kept box per lane and iteration, until every lane has drained its heads.
+                const LgGeom gc = lg_geom<FMT>(bx);
+                bool fallback = alive && gc.kind == 2;       // irregular candidate: scans the whole kept list
+                const bool probing = alive && gc.kind == 0;  // inert candidates cannot be suppressed
+                int l_lo = 0, l_hi = -1;
+                if (probing) {
+                    const float mc = fmaxf(gc.w, gc.h);
+                    // sizes a suppressor can have: (t*mc, mc/t), with slack; thr >= 0.05 on this path
+                    l_lo = lg_level(p.thr * mc * 0.999f);
+                    l_hi = lg_level(mc / p.thr * 1.001f);
+                    if (l_hi - l_lo > 12) { fallback = true; l_hi = l_lo - 1; }
+                }
+                u32 hb[16];
+                int hn = 0;
+                u32 cur = LG_EMPTY;
+                if (probing && !fallback) cur = sh_irr;      // irregular kept boxes: everyone checks them
+                int budget = 2 * m + 64;                     // chain-walk steps (a corrupted table cannot hang the GPU)
+                auto drain = [&]() {
+                    for (;;) {
+                        if (cur == LG_EMPTY && hn > 0) cur = hb[--hn];
+                        const bool busy = alive && !fallback && cur != LG_EMPTY && budget > 0;
+                        if (!__any_sync(0xffffffffu, busy)) break;
+                        if (busy) {
+                            --budget;
+                            if (nms_suppresses_fast(p.kept_box[cur], p.kept_area[cur], bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT)) alive = false;
+                            else cur = p.next[cur];
+                        }
+                    }
+                    hn = 0; cur = LG_EMPTY;
+                };
+                const int wl_lo = __reduce_min_sync(0xffffffffu, probing && !fallback ? l_lo : 0x7fffffff);
+                const int wl_hi = __reduce_max_sync(0xffffffffu, probing && !fallback ? l_hi : (int)0x80000000);
+                for (int L = wl_lo; L <= wl_hi; ++L) {
+                    int x0 = 0, y0 = 0, nx = 0, ncell = 0;
+                    if (probing && !fallback && alive && L >= l_lo && L <= l_hi) {
+                        const float cs = lg_pow2(L), inv = lg_pow2(-L);
+                        const float rx = (gc.w + cs) * 0.5f, ry = (gc.h + cs) * 0.5f;
+                        const float mx = rx * 1.001f + cs * 1e-3f + (fabsf(gc.cx) + rx) * 1e-6f;
+                        const float my = ry * 1.001f + cs * 1e-3f + (fabsf(gc.cy) + ry) * 1e-6f;
+                        const float fx0 = floorf((gc.cx - mx) * inv), fx1 = floorf((gc.cx + mx) * inv);
+                        const float fy0 = floorf((gc.cy - my) * inv), fy1 = floorf((gc.cy + my) * inv);
+                        if (!(fabsf(fx0) < 1.0e9f && fabsf(fx1) < 1.0e9f && fabsf(fy0) < 1.0e9f && fabsf(fy1) < 1.0e9f) ||
+                            fx1 - fx0 > 15.0f || fy1 - fy0 > 15.0f) {
+                            fallback = true;
+                        } else {
+                            x0 = (int)fx0; y0 = (int)fy0; nx = (int)fx1 - x0 + 1;
+                            ncell = nx * ((int)fy1 - y0 + 1);
+                        }
+                    }
+                    const int wn = __reduce_max_sync(0xffffffffu, ncell);
+                    for (int q = 0; q < wn; ++q) {
+                        if (q < ncell && alive && !fallback) {
+                            const int iy = y0 + q / nx, ix = x0 + q % nx;
+                            const u32 k = hhead[lg_hash(L, ix, iy) & hmask];
+                            if (k != LG_EMPTY) hb[hn++] = k;
+                        }
+                        if (__any_sync(0xffffffffu, hn >= 15)) drain();
+                    }
+                }
+                drain();
+                if (fallback && alive) {
+                    for (int j = 0; j < m && alive; ++j)
+                        if (nms_suppresses_fast(p.kept_box[seg0 + j], p.kept_area[seg0 + j], bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT)) alive = false;
                 }
             }
             // ---- b. the tile's live candidates, compacted in order
@@ -281,6 +412,21 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
                         p.kept_box[seg0 + pos] = tb[tid];
                         p.kept_area[seg0 + pos] = ta[tid];
                         p.keep[img + trank[tid]] = 1;
+                        if (GRID) {
+                            const LgGeom gk = lg_geom<FMT>(tb[tid]);
+                            const u32 idx = (u32)(seg0 + pos);
+                            bool placed = false;
+                            if (gk.kind == 0) {
+                                const int L = lg_level(fmaxf(gk.w, gk.h));
+                                const float inv = lg_pow2(-L);
+                                const float fx = floorf(gk.cx * inv), fy = floorf(gk.cy * inv);
+                                if (fabsf(fx) < 1.0e9f && fabsf(fy) < 1.0e9f) {
+                                    p.next[idx] = atomicExch(&hhead[lg_hash(L, (int)fx, (int)fy) & hmask], idx);
+                                    placed = true;
+                                }
+                            }
+                            if (!placed && gk.kind != 1) p.next[idx] = atomicExch(&sh_irr, idx);
+                        }
                     }
                 }
                 m += kpre[LG_WORDS];
@@ -413,6 +559,8 @@ int vy_box_nms_large(const RowParams &rp, int B, long long K, float overlap_thre
     unsigned char *keep = (unsigned char *)(ws + L.keep);
     const int sms = vy_sm_count();
     const int bitsB = lg_bits(B);
+    const bool exhaustive = (force_suppress & 0x100) != 0;
+    force_suppress &= 0xff;
     const bool all_pairs = force_suppress || rp.id_index < 0;
 
     VY_CUDA_CHECK(cudaMemsetAsync(ws + L.hdr, 0, L.hdr_bytes, st));
@@ -450,13 +598,20 @@ int vy_box_nms_large(const RowParams &rp, int B, long long K, float overlap_thre
     p.kept_box = (float4 *)(ws + L.kept_box); p.kept_area = (float *)(ws + L.kept_area); p.keep = keep;
     const size_t dyn = (size_t)LG_TILE * (16 + 16 + 4 + 4 + 4) + (size_t)LG_TILE * LG_WORDS * 4;
     const int grid = all_pairs ? (B < sms ? B : sms) : sms;
-    if (in_format == VY_FMT_CORNER) {
-        VY_CUDA_CHECK(cudaFuncSetAttribute(lg_nms_kernel<VY_FMT_CORNER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        VY_KERNEL(VY_K_NMS_LARGE, st, (lg_nms_kernel<VY_FMT_CORNER><<<grid, LG_NT, dyn, st>>>(p)));
-    } else {
-        VY_CUDA_CHECK(cudaFuncSetAttribute(lg_nms_kernel<VY_FMT_CENTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        VY_KERNEL(VY_K_NMS_LARGE, st, (lg_nms_kernel<VY_FMT_CENTER><<<grid, LG_NT, dyn, st>>>(p)));
+    // spatial index over the kept boxes unless the threshold is too small for the size bound to prune
+    // (or the caller asks for the exhaustive kernel: bit 0x100 of force_suppress, used by the tests)
+    const bool use_grid = overlap_thresh >= 0.05f && overlap_thresh < 1e30f && !exhaustive;
+    if (use_grid) {
+        p.hash_head = (u32 *)keys_a;             // both sorts are done: their input buffers are free
+        p.next = vals_a;
+        VY_CUDA_CHECK(cudaMemsetAsync(keys_a, 0xff, sizeof(u64) * (size_t)N, st));
     }
+#define LG_LAUNCH(FMT, GRID) do { \
+        VY_CUDA_CHECK(cudaFuncSetAttribute(lg_nms_kernel<FMT, GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+        VY_KERNEL(VY_K_NMS_LARGE, st, (lg_nms_kernel<FMT, GRID><<<grid, LG_NT, dyn, st>>>(p))); } while (0)
+    if (in_format == VY_FMT_CORNER) { if (use_grid) LG_LAUNCH(VY_FMT_CORNER, true); else LG_LAUNCH(VY_FMT_CORNER, false); }
+    else { if (use_grid) LG_LAUNCH(VY_FMT_CENTER, true); else LG_LAUNCH(VY_FMT_CENTER, false); }
+#undef LG_LAUNCH
     VY_LAUNCH_CHECK("lg_nms_kernel");
     const int nchunk = (int)((R + LG_CHUNK - 1) / LG_CHUNK);
     int *csum = (int *)(ws + L.csum);

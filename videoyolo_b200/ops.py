@@ -90,7 +90,7 @@ def yolo3_decode(heads, num_class: int, anchors, strides, agnostic: bool = False
 def box_nms(data: torch.Tensor, overlap_thresh: float = 0.5, valid_thresh: float = 0, topk: int = -1,
             coord_start: int = 2, score_index: int = 1, id_index: int = -1, background_id: int = -1,
             force_suppress: bool = False, in_format: str = "corner", out_format: str = "corner",
-            out_rows: Optional[int] = None, return_kept: bool = False):
+            out_rows: Optional[int] = None, return_kept: bool = False, _exhaustive: bool = False):
     """MXNet ``contrib.box_nms`` on a CUDA tensor; all leading dims are batch.
 
     Returns a tensor of the same shape as ``data`` (or with ``out_rows`` rows when given, which fuses
@@ -116,7 +116,7 @@ def box_nms(data: torch.Tensor, overlap_thresh: float = 0.5, valid_thresh: float
         ws = workspace(need, data.device)
         _lib.check(L.vy_box_nms_f32(data.data_ptr(), B, R, Wd, float(overlap_thresh), float(valid_thresh),
                                     int(topk), int(coord_start), int(score_index), int(id_index),
-                                    int(background_id), int(bool(force_suppress)), _FMT[in_format],
+                                    int(background_id), int(bool(force_suppress)) | (0x100 if _exhaustive else 0), _FMT[in_format],
                                     _FMT[out_format], rows, out.data_ptr(), kept.data_ptr(),
                                     ws.data_ptr(), ws.numel(), _stream()))
     return (out, kept) if return_kept else out
