@@ -118,7 +118,7 @@ def fusion_conv_leg(dev, B=8, T=3, iters=10):
 def temporal_tail_leg(dev, B=32, K=3, C=30, size=416, iters=10):
     """BASELINE configs[2] end to end on the device: ImageNet-VID (30 cls) 416^2, temporal window K=3:
     (B, K, channel, g, g) fp32 block outputs -> P-layout pack -> 3x3x3 tip conv (tcgen05) -> late 'max' join ->
-    1x1 prediction conv (library conv, fp32) -> fused decode + box_nms -> (ids, scores, bboxes).
+    1x1 prediction conv (same tcgen05 kernel, identity activation, fp32 out) -> fused decode + box_nms -> (ids, scores, bboxes).
     One window = one detection; CUDA events around the whole call, L2 flushed between calls."""
     import torch
     import videoyolo_b200 as vy
@@ -143,7 +143,7 @@ def temporal_tail_leg(dev, B=32, K=3, C=30, size=416, iters=10):
     return {"workload": "configs[2]: ImageNet-VID (30 cls) 416x416, K=3: tip fusion conv + max join + prediction conv + decode + NMS, batch %d windows" % B,
             "windows_per_s": round(B / (ms * 1e-3), 1), "ms_per_call": round(ms, 4),
             "library_kernel_ms_per_call": {k: round(v[0] / iters, 4) for k, v in prof.items()},
-            "note": "device-resident fp32 inputs; the 1x1 prediction conv is a library (cuDNN) conv; L2 flushed between calls"}
+            "note": "device-resident fp32 inputs; every kernel on the path is the library's own (no cuDNN/cuBLAS); L2 flushed between calls"}
 
 
 def load_traffic(config_name, kernel):

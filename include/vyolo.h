@@ -178,6 +178,10 @@ int vy_pack_f32_to_p_bf16(const float *x, long long stride_b, long long stride_c
                           int B, int C, int T, int H, int W, void *y_p, vy_stream_t stream);
 int vy_unpack_p_to_f32(const void *y_p, int p_is_f32, int B, int C, int T, int H, int W, float *x,
                        long long stride_b, long long stride_c, long long stride_t, vy_stream_t stream);
+/* the same for the first C of the Cp channels of a P-layout tensor (a conv whose Cout was padded to a multiple of 64,
+ * e.g. the 1x1 `prediction` conv of YOLOOutputV3, yolo3.py:62, with A*(5+classes) = 75 / 105 / 255 outputs) */
+int vy_unpack_p_channels_to_f32(const void *y_p, int p_is_f32, int B, int Cp, int C, int T, int H, int W, float *x,
+                                long long stride_b, long long stride_c, long long stride_t, vy_stream_t stream);
 
 /* TemporalPooling 'direct' style (layers.py:201-205) on P-layout data: x (T, inner) -> y (inner),
  * inner = B*(H+2)*(W+2)*C, mode 0 = max, 1 = mean.  bf16 in/out. */

@@ -72,9 +72,18 @@ def test_yolov3t_tail_matches_oracle_chain(vy, join, ctype):
         else:
             ref = bf16_round(oracle.temporal_pool(t, join).astype(np.float32))  # layers.py:201-205
         check(feats[i].cpu().numpy(), ref, "scale %d %s %s" % (i, join, ctype))
-    # ---- output layers + NMS tail: exact against the oracle on the GPU's own decoded rows
+    # ---- output layers: the head maps the forward pass used (native 1x1 conv on the bf16 tip for max/mean joins,
+    # library conv for 'cat') against the fp32 prediction conv on the oracle-checked features with bf16 weights
     with torch.no_grad():
-        heads = [o.prediction(f) for o, f in zip(net.tail.yolo_outputs, feats)]
+        heads = net.head_maps(*[torch.from_numpy(x).cuda() for x in xs])
+    for i, o in enumerate(net.tail.yolo_outputs):
+        wq = o.prediction.weight.detach()
+        if join != "cat":
+            wq = wq.to(torch.bfloat16).float()
+        with torch.no_grad():
+            ref_h = torch.nn.functional.conv2d(feats[i], wq, o.prediction.bias.detach()).cpu().numpy()
+        check(heads[i].cpu().numpy(), ref_h, "head %d %s" % (i, join))
+    # ---- NMS tail: exact against the oracle on the GPU's own decoded rows
     AN, ST = oracle.ANCHORS[::-1], oracle.STRIDES[::-1]
     dets = vy.yolo3_decode(heads, C, AN, ST).cpu().numpy()
     o_ids, o_sc, o_bb, o_rec = oracle.yolov3_tail(dets, return_record=True)

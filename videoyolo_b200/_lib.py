@@ -55,6 +55,8 @@ SIGNATURES = {
                               [ctypes.c_int] * 5 + [c_vp, c_vp]),
     "vy_unpack_p_to_f32": (ctypes.c_int, [c_vp] + [ctypes.c_int] * 6 + [c_vp, ctypes.c_longlong, ctypes.c_longlong,
                                                                         ctypes.c_longlong, c_vp]),
+    "vy_unpack_p_channels_to_f32": (ctypes.c_int, [c_vp] + [ctypes.c_int] * 7 + [c_vp, ctypes.c_longlong, ctypes.c_longlong,
+                                                                                 ctypes.c_longlong, c_vp]),
 }
 
 VY_OK = 0

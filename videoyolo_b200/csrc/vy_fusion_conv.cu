@@ -334,31 +334,39 @@ __global__ void vy_zero_border_kernel(__nv_bfloat16 *__restrict__ y, int H, int 
     }
 }
 
-// P layout (bf16 or fp32) -> (B, C, T, H, W)-strided fp32
+// P layout (bf16 or fp32, Cp channels per pixel) -> (B, C, T, H, W)-strided fp32 of its first C <= Cp channels
 template <typename TIn>
 __global__ void __launch_bounds__(LY_NT)
-vy_unpack_kernel(const TIn *__restrict__ y, int B, int C, int T, int H, int W, float *__restrict__ x,
+vy_unpack_kernel(const TIn *__restrict__ y, int B, int Cp, int C, int T, int H, int W, float *__restrict__ x,
                  long long sb, long long sc, long long st) {
     __shared__ float tile[LY_C][LY_P + 1];
     const int HW = H * W, Wp = W + 2;
     const int p0 = blockIdx.x * LY_P, c0 = blockIdx.y * LY_C;
     const int b = blockIdx.z % B, t = blockIdx.z / B;
-    const TIn *src = y + ((size_t)t * B + b) * (size_t)(H + 2) * Wp * C;
-    if (sizeof(TIn) == 2 && (C & 7) == 0) {                // 8 bf16 channels = one 16-byte load, 4 in flight per thread
-        for (int i = threadIdx.x; i < LY_P * (LY_C / 8); i += LY_NT) {
-            const int p = i / (LY_C / 8), c = (i % (LY_C / 8)) * 8;
+    const TIn *src = y + ((size_t)t * B + b) * (size_t)(H + 2) * Wp * Cp;
+    constexpr int V = 16 / (int)sizeof(TIn);               // channels per 16-byte load
+    if ((Cp % V) == 0) {                                   // vector loads, several in flight per thread
+        for (int i = threadIdx.x; i < LY_P * (LY_C / V); i += LY_NT) {
+            const int p = i / (LY_C / V), c = (i % (LY_C / V)) * V;
             const int pos = p0 + p;
-            uint4 q = make_uint4(0u, 0u, 0u, 0u);
-            if (pos < HW && c0 + c < C) {
-                const int h = pos / W, w = pos % W;
-                q = *(const uint4 *)((const __nv_bfloat16 *)src + ((size_t)(h + 1) * Wp + (w + 1)) * C + c0 + c);
-            }
-            const __nv_bfloat162 *qh = (const __nv_bfloat162 *)&q;
+            float f[V];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 f = __bfloat1622float2(qh[k]);
-                tile[c + 2 * k][p] = f.x; tile[c + 2 * k + 1][p] = f.y;
+            for (int k = 0; k < V; ++k) f[k] = 0.0f;
+            if (pos < HW && c0 + c < Cp) {                 // a vector never straddles the end of the pixel (Cp % V == 0)
+                const int h = pos / W, w = pos % W;
+                const uint4 q = *(const uint4 *)(src + ((size_t)(h + 1) * Wp + (w + 1)) * Cp + c0 + c);
+                if (sizeof(TIn) == 2) {
+                    const __nv_bfloat162 *qh = (const __nv_bfloat162 *)&q;
+#pragma unroll
+                    for (int k = 0; k < V / 2; ++k) { const float2 v = __bfloat1622float2(qh[k]); f[2 * k] = v.x; f[2 * k + 1] = v.y; }
+                } else {
+                    const float *qf = (const float *)&q;
+#pragma unroll
+                    for (int k = 0; k < V; ++k) f[k] = qf[k];
+                }
             }
+#pragma unroll
+            for (int k = 0; k < V; ++k) tile[c + k][p] = f[k];
         }
     } else {
         for (int i = threadIdx.x; i < LY_P * LY_C; i += LY_NT) {
@@ -367,7 +375,7 @@ vy_unpack_kernel(const TIn *__restrict__ y, int B, int C, int T, int H, int W, f
             float v = 0.0f;
             if (pos < HW && c0 + c < C) {
                 const int h = pos / W, w = pos % W;
-                v = (float)src[((size_t)(h + 1) * Wp + (w + 1)) * C + c0 + c];
+                v = (float)src[((size_t)(h + 1) * Wp + (w + 1)) * Cp + c0 + c];
             }
             tile[c][p] = v;
         }
@@ -496,21 +504,27 @@ extern "C" int vy_pack_f32_to_p_bf16(const float *x, long long stride_b, long lo
     return VY_OK;
 }
 
-extern "C" int vy_unpack_p_to_f32(const void *y_p, int p_is_f32, int B, int C, int T, int H, int W, float *x,
-                                  long long stride_b, long long stride_c, long long stride_t, vy_stream_t stream) {
+extern "C" int vy_unpack_p_channels_to_f32(const void *y_p, int p_is_f32, int B, int Cp, int C, int T, int H, int W, float *x,
+                                           long long stride_b, long long stride_c, long long stride_t, vy_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!x || !y_p || B < 1 || C < 1 || T < 1 || H < 1 || W < 1) VY_FAIL(VY_EINVAL, "vy_unpack_p_to_f32: bad arguments");
+    if (!x || !y_p || B < 1 || C < 1 || Cp < C || T < 1 || H < 1 || W < 1) VY_FAIL(VY_EINVAL, "vy_unpack_p_to_f32: bad arguments");
     if ((long long)T * B > 65535) VY_FAIL(VY_EUNSUPPORTED, "vy_unpack_p_to_f32: T*B must be <= 65535");
+    if (((uintptr_t)y_p & 15) != 0) VY_FAIL(VY_EALIGN, "vy_unpack_p_to_f32: y_p must be 16-byte aligned");
     const dim3 grid((H * W + LY_P - 1) / LY_P, (C + LY_C - 1) / LY_C, T * B);
     if (p_is_f32) {
-        VY_KERNEL(VY_K_LAYOUT, st, (vy_unpack_kernel<float><<<grid, LY_NT, 0, st>>>((const float *)y_p, B, C, T, H, W, x,
+        VY_KERNEL(VY_K_LAYOUT, st, (vy_unpack_kernel<float><<<grid, LY_NT, 0, st>>>((const float *)y_p, B, Cp, C, T, H, W, x,
                                                                                    stride_b, stride_c, stride_t)));
     } else {
         VY_KERNEL(VY_K_LAYOUT, st, (vy_unpack_kernel<__nv_bfloat16><<<grid, LY_NT, 0, st>>>(
-            (const __nv_bfloat16 *)y_p, B, C, T, H, W, x, stride_b, stride_c, stride_t)));
+            (const __nv_bfloat16 *)y_p, B, Cp, C, T, H, W, x, stride_b, stride_c, stride_t)));
     }
     VY_LAUNCH_CHECK("vy_unpack_kernel");
     return VY_OK;
+}
+
+extern "C" int vy_unpack_p_to_f32(const void *y_p, int p_is_f32, int B, int C, int T, int H, int W, float *x,
+                                  long long stride_b, long long stride_c, long long stride_t, vy_stream_t stream) {
+    return vy_unpack_p_channels_to_f32(y_p, p_is_f32, B, C, C, T, H, W, x, stride_b, stride_c, stride_t, stream);
 }
 
 extern "C" size_t vy_fusion_conv_workspace_bytes(int B, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw) {

@@ -220,9 +220,13 @@ def pack_p(x: torch.Tensor, layout: str = "NCDHW") -> PTensor:
     return PTensor(out, B, T, H, W, C)
 
 
-def unpack_p(p: PTensor, layout: str = "NCDHW") -> torch.Tensor:
-    """P layout (bf16 or fp32) -> fp32 CUDA tensor in a reference layout (see pack_p)."""
-    B, T, H, W, C = p.B, p.T, p.H, p.W, p.C
+def unpack_p(p: PTensor, layout: str = "NCDHW", channels: Optional[int] = None) -> torch.Tensor:
+    """P layout (bf16 or fp32) -> fp32 CUDA tensor in a reference layout (see pack_p).  ``channels``: only the
+    first ``channels`` of the tensor's channels (a conv whose Cout was padded to a multiple of 64)."""
+    B, T, H, W, Cp = p.B, p.T, p.H, p.W, p.C
+    C = Cp if channels is None else int(channels)
+    if not 1 <= C <= Cp:
+        raise ValueError("channels must be in [1, %d]" % Cp)
     if layout == "NCHW":
         if T != 1:
             raise ValueError("NCHW needs T == 1")
@@ -237,8 +241,8 @@ def unpack_p(p: PTensor, layout: str = "NCDHW") -> torch.Tensor:
     else:
         raise ValueError("layout must be NCHW, NCDHW or NTCHW")
     with torch.cuda.device(p.data.device):
-        _lib.check(_lib.lib().vy_unpack_p_to_f32(p.data.data_ptr(), int(p.data.dtype == torch.float32), B, C, T, H, W,
-                                                 out.data_ptr(), sb, sc, st, _stream()))
+        _lib.check(_lib.lib().vy_unpack_p_channels_to_f32(p.data.data_ptr(), int(p.data.dtype == torch.float32), B, Cp, C,
+                                                          T, H, W, out.data_ptr(), sb, sc, st, _stream()))
     return out
 
 

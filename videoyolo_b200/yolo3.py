@@ -114,7 +114,12 @@ class YOLOV3(torch.nn.Module):
         return heads
 
     def forward(self, *xs):
-        heads = self._heads(xs)
+        return self.forward_heads(*self._heads(xs))
+
+    def forward_heads(self, *heads):
+        """the tail from the head maps on (outputs of the prediction convs): decode, concat, box_nms, slice, split"""
+        for h, out in zip(heads, self.yolo_outputs):
+            out._check(h)
         C = len(self._classes)
         anchors = [o._anchors for o in self.yolo_outputs]
         strides = [o._stride for o in self.yolo_outputs]
@@ -163,9 +168,11 @@ class YOLOV3T(torch.nn.Module):
 
     def __init__(self, classes: Sequence[str], k: int = 3, k_join_type: str = "max", block_conv_type: str = "3",
                  channels: Sequence[int] = (512, 256, 128), anchors=None, strides=None,
-                 nms_thresh=0.45, nms_topk=400, post_nms=100, agnostic=False, **kwargs):
+                 nms_thresh=0.45, nms_topk=400, post_nms=100, agnostic=False, native_head=True, **kwargs):
         super().__init__()
         from .layers import Conv, TemporalPooling
+        self._native_head = bool(native_head)
+        self._head_cache = None
         assert k > 1, "3-D and 2+1-D convolutions need a temporal window (yolo3.py:981-983)"
         assert k_join_type in ("max", "mean", "cat")                      # yolo3.py:984
         assert block_conv_type in ("3", "21")
@@ -183,15 +190,20 @@ class YOLOV3T(torch.nn.Module):
     def set_nms(self, nms_thresh=0.45, nms_topk=400, post_nms=100):
         self.tail.set_nms(nms_thresh, nms_topk, post_nms)
 
-    def tip_features(self, *xs):
-        """the three joined tip feature maps (B, C', H, W) fp32 that feed the output layers"""
+    def _tips(self, xs):
         if len(xs) != len(self.tips):
             raise ValueError("expected %d inputs (stride 32,16,8 order)" % len(self.tips))
-        feats = []
+        tips = []
         for i, x in enumerate(xs):
             if x.dim() != 5 or x.shape[1] != self._k:
                 raise ValueError("input %d must be (B, K=%d, C, H, W)" % (i, self._k))
-            tip = self.tips[i](ops.pack_p(x, "NTCHW"))
+            tips.append(self.tips[i](ops.pack_p(x, "NTCHW")))
+        return tips
+
+    def tip_features(self, *xs):
+        """the three joined tip feature maps (B, C', H, W) fp32 that feed the output layers"""
+        feats = []
+        for i, tip in enumerate(self._tips(xs)):
             if self._join == "cat":
                 t = ops.unpack_p(tip, "NTCHW")                                  # (B, K, C, H, W)
                 feats.append(t.reshape(t.shape[0], -1, t.shape[3], t.shape[4]))  # reshape (0,-3,-2): yolo3.py:1136
@@ -199,8 +211,42 @@ class YOLOV3T(torch.nn.Module):
                 feats.append(ops.unpack_p(self.pools[i](tip), "NCHW"))
         return feats
 
+    def _head_weights(self):
+        """the 1x1 prediction convs (yolo3.py:62: Conv2D with bias) as fusion-conv operands: weight padded to a
+        multiple of 64 output channels in the kernel's (Cout, 1, 1, 1, Cin) bf16 layout, scale 1, shift = bias."""
+        convs = [o.prediction for o in self.tail.yolo_outputs]
+        key = tuple((c.weight._version, c.bias._version, c.weight.device) for c in convs)
+        if self._head_cache is None or self._head_cache[0] != key:
+            packed = []
+            with torch.no_grad():
+                for c in convs:
+                    n, cin = c.weight.shape[0], c.weight.shape[1]
+                    npad = (n + 63) // 64 * 64
+                    w = torch.zeros((npad, 1, 1, 1, cin), dtype=torch.bfloat16, device=c.weight.device)
+                    w[:n, 0, 0, 0] = c.weight.detach()[:, :, 0, 0].to(torch.bfloat16)
+                    shift = torch.zeros(npad, dtype=torch.float32, device=c.weight.device)
+                    shift[:n] = c.bias.detach().float()
+                    packed.append((w, torch.ones(npad, dtype=torch.float32, device=c.weight.device), shift, n))
+            self._head_cache = (key, packed)
+        return self._head_cache[1]
+
+    def head_maps(self, *xs):
+        """the three NCHW head maps (B, A*(5+C), H, W) fp32 = outputs of the prediction convs (yolo3.py:157).
+        native_head: the prediction conv runs in the fusion-conv kernel directly on the joined bf16 tip (identity
+        activation, bias as shift, fp32 output) and only the head map is converted to NCHW; otherwise the joined
+        tip is unpacked to fp32 and goes through the library conv of YOLOOutputV3."""
+        if not self._native_head or self._join == "cat":
+            feats = self.tip_features(*xs)
+            return [o.prediction(f) for o, f in zip(self.tail.yolo_outputs, feats)]
+        heads = []
+        for i, tip in enumerate(self._tips(xs)):
+            w, scale, shift, n = self._head_weights()[i]
+            pred = ops.fusion_conv(self.pools[i](tip), w, scale, shift, slope=1.0, out_f32=True)
+            heads.append(ops.unpack_p(pred, "NCHW", channels=n))
+        return heads
+
     def forward(self, *xs):
-        return self.tail(*self.tip_features(*xs))
+        return self.tail.forward_heads(*self.head_maps(*xs))
 
     @property
     def last_kept_rows(self):
