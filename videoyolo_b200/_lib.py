@@ -9,7 +9,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libvyolo.so")
+# VYOLO_LIB_VARIANT: development builds of tools/ (videoyolo_b200.build.build(variant=...)); unset in production
+_VARIANT = os.environ.get("VYOLO_LIB_VARIANT", "")
+SO_PATH = os.path.join(_HERE, "libvyolo%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 _LIB = None
 
 c_f32p = ctypes.POINTER(ctypes.c_float)

@@ -39,9 +39,12 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags=(), variant: str = "") -> str:
+    """variant / extra_flags: development builds (tools/): libvyolo_<variant>.so with extra nvcc flags, own objects."""
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "vyolo.h")]
+    OBJ = os.path.join(HERE, "csrc", "_obj" + ("_" + variant if variant else ""))
+    SO = os.path.join(HERE, "libvyolo%s.so" % ("_" + variant if variant else ""))
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
     jobs = []
@@ -49,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJ, os.path.basename(s)[:-3] + ".o")
         if force or _stale(o, [s] + hdrs):
             extra = ["-Xptxas", "-v"] if verbose else []
-            jobs.append(([nvcc] + NVCC_FLAGS + extra + ["-c", s, "-o", o], o))
+            jobs.append(([nvcc] + NVCC_FLAGS + list(extra_flags) + extra + ["-c", s, "-o", o], o))
     def run(job):
         cmd, o = job
         r = subprocess.run(cmd, capture_output=True, text=True)

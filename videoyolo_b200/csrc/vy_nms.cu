@@ -876,12 +876,14 @@ vy_rows_select_kernel(RowParams rp, SelPlan pl, SelGlobal g) {
 // ------------------------------------------------------------------------------------------------
 constexpr int FIN_NT_MAX = 1024;     // the kernel runs with 512 or 1024 threads (blockDim.x)
 constexpr int FIN_SLACK = 512;       // candidates beyond K that may reach the ranking sort
+constexpr int FIN_CMAX = 256;       // head-map classes up to this count are regrouped by counting instead of sorting
 constexpr int FIN_LCAP = 4096;       // candidate lists up to this length are staged in shared memory
 
 struct FinParams {
     int K, post_rows;            // rows written per image
     long long out_stride_rows;   // rows per image in `out` (== post_rows)
     float overlap_thresh;
+    float thr_lo, thr_hi;        // nms_suppresses_fast: where the reciprocal estimate decides (set by launch_finalize)
     int force_suppress, in_format, out_format;
     int W;                       // output row width (6 for heads)
     int fill_rest;               // 1: this kernel writes the -1 padding rows itself
@@ -924,21 +926,41 @@ __device__ __forceinline__ float4 fin_box(const VyHeads &hd, const RowParams &rp
     }
 }
 
-// Lower bound p of the K-th largest key of a list in global memory, with K <= #{keys >= p} <= K + slack
-// (MSB-first radix select, one coalesced sweep of the list per 8-bit digit).  n >= K, slack >= 0.
+// Lower bound p of the K-th largest key of a list, with K <= #{keys >= p} <= K + slack (MSB-first radix
+// select, one sweep of the list per 8-bit digit).  n >= K, slack >= 0.  The keys of a candidate list agree in
+// their leading bits (scores of one narrow range), so a first sweep takes the list's minimum and maximum and
+// the digits start right below the common prefix: one counting sweep usually settles the bound.
 static __device__ __noinline__ u64 fin_list_bound(SelBuf &S, const u64 *list, int n, int K, int slack) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    u64 prefix = 0;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    u64 *mm = (u64 *)S.queue;                           // [0] = min, [1] = max (the queue is idle in this kernel)
+    if (tid == 0) { mm[0] = ~0ull; mm[1] = 0ull; }
+    __syncthreads();
+    {
+        u64 lo = ~0ull, hi = 0ull;
+        for (int i = tid; i < n; i += nt) { const u64 k = list[i]; lo = k < lo ? k : lo; hi = k > hi ? k : hi; }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const u64 l2 = sel_shfl_xor_u64(lo, off), h2 = sel_shfl_xor_u64(hi, off);
+            lo = l2 < lo ? l2 : lo; hi = h2 > hi ? h2 : hi;
+        }
+        if (lane == 0) { atomicMin((unsigned long long *)&mm[0], (unsigned long long)lo); atomicMax((unsigned long long *)&mm[1], (unsigned long long)hi); }
+    }
+    __syncthreads();
+    const u64 kmin = mm[0], kmax = mm[1];
+    if (kmin == kmax) return kmin;
+    const int hb = 63 - __clzll((long long)(kmin ^ kmax));      // highest bit in which two keys differ
+    int shift = hb >= 7 ? hb - 7 : 0;
+    u64 prefix = shift + 8 >= 64 ? 0ull : (kmax >> (shift + 8)) << (shift + 8);
     int kk = K;
-    for (int shift = 56; shift >= 0; shift -= 8) {
+    for (;;) {
         if (tid < 256) S.hist[tid] = 0;
         __syncthreads();
-        // run-length aggregation: in the leading digits nearly all keys of a list agree, and
-        // same-address shared-memory atomics would serialise
+        // run-length aggregation: neighbouring keys of a thread often share the digit, and same-address
+        // shared-memory atomics would serialise
         u32 cur = 0xffffffffu, run = 0;
         for (int i = tid; i < n; i += nt) {
             const u64 k = list[i];
-            if (shift == 56 || ((k ^ prefix) >> (shift + 8)) == 0ull) {
+            if (shift + 8 >= 64 || ((k ^ prefix) >> (shift + 8)) == 0ull) {
                 const u32 d = (u32)(k >> shift) & 255u;
                 if (d != cur) { if (run) atomicAdd(&S.hist[cur], run); cur = d; run = 0; }
                 ++run;
@@ -958,28 +980,64 @@ static __device__ __noinline__ u64 fin_list_bound(SelBuf &S, const u64 *list, in
             }
             const u32 exc = inc - sum;
             if (exc < (u32)kk && (u32)kk <= inc) {
-                u32 run = exc;
+                u32 run2 = exc;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                    if (run + c[t] >= (u32)kk) { S.sel_digit = 255 - 8 * tid - t; S.sel_above = (int)run; S.sel_in = (int)c[t]; break; }
-                    run += c[t];
+                    if (run2 + c[t] >= (u32)kk) { S.sel_digit = 255 - 8 * tid - t; S.sel_above = (int)run2; S.sel_in = (int)c[t]; break; }
+                    run2 += c[t];
                 }
             }
         }
         __syncthreads();
         const int d = S.sel_digit, above = S.sel_above, inb = S.sel_in;
         __syncthreads();
-        prefix |= (u64)d << shift;
+        prefix |= (u64)d << shift;                      // (a digit window that overlaps the previous one repeats its bits)
         kk -= above;
-        if (inb - kk <= slack) break;
+        if (inb - kk <= slack || shift == 0) break;
+        shift = shift >= 8 ? shift - 8 : 0;
     }
     return prefix;
 }
 
-// One CTA per image.  Positions: "rank" = place in the global score order (what the operator's
-// output order is); "slot" = place after a stable regrouping by class, in which every class is one
-// contiguous segment still ordered by rank.  Suppression only ever happens inside a segment, so the
-// IoU bitmask and the greedy scan run over slots and touch (segment length)^2 pairs instead of K^2.
+// -DVY_FIN_TIMING (tools/fin_phases.py only): CTA 0 records clock64() at the phase boundaries
+#ifdef VY_FIN_TIMING
+#define FIN_T(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) vy_fin_clk[k] = clock64(); } while (0)
+extern "C" int vy_debug_fin_clocks(long long *out) {
+    return cudaMemcpyFromSymbol(out, vy_fin_clk, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
+}
+#else
+#define FIN_T(k) do { } while (0)
+#endif
+
+template <int SRC>
+__device__ __forceinline__ void fin_box_prefetch(const VyHeads &hd, const RowParams &rp, int b, u32 row) {
+    if (SRC == 0) {
+        int s = 0;
+        while (s + 1 < hd.n_scales && (long long)row >= hd.sc[s + 1].row_off) ++s;
+        const VyScale &sc = hd.sc[s];
+        const u32 rem = (row - (u32)sc.row_off) % (u32)sc.n_s;
+        const int pos = (int)(rem / (u32)hd.A), a = (int)(rem % (u32)hd.A);
+        const size_t HW = (size_t)sc.HW;
+        const float *p = sc.head + ((size_t)(b * hd.A + a) * hd.P) * HW + pos;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + k * HW));
+    } else {
+        const float *p = rp.data + ((size_t)b * (size_t)rp.R + row) * rp.W + rp.coord_start;
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+    }
+}
+
+// unique keys (the callers pad with distinct non-zero values): rank merges when the CTA has a thread per key
+__device__ __forceinline__ void fin_sort(u64 *keys, int npow2) {
+    if (npow2 <= (int)blockDim.x) sel_sort_desc_merge(keys, npow2);
+    else sel_sort_desc_fast(keys, npow2);
+}
+
+// One CTA of FIN_NT_MAX >= K threads per image.  Positions: "rank" = place in the global score order (what
+// the operator's output order is); "slot" = place after a stable regrouping by class, in which every class
+// is one contiguous segment still ordered by rank.  Suppression only ever happens inside a segment, so the
+// IoU tests run over (segment length)^2 pairs instead of K^2, and segments that share no 32-slot block are
+// resolved by different warps.
 template <int SRC>   // 0: head maps, 1: rows
 __global__ void __launch_bounds__(FIN_NT_MAX)
 vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinParams fp) {
@@ -990,6 +1048,8 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     const int b = blockIdx.x;
     const int K = pl.K;
     const int nwK = (K + 31) >> 5;
+    const u32 lt_mask = (1u << lane) - 1u;
+    FIN_T(0);
     int cp2 = 32;
     while (cp2 < K + FIN_SLACK) cp2 <<= 1;
     u64 *cand = (u64 *)dyn;                            // cp2 >= K + FIN_SLACK candidates (sorted in place)
@@ -999,202 +1059,361 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     int *seg_end = cls + K;                            // K      by slot
     int *slot_of_rank = seg_end + K;                   // K
     int *rank_of_slot = slot_of_rank + K;              // K
-    u32 *mask = (u32 *)(rank_of_slot + K);             // K * nwK, by slot
-    u32 *rowany = mask + (size_t)K * nwK;              // 32     by slot
-    u32 *keepw = rowany + 32;                          // 32     by rank
-    int *kprefix = (int *)(keepw + 32);                // 33 (+3 pad)
-    u64 *lbuf = (u64 *)(((uintptr_t)(kprefix + 36) + 15) & ~(uintptr_t)15);   // FIN_LCAP: a short candidate list, staged
+    u32 *supby = (u32 *)(rank_of_slot + K);            // K * nwK: [j][rb] = rows of slot block rb that would suppress slot j
+    u32 *begw = supby + (size_t)K * nwK;               // 32     by slot: first slot of a segment
+    u32 *keeps = begw + 32;                            // 32     by slot: survivors
+    u32 *keepw = keeps + 32;                           // 32     by rank: survivors
+    int *rb0 = (int *)(keepw + 32);                    // 32 (+4 pad): first slot block whose segments reach block cb
+    u64 *lbuf = (u64 *)(((uintptr_t)(rb0 + 36) + 15) & ~(uintptr_t)15);   // FIN_LCAP: a short candidate list, staged
 
     // ---- 1. exact top-K of the image's candidate list, sorted descending
     // streaming path: the streamed list, unless it was unusable and the rescue pass rebuilt g.list
     const bool use_s = g.scount != nullptr && stream_list_ok(g, b, K);
     const int n_list = use_s ? g.scount[b] : min(g.count[b], pl.list_cap);
     const u64 *list = use_s ? g.slist + (size_t)b * g.slist_cap : g.list + (size_t)b * pl.list_cap;
-    if (tid == 0) { S.count = 0; S.thr = use_s ? ~g.sthr[b] : g.thr[b]; }
-    if (n_list > K + FIN_SLACK && n_list <= fp.lcap) {
+    if (tid == 0) { S.count = 0; S.flag = 0; S.thr = use_s ? ~g.sthr[b] : g.thr[b]; }
+    if (tid < 32) keeps[tid] = 0u;
+    // the ranking sort works on a power-of-two buffer: let through what fills the one K + 64 needs anyway
+    int slack;
+    { int t2 = 64; while (t2 < K + 64) t2 <<= 1; slack = min(min(t2, FIN_NT_MAX) - K, FIN_SLACK); }
+    if (n_list > K + slack && n_list <= fp.lcap) {
         // the radix sweeps below then never leave the SM
         for (int i = tid; i < n_list; i += FIN_NT) lbuf[i] = list[i];
         list = lbuf;
     }
     __syncthreads();
-    if (n_list > K + FIN_SLACK) {
-        // long list: bound its K-th largest key first, so that one sweep leaves <= K + FIN_SLACK keys
-        const u64 p = fin_list_bound(S, list, n_list, K, FIN_SLACK);
+    FIN_T(1);
+    if (n_list > K + slack) {
+        // long list: bound its K-th largest key first, so that one sweep leaves <= K + slack keys
+        const u64 p = fin_list_bound(S, list, n_list, K, slack);
         const u64 cur = S.thr;
         __syncthreads();
         if (tid == 0 && p > cur) S.thr = p;
         __syncthreads();
     }
+    FIN_T(2);
     u64 *keyr = S.keys;                                 // the K best by rank (K <= SEL_KMAX <= SEL_CAP)
     {
         const u64 thr = S.thr;
-        for (int i = tid; i < n_list; i += FIN_NT) {
-            const u64 key = list[i];
-            if (key >= thr) { const int slot = atomicAdd(&S.count, 1); if (slot < K + FIN_SLACK) cand[slot] = key; }
+        for (int i0 = 0; i0 < n_list; i0 += FIN_NT) {   // CTA-uniform trip count: one shared-memory atomic per warp
+            const int i = i0 + tid;
+            const u64 key = i < n_list ? list[i] : 0ull;
+            const bool in = i < n_list && key >= thr;
+            const u32 bal = __ballot_sync(0xffffffffu, in);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&S.count, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int slot = base + __popc(bal & lt_mask);
+                if (in && slot < K + FIN_SLACK) cand[slot] = key;
+            }
         }
     }
     __syncthreads();
+    FIN_T(3);
     const int m1 = min(S.count, K + FIN_SLACK);
     const int m = min(m1, K);                           // <= K candidates take part
+    const int nw = (m + 31) >> 5;
     // rank: keys are unique (the row is part of the key), so a descending sort IS the operator's
-    // stable order; bitonic network over the zero-padded buffer
+    // stable order; the buffer is padded with distinct values below every real key
     {
         int np2 = 32;
         while (np2 < m1) np2 <<= 1;
-        for (int i = m1 + tid; i < np2; i += FIN_NT) cand[i] = 0ull;
+        for (int i = m1 + tid; i < np2; i += FIN_NT) cand[i] = (u64)(np2 - i);
         __syncthreads();
-        sel_sort_desc_fast(cand, np2);
-        for (int i = tid; i < m; i += FIN_NT) keyr[i] = cand[i];
+        fin_sort(cand, np2);
     }
-    for (int i = tid; i < m * nwK; i += FIN_NT) mask[i] = 0u;
-    if (tid < 32) { rowany[tid] = 0; keepw[tid] = 0; }
-    __syncthreads();
+    // thread i < m owns rank i from here on (FIN_NT >= K)
+    u64 mykey = 0ull;
+    if (tid < m) {
+        mykey = cand[tid];
+        keyr[tid] = mykey;
+        fin_box_prefetch<SRC>(hd, rp, b, vy_key_row(mykey));    // the box logits travel while the classes are sorted
+    }
+    FIN_T(4);
 
-    // ---- 2. regroup by class, stable in rank: ascending sort of (class, rank) pairs
+    // ---- 2. regroup by class, stable in rank
     const bool all_pairs = fp.force_suppress || (SRC == 1 && rp.id_index < 0) || (SRC == 0 && hd.agnostic);
-    if (!all_pairs) {
+    // head maps with a bounded class count: counting sort (per-warp class counts, match_any for the place
+    // inside the warp); anything else: ascending sort of (class, rank) pairs
+    const bool counted = !all_pairs && SRC == 0 && hd.C <= FIN_CMAX;
+    if (counted) {
+        const int C = hd.C;
+        unsigned short *cntw = (unsigned short *)cand;  // [nw][C]; the ranked keys live in keyr / registers by now
+        u32 *cstart = S.hist;                           // [C]
+        __syncthreads();                                // every thread has read its cand[tid]
+        for (int i = tid; i < nw * C; i += FIN_NT) cntw[i] = 0;
+        __syncthreads();
+        int c = 0;
+        if (tid < m) c = fin_class<SRC>(hd, rp, b, vy_key_row(mykey));
+        const u32 peers = __match_any_sync(0xffffffffu, tid < m ? c : -1 - lane);
+        const int intra = __popc(peers & lt_mask);
+        if (tid < m && intra == 0) cntw[warp * C + c] = (unsigned short)__popc(peers);
+        __syncthreads();
+        if (tid < C) {                                  // per class: exclusive prefix over the warps, total
+            int run = 0;
+            for (int w = 0; w < nw; ++w) { const int v = cntw[w * C + tid]; cntw[w * C + tid] = (unsigned short)run; run += v; }
+            cstart[tid] = (u32)run;
+        }
+        __syncthreads();
+        if (warp == 0) {                                // exclusive scan of the class totals (C <= 256: 8 per lane)
+            u32 v[FIN_CMAX / 32], sum = 0;
+#pragma unroll
+            for (int t = 0; t < FIN_CMAX / 32; ++t) { const int idx = lane * (FIN_CMAX / 32) + t; v[t] = idx < C ? cstart[idx] : 0u; sum += v[t]; }
+            u32 incl = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const u32 y = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += y;
+            }
+            u32 run = incl - sum;
+#pragma unroll
+            for (int t = 0; t < FIN_CMAX / 32; ++t) { const int idx = lane * (FIN_CMAX / 32) + t; if (idx < C) { cstart[idx] = run; run += v[t]; } }
+        }
+        __syncthreads();
+        if (tid < m) {
+            const int slot = (int)cstart[c] + (int)cntw[warp * C + c] + intra;
+            slot_of_rank[tid] = slot;
+            rank_of_slot[slot] = tid;
+            cls[slot] = c;
+        }
+        __syncthreads();
+    } else if (!all_pairs) {
         int mp2 = 32;
         while (mp2 < m) mp2 <<= 1;
+        // (the read of cand[tid] above and this write are by the same thread)
         for (int i = tid; i < mp2; i += FIN_NT) {
-            u64 k = 0ull;                               // padding: ~0 = last in ascending order
-            if (i < m) k = ~(((u64)((u32)fin_class<SRC>(hd, rp, b, vy_key_row(keyr[i])) ^ 0x80000000u) << 32) | (u64)i);
+            u64 k = (u64)(mp2 - i);                     // padding: distinct, below every real key = last in ascending order
+            if (i < m) k = ~(((u64)((u32)fin_class<SRC>(hd, rp, b, vy_key_row(mykey)) ^ 0x80000000u) << 32) | (u64)i);
             cand[i] = k;
         }
         __syncthreads();
-        sel_sort_desc_fast(cand, mp2);                  // descending in ~key = ascending in (class, rank)
-        for (int slot = tid; slot < m; slot += FIN_NT) {
-            const u64 k = ~cand[slot];
-            const int rank = (int)(u32)(k & 0xffffffffull);
-            slot_of_rank[rank] = slot;
-            rank_of_slot[slot] = rank;
-            cls[slot] = (int)((u32)(k >> 32) ^ 0x80000000u);
+        fin_sort(cand, mp2);                            // descending in ~key = ascending in (class, rank)
+    } else {
+        __syncthreads();                                // keyr
+    }
+    FIN_T(5);
+    // thread j < m owns slot j: its box, and whether it opens a segment
+    bool beg = false;
+    {
+        if (tid < m) {
+            int rank = tid, c = 0;
+            beg = tid == 0;
+            if (counted) {
+                rank = rank_of_slot[tid];
+                c = cls[tid];
+                if (tid > 0) beg = cls[tid - 1] != c;
+            } else if (!all_pairs) {
+                const u64 k = ~cand[tid];
+                rank = (int)(u32)(k & 0xffffffffull);
+                c = (int)((u32)(k >> 32) ^ 0x80000000u);
+                if (tid > 0) beg = (u32)(~cand[tid - 1] >> 32) != (u32)(k >> 32);
+                cls[tid] = c;
+                rank_of_slot[tid] = rank;
+                slot_of_rank[rank] = tid;
+            } else {
+                cls[tid] = 0;
+                rank_of_slot[tid] = tid;
+                slot_of_rank[tid] = tid;
+            }
+            const float4 bx = fin_box<SRC>(hd, rp, b, vy_key_row(keyr[rank]));
+            box[tid] = bx;
+            area[tid] = nms_area(bx, fp.in_format);
+        }
+        const u32 bw = __ballot_sync(0xffffffffu, beg);
+        if (lane == 0) begw[warp] = bw;
+    }
+    __syncthreads();
+    FIN_T(6);
+    if (tid < m) {                                      // segment end = next opening slot
+        int w = warp;
+        u32 bits = lane == 31 ? 0u : (begw[w] >> (lane + 1)) << (lane + 1);
+        int e = m;
+        for (;;) {
+            if (bits) { e = (w << 5) + __ffs(bits) - 1; break; }
+            if (++w >= nw) break;
+            bits = begw[w];
+        }
+        seg_end[tid] = e;
+        if (beg) atomicMax(&S.flag, e - tid);           // longest segment
+    }
+    if (tid < nw) {                                     // block of the segment start of slot 32 * tid (slot 0 opens one)
+        int w = tid;
+        if (!(begw[w] & 1u)) { do { --w; } while (begw[w] == 0u); }
+        rb0[tid] = w;
+    }
+    __syncthreads();
+    FIN_T(7);
+
+    const bool short_segs = S.flag <= 64;
+    if (short_segs) {
+        // ---- 3s/4s. segments of <= 64 slots (the per-class case): a lane per reference slot i tests its followers
+        // i+1 .. in step, the hits of a slot are a 64-bit word relative to it; then the first slot of every segment
+        // runs the greedy pass over its segment alone
+        u64 *rowrel = cand;                             // [m] (cand is free from here on)
+        u64 rel = 0ull;
+        int e = 0;
+        float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ai = 0.f;
+        if (tid < m) { e = seg_end[tid]; bi = box[tid]; ai = area[tid]; }
+        const int trip = __reduce_max_sync(0xffffffffu, tid < m ? e - tid - 1 : 0);
+        for (int k = 1; k <= trip; ++k) {
+            const int j = tid + k;
+            if (j < e && nms_suppresses_fast(bi, ai, box[j], area[j], fp.overlap_thresh, fp.thr_lo, fp.thr_hi, fp.in_format))
+                rel |= 1ull << (k - 1);
+        }
+        if (tid < m) rowrel[tid] = rel;
+        __syncthreads();
+        FIN_T(8);
+        if (tid < m && beg) {
+            const int len = e - tid;
+            u64 removed = 0ull, kept = 0ull;
+            for (int k = 0; k < len; ++k) {
+                if (!((removed >> k) & 1ull)) { kept |= 1ull << k; removed |= (rowrel[tid + k] << 1) << k; }
+            }
+            const int sh = tid & 31, w0 = tid >> 5;
+            const u64 lo = kept << sh, hi = sh ? kept >> (64 - sh) : 0ull;
+            if ((u32)lo) atomicOr(&keeps[w0], (u32)lo);
+            if ((u32)(lo >> 32)) atomicOr(&keeps[w0 + 1], (u32)(lo >> 32));
+            if ((u32)hi) atomicOr(&keeps[w0 + 2], (u32)hi);
         }
     } else {
-        for (int i = tid; i < m; i += FIN_NT) { slot_of_rank[i] = i; rank_of_slot[i] = i; cls[i] = 0; }
-    }
-    __syncthreads();
-    for (int i = tid; i < m; i += FIN_NT) {
-        const int slot = slot_of_rank[i];
-        const float4 bx = fin_box<SRC>(hd, rp, b, vy_key_row(keyr[i]));
-        box[slot] = bx;
-        area[slot] = nms_area(bx, fp.in_format);
-    }
-    __syncthreads();
-    for (int j = tid; j < m; j += FIN_NT) {
-        int e = j + 1;
-        if (all_pairs) e = m;
-        else { const int c = cls[j]; while (e < m && cls[e] == c) ++e; }
-        seg_end[j] = e;
-    }
-    __syncthreads();
-
-    // ---- 3. suppression bitmask, one warp per reference slot, 32 candidate slots per ballot
-    const int nw = (m + 31) >> 5;
-    for (int i = warp; i < m; i += nwarps) {
-        const int e = seg_end[i];
-        if (e <= i + 1) continue;                       // alone in its class
-        const float4 bi = box[i];
-        const float ai = area[i];
-        u32 any = 0;
-        for (int w = i >> 5; w <= (e - 1) >> 5; ++w) {
-            const int jx = (w << 5) + lane;
-            bool sup = false;
-            if (jx > i && jx < e) {
-                const float4 bj = box[jx];
-                float inter = nms_isect(bi.x, bi.z, bj.x, bj.z, fp.in_format);
-                inter = __fmul_rn(inter, nms_isect(bi.y, bi.w, bj.y, bj.w, fp.in_format));
-                const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, area[jx]), inter));
-                sup = iou > fp.overlap_thresh;
-            }
-            const u32 bits = __ballot_sync(0xffffffffu, sup);
-            if (lane == 0 && bits) mask[(size_t)i * nwK + w] = bits;
-            any |= bits;
+    // ---- 3. suppression tests in 32 x 32 tiles: tile (rb, cb) exists when a segment reaches from slot block rb
+    // into slot block cb; lane = candidate slot j of block cb, rows i of block rb in turn (a row no segment of
+    // which reaches the block is skipped by the whole warp)
+    {
+        const int r0 = lane < nw ? rb0[lane] : 0;
+        const int cnt = lane < nw ? lane - r0 + 1 : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
         }
-        if (lane == 0 && any) atomicOr(&rowany[i >> 5], 1u << (i & 31));
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int t = warp; t < total; t += nwarps) {
+            const int cb = __popc(__ballot_sync(0xffffffffu, lane < nw && incl <= t));
+            const int rb = __shfl_sync(0xffffffffu, r0, cb) + (t - __shfl_sync(0xffffffffu, incl - cnt, cb));
+            const int j = (cb << 5) + lane;
+            float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+            float aj = 0.f;
+            if (j < m) { bj = box[j]; aj = area[j]; }
+            u32 d = 0;
+            const int i0 = rb << 5, c0 = cb << 5;
+            // rows of the block with a follower in this column block (lane = row), then two rows per step
+            const int myrow = i0 + lane;
+            const int e_l = myrow < m ? seg_end[myrow] : 0;
+            u32 rows = __ballot_sync(0xffffffffu, e_l > max(myrow + 1, c0));
+            while (rows) {
+                const int ia = __ffs(rows) - 1;
+                rows &= rows - 1;
+                const int ib = rows ? __ffs(rows) - 1 : ia;
+                rows &= rows - 1;                       // (0 & anything stays 0)
+                const int ea = __shfl_sync(0xffffffffu, e_l, ia), eb = __shfl_sync(0xffffffffu, e_l, ib);
+                const float4 ba = box[i0 + ia], bb = box[i0 + ib];
+                const float aa = area[i0 + ia], ab = area[i0 + ib];
+                // both tests unconditionally (side by side in the pipeline); lanes outside a row's segment drop theirs
+                const bool ha = nms_suppresses_fast(ba, aa, bj, aj, fp.overlap_thresh, fp.thr_lo, fp.thr_hi, fp.in_format);
+                const bool hb = nms_suppresses_fast(bb, ab, bj, aj, fp.overlap_thresh, fp.thr_lo, fp.thr_hi, fp.in_format);
+                if (ha && j > i0 + ia && j < ea) d |= 1u << ia;
+                if (hb && j > i0 + ib && j < eb) d |= 1u << ib;     // (ib == ia repeats the same bit)
+            }
+            if (j < m) supby[(size_t)j * nwK + rb] = d;
+        }
     }
     __syncthreads();
+    FIN_T(8);
 
-    // ---- 4. greedy scan over slots (warp 0).  lane w holds the suppressed-bits of slot word w.
-    if (warp == 0) {
-        u32 removed = 0;
-        for (int blk = 0; blk < nw; ++blk) {
-            const int r = (blk << 5) + lane;
-            const u32 validm = (m - (blk << 5) >= 32) ? 0xffffffffu : ((1u << (m - (blk << 5))) - 1u);
-            const u32 ra = rowany[blk] & validm;
-            const u32 diag = (r < m && ((ra >> lane) & 1u)) ? mask[(size_t)r * nwK + blk] : 0u;
-            u32 rem = __shfl_sync(0xffffffffu, removed, blk);
-            u32 pend = ra;                              // references with a non-empty row, in order
-            while (pend) {
+    // ---- 4. greedy resolution, one warp per chain of slot blocks linked by a straddling segment (block cb
+    // starts a chain when rb0[cb] == cb).  Lane = slot; keeps[rb] of the earlier blocks of a chain were written
+    // by this warp.
+    if (warp < nw && rb0[warp] == warp) {
+        for (int cb = warp; cb < nw; ++cb) {
+            const int r0 = rb0[cb];
+            if (cb > warp && r0 == cb) break;
+            const int j = (cb << 5) + lane;
+            bool rem = false;
+            u32 d = 0;
+            if (j < m) {
+                for (int rb = r0; rb < cb; ++rb) rem |= (supby[(size_t)j * nwK + rb] & keeps[rb]) != 0u;
+                d = supby[(size_t)j * nwK + cb];
+            }
+            const bool live = j < m && !rem;
+            u32 keepbits = __ballot_sync(0xffffffffu, live && d == 0u);
+            u32 pend = __ballot_sync(0xffffffffu, live && d != 0u);
+            while (pend) {                              // in slot order: everything below bit i is final
                 const int i = __ffs(pend) - 1;
                 pend &= pend - 1;
-                const u32 di = __shfl_sync(0xffffffffu, diag, i);
-                if (!((rem >> i) & 1u)) rem |= di;
+                if (__shfl_sync(0xffffffffu, (int)((d & keepbits) == 0u), i)) keepbits |= 1u << i;
             }
-            const u32 keep = ~rem & validm;
-            // survivors by rank
-            if (r < m && ((keep >> lane) & 1u)) {
-                const int rank = rank_of_slot[r];
-                atomicOr(&keepw[rank >> 5], 1u << (rank & 31));
-            }
-            u32 act = keep & ra;                        // surviving references reach into later words
-            if (lane > blk && lane < nw) {
-                u32 acc = 0;
-                while (act) {
-                    const int i = __ffs(act) - 1;
-                    act &= act - 1;
-                    acc |= mask[(size_t)((blk << 5) + i) * nwK + lane];
-                }
-                removed |= acc;
-            }
+            if (lane == 0) keeps[cb] = keepbits;
+            __syncwarp();
         }
     }
-    __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        for (int w = 0; w < nw; ++w) { kprefix[w] = run; run += __popc(keepw[w]); }
-        kprefix[32] = run;
     }
     __syncthreads();
-    const int n_keep = kprefix[32];
+    FIN_T(9);
+    // survivors by rank
+    u32 kb;
+    {
+        bool kept = false;
+        if (tid < m) { const int slot = slot_of_rank[tid]; kept = (keeps[slot >> 5] >> (slot & 31)) & 1u; }
+        kb = __ballot_sync(0xffffffffu, kept);
+        if (lane == 0) keepw[warp] = kb;
+    }
+    __syncthreads();
+    int n_keep, p_base;
+    {
+        const int c = lane < nw ? __popc(keepw[lane]) : 0;
+        int incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        n_keep = __shfl_sync(0xffffffffu, incl, 31);
+        p_base = __shfl_sync(0xffffffffu, incl - c, warp);
+    }
+    FIN_T(10);
 
     // ---- 5. survivors to the front in score order; the rest is -1
     const int W = fp.W;
     float *out_b = fp.out + (size_t)b * (size_t)fp.out_stride_rows * W;
     int *kept_b = fp.kept_rows ? fp.kept_rows + (size_t)b * (size_t)fp.out_stride_rows : nullptr;
-    for (int i = tid; i < m; i += FIN_NT) {
-        const u32 kw = keepw[i >> 5];
-        if (!((kw >> (i & 31)) & 1u)) continue;
-        const int p = kprefix[i >> 5] + __popc(kw & ((1u << (i & 31)) - 1u));
-        if (p >= fp.post_rows) continue;
-        const u64 key = keyr[i];
-        const u32 row = vy_key_row(key);
-        float *o = out_b + (size_t)p * W;
-        if (SRC == 0) {
-            const int j = slot_of_rank[i];
-            const float4 bx = box[j];
-            o[0] = (float)(all_pairs && !hd.agnostic ? fin_class<SRC>(hd, rp, b, row) : cls[j]);
-            o[1] = vy_key_score(key);
-            o[2] = bx.x; o[3] = bx.y; o[4] = bx.z; o[5] = bx.w;
-        } else {
-            const float *src = rp.data + ((size_t)b * (size_t)rp.R + row) * rp.W;
-            for (int c = 0; c < W; ++c) o[c] = src[c];
-            if (fp.in_format != fp.out_format) {
-                float *q = o + rp.coord_start;
-                if (!(q[0] < 0)) {
-                    if (fp.out_format == VY_FMT_CENTER) {   // corner_to_center
-                        const float l = q[0], t = q[1], r2 = q[2], bt = q[3];
-                        q[0] = __fdiv_rn(__fadd_rn(l, r2), 2.0f); q[1] = __fdiv_rn(__fadd_rn(t, bt), 2.0f);
-                        q[2] = __fsub_rn(r2, l); q[3] = __fsub_rn(bt, t);
-                    } else {                                 // center_to_corner
-                        const float x = q[0], y = q[1];
-                        const float hw = __fdiv_rn(q[2], 2.0f), hh = __fdiv_rn(q[3], 2.0f);
-                        q[0] = __fsub_rn(x, hw); q[1] = __fsub_rn(y, hh);
-                        q[2] = __fadd_rn(x, hw); q[3] = __fadd_rn(y, hh);
+    if (tid < m && ((kb >> lane) & 1u)) {
+        const int i = tid;
+        const int p = p_base + __popc(kb & lt_mask);
+        if (p < fp.post_rows) {
+            const u64 key = mykey;
+            const u32 row = vy_key_row(key);
+            float *o = out_b + (size_t)p * W;
+            if (SRC == 0) {
+                const int j = slot_of_rank[i];
+                const float4 bx = box[j];
+                o[0] = (float)(all_pairs && !hd.agnostic ? fin_class<SRC>(hd, rp, b, row) : cls[j]);
+                o[1] = vy_key_score(key);
+                o[2] = bx.x; o[3] = bx.y; o[4] = bx.z; o[5] = bx.w;
+            } else {
+                const float *src = rp.data + ((size_t)b * (size_t)rp.R + row) * rp.W;
+                for (int c = 0; c < W; ++c) o[c] = src[c];
+                if (fp.in_format != fp.out_format) {
+                    float *q = o + rp.coord_start;
+                    if (!(q[0] < 0)) {
+                        if (fp.out_format == VY_FMT_CENTER) {   // corner_to_center
+                            const float l = q[0], t = q[1], r2 = q[2], bt = q[3];
+                            q[0] = __fdiv_rn(__fadd_rn(l, r2), 2.0f); q[1] = __fdiv_rn(__fadd_rn(t, bt), 2.0f);
+                            q[2] = __fsub_rn(r2, l); q[3] = __fsub_rn(bt, t);
+                        } else {                                 // center_to_corner
+                            const float x = q[0], y = q[1];
+                            const float hw = __fdiv_rn(q[2], 2.0f), hh = __fdiv_rn(q[3], 2.0f);
+                            q[0] = __fsub_rn(x, hw); q[1] = __fsub_rn(y, hh);
+                            q[2] = __fadd_rn(x, hw); q[3] = __fadd_rn(y, hh);
+                        }
                     }
                 }
             }
+            if (kept_b) kept_b[p] = (int)row;
         }
-        if (kept_b) kept_b[p] = (int)row;
     }
     if (fp.fill_rest) {
         const int first = min(n_keep, fp.post_rows);
@@ -1203,7 +1422,9 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
         for (long long i = tid; i < total; i += FIN_NT) o[i] = -1.0f;
         if (kept_b) for (int i = first + tid; i < fp.post_rows; i += FIN_NT) kept_b[i] = -1;
     }
+    FIN_T(11);
 }
+
 
 __global__ void vy_fill_kernel(float *out, int *kept, size_t n_out, size_t n_kept) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -1219,7 +1440,7 @@ static size_t fin_dyn_smem(int K, int *lcap) {
     const int nwK = (K + 31) / 32;
     size_t cp2 = 32;
     while (cp2 < (size_t)(K + FIN_SLACK)) cp2 <<= 1;
-    const size_t base = cp2 * 8 + (size_t)K * (16 + 4 + 4 + 4 + 4 + 4) + (size_t)K * nwK * 4 + 32 * 4 + 32 * 4 + 36 * 4 + 16;
+    const size_t base = cp2 * 8 + (size_t)K * (16 + 4 + 4 + 4 + 4 + 4) + (size_t)K * nwK * 4 + 3 * 32 * 4 + 36 * 4 + 16;
     const size_t budget = 227 * 1024 - sizeof(SelBuf) - 2048;        // per-CTA limit minus the static part
     int cap = FIN_LCAP;
     if (base + (size_t)cap * 8 > budget) cap = 0;
@@ -1379,6 +1600,14 @@ template <int SRC>
 static int launch_finalize(const VyHeads &hd, const RowParams &rp, const SelPlan &pl, const SelGlobal &g,
                            FinParams fp, int B, cudaStream_t st) {
     const size_t dyn = fin_dyn_smem(pl.K, &fp.lcap);
+    if (pl.K > FIN_NT_MAX) VY_FAIL(VY_EINVAL, "finalize: K exceeds the CTA size");      // a thread per rank / slot
+    if (fp.overlap_thresh > 0.0f && fp.overlap_thresh < 1e30f) {
+        fp.thr_lo = fp.overlap_thresh * (1.0f - 9.5367431640625e-07f);      // 2^-20 (vy_nms_math.cuh)
+        fp.thr_hi = fp.overlap_thresh * (1.0f + 9.5367431640625e-07f);
+    } else {            // thr <= 0 (or absurd): always the exact division
+        fp.thr_lo = -INFINITY;
+        fp.thr_hi = INFINITY;
+    }
     VY_CUDA_CHECK(cudaFuncSetAttribute(vy_nms_finalize_kernel<SRC>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     // 1024 threads: the kernel is a chain of short barrier-separated phases, more warps hide their latencies

@@ -259,3 +259,85 @@ static __device__ __noinline__ void sel_sort_desc_fast(u64 *keys, int npow2) {
         __syncthreads();
     }
 }
+
+// Descending sort of keys[0..npow2), 32 <= npow2 <= blockDim.x, as a chain of short phases instead of a
+// bitonic network's log^2 dependent stages: every warp sorts its run of 32 keys in registers (15 shuffle
+// stages), then rounds of 4-way (last round possibly 2-way) RANK merges: a key's place in the merged run
+// is its place in its own run plus, for every sibling run, the number of keys there that precede it --
+// log2(L)+1 probes of a binary search each, the searches of the sibling runs independent of one another.
+// Equal keys are ordered by the run they came from (sibling runs to the left count their equals too), so
+// the places are a permutation whatever the input.  2 CTA barriers per round; every thread of the CTA calls it.
+#ifdef VY_FIN_TIMING
+__device__ long long vy_fin_clk[16];
+#endif
+// While the rounds run, element p of the buffer lives at p ^ ((p >> 4) & 15): the probes of one binary-search
+// step sit a multiple of 16 keys apart (one shared-memory bank pair), the swizzle spreads them over the banks.
+__device__ __forceinline__ int sel_swz(int p) { return p ^ ((p >> 4) & 15); }
+static __device__ __noinline__ void sel_sort_desc_merge(u64 *keys, int npow2) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool act = tid < npow2;                      // whole warps
+    // the register phase runs in every warp (idle ones sort zeros): shuffles under a branch the compiler cannot
+    // prove warp-uniform cost a collective sequence each
+    u64 x = act ? keys[tid] : 0ull;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const u64 y = sel_shfl_xor_u64(x, j);
+            const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0);
+            x = keep_max ? (x > y ? x : y) : (x < y ? x : y);
+        }
+    }
+    if (npow2 == 32) {
+        if (act) keys[tid] = x;
+        __syncthreads();
+        return;
+    }
+    if (act) keys[sel_swz(tid)] = x;
+    __syncthreads();
+#ifdef VY_FIN_TIMING
+    int tslot = 12;
+    if (blockIdx.x == 0 && tid == 0) vy_fin_clk[tslot] = clock64();
+#endif
+    for (int L = 32; L < npow2;) {
+        const int F = (L * 4 <= npow2) ? 4 : 2;
+        const int G = L * F;
+        int pos = 0;
+        if (act) {
+            const int g0 = tid & ~(G - 1);
+            const int myrun = (tid - g0) / L;          // warp-uniform (L >= 32)
+            int cnt[3] = {0, 0, 0};
+            int r[3];
+            u64 xq[3];
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                int q = myrun + 1 + o;
+                if (q >= F) q -= F;
+                r[o] = g0 + q * L;
+                xq[o] = x - (u64)(q < myrun ? 1 : 0);   // runs to the left: their equals precede me (x >= 1)
+            }
+            const int no = F - 1;
+            for (int s = L >> 1; s > 0; s >>= 1) {
+#pragma unroll
+                for (int o = 0; o < 3; ++o)
+                    if (o < no && keys[sel_swz(r[o] + cnt[o] + s - 1)] > xq[o]) cnt[o] += s;
+            }
+#pragma unroll
+            for (int o = 0; o < 3; ++o)
+                if (o < no && keys[sel_swz(r[o] + cnt[o])] > xq[o]) ++cnt[o];
+            pos = g0 + (tid & (L - 1));
+#pragma unroll
+            for (int o = 0; o < 3; ++o) if (o < no) pos += cnt[o];
+        }
+        const bool last = G >= npow2;                  // the last round leaves the keys in natural order
+        __syncthreads();
+        if (act) keys[last ? pos : sel_swz(pos)] = x;
+        __syncthreads();
+        if (act && !last) x = keys[sel_swz(tid)];
+        L = G;
+#ifdef VY_FIN_TIMING
+        ++tslot;
+        if (blockIdx.x == 0 && tid == 0 && tslot < 16) vy_fin_clk[tslot] = clock64();
+#endif
+    }
+}
