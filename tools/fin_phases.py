@@ -15,7 +15,7 @@ from videoyolo_b200.synth import random_heads_cuda
 AN, ST = vy.ANCHORS[::-1], vy.STRIDES[::-1]
 dev = torch.device("cuda:0")
 L = _lib.lib()
-NAMES = ["stage list", "radix bound", "compact", "rank sort", "class sort", "box decode", "seg_end", "bitmask",
+NAMES = ["front (sort)", "general front", "-", "prefetch", "class sort", "box decode", "seg_end", "bitmask",
          "greedy scan", "prefix", "output"]
 for name, B, C, size, regime in [("coco608_b64_R", 64, 80, 608, "R"), ("coco608_b64_T", 64, 80, 608, "T"),
                                  ("voc416_b1_R", 1, 20, 416, "R"), ("vid320_b256_R", 256, 30, 320, "R")]:
@@ -31,6 +31,13 @@ for name, B, C, size, regime in [("coco608_b64_R", 64, 80, 608, "R"), ("coco608_
             for k in range(11):
                 acc[k] += (clk[k + 1] - clk[k]) / n
     print("   last merge sort (rank sort when classes are counted): start->warp-sorted %d, rounds %s" % (clk[12] - clk[3], [clk[k + 1] - clk[k] for k in range(12, 15)]))
+    nb = min(B, 1024)
+    ct = (ctypes.c_longlong * (4 * nb))()
+    assert L.vy_debug_fin_ctas(ct, nb) == 0
+    rows = sorted([tuple(ct[4 * i:4 * i + 4]) for i in range(nb)])
+    sms = [r[1] for r in rows]
+    print("   per CTA cycles: min %d median %d max %d | distinct SMs %d of %d CTAs | slowest: %s" % (
+        rows[0][0], rows[nb // 2][0], rows[-1][0], len(set(sms)), nb, rows[-3:]))
     tot = sum(acc)
     print("%s: finalize CTA 0 = %.0f cycles" % (name, tot))
     for k in range(11):

@@ -999,11 +999,107 @@ static __device__ __noinline__ u64 fin_list_bound(SelBuf &S, const u64 *list, in
     return prefix;
 }
 
+// Front end of the finalize kernel for lists of <= FIN_BK_MAXN keys: the exact top-K, sorted, in three light
+// passes instead of bound + compaction + sort.  The keys of a list agree in their leading bits (scores of one
+// narrow range), so FIN_BK_BINS counting bins laid right below the common prefix hold about one key each:
+// histogram, descending scan (= where every bin starts in the sorted order, and which bin holds the K-th
+// key), scatter into the bins, and a rank inside each bin (usually of one or two keys).  Every thread keeps
+// its <= 4 keys in registers throughout; the list is read once.
+// Returns m1 = #{keys in the bins down to the K-th key's} (>= min(n, K)) with keyr[0 .. min(m1, K)) sorted
+// descending, or -1 (CTA-uniform, nothing written) when that many keys would not fit the CTA.
+constexpr int FIN_BK_BINS = 2048;
+constexpr int FIN_BK_MAXN = 4 * FIN_NT_MAX;
+static __device__ __noinline__ int fin_front_buckets(SelBuf &S, const u64 *list, int n, int K,
+                                                     u32 *hist, u32 *excl, u64 *out, u64 *keyr) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u64 *mm = (u64 *)S.queue;                           // [0] = min, [1] = max (the queue is idle in this kernel)
+    u64 k[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int i = tid + q * FIN_NT_MAX; k[q] = i < n ? list[i] : 0ull; }
+    hist[tid] = 0u; hist[tid + FIN_NT_MAX] = 0u;
+    if (tid == 0) { mm[0] = ~0ull; mm[1] = 0ull; S.sel_digit = 0; S.sel_in = n; }
+    __syncthreads();
+    {
+        u64 lo = ~0ull, hi = 0ull;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (k[q]) { lo = k[q] < lo ? k[q] : lo; hi = k[q] > hi ? k[q] : hi; }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const u64 l2 = sel_shfl_xor_u64(lo, off), h2 = sel_shfl_xor_u64(hi, off);
+            lo = l2 < lo ? l2 : lo; hi = h2 > hi ? h2 : hi;
+        }
+        if (lane == 0 && hi) { atomicMin((unsigned long long *)&mm[0], (unsigned long long)lo); atomicMax((unsigned long long *)&mm[1], (unsigned long long)hi); }
+    }
+    __syncthreads();
+    const u64 kx = mm[0] ^ mm[1];
+    const int hb = kx ? 63 - __clzll((long long)kx) : 0;     // highest bit in which two keys differ
+    const int shift = hb >= 10 ? hb - 10 : 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (k[q]) atomicAdd(&hist[(u32)(k[q] >> shift) & (FIN_BK_BINS - 1)], 1u);
+    __syncthreads();
+    // descending scan: thread t owns bins 2047 - 2t and 2046 - 2t
+    const int d0 = FIN_BK_BINS - 1 - 2 * tid, d1 = d0 - 1;
+    const u32 h0 = hist[d0], h1 = hist[d1];
+    u32 incl = h0 + h1;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const u32 v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    u32 *wsum = S.hist;                                 // [32]
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const u32 v = wsum[lane];
+        u32 inc2 = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const u32 y = __shfl_up_sync(0xffffffffu, inc2, off);
+            if (lane >= off) inc2 += y;
+        }
+        wsum[lane] = inc2 - v;
+    }
+    __syncthreads();
+    const u32 base = wsum[warp] + incl - (h0 + h1);     // keys in the bins above d0
+    excl[d0] = base;
+    excl[d1] = base + h0;
+    if (base < (u32)K && (u32)K <= base + h0 + h1) {    // the K-th key's bin (none: fewer than K keys, the defaults stand)
+        const bool first = (u32)K <= base + h0;
+        S.sel_digit = first ? d0 : d1;
+        S.sel_in = (int)(first ? base + h0 : base + h0 + h1);
+    }
+    __syncthreads();
+    const int kbin = S.sel_digit, m1 = S.sel_in;
+    if (m1 > FIN_NT_MAX) return -1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (k[q]) {
+            const u32 bin = (u32)(k[q] >> shift) & (FIN_BK_BINS - 1);
+            if ((int)bin >= kbin) out[excl[bin] + atomicSub(&hist[bin], 1u) - 1u] = k[q];
+        }
+    }
+    __syncthreads();
+    if (tid < m1) {
+        const u64 key = out[tid];
+        const u32 bin = (u32)(key >> shift) & (FIN_BK_BINS - 1);
+        const u32 a = excl[bin], e = bin ? excl[bin - 1] : (u32)n;
+        u32 rank = a;
+        for (u32 q = a; q < e; ++q) rank += out[q] > key ? 1u : 0u;
+        if (rank < (u32)K) keyr[rank] = key;
+    }
+    __syncthreads();
+    return m1;
+}
+
 // -DVY_FIN_TIMING (tools/fin_phases.py only): CTA 0 records clock64() at the phase boundaries
 #ifdef VY_FIN_TIMING
 #define FIN_T(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) vy_fin_clk[k] = clock64(); } while (0)
+__device__ long long vy_fin_cta[1024][4];          // per CTA: cycles, SM id, list length, m1
 extern "C" int vy_debug_fin_clocks(long long *out) {
     return cudaMemcpyFromSymbol(out, vy_fin_clk, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
+}
+extern "C" int vy_debug_fin_ctas(long long *out, int n) {
+    return cudaMemcpyFromSymbol(out, vy_fin_cta, sizeof(long long) * 4 * n) == cudaSuccess ? 0 : -1;
 }
 #else
 #define FIN_T(k) do { } while (0)
@@ -1033,6 +1129,57 @@ __device__ __forceinline__ void fin_sort(u64 *keys, int npow2) {
     else sel_sort_desc_fast(keys, npow2);
 }
 
+// General front end: bound the K-th largest key (lists longer than K + slack), compact what is at or above the
+// bound into cand, sort.  Returns m1 <= K + FIN_SLACK with cand[0 .. m1) sorted descending.
+static __device__ __noinline__ int fin_front_general(SelBuf &S, const u64 *list, int n_list, int K, u64 *cand,
+                                                     u64 *lbuf, int lcap) {
+    const int tid = threadIdx.x, lane = tid & 31, FIN_NT = (int)blockDim.x;
+    const u32 lt_mask = (1u << lane) - 1u;
+    // the ranking sort works on a power-of-two buffer: let through what fills the one K + 64 needs anyway
+    int slack;
+    { int t2 = 64; while (t2 < K + 64) t2 <<= 1; slack = min(min(t2, FIN_NT_MAX) - K, FIN_SLACK); }
+    if (n_list > K + slack && n_list <= lcap) {
+        // the radix sweeps below then never leave the SM
+        for (int i = tid; i < n_list; i += FIN_NT) lbuf[i] = list[i];
+        list = lbuf;
+    }
+    __syncthreads();
+    if (n_list > K + slack) {
+        // long list: bound its K-th largest key first, so that one sweep leaves <= K + slack keys
+        const u64 p = fin_list_bound(S, list, n_list, K, slack);
+        const u64 cur = S.thr;
+        __syncthreads();
+        if (tid == 0 && p > cur) S.thr = p;
+        __syncthreads();
+    }
+    {
+        const u64 thr = S.thr;
+        for (int i0 = 0; i0 < n_list; i0 += FIN_NT) {   // CTA-uniform trip count: one shared-memory atomic per warp
+            const int i = i0 + tid;
+            const u64 key = i < n_list ? list[i] : 0ull;
+            const bool in = i < n_list && key >= thr;
+            const u32 bal = __ballot_sync(0xffffffffu, in);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&S.count, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int slot = base + __popc(bal & lt_mask);
+                if (in && slot < K + FIN_SLACK) cand[slot] = key;
+            }
+        }
+    }
+    __syncthreads();
+    const int m1 = min(S.count, K + FIN_SLACK);
+    // rank: keys are unique (the row is part of the key), so a descending sort IS the operator's
+    // stable order; the buffer is padded with distinct values below every real key
+    int np2 = 32;
+    while (np2 < m1) np2 <<= 1;
+    for (int i = m1 + tid; i < np2; i += FIN_NT) cand[i] = (u64)(np2 - i);
+    __syncthreads();
+    fin_sort(cand, np2);
+    return m1;
+}
+
 // One CTA of FIN_NT_MAX >= K threads per image.  Positions: "rank" = place in the global score order (what
 // the operator's output order is); "slot" = place after a stable regrouping by class, in which every class
 // is one contiguous segment still ordered by rank.  Suppression only ever happens inside a segment, so the
@@ -1050,6 +1197,9 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     const int nwK = (K + 31) >> 5;
     const u32 lt_mask = (1u << lane) - 1u;
     FIN_T(0);
+#ifdef VY_FIN_TIMING
+    const long long t_start = clock64();
+#endif
     int cp2 = 32;
     while (cp2 < K + FIN_SLACK) cp2 <<= 1;
     u64 *cand = (u64 *)dyn;                            // cp2 >= K + FIN_SLACK candidates (sorted in place)
@@ -1073,63 +1223,24 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     const u64 *list = use_s ? g.slist + (size_t)b * g.slist_cap : g.list + (size_t)b * pl.list_cap;
     if (tid == 0) { S.count = 0; S.flag = 0; S.thr = use_s ? ~g.sthr[b] : g.thr[b]; }
     if (tid < 32) keeps[tid] = 0u;
-    // the ranking sort works on a power-of-two buffer: let through what fills the one K + 64 needs anyway
-    int slack;
-    { int t2 = 64; while (t2 < K + 64) t2 <<= 1; slack = min(min(t2, FIN_NT_MAX) - K, FIN_SLACK); }
-    if (n_list > K + slack && n_list <= fp.lcap) {
-        // the radix sweeps below then never leave the SM
-        for (int i = tid; i < n_list; i += FIN_NT) lbuf[i] = list[i];
-        list = lbuf;
-    }
-    __syncthreads();
-    FIN_T(1);
-    if (n_list > K + slack) {
-        // long list: bound its K-th largest key first, so that one sweep leaves <= K + slack keys
-        const u64 p = fin_list_bound(S, list, n_list, K, slack);
-        const u64 cur = S.thr;
-        __syncthreads();
-        if (tid == 0 && p > cur) S.thr = p;
-        __syncthreads();
-    }
-    FIN_T(2);
     u64 *keyr = S.keys;                                 // the K best by rank (K <= SEL_KMAX <= SEL_CAP)
-    {
-        const u64 thr = S.thr;
-        for (int i0 = 0; i0 < n_list; i0 += FIN_NT) {   // CTA-uniform trip count: one shared-memory atomic per warp
-            const int i = i0 + tid;
-            const u64 key = i < n_list ? list[i] : 0ull;
-            const bool in = i < n_list && key >= thr;
-            const u32 bal = __ballot_sync(0xffffffffu, in);
-            if (bal) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&S.count, __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const int slot = base + __popc(bal & lt_mask);
-                if (in && slot < K + FIN_SLACK) cand[slot] = key;
-            }
-        }
+    int m1 = -1;
+    if (n_list <= FIN_BK_MAXN && fp.lcap >= FIN_BK_MAXN)
+        m1 = fin_front_buckets(S, list, n_list, K, (u32 *)cand, (u32 *)lbuf, lbuf + FIN_BK_BINS / 2, keyr);
+    FIN_T(1);
+    u64 mykey = 0ull;
+    if (m1 < 0) {
+        // general path (lists beyond the bucket front end's reach): bound, compact, sort
+        m1 = fin_front_general(S, list, n_list, K, cand, lbuf, fp.lcap);
+        if (tid < min(m1, K)) { mykey = cand[tid]; keyr[tid] = mykey; }
+    } else {
+        if (tid < min(m1, K)) mykey = keyr[tid];
     }
-    __syncthreads();
-    FIN_T(3);
-    const int m1 = min(S.count, K + FIN_SLACK);
+    FIN_T(2); FIN_T(3);
     const int m = min(m1, K);                           // <= K candidates take part
     const int nw = (m + 31) >> 5;
-    // rank: keys are unique (the row is part of the key), so a descending sort IS the operator's
-    // stable order; the buffer is padded with distinct values below every real key
-    {
-        int np2 = 32;
-        while (np2 < m1) np2 <<= 1;
-        for (int i = m1 + tid; i < np2; i += FIN_NT) cand[i] = (u64)(np2 - i);
-        __syncthreads();
-        fin_sort(cand, np2);
-    }
     // thread i < m owns rank i from here on (FIN_NT >= K)
-    u64 mykey = 0ull;
-    if (tid < m) {
-        mykey = cand[tid];
-        keyr[tid] = mykey;
-        fin_box_prefetch<SRC>(hd, rp, b, vy_key_row(mykey));    // the box logits travel while the classes are sorted
-    }
+    if (tid < m) fin_box_prefetch<SRC>(hd, rp, b, vy_key_row(mykey));    // the box logits travel while the classes are sorted
     FIN_T(4);
 
     // ---- 2. regroup by class, stable in rank
@@ -1423,6 +1534,13 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
         if (kept_b) for (int i = first + tid; i < fp.post_rows; i += FIN_NT) kept_b[i] = -1;
     }
     FIN_T(11);
+#ifdef VY_FIN_TIMING
+    if (tid == 0 && b < 1024) {
+        u32 smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        vy_fin_cta[b][0] = clock64() - t_start; vy_fin_cta[b][1] = smid; vy_fin_cta[b][2] = n_list; vy_fin_cta[b][3] = m1;
+    }
+#endif
 }
 
 
