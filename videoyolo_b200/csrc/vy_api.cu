@@ -30,6 +30,10 @@ static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof_recs;
 static thread_local cudaEvent_t g_prof_open = nullptr;
 
+bool vy_pdl_enabled() {
+    static const bool on = getenv("VY_NO_PDL") == nullptr;
+    return on;
+}
 void vy_prof_pre(int id, cudaStream_t st) {
     if (id < 0 || id >= VY_K_COUNT) return;
     g_launches[id].fetch_add(1, std::memory_order_relaxed);

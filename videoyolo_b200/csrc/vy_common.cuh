@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include "../../include/vyolo.h"
 
 typedef unsigned long long u64;
@@ -25,6 +27,28 @@ int vy_sm_count();   // cached cudaDevAttrMultiProcessorCount of the current dev
 void vy_prof_pre(int kernel_id, cudaStream_t st);
 void vy_prof_post(int kernel_id, cudaStream_t st);
 #define VY_KERNEL(id, st, ...) do { vy_prof_pre((id), (st)); __VA_ARGS__; vy_prof_post((id), (st)); } while (0)
+
+// ---- programmatic dependent launch (PDL): a kernel launched with vy_launch(..., pdl = true) may become
+// resident while its predecessor in the stream is still running; it must call vy_grid_dep_wait() before it
+// touches anything the predecessor wrote (a no-op without the attribute), and a predecessor lets its
+// dependents in early with vy_grid_dep_trigger().  Hides the launch latency and ramp between the short
+// kernels of one call.
+__device__ __forceinline__ void vy_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void vy_grid_dep_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool vy_pdl_enabled();           // false with VY_NO_PDL=1 in the environment (A/B timing)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t vy_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl && vy_pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // ------------------------------------------------------------------ head-map description
 // One YOLO output scale (yolo3.py:43-74): NCHW head map + the constants the decode needs.

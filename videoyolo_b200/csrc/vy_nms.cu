@@ -324,6 +324,8 @@ __global__ void __launch_bounds__(SEL_NT, SEL_CTAS_PER_SM)
 vy_decode_select_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl, SelGlobal g) {
     __shared__ SelBuf S;
     const int tid = threadIdx.x;
+    vy_grid_dep_trigger();
+    vy_grid_dep_wait();
     for (int job = blockIdx.x; job < pl.n_jobs; job += gridDim.x) {
         const int b = job / pl.G;
         // streaming path: this kernel is the rescue pass and only serves images whose streamed
@@ -495,6 +497,7 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
             }
         }
     }
+    vy_grid_dep_trigger();                              // loads done: the rest of this CTA is shared-memory work
     // ---- CTA-wide: Ksq-th largest of the keys (MSB-first radix select over the parked keys); fewer than
     // Ksq keys in all (seen in the first pass: no bin reaches the rank) leave the bound at 0
     if (tid == 0) sh_digit = -1;
@@ -747,6 +750,7 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
     u64 *wbuf = wbuf_all[wid];
     float4 *ring_lane = (float4 *)str_dyn + (size_t)wid * STR_RING * 32 + lane;
     const u32 lt_mask = (1u << lane) - 1u;
+    bool dep_waited = false;                            // the sample kernel's bounds are first read below
     const long long n_warps = (long long)gridDim.x * (STR_NT / 32);
     for (long long unit = (long long)blockIdx.x * (STR_NT / 32) + wid; unit < pl.n_units; unit += n_warps) {
         const int b = (int)(unit / pl.units_per_image);
@@ -778,6 +782,7 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
         un.row0 = (u32)(sc.row_off + (long long)pos0 * hd.A + a);
         un.n_s = (u32)sc.n_s; un.A = (u32)hd.A;
         un.valid_thresh = pl.valid_thresh;
+        if (!dep_waited) { vy_grid_dep_wait(); dep_waited = true; }
         un.thr = ~g.sthr[b];
         const float smin = fmaxf(un.thr ? vy_key_score(un.thr) : pl.valid_thresh, pl.valid_thresh);
         {
@@ -800,6 +805,7 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
             __syncwarp();
         }
     }
+    vy_grid_dep_trigger();                              // (a trigger at the start lets the dependents crowd the tail: measured slower)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1004,25 +1010,26 @@ static __device__ __noinline__ u64 fin_list_bound(SelBuf &S, const u64 *list, in
 // narrow range), so FIN_BK_BINS counting bins laid right below the common prefix hold about one key each:
 // histogram, descending scan (= where every bin starts in the sorted order, and which bin holds the K-th
 // key), scatter into the bins, and a rank inside each bin (usually of one or two keys).  Every thread keeps
-// its <= 4 keys in registers throughout; the list is read once.
+// its <= FIN_BK_KPT keys in registers throughout; the list is read once.
 // Returns m1 = #{keys in the bins down to the K-th key's} (>= min(n, K)) with keyr[0 .. min(m1, K)) sorted
 // descending, or -1 (CTA-uniform, nothing written) when that many keys would not fit the CTA.
 constexpr int FIN_BK_BINS = 2048;
-constexpr int FIN_BK_MAXN = 4 * FIN_NT_MAX;
+constexpr int FIN_BK_KPT = 8;         // keys per thread
+constexpr int FIN_BK_MAXN = FIN_BK_KPT * FIN_NT_MAX;
 static __device__ __noinline__ int fin_front_buckets(SelBuf &S, const u64 *list, int n, int K,
                                                      u32 *hist, u32 *excl, u64 *out, u64 *keyr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     u64 *mm = (u64 *)S.queue;                           // [0] = min, [1] = max (the queue is idle in this kernel)
-    u64 k[4];
+    u64 k[FIN_BK_KPT];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { const int i = tid + q * FIN_NT_MAX; k[q] = i < n ? list[i] : 0ull; }
+    for (int q = 0; q < FIN_BK_KPT; ++q) { const int i = tid + q * FIN_NT_MAX; k[q] = i < n ? list[i] : 0ull; }
     hist[tid] = 0u; hist[tid + FIN_NT_MAX] = 0u;
     if (tid == 0) { mm[0] = ~0ull; mm[1] = 0ull; S.sel_digit = 0; S.sel_in = n; }
     __syncthreads();
     {
         u64 lo = ~0ull, hi = 0ull;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) if (k[q]) { lo = k[q] < lo ? k[q] : lo; hi = k[q] > hi ? k[q] : hi; }
+        for (int q = 0; q < FIN_BK_KPT; ++q) if (k[q]) { lo = k[q] < lo ? k[q] : lo; hi = k[q] > hi ? k[q] : hi; }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             const u64 l2 = sel_shfl_xor_u64(lo, off), h2 = sel_shfl_xor_u64(hi, off);
@@ -1035,7 +1042,7 @@ static __device__ __noinline__ int fin_front_buckets(SelBuf &S, const u64 *list,
     const int hb = kx ? 63 - __clzll((long long)kx) : 0;     // highest bit in which two keys differ
     const int shift = hb >= 10 ? hb - 10 : 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) if (k[q]) atomicAdd(&hist[(u32)(k[q] >> shift) & (FIN_BK_BINS - 1)], 1u);
+    for (int q = 0; q < FIN_BK_KPT; ++q) if (k[q]) atomicAdd(&hist[(u32)(k[q] >> shift) & (FIN_BK_BINS - 1)], 1u);
     __syncthreads();
     // descending scan: thread t owns bins 2047 - 2t and 2046 - 2t
     const int d0 = FIN_BK_BINS - 1 - 2 * tid, d1 = d0 - 1;
@@ -1072,7 +1079,7 @@ static __device__ __noinline__ int fin_front_buckets(SelBuf &S, const u64 *list,
     const int kbin = S.sel_digit, m1 = S.sel_in;
     if (m1 > FIN_NT_MAX) return -1;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < FIN_BK_KPT; ++q) {
         if (k[q]) {
             const u32 bin = (u32)(k[q] >> shift) & (FIN_BK_BINS - 1);
             if ((int)bin >= kbin) out[excl[bin] + atomicSub(&hist[bin], 1u) - 1u] = k[q];
@@ -1218,6 +1225,7 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
 
     // ---- 1. exact top-K of the image's candidate list, sorted descending
     // streaming path: the streamed list, unless it was unusable and the rescue pass rebuilt g.list
+    vy_grid_dep_wait();
     const bool use_s = g.scount != nullptr && stream_list_ok(g, b, K);
     const int n_list = use_s ? g.scount[b] : min(g.count[b], pl.list_cap);
     const u64 *list = use_s ? g.slist + (size_t)b * g.slist_cap : g.list + (size_t)b * pl.list_cap;
@@ -1225,7 +1233,7 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     if (tid < 32) keeps[tid] = 0u;
     u64 *keyr = S.keys;                                 // the K best by rank (K <= SEL_KMAX <= SEL_CAP)
     int m1 = -1;
-    if (n_list <= FIN_BK_MAXN && fp.lcap >= FIN_BK_MAXN)
+    if (n_list <= FIN_BK_MAXN && fp.lcap >= 2 * FIN_BK_BINS)
         m1 = fin_front_buckets(S, list, n_list, K, (u32 *)cand, (u32 *)lbuf, lbuf + FIN_BK_BINS / 2, keyr);
     FIN_T(1);
     u64 mykey = 0ull;
@@ -1730,7 +1738,7 @@ static int launch_finalize(const VyHeads &hd, const RowParams &rp, const SelPlan
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     // 1024 threads: the kernel is a chain of short barrier-separated phases, more warps hide their latencies
     // (measured 41 us against 47 us with 512 threads at K = 400)
-    VY_KERNEL(VY_K_FINALIZE, st, (vy_nms_finalize_kernel<SRC><<<B, FIN_NT_MAX, dyn, st>>>(hd, rp, pl, g, fp)));
+    VY_KERNEL(VY_K_FINALIZE, st, (vy_launch(vy_nms_finalize_kernel<SRC>, dim3(B), dim3(FIN_NT_MAX), dyn, st, true, hd, rp, pl, g, fp)));
     VY_LAUNCH_CHECK("vy_nms_finalize_kernel");
     return VY_OK;
 }
@@ -1778,12 +1786,14 @@ extern "C" int vy_decode_nms_f32(const float *const *head, const int *H, const i
         long long ctas = (pl.n_units + STR_NT / 32 - 1) / (STR_NT / 32);
         const long long resident = (long long)STR_CTAS_PER_SM * vy_sm_count();
         if (ctas > resident) ctas = resident;
+        // PDL on this launch only in the latency regime (grid below one wave): on a full machine the early
+        // CTAs crowd the sample kernel's tail (measured: -4 % at COCO 608 x 64, +15 % at VOC 416 x 1)
         const size_t ring_bytes = (size_t)(STR_NT / 32) * STR_RING * 32 * sizeof(float4);
         VY_CUDA_CHECK(cudaFuncSetAttribute(vy_decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
-        VY_KERNEL(VY_K_STREAM, st, (vy_decode_stream_kernel<<<(unsigned)ctas, STR_NT, ring_bytes, st>>>(hd, pl, g)));
+        VY_KERNEL(VY_K_STREAM, st, (vy_launch(vy_decode_stream_kernel, dim3((unsigned)ctas), dim3(STR_NT), ring_bytes, st, ctas < resident, hd, pl, g)));
         VY_LAUNCH_CHECK("vy_decode_stream_kernel");
     }
-    VY_KERNEL(VY_K_SELECT_HEADS, st, (vy_decode_select_kernel<<<select_grid(pl.n_jobs), SEL_NT, 0, st>>>(hd, pl, g)));
+    VY_KERNEL(VY_K_SELECT_HEADS, st, (vy_launch(vy_decode_select_kernel, dim3(select_grid(pl.n_jobs)), dim3(SEL_NT), 0, st, true, hd, pl, g)));
     VY_LAUNCH_CHECK("vy_decode_select_kernel");
     FinParams fp;
     fp.K = pl.K; fp.post_rows = post_nms; fp.out_stride_rows = post_nms;
