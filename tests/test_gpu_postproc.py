@@ -343,6 +343,37 @@ def test_fused_variants(vy):
     _fused_vs_oracle(vy, [np.zeros_like(h) for h in heads], 20)         # every score == 0.25
 
 
+def test_finalize_branches(vy):
+    """Every branch of the finalize kernel against the oracle: counting regroup vs (class, rank) sort
+    (more than 256 classes), short-segment lanes vs 32x32 tiles with chained blocks (2-3 classes: segments
+    of >100 slots that straddle many blocks), topk at the CTA size, and lists the bucket front end hands to
+    the general path (one bin holding far more keys than the CTA has threads)."""
+    rng = np.random.RandomState(21)
+    _fused_vs_oracle(vy, random_heads(rng, 2, 300, 96), 300)                       # C > FIN_CMAX: sort regroup
+    _fused_vs_oracle(vy, random_heads(rng, 2, 300, 96), 300, topk=1024, post_nms=1024)
+    for C in (2, 3):
+        heads = random_heads(rng, 3, C, 416)
+        _fused_vs_oracle(vy, heads, C)                                             # long segments: tiles + chains
+        _fused_vs_oracle(vy, heads, C, topk=1024, post_nms=1024)
+        _fused_vs_oracle(vy, heads, C, topk=70, post_nms=100)                      # one or two blocks
+        _fused_vs_oracle(vy, heads, C, force=True, topk=64)                        # all pairs, short path
+        _fused_vs_oracle(vy, heads, C, force=True, topk=65)                        # all pairs, tiles
+    # rows: a fat bin at the K-th key (2000 equal scores, keys differ only in the row) under a few spread ones
+    for n_eq, topk in ((2000, 400), (6000, 400), (2000, 1024), (9000, 100)):
+        d = _rand_dets(rng, 2, n_eq + 300, 5)
+        d[:, :n_eq, 1] = 0.5
+        d[:, n_eq:, 1] = rng.uniform(0.5, 1.0, size=(2, 300)).astype(np.float32)
+        d[:, n_eq + 250:, 1] = rng.uniform(1e-3, 1e-2, size=(2, 50)).astype(np.float32)
+        d = d[:, rng.permutation(d.shape[1])]
+        _check_nms(vy, d, overlap_thresh=0.45, valid_thresh=0.0, topk=topk, id_index=0)
+        _check_nms(vy, d, overlap_thresh=0.45, valid_thresh=0.0, topk=topk, id_index=0, force_suppress=True)
+    # scores spanning many binades, negative ones included
+    d = _rand_dets(rng, 2, 5000, 7)
+    d[..., 1] = (rng.standard_normal((2, 5000)) * np.exp(rng.uniform(-20, 3, size=(2, 5000)))).astype(np.float32)
+    _check_nms(vy, d, overlap_thresh=0.45, valid_thresh=-1e9, topk=700, id_index=0)
+    _check_nms(vy, d, overlap_thresh=0.45, valid_thresh=0.0, topk=33, id_index=0)
+
+
 def test_fused_ascending_plane_order(vy):
     """class logits increasing with the class index: later planes always beat the running threshold."""
     rng = np.random.RandomState(4)
