@@ -679,11 +679,80 @@ __device__ __forceinline__ void str_issue(const float *q0, size_t HW, int nplane
     cp_async_commit();
 }
 
+// ---- hits of the 128-bit path are QUEUED, not scored, where they are found: an entry names the element
+// (class plane, owning lane, position of its float4), 32 bits in a warp-private queue.  Full batches of 32
+// entries are then scored one per lane: the logit and the objectness come back from L2 (cp.async.cg left
+// them there), the score is the decode kernel's, the key is tested against the image's bound and survivors go
+// to the warp's key buffer as before.  A hit costs a few instructions in the streaming loop instead of a
+// divergent detour through two sigmoids with one or two lanes active.
+constexpr int STR_HQ = 64;                              // entries per warp (a batch leaves at 32)
+__device__ __forceinline__ void str_hq_score(const StrUnit &un, const u32 *hq, int n, u64 *wbuf, int &cnt,
+                                             int b, const SelGlobal &g, int lane, u32 lt_mask) {
+    bool ok = false;
+    u64 key = 0;
+    // from lane 0's pointer / row (always a live lane; an idle lane's own ones point at position 0)
+    const u32 row00 = __shfl_sync(0xffffffffu, un.row0, 0);
+    const float *pc0 = (const float *)__shfl_sync(0xffffffffu, (unsigned long long)un.pc, 0);
+    if (lane < n) {
+        const u32 e = hq[lane];
+        const int plane = (int)(e >> 7), ls = (int)((e >> 2) & 31u), v = (int)(e & 3u);
+        const float *q = pc0 + ls * 4 + v;
+        const float tv = vy_ldg32(q + (size_t)plane * un.HW);
+        const float to = vy_ldg32(q - un.HW);                           // objectness plane = class plane 0 minus one plane
+        const float sv = vy_score(tv, vy_sigmoid(to));
+        if (sv > un.valid_thresh) {
+            key = vy_make_key(sv, row00 + (u32)(ls * 4 + v) * un.A + (u32)plane * un.n_s);
+            ok = key >= un.thr;
+        }
+    }
+    const u32 bal = __ballot_sync(0xffffffffu, ok);
+    if (bal) {
+        if (ok) wbuf[cnt + __popc(bal & lt_mask)] = key;
+        cnt += __popc(bal);
+        __syncwarp();
+        if (cnt >= 32) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(g.scount + b, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const u64 k0 = wbuf[lane], k1 = wbuf[32 + lane];
+            if (base + lane < g.slist_cap) g.slist[(size_t)b * g.slist_cap + base + lane] = k0;
+            __syncwarp();
+            wbuf[lane] = k1;
+            cnt -= 32;
+            __syncwarp();
+        }
+    }
+}
+// enqueue the set bits of `mask` (bit u*4+v = plane c + u, position v of this lane's float4); warp-uniform entry
+__device__ __forceinline__ void str_hq_push(const StrUnit &un, u32 mask, int c, u32 *hq, int &qn, u64 *wbuf,
+                                            int &cnt, int b, const SelGlobal &g, int lane, u32 lt_mask) {
+    do {
+        const bool has = mask != 0u;
+        const u32 bal = __ballot_sync(0xffffffffu, has);
+        if (has) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            hq[qn + __popc(bal & lt_mask)] = ((u32)(c + (k >> 2)) << 7) | ((u32)lane << 2) | (u32)(k & 3);
+        }
+        qn += __popc(bal);
+        __syncwarp();
+        if (qn >= 32) {
+            str_hq_score(un, hq, 32, wbuf, cnt, b, g, lane, lt_mask);
+            const u32 rest = hq[32 + lane];
+            __syncwarp();
+            hq[lane] = rest;
+            qn -= 32;
+            __syncwarp();
+        }
+    } while (__any_sync(0xffffffffu, mask != 0u));
+}
+
 // consume: the prologue (groups 0 .. STR_NG-1) has been issued by the caller.  The full groups run without
 // any per-plane predicate, with a running ring slot and a running refill pointer (the loop is issue-sensitive:
 // every instruction saved here is a memory request issued earlier); a partial last group takes the general path.
-__device__ __forceinline__ void str_unit_async(const StrUnit &un, float4 *ring_lane, u64 *wbuf, int &cnt, int b,
-                                               const SelGlobal &g, int lane, u32 lt_mask) {
+__device__ __forceinline__ void str_unit_async(const StrUnit &un, float4 *ring_lane, u32 *hq, u64 *wbuf, int &cnt,
+                                               int b, const SelGlobal &g, int lane, u32 lt_mask) {
+    int qn = 0;                                            // entries waiting in hq (warp-uniform)
     const int nplanes = un.c1 - un.c0;
     const int nfull = nplanes / STR_UN;                    // groups with all STR_UN planes
     const int ngroups = (nplanes + STR_UN - 1) / STR_UN;
@@ -706,8 +775,7 @@ __device__ __forceinline__ void str_unit_async(const StrUnit &un, float4 *ring_l
         for (int u = 0; u < STR_UN; ++u)
 #pragma unroll
             for (int v = 0; v < 4; ++v) mask |= (t[u][v] >= un.tcmin[v]) ? (1u << (u * 4 + v)) : 0u;
-        // hits re-read their logit from the ring, so the slot is refilled only afterwards
-        str_hits<true>(un, mask, un.c0 + gi * STR_UN, wbuf, cnt, b, g, lane, lt_mask, rs);
+        // the slot is free as soon as it has been tested: refill first, then look after the hits
         if (gi + STR_NG < nfull) {
 #pragma unroll
             for (int u = 0; u < STR_UN; ++u) cp_async16(rs + u * 32, refill + (size_t)u * plane_bytes);
@@ -715,6 +783,7 @@ __device__ __forceinline__ void str_unit_async(const StrUnit &un, float4 *ring_l
         } else {
             str_issue(q0, un.HW, nplanes, gi + STR_NG, ring_lane);
         }
+        if (__any_sync(0xffffffffu, mask != 0u)) str_hq_push(un, mask, un.c0 + gi * STR_UN, hq, qn, wbuf, cnt, b, g, lane, lt_mask);
         refill += (size_t)STR_UN * plane_bytes;
         slot = slot + STR_UN == STR_RING ? 0 : slot + STR_UN;
     }
@@ -736,15 +805,17 @@ __device__ __forceinline__ void str_unit_async(const StrUnit &un, float4 *ring_l
         for (int u = 0; u < STR_UN; ++u)
 #pragma unroll
             for (int v = 0; v < 4; ++v) mask |= (t[u][v] >= un.tcmin[v]) ? (1u << (u * 4 + v)) : 0u;
-        str_hits<true>(un, mask, un.c0 + gi * STR_UN, wbuf, cnt, b, g, lane, lt_mask, rs);
+        if (__any_sync(0xffffffffu, mask != 0u)) str_hq_push(un, mask, un.c0 + gi * STR_UN, hq, qn, wbuf, cnt, b, g, lane, lt_mask);
         cp_async_commit();                                 // keeps the group count uniform
         slot = slot + STR_UN == STR_RING ? 0 : slot + STR_UN;
     }
+    if (qn > 0) str_hq_score(un, hq, qn, wbuf, cnt, b, g, lane, lt_mask);
 }
 
 __global__ void __launch_bounds__(STR_NT, STR_CTAS_PER_SM)
 vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl, SelGlobal g) {
     __shared__ u64 wbuf_all[STR_NT / 32][64];
+    __shared__ u32 hq_all[STR_NT / 32][STR_HQ];
     extern __shared__ __align__(16) unsigned char str_dyn[];          // [STR_NT/32][STR_RING][32] float4
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     u64 *wbuf = wbuf_all[wid];
@@ -795,7 +866,7 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
             }
         }
         int cnt = 0;                                       // keys waiting in wbuf (warp-uniform)
-        if (vec) str_unit_async(un, ring_lane, wbuf, cnt, b, g, lane, lt_mask);
+        if (vec) str_unit_async(un, ring_lane, hq_all[wid], wbuf, cnt, b, g, lane, lt_mask);
         else str_unit<false>(un, wbuf, cnt, b, g, lane, lt_mask);
         if (cnt > 0) {
             int base = 0;
