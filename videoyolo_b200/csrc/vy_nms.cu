@@ -723,10 +723,22 @@ __device__ __forceinline__ void str_hq_score(const StrUnit &un, const u32 *hq, i
         }
     }
 }
-// enqueue the set bits of `mask` (bit u*4+v = plane c + u, position v of this lane's float4); warp-uniform entry
+// enqueue the set bits of `mask` (bit u*4+v = plane c + u, position v of this lane's float4); warp-uniform entry.
+// One pass takes the lowest bit of every lane at once (the usual case: a hit or two in the group); what is
+// left then sits in a few lanes (a confident box passes in many classes) and is unloaded lane by lane, the 16
+// bits of the source lane's mask spread over 16 lanes.
+__device__ __forceinline__ void str_hq_drain32(const StrUnit &un, u32 *hq, int &qn, u64 *wbuf, int &cnt, int b,
+                                               const SelGlobal &g, int lane, u32 lt_mask) {
+    str_hq_score(un, hq, 32, wbuf, cnt, b, g, lane, lt_mask);
+    const u32 rest = hq[32 + lane];
+    __syncwarp();
+    hq[lane] = rest;
+    qn -= 32;
+    __syncwarp();
+}
 __device__ __forceinline__ void str_hq_push(const StrUnit &un, u32 mask, int c, u32 *hq, int &qn, u64 *wbuf,
                                             int &cnt, int b, const SelGlobal &g, int lane, u32 lt_mask) {
-    do {
+    {
         const bool has = mask != 0u;
         const u32 bal = __ballot_sync(0xffffffffu, has);
         if (has) {
@@ -736,15 +748,19 @@ __device__ __forceinline__ void str_hq_push(const StrUnit &un, u32 mask, int c, 
         }
         qn += __popc(bal);
         __syncwarp();
-        if (qn >= 32) {
-            str_hq_score(un, hq, 32, wbuf, cnt, b, g, lane, lt_mask);
-            const u32 rest = hq[32 + lane];
-            __syncwarp();
-            hq[lane] = rest;
-            qn -= 32;
-            __syncwarp();
-        }
-    } while (__any_sync(0xffffffffu, mask != 0u));
+        if (qn >= 32) str_hq_drain32(un, hq, qn, wbuf, cnt, b, g, lane, lt_mask);
+    }
+    u32 left = __ballot_sync(0xffffffffu, mask != 0u);
+    while (left) {
+        const int src = __ffs(left) - 1;
+        left &= left - 1;
+        const u32 m = __shfl_sync(0xffffffffu, mask, src);          // <= 16 bits (STR_UN planes x 4 positions)
+        if ((m >> lane) & 1u)
+            hq[qn + __popc(m & lt_mask)] = ((u32)(c + (lane >> 2)) << 7) | ((u32)src << 2) | (u32)(lane & 3);
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) str_hq_drain32(un, hq, qn, wbuf, cnt, b, g, lane, lt_mask);
+    }
 }
 
 // consume: the prologue (groups 0 .. STR_NG-1) has been issued by the caller.  The full groups run without
