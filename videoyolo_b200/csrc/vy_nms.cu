@@ -413,6 +413,13 @@ vy_decode_select_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
 //   vy_decode_select_kernel   (above) runs afterwards for images whose list overflowed -- a sample
 //                             that misjudged the distribution -- and normally exits at once.
 // ------------------------------------------------------------------------------------------------
+// The sample only ESTIMATES a score of rank ~4K (the result never depends on it), and its 68 sigmoids per thread
+// were bound by the MUFU pipe at two ops each: one tanh.approx per sigmoid here (relative error ~2^-11).
+__device__ __forceinline__ float samp_sigmoid(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+}
 constexpr int SAMP_NT = 512;
 constexpr int SAMP_MAXK = 16;      // class planes per thread
 constexpr int SAMP_BATCH = 8;      // of which this many are loaded together
@@ -481,7 +488,7 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
             }
             if (k0 == 0) {
 #pragma unroll
-                for (int v = 0; v < 4; ++v) cf[v] = v < r.nv ? vy_sigmoid(to[v]) : 0.0f;
+                for (int v = 0; v < 4; ++v) cf[v] = v < r.nv ? samp_sigmoid(to[v]) : 0.0f;
             }
             // sigmoid is monotonic but the objectness differs per position, so all <= 4 candidates are
             // scored; the best one is a score of the image, and any subset of an image's scores will do
@@ -491,7 +498,7 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
                 if (c < c_hi) {
                     float best = 0.0f;
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) if (v < r.nv) best = fmaxf(best, vy_score(tc[k][v], cf[v]));
+                    for (int v = 0; v < 4; ++v) if (v < r.nv) best = fmaxf(best, samp_sigmoid(tc[k][v]) * cf[v]);
                     if (best > pl.valid_thresh) { skey[k0 + k][tid] = vy_f2ord(best); ++n_mine; }
                 }
             }
