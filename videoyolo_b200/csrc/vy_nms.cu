@@ -1099,7 +1099,7 @@ static __device__ __noinline__ u64 fin_list_bound(SelBuf &S, const u64 *list, in
     return prefix;
 }
 
-// Front end of the finalize kernel for lists of <= FIN_BK_MAXN keys: the exact top-K, sorted, in three light
+// Front end of the finalize kernel for lists of <= FIN_BK_KPT keys per thread: the exact top-K, sorted, in three light
 // passes instead of bound + compaction + sort.  The keys of a list agree in their leading bits (scores of one
 // narrow range), so FIN_BK_BINS counting bins laid right below the common prefix hold about one key each:
 // histogram, descending scan (= where every bin starts in the sorted order, and which bin holds the K-th
@@ -1109,15 +1109,14 @@ static __device__ __noinline__ u64 fin_list_bound(SelBuf &S, const u64 *list, in
 // descending, or -1 (CTA-uniform, nothing written) when that many keys would not fit the CTA.
 constexpr int FIN_BK_BINS = 2048;
 constexpr int FIN_BK_KPT = 8;         // keys per thread
-constexpr int FIN_BK_MAXN = FIN_BK_KPT * FIN_NT_MAX;
 static __device__ __noinline__ int fin_front_buckets(SelBuf &S, const u64 *list, int n, int K,
                                                      u32 *hist, u32 *excl, u64 *out, u64 *keyr) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = (int)blockDim.x;   // nt = 512 or 1024
     u64 *mm = (u64 *)S.queue;                           // [0] = min, [1] = max (the queue is idle in this kernel)
     u64 k[FIN_BK_KPT];
 #pragma unroll
-    for (int q = 0; q < FIN_BK_KPT; ++q) { const int i = tid + q * FIN_NT_MAX; k[q] = i < n ? list[i] : 0ull; }
-    hist[tid] = 0u; hist[tid + FIN_NT_MAX] = 0u;
+    for (int q = 0; q < FIN_BK_KPT; ++q) { const int i = tid + q * nt; k[q] = i < n ? list[i] : 0ull; }
+    for (int i = tid; i < FIN_BK_BINS; i += nt) hist[i] = 0u;
     if (tid == 0) { mm[0] = ~0ull; mm[1] = 0ull; S.sel_digit = 0; S.sel_in = n; }
     __syncthreads();
     {
@@ -1138,10 +1137,13 @@ static __device__ __noinline__ int fin_front_buckets(SelBuf &S, const u64 *list,
 #pragma unroll
     for (int q = 0; q < FIN_BK_KPT; ++q) if (k[q]) atomicAdd(&hist[(u32)(k[q] >> shift) & (FIN_BK_BINS - 1)], 1u);
     __syncthreads();
-    // descending scan: thread t owns bins 2047 - 2t and 2046 - 2t
-    const int d0 = FIN_BK_BINS - 1 - 2 * tid, d1 = d0 - 1;
-    const u32 h0 = hist[d0], h1 = hist[d1];
-    u32 incl = h0 + h1;
+    // descending scan: thread t owns the `per` bins from 2047 - per * t downwards (per = 2 or 4)
+    const int per = FIN_BK_BINS / nt;
+    const int d0 = FIN_BK_BINS - 1 - per * tid;
+    u32 h[4], hsum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { h[j] = j < per ? hist[d0 - j] : 0u; hsum += h[j]; }
+    u32 incl = hsum;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const u32 v = __shfl_up_sync(0xffffffffu, incl, off);
@@ -1151,7 +1153,7 @@ static __device__ __noinline__ int fin_front_buckets(SelBuf &S, const u64 *list,
     if (lane == 31) wsum[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        const u32 v = wsum[lane];
+        const u32 v = lane < (nt >> 5) ? wsum[lane] : 0u;
         u32 inc2 = v;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -1161,17 +1163,23 @@ static __device__ __noinline__ int fin_front_buckets(SelBuf &S, const u64 *list,
         wsum[lane] = inc2 - v;
     }
     __syncthreads();
-    const u32 base = wsum[warp] + incl - (h0 + h1);     // keys in the bins above d0
-    excl[d0] = base;
-    excl[d1] = base + h0;
-    if (base < (u32)K && (u32)K <= base + h0 + h1) {    // the K-th key's bin (none: fewer than K keys, the defaults stand)
-        const bool first = (u32)K <= base + h0;
-        S.sel_digit = first ? d0 : d1;
-        S.sel_in = (int)(first ? base + h0 : base + h0 + h1);
+    {
+        u32 run = wsum[warp] + incl - hsum;             // keys in the bins above d0
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < per) {
+                excl[d0 - j] = run;
+                if (run < (u32)K && (u32)K <= run + h[j]) {     // the K-th key's bin (none: fewer than K keys, the defaults stand)
+                    S.sel_digit = d0 - j;
+                    S.sel_in = (int)(run + h[j]);
+                }
+                run += h[j];
+            }
+        }
     }
     __syncthreads();
     const int kbin = S.sel_digit, m1 = S.sel_in;
-    if (m1 > FIN_NT_MAX) return -1;
+    if (m1 > nt) return -1;
 #pragma unroll
     for (int q = 0; q < FIN_BK_KPT; ++q) {
         if (k[q]) {
@@ -1327,7 +1335,7 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     if (tid < 32) keeps[tid] = 0u;
     u64 *keyr = S.keys;                                 // the K best by rank (K <= SEL_KMAX <= SEL_CAP)
     int m1 = -1;
-    if (n_list <= FIN_BK_MAXN && fp.lcap >= 2 * FIN_BK_BINS)
+    if (n_list <= FIN_BK_KPT * FIN_NT && fp.lcap >= 2 * FIN_BK_BINS)
         m1 = fin_front_buckets(S, list, n_list, K, (u32 *)cand, (u32 *)lbuf, lbuf + FIN_BK_BINS / 2, keyr);
     FIN_T(1);
     u64 mykey = 0ull;
@@ -1821,6 +1829,9 @@ static int launch_finalize(const VyHeads &hd, const RowParams &rp, const SelPlan
                            FinParams fp, int B, cudaStream_t st) {
     const size_t dyn = fin_dyn_smem(pl.K, &fp.lcap);
     if (pl.K > FIN_NT_MAX) VY_FAIL(VY_EINVAL, "finalize: K exceeds the CTA size");      // a thread per rank / slot
+    // 1024 threads: the kernel is a chain of short barrier-separated phases, more warps hide their latencies; but at
+    // 64 registers that is one CTA per SM, so a batch beyond one wave runs 512-thread CTAs, two to an SM (K permitting)
+    const int fin_nt = (pl.K <= FIN_NT_MAX / 2 && B > vy_sm_count()) ? FIN_NT_MAX / 2 : FIN_NT_MAX;
     if (fp.overlap_thresh > 0.0f && fp.overlap_thresh < 1e30f) {
         fp.thr_lo = fp.overlap_thresh * (1.0f - 9.5367431640625e-07f);      // 2^-20 (vy_nms_math.cuh)
         fp.thr_hi = fp.overlap_thresh * (1.0f + 9.5367431640625e-07f);
@@ -1830,9 +1841,7 @@ static int launch_finalize(const VyHeads &hd, const RowParams &rp, const SelPlan
     }
     VY_CUDA_CHECK(cudaFuncSetAttribute(vy_nms_finalize_kernel<SRC>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    // 1024 threads: the kernel is a chain of short barrier-separated phases, more warps hide their latencies
-    // (measured 41 us against 47 us with 512 threads at K = 400)
-    VY_KERNEL(VY_K_FINALIZE, st, (vy_launch(vy_nms_finalize_kernel<SRC>, dim3(B), dim3(FIN_NT_MAX), dyn, st, true, hd, rp, pl, g, fp)));
+    VY_KERNEL(VY_K_FINALIZE, st, (vy_launch(vy_nms_finalize_kernel<SRC>, dim3(B), dim3(fin_nt), dyn, st, true, hd, rp, pl, g, fp)));
     VY_LAUNCH_CHECK("vy_nms_finalize_kernel");
     return VY_OK;
 }
