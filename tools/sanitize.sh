@@ -1,7 +1,9 @@
-# compute-sanitizer over a small slice of the GPU parity tests (memcheck, then racecheck on the NMS kernels)
-out=gpurun_out/sanitize_$1.log
+# compute-sanitizer over a small slice of the GPU parity tests: memcheck, then racecheck on the selection / NMS kernels
+# usage (under gpurun): bash tools/sanitize.sh <tag>
+tag=${1:-run}
 timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_postproc.py -m gpu -x -q \
-  -k "known_answers or fused_variants or (bit_exact_random and 3000) or large_argument_variants or bbox_iou or yolo_output_block" > $out 2>&1
-tail -15 $out
-timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_fusion_conv.py -m gpu -x -q -k "matches_oracle or dwconv or roundtrip" > gpurun_out/sanitize_conv_$1.log 2>&1
-tail -8 gpurun_out/sanitize_conv_$1.log
+  -k "known_answers or fused_variants or finalize_branches or (bit_exact_random and 3000) or bbox_iou or yolo_output_block" > gpurun_out/${tag}_memcheck_postproc.log 2>&1
+tail -6 gpurun_out/${tag}_memcheck_postproc.log
+timeout 900 compute-sanitizer --tool racecheck --racecheck-report analysis --print-limit 10 python -m pytest tests/test_gpu_postproc.py -m gpu -x -q \
+  -k "known_answers or (fused_equals and 416 and 20) or finalize_branches or (bit_exact_random and 3000 and 400)" > gpurun_out/${tag}_racecheck_postproc.log 2>&1
+tail -10 gpurun_out/${tag}_racecheck_postproc.log

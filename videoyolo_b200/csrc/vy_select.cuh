@@ -156,7 +156,10 @@ static __device__ int sel_compact(SelBuf &S, int n, int K, bool exact) {
     if (n <= K) return n;
     const u64 p = sel_rank_bound(S, n, K, exact ? 0 : (K >> 2));
     __syncthreads();
-    if (threadIdx.x == 0 && p > S.thr) S.thr = p;
+    if (threadIdx.x == 0) {                            // (volatile: the read must not be hoisted above the predicate)
+        const u64 cur = *(volatile u64 *)&S.thr;
+        if (p > cur) S.thr = p;
+    }
     return sel_drop_below(S, n, p);
 }
 
@@ -293,6 +296,7 @@ static __device__ __noinline__ void sel_sort_desc_merge(u64 *keys, int npow2) {
         __syncthreads();
         return;
     }
+    __syncwarp();                                      // the swizzle permutes inside a warp: every lane has read its key
     if (act) keys[sel_swz(tid)] = x;
     __syncthreads();
 #ifdef VY_FIN_TIMING
