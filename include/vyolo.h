@@ -133,6 +133,17 @@ int vy_bbox_iou_f64(const double *a, int N, int lda, const double *b, int M, int
                     double offset, double *out, vy_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Batched pairwise IoU of the dynamic-target step ("next" row f4).
+ * Replaces: gluoncv.nn.bbox.BBoxBatchIOU as called at models/definitions/yolo/yolo_target.py:171,202
+ *           (defaults: corner format, offset 0, eps 1e-15), fused with `ious.max(axis=-1)` (:203) and the
+ *           ignore mask `(ious_max > ignore_iou_thresh) * -1` (:204).
+ *   a (B, N, 4), b (B, M, 4) corner boxes, 16-byte aligned; any of the outputs may be NULL (not all):
+ *   ious (B, N, M), ious_max (B, N), objness (B, N) = -1 where ious_max > ignore_thresh else 0.
+ *   Accounted under VY_K_IOU. */
+int vy_bbox_batch_iou_f32(const float *a, const float *b, int B, int N, int M, float offset, float eps,
+                          float ignore_thresh, float *ious, float *ious_max, float *objness, vy_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * The consumer step that follows net(x) in the reference, on the device.
  * Replaces: `bboxes.clip(0, W)` (detect_yolo3.py:226, train_yolov3.py:477), `valid_pred = id >= 0` and
  *           `box / W` (detect_yolo3.py:254-258) -- the part of detect()/validate() between the forward and

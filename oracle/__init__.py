@@ -291,6 +291,29 @@ def bbox_iou(bbox_a: np.ndarray, bbox_b: np.ndarray, offset=0) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------- fusion conv
+def bbox_batch_iou(a: np.ndarray, b: np.ndarray, offset=0.0, eps=1e-15) -> np.ndarray:
+    """gluoncv.nn.bbox.BBoxBatchIOU (corner format) as called at models/definitions/yolo/yolo_target.py:171,202.
+    gluoncv is an un-vendored, unpinned dependency of the reference (requirements.txt:2): restated from its published
+    source -- clip(min(r) - max(l) + offset, 0, float16.max) per axis, i / (area_a + area_b - i + eps) -- fp32 op for op.
+    a (B, N, 4), b (B, M, 4) -> (B, N, M)."""
+    a = np.asarray(a, np.float32)
+    b = np.asarray(b, np.float32)
+    off, e = np.float32(offset), np.float32(eps)
+    al, at, ar, ab = (a[..., k] for k in range(4))
+    bl, bt, br, bb = (b[..., k] for k in range(4))
+    left = np.maximum(al[..., :, None], bl[..., None, :])
+    right = np.minimum(ar[..., :, None], br[..., None, :])
+    top = np.maximum(at[..., :, None], bt[..., None, :])
+    bot = np.minimum(ab[..., :, None], bb[..., None, :])
+    iw = np.clip(right - left + off, np.float32(0), np.float32(6.55040e+04))
+    ih = np.clip(bot - top + off, np.float32(0), np.float32(6.55040e+04))
+    i = iw * ih
+    area_a = ((ar - al + off) * (ab - at + off))[..., :, None]
+    area_b = ((br - bl + off) * (bb - bt + off))[..., None, :]
+    union = (area_a + area_b) - i
+    return (i / (union + e)).astype(np.float32)
+
+
 def conv_bn_leaky(x, w, gamma, beta, mean, var, padding, stride=1, eps=1e-5, slope=0.1, groups=1):
     """LeakyReLU_0.1(BN_eps1e-5(ConvND(x))), use_bias=False -- layers.py:63-79.
 

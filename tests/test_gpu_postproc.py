@@ -566,3 +566,29 @@ def test_bbox_iou_against_reference_outputs(vy, golden_dir):
         np.testing.assert_allclose(got32, z[n + "_iou"], rtol=2e-4, atol=1e-6, equal_nan=True, err_msg=n)
     with pytest.raises(IndexError):
         vy.bbox_iou(torch.zeros(2, 3).cuda(), torch.zeros(2, 4).cuda())
+
+
+def test_bbox_batch_iou_matches_oracle(vy):
+    """"next" row f4: BBoxBatchIOU + max + ignore mask of the dynamic-target step (yolo_target.py:202-204), bit-exact
+    against the fp32 restatement (same operation order, un-contracted arithmetic)."""
+    rng = np.random.RandomState(8)
+    for B, N, M in [(3, 1000, 7), (2, 10647, 50), (1, 333, 300), (4, 1, 1)]:
+        a = rng.uniform(0, 416, size=(B, N, 4)).astype(np.float32)
+        a[..., 2:] = a[..., :2] + rng.uniform(0, 200, size=(B, N, 2)).astype(np.float32)
+        b = rng.uniform(0, 416, size=(B, M, 4)).astype(np.float32)
+        b[..., 2:] = b[..., :2] + rng.uniform(1, 200, size=(B, M, 2)).astype(np.float32)
+        if M > 2:
+            b[:, M // 2:] = -1.0                                           # the reference pads gt rows with -1
+        exp = oracle.bbox_batch_iou(a, b)
+        got = vy.bbox_batch_iou(dev(a), dev(b))
+        np.testing.assert_array_equal(got.cpu().numpy(), exp)
+        ious, imax, obj = vy.bbox_batch_iou(dev(a), dev(b), ignore_iou_thresh=0.7)
+        np.testing.assert_array_equal(ious.cpu().numpy(), exp)
+        np.testing.assert_array_equal(imax.cpu().numpy(), exp.max(axis=-1, keepdims=True))
+        np.testing.assert_array_equal(obj.cpu().numpy(), (exp.max(axis=-1, keepdims=True) > 0.7) * -1.0)
+        none, imax2, obj2 = vy.bbox_batch_iou(dev(a), dev(b), ignore_iou_thresh=0.7, return_ious=False)
+        assert none is None
+        np.testing.assert_array_equal(imax2.cpu().numpy(), imax.cpu().numpy())
+        np.testing.assert_array_equal(obj2.cpu().numpy(), obj.cpu().numpy())
+    with pytest.raises(ValueError):
+        vy.bbox_batch_iou(dev(np.zeros((2, 3, 4), np.float32)), dev(np.zeros((3, 3, 4), np.float32)))

@@ -228,3 +228,28 @@ def test_conv1d_temporal_merge_closed_form():
     ref = (s - m.reshape(sh)) / np.sqrt(v.reshape(sh) + 1e-5) * g.reshape(sh) + b.reshape(sh)
     ref = np.where(ref > 0, ref, 0.1 * ref)
     np.testing.assert_allclose(y, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_bbox_batch_iou_against_plain_loops():
+    """oracle.bbox_batch_iou (gluoncv BBoxBatchIOU restated, yolo_target.py:171,202) against the formula written out
+    box by box in fp32, including the -1 padding rows the reference's gt tensors carry."""
+    rng = np.random.RandomState(5)
+    a = rng.uniform(0, 100, size=(2, 9, 4)).astype(np.float32)
+    a[..., 2:] += a[..., :2]
+    b = rng.uniform(0, 100, size=(2, 4, 4)).astype(np.float32)
+    b[..., 2:] += b[..., :2]
+    b[:, -1] = -1.0
+    got = oracle.bbox_batch_iou(a, b)
+    f = np.float32
+    for i in range(2):
+        for n in range(9):
+            for m in range(4):
+                p, q = a[i, n], b[i, m]
+                iw = min(max(f(min(p[2], q[2]) - max(p[0], q[0])), f(0)), f(65504.0))
+                ih = min(max(f(min(p[3], q[3]) - max(p[1], q[1])), f(0)), f(65504.0))
+                inter = f(iw * ih)
+                union = f(f(f((p[2] - p[0]) * (p[3] - p[1])) + f((q[2] - q[0]) * (q[3] - q[1]))) - inter)
+                assert got[i, n, m] == f(inter / f(union + f(1e-15)))
+    assert got.shape == (2, 9, 4) and (got[:, :, -1] == 0).all()          # a padding box overlaps nothing
+    same = oracle.bbox_batch_iou(a, a)
+    np.testing.assert_allclose(same[0].diagonal(), 1.0, rtol=1e-6)

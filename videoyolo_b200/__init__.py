@@ -5,10 +5,10 @@ reference's own block/operator names.  Host code is Python over a C ABI (include
 PyTorch supplies device buffers, streams and torch.distributed only.  No CPU fallback.
 """
 from . import _lib, ops, parallel
-from .ops import bbox_iou, box_nms, yolo3_decode, yolo3_decode_nms
+from .ops import bbox_batch_iou, bbox_iou, box_nms, yolo3_decode, yolo3_decode_nms
 from .layers import Conv, Conv1D, TemporalPooling, TimeDistributed
 from .yolo3 import ANCHORS, STRIDES, YOLOOutputV3, YOLOV3, YOLOV3T, YOLOV3_noback, get_yolov3_postprocess
 
-__all__ = ["bbox_iou", "box_nms", "yolo3_decode", "yolo3_decode_nms", "YOLOOutputV3", "YOLOV3",
+__all__ = ["bbox_batch_iou", "bbox_iou", "box_nms", "yolo3_decode", "yolo3_decode_nms", "YOLOOutputV3", "YOLOV3",
            "YOLOV3_noback", "YOLOV3T", "Conv", "Conv1D", "TemporalPooling", "TimeDistributed", "get_yolov3_postprocess",
            "ANCHORS", "STRIDES", "ops", "parallel"]

@@ -1,5 +1,6 @@
 // vy_iou.cu -- pairwise IoU, utils/bbox.py:11-38 (same operation order as the numpy source).
 #include "vy_common.cuh"
+#include <math_constants.h>
 
 template <typename T>
 __global__ void vy_bbox_iou_kernel(const T *__restrict__ a, int N, int lda, const T *__restrict__ b, int M,
@@ -41,6 +42,74 @@ extern "C" int vy_bbox_iou_f32(const float *a, int N, int lda, const float *b, i
 extern "C" int vy_bbox_iou_f64(const double *a, int N, int lda, const double *b, int M, int ldb, double offset,
                                double *out, vy_stream_t st) {
     return launch_iou<double>(a, N, lda, b, M, ldb, offset, out, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched pairwise IoU of the dynamic-target step (models/definitions/yolo/yolo_target.py:171,202-204:
+// batch_ious = BBoxBatchIOU()(box_preds, gt_boxes); ious_max = batch_ious.max(-1); objness = -(ious_max > thr)).
+// BBoxBatchIOU is gluoncv.nn.bbox (not vendored in the reference); its arithmetic, restated in oracle/:
+//   iw = clip(min(ar, br) - max(al, bl) + offset, 0, 65504), ih likewise, i = iw * ih,
+//   area = (r - l + offset) * (b - t + offset), iou = i / (area_a + area_b - i + eps)      -- corner format.
+// One thread per predicted box: the M ground-truth boxes of its image sit in shared memory; the (B, N, M) tensor
+// is optional -- the maximum over M and the ignore mask are produced in the same pass.
+constexpr int BIOU_NT = 256;
+constexpr int BIOU_MTILE = 256;
+__global__ void __launch_bounds__(BIOU_NT)
+vy_bbox_batch_iou_kernel(const float *__restrict__ a, const float *__restrict__ b, int N, int M, float offset,
+                         float eps, float ignore_thresh, float *__restrict__ ious, float *__restrict__ ious_max,
+                         float *__restrict__ objness) {
+    __shared__ float4 gt[BIOU_MTILE];
+    __shared__ float gt_area[BIOU_MTILE];
+    const int img = blockIdx.y;
+    const int n = blockIdx.x * BIOU_NT + threadIdx.x;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N) bx = *reinterpret_cast<const float4 *>(a + ((size_t)img * N + n) * 4);
+    const float area_a = (bx.z - bx.x + offset) * (bx.w - bx.y + offset);
+    float best = -CUDART_INF_F;
+    for (int m0 = 0; m0 < M; m0 += BIOU_MTILE) {
+        const int mt = min(BIOU_MTILE, M - m0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < mt; j += BIOU_NT) {
+            const float4 g = *reinterpret_cast<const float4 *>(b + ((size_t)img * M + m0 + j) * 4);
+            gt[j] = g;
+            gt_area[j] = (g.z - g.x + offset) * (g.w - g.y + offset);
+        }
+        __syncthreads();
+        if (n < N) {
+            float *o = ious ? ious + ((size_t)img * N + n) * M + m0 : nullptr;
+            for (int j = 0; j < mt; ++j) {
+                const float4 g = gt[j];
+                const float left = fmaxf(bx.x, g.x), right = fminf(bx.z, g.z);
+                const float top = fmaxf(bx.y, g.y), bot = fminf(bx.w, g.w);
+                const float iw = fminf(fmaxf(right - left + offset, 0.0f), 6.55040e+04f);
+                const float ih = fminf(fmaxf(bot - top + offset, 0.0f), 6.55040e+04f);
+                const float inter = iw * ih;
+                const float v = inter / (area_a + gt_area[j] - inter + eps);
+                if (o) o[j] = v;
+                best = fmaxf(best, v);
+            }
+        }
+    }
+    if (n < N) {
+        if (ious_max) ious_max[(size_t)img * N + n] = best;
+        if (objness) objness[(size_t)img * N + n] = best > ignore_thresh ? -1.0f : 0.0f;   // yolo_target.py:204
+    }
+}
+
+extern "C" int vy_bbox_batch_iou_f32(const float *a, const float *b, int B, int N, int M, float offset, float eps,
+                                     float ignore_thresh, float *ious, float *ious_max, float *objness,
+                                     vy_stream_t st) {
+    if (B < 0 || N < 0 || M < 1) VY_FAIL(VY_EINVAL, "bbox_batch_iou: need B, N >= 0 and M >= 1");
+    if (B == 0 || N == 0) return VY_OK;
+    if (!a || !b || (!ious && !ious_max && !objness)) VY_FAIL(VY_EINVAL, "bbox_batch_iou: null pointer");
+    if ((((uintptr_t)a) | ((uintptr_t)b)) & 15) VY_FAIL(VY_EALIGN, "bbox_batch_iou: boxes must be 16-byte aligned");
+    if (B > 65535) VY_FAIL(VY_EINVAL, "bbox_batch_iou: B > 65535");
+    const dim3 grid((unsigned)((N + BIOU_NT - 1) / BIOU_NT), (unsigned)B);
+    VY_KERNEL(VY_K_IOU, (cudaStream_t)st,
+              (vy_bbox_batch_iou_kernel<<<grid, BIOU_NT, 0, (cudaStream_t)st>>>(a, b, N, M, offset, eps, ignore_thresh,
+                                                                                ious, ious_max, objness)));
+    VY_LAUNCH_CHECK("vy_bbox_batch_iou_kernel");
+    return VY_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -166,6 +166,34 @@ def bbox_iou(bbox_a: torch.Tensor, bbox_b: torch.Tensor, offset=0) -> torch.Tens
     return out
 
 
+def bbox_batch_iou(a: torch.Tensor, b: torch.Tensor, offset=0, eps=1e-15, ignore_iou_thresh: Optional[float] = None,
+                   return_ious: bool = True):
+    """gluoncv ``BBoxBatchIOU()(a, b)`` as the dynamic-target step calls it (yolo_target.py:171,202): corner boxes
+    a (B, N, 4), b (B, M, 4) -> ious (B, N, M).  With ``ignore_iou_thresh`` the two lines that follow in the
+    reference are fused into the same pass and returned as well: ``ious_max`` (B, N, 1) (:203) and
+    ``objness_t = (ious_max > thresh) * -1`` (B, N, 1) (:204); ``return_ious=False`` then skips the (B, N, M) write.
+    Returns ious | (ious_or_None, ious_max, objness_t)."""
+    a = _need_cuda(a, "a")
+    b = _need_cuda(b, "b")
+    if a.dim() != 3 or b.dim() != 3 or a.shape[2] != 4 or b.shape[2] != 4 or a.shape[0] != b.shape[0]:
+        raise ValueError("bbox_batch_iou: a (B, N, 4) and b (B, M, 4) expected")
+    B, N, M = a.shape[0], a.shape[1], b.shape[1]
+    if M < 1:
+        raise ValueError("bbox_batch_iou: b needs at least one box per image")
+    fused = ignore_iou_thresh is not None
+    if not fused and not return_ious:
+        raise ValueError("bbox_batch_iou: nothing to return")
+    ious = torch.empty((B, N, M), dtype=torch.float32, device=a.device) if return_ious else None
+    imax = torch.empty((B, N, 1), dtype=torch.float32, device=a.device) if fused else None
+    obj = torch.empty((B, N, 1), dtype=torch.float32, device=a.device) if fused else None
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().vy_bbox_batch_iou_f32(
+            a.data_ptr(), b.data_ptr(), B, N, M, float(offset), float(eps), float(ignore_iou_thresh if fused else 0.0),
+            ious.data_ptr() if ious is not None else None, imax.data_ptr() if fused else None,
+            obj.data_ptr() if fused else None, _stream()))
+    return (ious, imax, obj) if fused else ious
+
+
 def detect_consume(dets: torch.Tensor, size: float):
     """The device part of what detect()/validate() do with net(x)'s output (detect_yolo3.py:226,254-258):
     returns (bboxes clipped to [0, size] (B,P,4), normalised boxes of the valid rows (B,P,4; -1 elsewhere),
