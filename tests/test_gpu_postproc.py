@@ -592,3 +592,16 @@ def test_bbox_batch_iou_matches_oracle(vy):
         np.testing.assert_array_equal(obj2.cpu().numpy(), obj.cpu().numpy())
     with pytest.raises(ValueError):
         vy.bbox_batch_iou(dev(np.zeros((2, 3, 4), np.float32)), dev(np.zeros((3, 3, 4), np.float32)))
+
+
+def test_empty_batch(vy):
+    """B = 0 gives empty results of the right shape from every entry point (no launch)."""
+    heads = [dev(np.zeros((0, 75, g, g), np.float32)) for g in oracle.grid_sizes(416)]
+    out, kept = vy.yolo3_decode_nms(heads, 20, AN, ST)
+    assert tuple(out.shape) == (0, 100, 6) and tuple(kept.shape) == (0, 100)
+    assert tuple(vy.yolo3_decode(heads, 20, AN, ST).shape) == (0, 212940, 6)
+    assert tuple(vy.box_nms(dev(np.zeros((0, 50, 6), np.float32))).shape) == (0, 50, 6)
+    assert tuple(vy.box_nms(dev(np.zeros((2, 0, 6), np.float32))).shape) == (2, 0, 6)
+    net = vy.get_yolov3_postprocess(["c"] * 20)
+    ids, scores, bboxes = net(*heads)
+    assert tuple(ids.shape) == (0, 100, 1) and tuple(bboxes.shape) == (0, 100, 4)

@@ -81,6 +81,8 @@ def yolo3_decode(heads, num_class: int, anchors, strides, agnostic: bool = False
         out = _need_cuda(out, "out")
         if tuple(out.shape) != (B, R, 6):
             raise ValueError("out must be (B, R, 6) = %s" % ((B, R, 6),))
+    if B == 0:
+        return out
     with torch.cuda.device(heads[0].device):
         _lib.check(_lib.lib().vy_decode_f32(ptrs, H, W, st, an, n, B, A, num_class, int(agnostic),
                                             out.data_ptr(), _stream()))
@@ -136,6 +138,8 @@ def yolo3_decode_nms(heads, num_class: int, anchors, strides, nms_thresh: float 
         out = torch.empty((B, post_nms, 6), dtype=torch.float32, device=dev)
     if kept is None:
         kept = torch.empty((B, post_nms), dtype=torch.int32, device=dev)
+    if B == 0:                                           # an empty batch is an empty result (MXNet operators agree)
+        return out, kept
     L = _lib.lib()
     with torch.cuda.device(dev):
         need = L.vy_decode_nms_workspace_bytes(H, W, n, B, A, num_class, int(agnostic), int(topk))
