@@ -198,6 +198,15 @@ int vy_unpack_p_channels_to_f32(const void *y_p, int p_is_f32, int B, int Cp, in
  * inner = B*(H+2)*(W+2)*C, mode 0 = max, 1 = mean.  bf16 in/out. */
 int vy_temporal_pool_bf16(const void *x, int T, long inner, int mode, void *y, vy_stream_t stream);
 
+/* The join between two scales of the YOLO neck on P-layout data ("next" row f2).
+ * Replaces: `_upsample(x, stride=2)` (layers.py:11-20: pixel repeat), `F.slice_like(upsample, route_now, axes=(3,4))` and
+ *           `F.concat(..., route_now, dim=2)` (yolo3.py:1170-1177; 4-D variant :1177).
+ *   up    (T, B, Hu+2, Wu+2, Cu) bf16, route (T, B, H+2, W+2, Cr) bf16, 2*Hu >= H, 2*Wu >= W (slice_like crops)
+ *   out   (T, B, H+2, W+2, Cu+Cr) bf16 = [upsampled | route] per pixel, zero border
+ *   requires Cu % 8 == 0 and Cr % 8 == 0.  Accounted under VY_K_LAYOUT. */
+int vy_upsample_concat_bf16(const void *up, const void *route, int B, int T, int H, int W, int Hu, int Wu,
+                            int Cu, int Cr, void *out, vy_stream_t stream);
+
 /* Depthwise temporal merge of a window of T frames into one.
  * Replaces: _conv1d(channels, kernel=T, padding=0, strides=1), models/definitions/layers.py:50-60
  *           = Conv3D(kernel (T,1,1), groups=channels, use_bias=False) + BatchNorm + LeakyReLU(0.1), as

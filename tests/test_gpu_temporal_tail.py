@@ -124,3 +124,71 @@ def test_layer_blocks(vy):
     check(z, ref[:, :, 0], "conv1d")
     with pytest.raises(ValueError):
         vy.Conv("3", 64, 3, 1, 2, in_channels=64)          # strided cells are not on this path
+
+
+def test_upsample_concat(vy):
+    """_upsample x2 + slice_like + channel concat (layers.py:11-20, yolo3.py:1170-1175) on P-layout data: exact."""
+    rng = np.random.RandomState(11)
+    for (B, K, Cu, Cr, hu, h) in [(2, 3, 64, 128, 5, 10), (1, 2, 8, 8, 7, 13), (2, 1, 128, 64, 13, 26)]:
+        up = bf16_round(rng.normal(size=(B, K, Cu, hu, hu)))
+        rt = bf16_round(rng.normal(size=(B, K, Cr, h, h)))
+        y = vy.ops.upsample_concat(vy.ops.pack_p(torch.from_numpy(up).cuda(), "NTCHW"),
+                                   vy.ops.pack_p(torch.from_numpy(rt).cuda(), "NTCHW"))
+        assert (y.B, y.T, y.H, y.W, y.C) == (B, K, h, h, Cu + Cr)
+        got = vy.ops.unpack_p(y, "NTCHW").cpu().numpy()
+        ref_up = up.repeat(2, axis=-1).repeat(2, axis=-2)[..., :h, :h]                 # _upsample + slice_like
+        np.testing.assert_array_equal(got, np.concatenate([ref_up, rt], axis=2))
+        d = y.data.float().cpu().numpy()                                               # the border stays zero
+        assert not d[:, :, 0].any() and not d[:, :, -1].any() and not d[:, :, :, 0].any() and not d[:, :, :, -1].any()
+    with pytest.raises(ValueError):
+        vy.ops.upsample_concat(vy.ops.pack_p(torch.zeros(1, 1, 8, 3, 3).cuda(), "NTCHW"),
+                               vy.ops.pack_p(torch.zeros(1, 1, 8, 9, 9).cuda(), "NTCHW"))
+
+
+@pytest.mark.parametrize("join,ctype", [("max", "3"), ("mean", "21")])
+def test_yolov3t_neck_matches_oracle_chain(vy, join, ctype):
+    """"next" row f2: the whole post-backbone part of YOLOV3T (detection blocks, transitions, upsample + concat, late
+    join, outputs, NMS; yolo3.py:1126-1206) against the CPU oracle chain.  The block-body outputs (``route``) are compared
+    scale by scale with a tolerance that grows with the depth of the bf16 chain; the NMS tail is exact on the GPU's own
+    head maps, as for the tail alone."""
+    rng = np.random.RandomState(31 + len(join))
+    torch.manual_seed(7)
+    B, K, C, size = 1, 3, 20, 96
+    stage_channels, channels = (128, 64, 64), (64, 64, 64)
+    net = vy.YOLOV3TNeck(["c%d" % i for i in range(C)], k=K, k_join_type=join, block_conv_type=ctype,
+                         stage_channels=stage_channels, channels=channels).cuda().eval()
+    randomize_bn(net, rng)
+    rs = [bf16_round(rng.normal(0, 1, size=(B, K, c, g, g))) for c, g in zip(stage_channels, oracle.grid_sizes(size))]
+    with torch.no_grad():
+        routes = net.routes(*[torch.from_numpy(r).cuda() for r in rs])
+        ids, scores, bboxes = net(*[torch.from_numpy(r).cuda() for r in rs])
+
+    def run_conv(conv, y):                                 # a Conv module = one or two cells (layers.py:135-158)
+        for cell in conv.cells:
+            y = oracle_cell(cell, y)
+        return y
+
+    x = rs[0].transpose(0, 2, 1, 3, 4)                     # NCDHW
+    for i, block in enumerate(net.blocks):
+        for conv in block.body:
+            x = run_conv(conv, x)
+        got = vy.ops.unpack_p(routes[i], "NCDHW").cpu().numpy()
+        scale = np.abs(x).max()
+        assert np.abs(got - x).max() <= 2e-2 * (i + 1) * scale, ("route %d" % i, np.abs(got - x).max(), scale)
+        if i + 1 < len(net.blocks):
+            t = x.transpose(0, 2, 1, 3, 4)                 # (B, K, C, H, W): TimeDistributed folds K into the batch
+            t = t.reshape((B * K,) + t.shape[2:])[:, :, None]          # (B*K, C, 1, H, W)
+            t = run_conv(net.transitions[i].model, t)[:, :, 0].reshape((B, K, -1) + t.shape[3:])
+            g = rs[i + 1].shape[-1]
+            up = t.repeat(2, axis=-1).repeat(2, axis=-2)[..., :g, :g]  # _upsample + slice_like
+            x = np.concatenate([up, rs[i + 1]], axis=2).transpose(0, 2, 1, 3, 4)
+    # the tail: exact against the oracle on the GPU's own head maps
+    with torch.no_grad():
+        heads = net.head.head_maps(*routes)
+    AN, ST = oracle.ANCHORS[::-1], oracle.STRIDES[::-1]
+    dets = vy.yolo3_decode(heads, C, AN, ST).cpu().numpy()
+    o_ids, o_sc, o_bb, o_rec = oracle.yolov3_tail(dets, return_record=True)
+    np.testing.assert_array_equal(net.last_kept_rows.cpu().numpy(), o_rec)
+    np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
+    np.testing.assert_array_equal(scores.cpu().numpy(), o_sc)
+    np.testing.assert_array_equal(bboxes.cpu().numpy(), o_bb)

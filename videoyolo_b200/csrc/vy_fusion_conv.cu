@@ -602,6 +602,51 @@ extern "C" int vy_temporal_pool_bf16(const void *x, int T, long inner, int mode,
     return VY_OK;
 }
 
+// _upsample(x, 2) + slice_like + channel concat of the YOLO neck (layers.py:11-20, yolo3.py:1170-1177) on P-layout
+// data: out[f][y][x] = [ up[f][y/2][x/2] (Cu channels) | route[f][y][x] (Cr channels) ], zero border.  One thread per
+// 16-byte vector (8 channels) of the output.
+__global__ void vy_upsample_concat_kernel(const uint4 *__restrict__ up, const uint4 *__restrict__ route, int F, int H, int W,
+                                          int Hu, int Wu, int Cu8, int Cr8, uint4 *__restrict__ out) {
+    const int Hp = H + 2, Wp = W + 2, Co8 = Cu8 + Cr8;
+    const long long total = (long long)F * Hp * Wp * Co8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % Co8);
+        long long pix = i / Co8;
+        const int wp = (int)(pix % Wp);
+        pix /= Wp;
+        const int hp = (int)(pix % Hp);
+        const long long f = pix / Hp;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (hp >= 1 && hp <= H && wp >= 1 && wp <= W) {
+            if (v < Cu8) {
+                const int hu = (hp - 1) / 2 + 1, wu = (wp - 1) / 2 + 1;       // nearest (pixel repeat), in padded coordinates
+                o = up[((f * (Hu + 2) + hu) * (Wu + 2) + wu) * Cu8 + v];
+            } else {
+                o = route[((f * Hp + hp) * Wp + wp) * Cr8 + (v - Cu8)];
+            }
+        }
+        out[i] = o;
+    }
+}
+
+extern "C" int vy_upsample_concat_bf16(const void *up, const void *route, int B, int T, int H, int W, int Hu, int Wu,
+                                       int Cu, int Cr, void *out, vy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!up || !route || !out || B < 1 || T < 1 || H < 1 || W < 1 || Hu < 1 || Wu < 1 || Cu < 1 || Cr < 1)
+        VY_FAIL(VY_EINVAL, "vy_upsample_concat_bf16: bad arguments");
+    if (2 * Hu < H || 2 * Wu < W) VY_FAIL(VY_EINVAL, "vy_upsample_concat_bf16: the upsampled map must cover the route (slice_like only crops)");
+    if (Cu % 8 != 0 || Cr % 8 != 0 || (((uintptr_t)up | (uintptr_t)route | (uintptr_t)out) & 15) != 0)
+        VY_FAIL(VY_EALIGN, "vy_upsample_concat_bf16: channels must be multiples of 8 and pointers 16-byte aligned");
+    const long long total = (long long)B * T * (H + 2) * (W + 2) * ((Cu + Cr) / 8);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)vy_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    VY_KERNEL(VY_K_LAYOUT, st, (vy_upsample_concat_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+        (const uint4 *)up, (const uint4 *)route, B * T, H, W, Hu, Wu, Cu / 8, Cr / 8, (uint4 *)out)));
+    VY_LAUNCH_CHECK("vy_upsample_concat_kernel");
+    return VY_OK;
+}
+
 extern "C" int vy_temporal_dwconv_bf16(const void *x, const float *w, const float *scale, const float *shift,
                                        float leaky_slope, int B, int T, int H, int W, int C, void *y, vy_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;

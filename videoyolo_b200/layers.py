@@ -4,6 +4,7 @@
     TemporalPooling(k, type)                          layers.py:161-205  ('direct' style: max / mean over the K frames)
     TimeDistributed(model)                            layers.py:208-264  (fold K into the batch axis)
     Conv1D(channel, kernel)                           layers.py:50-60    (_conv1d: depthwise temporal merge of a window)
+    YOLODetectionBlockV3(channel, conv_type)          yolo3.py:200-263   (body of five cells -> route, tip conv -> tip)
 
 Activations travel between these blocks as ``ops.PTensor`` (the library's P layout, include/vyolo.h): pack the
 reference's (B, K, C, H, W) / NCDHW fp32 tensor once with ``ops.pack_p`` and unpack the last output with
@@ -131,3 +132,34 @@ class Conv1D(torch.nn.Module):
         with torch.no_grad():
             scale, shift = ops.fold_bn(self.gamma.detach(), self.beta.detach(), self.running_mean, self.running_var)
         return ops.temporal_dwconv(x, self.weight.detach(), scale, shift, 0.1)
+
+
+class YOLODetectionBlockV3(torch.nn.Module):
+    """YOLO V3 detection block (models/definitions/yolo/yolo3.py:200-263): body = 2 x [1x1 reduce to ``channel``,
+    3x3 expand to ``2*channel``] + 1x1 reduce (:225-247), tip = 3x3 expand (:250-253); returns ``(route, tip)``.
+    ``conv_type`` '3' / '21': the 1x1 cells are 1x1x1 3-D convs and the 3x3 cells ``Conv(conv_type, ...)`` (:229-243);
+    '2': all cells 2-D (the block then sits under ``TimeDistributed`` in the temporal models, yolo3.py:1035-1037).
+    P-layout activations in and out (the reference's swapaxes(1, 2) :256-262 is a no-op in that layout)."""
+
+    def __init__(self, channel, conv_type="2", in_channels=None, **kwargs):
+        super().__init__()
+        assert channel % 2 == 0, "channel {} cannot be divided by 2".format(channel)      # yolo3.py:222
+        assert conv_type in ("2", "3", "21")
+        if in_channels is None:
+            raise ValueError("in_channels is required (Gluon infers it at the first call; this mirror does not)")
+        self._conv_type = conv_type
+        one = "3" if conv_type in ("3", "21") else "2"
+        cells, cin = [], in_channels
+        for _ in range(2):
+            cells.append(Conv(one, channel, 1, 0, 1, in_channels=cin))
+            cells.append(Conv(conv_type, channel * 2, 3, 1, 1, in_channels=channel))
+            cin = channel * 2
+        cells.append(Conv(one, channel, 1, 0, 1, in_channels=cin))
+        self.body = torch.nn.ModuleList(cells)
+        self.tip = Conv(conv_type, channel * 2, 3, 1, 1, in_channels=channel)
+
+    def forward(self, x: ops.PTensor):
+        route = x
+        for cell in self.body:
+            route = cell(route)
+        return route, self.tip(route)

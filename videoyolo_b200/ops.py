@@ -330,6 +330,22 @@ def temporal_pool(x: PTensor, type: str = "max") -> PTensor:
     return PTensor(y, x.B, 1, x.H, x.W, x.C)
 
 
+def upsample_concat(up: PTensor, route: PTensor) -> PTensor:
+    """``concat(slice_like(_upsample(up, 2), route), route)`` along channels (layers.py:11-20, yolo3.py:1170-1177):
+    the join between two scales of the YOLO neck, P layout in and out."""
+    if up.data.dtype != torch.bfloat16 or route.data.dtype != torch.bfloat16:
+        raise TypeError("upsample_concat takes bf16 P-layout activations")
+    if up.B != route.B or up.T != route.T:
+        raise ValueError("upsample_concat: batch / frames differ")
+    if 2 * up.H < route.H or 2 * up.W < route.W:
+        raise ValueError("upsample_concat: the upsampled map must cover the route")
+    y = torch.empty((route.T, route.B, route.H + 2, route.W + 2, up.C + route.C), dtype=torch.bfloat16, device=route.data.device)
+    with torch.cuda.device(route.data.device):
+        _lib.check(_lib.lib().vy_upsample_concat_bf16(up.data.data_ptr(), route.data.data_ptr(), route.B, route.T,
+                                                      route.H, route.W, up.H, up.W, up.C, route.C, y.data_ptr(), _stream()))
+    return PTensor(y, route.B, route.T, route.H, route.W, up.C + route.C)
+
+
 def temporal_dwconv(x: PTensor, weight: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
                     slope: float = 0.1) -> PTensor:
     """``_conv1d`` (layers.py:50-60) over a window of exactly ``x.T`` frames: depthwise Conv3D with kernel

@@ -195,6 +195,11 @@ class YOLOV3T(torch.nn.Module):
             raise ValueError("expected %d inputs (stride 32,16,8 order)" % len(self.tips))
         tips = []
         for i, x in enumerate(xs):
+            if isinstance(x, ops.PTensor):                 # already in the library's layout (YOLOV3TNeck)
+                if x.T != self._k:
+                    raise ValueError("input %d must hold K=%d frames" % (i, self._k))
+                tips.append(self.tips[i](x))
+                continue
             if x.dim() != 5 or x.shape[1] != self._k:
                 raise ValueError("input %d must be (B, K=%d, C, H, W)" % (i, self._k))
             tips.append(self.tips[i](ops.pack_p(x, "NTCHW")))
@@ -251,6 +256,63 @@ class YOLOV3T(torch.nn.Module):
     @property
     def last_kept_rows(self):
         return self.tail.last_kept_rows
+
+
+class YOLOV3TNeck(torch.nn.Module):
+    """Everything of ``YOLOV3T.hybrid_forward`` after the backbone stages, late join (yolo3.py:1126-1206): per scale the
+    detection block (:1131-1132), the late join of its tip (:1134-1138), the output layer (:1159); between scales the
+    1x1 transition (:1167, a TimeDistributed 2-D cell :1050), ``_upsample`` x2 + ``slice_like`` + channel concat with the
+    backbone's route of the next scale (:1170-1175); then concat -> box_nms -> slice (:1195-1206).
+
+    ``net(r32, r16, r8)`` takes the three stage outputs, each (B, K, C_i, H_i, W_i) fp32 on a CUDA device (deep to
+    shallow; Darknet-53: 1024, 512, 256 channels).  Every convolution runs in the tcgen05 fusion-conv kernel on bf16
+    P-layout activations; the join between scales is ``vy_upsample_concat_bf16``; tip / join / prediction / decode / NMS
+    are the ``YOLOV3T`` tail above."""
+
+    def __init__(self, classes: Sequence[str], k: int = 3, k_join_type: str = "max", block_conv_type: str = "3",
+                 stage_channels: Sequence[int] = (1024, 512, 256), channels: Sequence[int] = (512, 256, 128), **kwargs):
+        super().__init__()
+        from .layers import Conv, TimeDistributed, YOLODetectionBlockV3
+        assert len(stage_channels) == len(channels)
+        self.head = YOLOV3T(classes, k=k, k_join_type=k_join_type, block_conv_type=block_conv_type, channels=channels, **kwargs)
+        blocks, transitions, cin = [], [], stage_channels[0]
+        for i, c in enumerate(channels):
+            blocks.append(YOLODetectionBlockV3(c, block_conv_type, in_channels=cin))
+            if i + 1 < len(channels):
+                transitions.append(TimeDistributed(Conv("2", channels[i + 1], 1, 0, 1, in_channels=c)))   # yolo3.py:1048-1051
+                cin = channels[i + 1] + stage_channels[i + 1]
+        self.blocks = torch.nn.ModuleList(blocks)
+        self.transitions = torch.nn.ModuleList(transitions)
+        for i, b in enumerate(self.blocks):               # the block's tip conv IS the head's tip conv (one set of weights)
+            b.tip = self.head.tips[i]
+
+    @property
+    def classes(self):
+        return self.head.classes
+
+    def set_nms(self, nms_thresh=0.45, nms_topk=400, post_nms=100):
+        self.head.set_nms(nms_thresh, nms_topk, post_nms)
+
+    def routes(self, *rs):
+        """the three block-body outputs (``route`` of yolo3.py:258) as P-layout activations, deep to shallow"""
+        if len(rs) != len(self.blocks):
+            raise ValueError("expected %d stage outputs (deep to shallow)" % len(self.blocks))
+        outs = []
+        x = ops.pack_p(rs[0], "NTCHW")
+        for i, block in enumerate(self.blocks):
+            for cell in block.body:
+                x = cell(x)
+            outs.append(x)
+            if i + 1 < len(self.blocks):
+                x = ops.upsample_concat(self.transitions[i](x), ops.pack_p(rs[i + 1], "NTCHW"))
+        return outs
+
+    def forward(self, *rs):
+        return self.head(*self.routes(*rs))
+
+    @property
+    def last_kept_rows(self):
+        return self.head.last_kept_rows
 
 
 def get_yolov3_postprocess(classes, agnostic=False, in_channels=None, **kwargs) -> YOLOV3:
