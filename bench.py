@@ -146,6 +146,43 @@ def temporal_tail_leg(dev, B=32, K=3, C=30, size=416, iters=10):
             "note": "device-resident fp32 inputs; every kernel on the path is the library's own (no cuDNN/cuBLAS); L2 flushed between calls"}
 
 
+def temporal_neck_leg(dev, B=8, K=3, C=30, size=416, iters=10):
+    """The whole post-backbone part of the temporal detector on the device: Darknet-53 stage
+    outputs (B, K, 1024/512/256, g, g) fp32 -> detection blocks (five cells + tip, 3-D convs), transitions, upsample +
+    concat, late 'max' join, prediction conv, fused decode + box_nms.  FLOPs by the SURVEY formula over every conv cell."""
+    import torch
+    import videoyolo_b200 as vy
+    from videoyolo_b200 import _lib
+    torch.manual_seed(9)
+    net = vy.YOLOV3TNeck(["c%d" % i for i in range(C)], k=K, k_join_type="max", block_conv_type="3").to(dev).eval()
+    rs = [torch.randn((B, K, c, g, g), device=dev) for c, g in zip((1024, 512, 256), grid_sizes(size))]
+    flops = 0.0
+    for i, (blk, g) in enumerate(zip(net.blocks, grid_sizes(size))):
+        convs = list(blk.body) + [net.head.tips[i]] + ([net.transitions[i].model] if i < len(net.transitions) else [])
+        for conv in convs:
+            for cell in conv.cells:
+                co, ci = cell.weight.shape[0], cell.weight.shape[1]
+                flops += 2.0 * B * K * g * g * co * ci * cell.k3[0] * cell.k3[1] * cell.k3[2]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    with torch.no_grad():
+        for _ in range(3):
+            net(*rs)
+        _lib.prof_enable(True); _lib.prof_read()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); net(*rs); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        prof = _lib.prof_read(); _lib.prof_enable(False)
+    ms = sorted(ts)[len(ts) // 2]
+    return {"workload": "YOLOV3T after the backbone (yolo3.py:1126-1206), VID 30 cls 416x416, K=3, 3-D convs, batch %d windows" % B,
+            "windows_per_s": round(B / (ms * 1e-3), 1), "ms_per_call": round(ms, 4),
+            "gflop_per_window": round(flops / B / 1e9, 1), "tflops_formula": round(flops / (ms * 1e-3) / 1e12, 1),
+            "library_kernel_ms_per_call": {k: round(v[0] / iters, 4) for k, v in prof.items()}}
+
+
 def load_traffic(config_name, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
     `ncu --set full` capture (profiles/roofline_traffic.json), or None."""
@@ -471,6 +508,7 @@ def main():
         try:
             conv = fusion_conv_leg(dev)
             conv["temporal_tail"] = temporal_tail_leg(dev)
+            conv["temporal_neck"] = temporal_neck_leg(dev)
         except Exception as e:                     # the headline line must still be printed
             conv = {"error": str(e)[:200]}
 
