@@ -192,3 +192,20 @@ def test_yolov3t_neck_matches_oracle_chain(vy, join, ctype):
     np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
     np.testing.assert_array_equal(scores.cpu().numpy(), o_sc)
     np.testing.assert_array_equal(bboxes.cpu().numpy(), o_bb)
+
+
+def test_graphed_module_equals_eager(vy):
+    """The neck captured in a CUDA graph (pipeline.GraphedModule) replays to exactly the eager results, also on new inputs."""
+    from videoyolo_b200.pipeline import GraphedModule
+    torch.manual_seed(3)
+    net = vy.YOLOV3TNeck(["c%d" % i for i in range(20)], k=3, stage_channels=(128, 64, 64), channels=(64, 64, 64)).cuda().eval()
+    mk = lambda: [torch.randn((2, 3, c, g, g), device="cuda") for c, g in zip((128, 64, 64), oracle.grid_sizes(96))]
+    g = GraphedModule(net, mk())
+    for _ in range(2):
+        xs = mk()
+        with torch.no_grad():
+            ref = [t.clone() for t in net(*xs)]
+        out = g(*xs)
+        torch.cuda.synchronize()
+        for a, b in zip(out, ref):
+            assert torch.equal(a, b)

@@ -126,3 +126,36 @@ class GraphedDetector:
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.out, self.kept
+
+
+class GraphedModule:
+    """Any block of this package (``YOLOV3T``, ``YOLOV3TNeck``, ...) for inputs of a FIXED shape, captured once in a CUDA
+    graph: the temporal tail / neck is a chain of ~15-45 short launches through ctypes, and a replay removes the host
+    from between them.  The library never allocates or synchronises and the blocks' intermediate tensors come from the
+    graph's private pool (stable addresses, so the TMA descriptors built at capture time stay valid).
+
+    ``g(*inputs)`` copies the inputs into the static ones (device-to-device) and replays; returns the static outputs
+    (overwritten by the next replay)."""
+
+    def __init__(self, module, example_inputs: Sequence[torch.Tensor], warmup: int = 2):
+        self.module = module
+        self.inputs = [x.clone() for x in example_inputs]
+        dev = self.inputs[0].device
+        self._stream = torch.cuda.Stream(dev)
+        self._stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._stream), torch.no_grad():
+            for _ in range(max(1, warmup)):                    # sizes cached workspaces, packs weights, folds BN
+                module(*self.inputs)
+        self._stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self._stream), torch.no_grad():
+            self.outputs = module(*self.inputs)
+
+    def __call__(self, *inputs):
+        if inputs:
+            if len(inputs) != len(self.inputs):
+                raise ValueError("expected %d inputs" % len(self.inputs))
+            for dst, src in zip(self.inputs, inputs):
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.outputs
