@@ -133,6 +133,39 @@ def decode_numpy(pred: np.ndarray, anchors, stride: float, num_class: int, agnos
     return det.transpose(1, 0, 2, 3, 4).reshape(B, -1, 6).astype(np.float32)       # :197
 
 
+def decode_torch_graph(heads, num_class: int, strides=None, anchors=None):
+    """The Gluon GRAPH of the reference restated operator by operator on torch CPU tensors (one multi-threaded library
+    op per MXNet op, every intermediate materialised, the C-times tiled box tensor and the scale concat included:
+    yolo3.py:158-197, :523) -- what an MXNet CPU run of the same graph executes, as opposed to the fused C loop of
+    decode_c.  Used by bench.py's cpu_baseline as the "graph-faithful" figure.  Returns (B, R, 6)."""
+    import torch
+    strides = list(strides) if strides is not None else STRIDES[::-1]
+    anchors = list(anchors) if anchors is not None else ANCHORS[::-1]
+    dets = []
+    for h, stride, an in zip(heads, strides, anchors):
+        pred = torch.as_tensor(h, dtype=torch.float32)
+        anc = torch.tensor(an, dtype=torch.float32).reshape(1, 1, -1, 2)
+        A, P = anc.shape[2], 5 + num_class
+        B, _, H, W = pred.shape
+        p = pred.reshape(B, A * P, H * W).transpose(1, 2).reshape(B, H * W, A, P)          # :158-160
+        raw_centers, raw_scales = p[..., 0:2], p[..., 2:4]                                 # :162-163
+        objness, class_pred = p[..., 4:5], p[..., 5:]                                      # :164-165
+        gy, gx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+        offsets = torch.stack((gx, gy), dim=-1).reshape(1, -1, 1, 2)                       # :67-74, :168-170
+        box_centers = (torch.sigmoid(raw_centers) + offsets) * float(stride)               # :172
+        box_scales = torch.exp(raw_scales) * anc                                           # :173
+        confidence = torch.sigmoid(objness)                                                # :174
+        class_score = torch.sigmoid(class_pred) * confidence                               # :175
+        wh = box_scales / 2.0                                                              # :176
+        bbox = torch.cat((box_centers - wh, box_centers + wh), dim=-1)                     # :177
+        bboxes = bbox.unsqueeze(0).repeat(num_class, 1, 1, 1, 1)                           # :191 tile
+        scores = class_score.permute(3, 0, 1, 2).unsqueeze(-1)                             # :192
+        ids = scores * 0 + torch.arange(num_class, dtype=torch.float32).reshape(-1, 1, 1, 1, 1)   # :194
+        det = torch.cat((ids, scores, bboxes), dim=-1)                                     # :195
+        dets.append(det.permute(1, 0, 2, 3, 4).reshape(B, -1, 6))                          # :197
+    return torch.cat(dets, dim=1).numpy()                                                  # :523
+
+
 def decode_c(heads: Sequence[np.ndarray], num_class: int, strides=None, anchors=None,
              agnostic: bool = False) -> np.ndarray:
     """Decode the three head maps (order: stride 32, 16, 8) and concatenate along rows

@@ -253,3 +253,15 @@ def test_bbox_batch_iou_against_plain_loops():
     assert got.shape == (2, 9, 4) and (got[:, :, -1] == 0).all()          # a padding box overlaps nothing
     same = oracle.bbox_batch_iou(a, a)
     np.testing.assert_allclose(same[0].diagonal(), 1.0, rtol=1e-6)
+
+
+def test_decode_torch_graph_equals_numpy_graph():
+    """the torch-CPU graph restatement (bench.py's graph-faithful CPU figure) against the numpy one: same rows, same order"""
+    rng = np.random.RandomState(2)
+    C, size = 7, 96
+    heads = [rng.normal(size=(2, 3 * (5 + C), g, g)).astype(np.float32) for g in oracle.grid_sizes(size)]
+    ref = np.concatenate([oracle.decode_numpy(h, a, s, C) for h, a, s in zip(heads, oracle.ANCHORS[::-1], oracle.STRIDES[::-1])], axis=1)
+    got = oracle.decode_torch_graph(heads, C)
+    assert got.shape == ref.shape
+    np.testing.assert_array_equal(got[..., 0], ref[..., 0])
+    np.testing.assert_allclose(got[..., 1:], ref[..., 1:], rtol=1e-5, atol=1e-5 * size)      # libm vs torch exp
