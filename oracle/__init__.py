@@ -24,6 +24,8 @@ Functions and what they follow:
   yolov3_tail         yolo3.py:523-534 (concat -> box_nms -> slice post_nms -> split)
   bbox_iou            utils/bbox.py:11-38
   conv_bn_leaky       models/definitions/layers.py:63-89,135-158 (torch CPU fp32 engine)
+  bbox_batch_iou      gluoncv BBoxBatchIOU as called at models/definitions/yolo/yolo_target.py:171,202
+  decode_torch_graph  the Gluon graph of yolo3.py:158-197,:523 op by op on torch CPU (bench.py's graph-faithful CPU figure)
 """
 from __future__ import annotations
 
