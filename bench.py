@@ -308,6 +308,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-conv", action="store_true", help="skip the fusion-conv (tensor-pipe) leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the short legs over the other BASELINE workloads")
     ap.add_argument("--streams", type=int, default=4,
                     help="CUDA streams the timed steps alternate over (1 = every step waits for the one before)")
     args = ap.parse_args()
@@ -512,6 +513,36 @@ def main():
         except Exception as e:                     # the headline line must still be printed
             conv = {"error": str(e)[:200]}
 
+    # ---- the other device-resident workloads of BASELINE.json, same method, short (N=1 default run only): the metric's
+    # own 416^2 / 10647-box shape at batch 128 (configs[3]'s shape with the reference's NMS arguments) and configs[4]
+    other = None
+    if rank == 0 and world == 1 and args.config == "coco608_b64" and flush is None and not args.no_other:
+        other = {}
+        for name in ("stress416_b128", "vid320_b256"):
+            lbl2, C2, size2, B2 = CONFIGS[name]
+            h2 = random_heads_cuda(B2, C2, size2, 4321, dev, regime=args.regime)
+            o2 = [(torch.empty((B2, NMS["post_nms"], 6), dtype=torch.float32, device=dev),
+                   torch.empty((B2, NMS["post_nms"]), dtype=torch.int32, device=dev)) for _ in range(n_streams)]
+
+            def step2(i=0, n=1, h2=h2, C2=C2, o2=o2):
+                o, k = o2[i % n]
+                if n == 1:
+                    vy.yolo3_decode_nms(h2, C2, AN, ST, out=o, kept=k, **NMS)
+                else:
+                    with torch.cuda.stream(side[i % n]):
+                        vy.yolo3_decode_nms(h2, C2, AN, ST, out=o, kept=k, **NMS)
+            k2 = min(args.steps, 50)
+            ms_a = timed(step2, k2, 5, None, n_streams)
+            ms_b = timed(step2, k2, 3, None, 1)
+            inb2, outb2 = frame_bytes(C2, size2, NMS["post_nms"])
+            tot2 = (inb2 + outb2) * B2
+            other[name] = {"workload": lbl2, "steps": k2, "streams": n_streams,
+                           "value": round(B2 * k2 / (ms_a * 1e-3), 1), "value_single_stream": round(B2 * k2 / (ms_b * 1e-3), 1),
+                           "unit": "frames/s",
+                           "step_frac": round(tot2 / (ms_a / k2 * 1e-3) / 1e9 / peak, 4),
+                           "step_frac_single_stream": round(tot2 / (ms_b / k2 * 1e-3) / 1e9 / peak, 4)}
+            del h2, o2
+
     # ---- cpu baseline (rank 0, N=1 only): oracle port on a bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -561,7 +592,7 @@ def main():
                                  else "L2 flushed between steps (256 MiB write)",
                            "streams": n_streams},
                 "value_single_stream": world * B * args.steps / (ms_serial * 1e-3),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fusion_conv": conv, "gpu_launches": gpu_launches,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fusion_conv": conv, "other_workloads": other, "gpu_launches": gpu_launches,
                 "launches_per_step": per_step, "clocks": sampler.summary()}
         print(json.dumps(line))
     if world > 1:
