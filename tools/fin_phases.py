@@ -31,6 +31,10 @@ for name, B, C, size, regime in [("coco608_b64_R", 64, 80, 608, "R"), ("coco608_
             for k in range(11):
                 acc[k] += (clk[k + 1] - clk[k]) / n
     print("   last merge sort (rank sort when classes are counted): start->warp-sorted %d, rounds %s" % (clk[12] - clk[3], [clk[k + 1] - clk[k] for k in range(12, 15)]))
+    fc = (ctypes.c_longlong * 16)()
+    if L.vy_debug_fin_front_clocks(fc) == 0:
+        print("   bucket front: load+zero %d | min/max %d | histogram %d | scan+K-th bin %d | scatter %d | in-bin rank %d" % tuple(
+            fc[k + 1] - fc[k] for k in range(6)))
     nb = min(B, 1024)
     ct = (ctypes.c_longlong * (4 * nb))()
     assert L.vy_debug_fin_ctas(ct, nb) == 0

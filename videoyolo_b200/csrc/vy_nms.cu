@@ -1107,18 +1107,29 @@ static __device__ __noinline__ u64 fin_list_bound(SelBuf &S, const u64 *list, in
 // its <= FIN_BK_KPT keys in registers throughout; the list is read once.
 // Returns m1 = #{keys in the bins down to the K-th key's} (>= min(n, K)) with keyr[0 .. min(m1, K)) sorted
 // descending, or -1 (CTA-uniform, nothing written) when that many keys would not fit the CTA.
+#ifdef VY_FIN_TIMING
+__device__ long long vy_fin_front_clk[16];
+#define FIN_TB(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) vy_fin_front_clk[k] = clock64(); } while (0)
+extern "C" int vy_debug_fin_front_clocks(long long *out) {
+    return cudaMemcpyFromSymbol(out, vy_fin_front_clk, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
+}
+#else
+#define FIN_TB(k) do { } while (0)
+#endif
 constexpr int FIN_BK_BINS = 2048;
 constexpr int FIN_BK_KPT = 8;         // keys per thread
 static __device__ __noinline__ int fin_front_buckets(SelBuf &S, const u64 *list, int n, int K,
                                                      u32 *hist, u32 *excl, u64 *out, u64 *keyr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = (int)blockDim.x;   // nt = 512 or 1024
     u64 *mm = (u64 *)S.queue;                           // [0] = min, [1] = max (the queue is idle in this kernel)
+    FIN_TB(0);
     u64 k[FIN_BK_KPT];
 #pragma unroll
     for (int q = 0; q < FIN_BK_KPT; ++q) { const int i = tid + q * nt; k[q] = i < n ? list[i] : 0ull; }
     for (int i = tid; i < FIN_BK_BINS; i += nt) hist[i] = 0u;
     if (tid == 0) { mm[0] = ~0ull; mm[1] = 0ull; S.sel_digit = 0; S.sel_in = n; }
     __syncthreads();
+    FIN_TB(1);
     {
         u64 lo = ~0ull, hi = 0ull;
 #pragma unroll
@@ -1131,12 +1142,14 @@ static __device__ __noinline__ int fin_front_buckets(SelBuf &S, const u64 *list,
         if (lane == 0 && hi) { atomicMin((unsigned long long *)&mm[0], (unsigned long long)lo); atomicMax((unsigned long long *)&mm[1], (unsigned long long)hi); }
     }
     __syncthreads();
+    FIN_TB(2);
     const u64 kx = mm[0] ^ mm[1];
     const int hb = kx ? 63 - __clzll((long long)kx) : 0;     // highest bit in which two keys differ
     const int shift = hb >= 10 ? hb - 10 : 0;
 #pragma unroll
     for (int q = 0; q < FIN_BK_KPT; ++q) if (k[q]) atomicAdd(&hist[(u32)(k[q] >> shift) & (FIN_BK_BINS - 1)], 1u);
     __syncthreads();
+    FIN_TB(3);
     // descending scan: thread t owns the `per` bins from 2047 - per * t downwards (per = 2 or 4)
     const int per = FIN_BK_BINS / nt;
     const int d0 = FIN_BK_BINS - 1 - per * tid;
@@ -1178,6 +1191,7 @@ static __device__ __noinline__ int fin_front_buckets(SelBuf &S, const u64 *list,
         }
     }
     __syncthreads();
+    FIN_TB(4);
     const int kbin = S.sel_digit, m1 = S.sel_in;
     if (m1 > nt) return -1;
 #pragma unroll
@@ -1188,6 +1202,7 @@ static __device__ __noinline__ int fin_front_buckets(SelBuf &S, const u64 *list,
         }
     }
     __syncthreads();
+    FIN_TB(5);
     if (tid < m1) {
         const u64 key = out[tid];
         const u32 bin = (u32)(key >> shift) & (FIN_BK_BINS - 1);
@@ -1197,6 +1212,7 @@ static __device__ __noinline__ int fin_front_buckets(SelBuf &S, const u64 *list,
         if (rank < (u32)K) keyr[rank] = key;
     }
     __syncthreads();
+    FIN_TB(6);
     return m1;
 }
 
