@@ -977,7 +977,17 @@ vy_rows_select_kernel(RowParams rp, SelPlan pl, SelGlobal g) {
 constexpr int FIN_NT_MAX = 1024;     // the kernel runs with 512 or 1024 threads (blockDim.x)
 constexpr int FIN_SLACK = 512;       // candidates beyond K that may reach the ranking sort
 constexpr int FIN_CMAX = 256;       // head-map classes up to this count are regrouped by counting instead of sorting
-constexpr int FIN_LCAP = 4096;       // candidate lists up to this length are staged in shared memory
+constexpr int FIN_LCAP = 2048;       // candidate lists up to this length are staged in shared memory (general front)
+// static shared memory of the finalize kernel (the selection kernels' SelBuf carries 24 KB it has no use for: the
+// smaller the CTA's footprint, the more streaming CTAs of a neighbouring stream stay resident beside it)
+struct FinBuf {
+    u64 keys[FIN_NT_MAX];        // the K best by rank
+    u32 hist[256];
+    u64 mm[2];                   // min / max key of a list
+    u64 thr;                     // inclusive lower bound of the general front
+    int count, flag;
+    int sel_digit, sel_above, sel_in;
+};
 
 struct FinParams {
     int K, post_rows;            // rows written per image
@@ -1030,9 +1040,9 @@ __device__ __forceinline__ float4 fin_box(const VyHeads &hd, const RowParams &rp
 // select, one sweep of the list per 8-bit digit).  n >= K, slack >= 0.  The keys of a candidate list agree in
 // their leading bits (scores of one narrow range), so a first sweep takes the list's minimum and maximum and
 // the digits start right below the common prefix: one counting sweep usually settles the bound.
-static __device__ __noinline__ u64 fin_list_bound(SelBuf &S, const u64 *list, int n, int K, int slack) {
+static __device__ __noinline__ u64 fin_list_bound(FinBuf &S, const u64 *list, int n, int K, int slack) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-    u64 *mm = (u64 *)S.queue;                           // [0] = min, [1] = max (the queue is idle in this kernel)
+    u64 *mm = S.mm;                                     // [0] = min, [1] = max
     if (tid == 0) { mm[0] = ~0ull; mm[1] = 0ull; }
     __syncthreads();
     {
@@ -1118,10 +1128,10 @@ extern "C" int vy_debug_fin_front_clocks(long long *out) {
 #endif
 constexpr int FIN_BK_BINS = 2048;
 constexpr int FIN_BK_KPT = 8;         // keys per thread
-static __device__ __noinline__ int fin_front_buckets(SelBuf &S, const u64 *list, int n, int K,
+static __device__ __noinline__ int fin_front_buckets(FinBuf &S, const u64 *list, int n, int K,
                                                      u32 *hist, u32 *excl, u64 *out, u64 *keyr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = (int)blockDim.x;   // nt = 512 or 1024
-    u64 *mm = (u64 *)S.queue;                           // [0] = min, [1] = max (the queue is idle in this kernel)
+    u64 *mm = S.mm;                                     // [0] = min, [1] = max
     FIN_TB(0);
     u64 k[FIN_BK_KPT];
 #pragma unroll
@@ -1256,7 +1266,7 @@ __device__ __forceinline__ void fin_sort(u64 *keys, int npow2) {
 
 // General front end: bound the K-th largest key (lists longer than K + slack), compact what is at or above the
 // bound into cand, sort.  Returns m1 <= K + FIN_SLACK with cand[0 .. m1) sorted descending.
-static __device__ __noinline__ int fin_front_general(SelBuf &S, const u64 *list, int n_list, int K, u64 *cand,
+static __device__ __noinline__ int fin_front_general(FinBuf &S, const u64 *list, int n_list, int K, u64 *cand,
                                                      u64 *lbuf, int lcap) {
     const int tid = threadIdx.x, lane = tid & 31, FIN_NT = (int)blockDim.x;
     const u32 lt_mask = (1u << lane) - 1u;
@@ -1313,7 +1323,7 @@ static __device__ __noinline__ int fin_front_general(SelBuf &S, const u64 *list,
 template <int SRC>   // 0: head maps, 1: rows
 __global__ void __launch_bounds__(FIN_NT_MAX)
 vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinParams fp) {
-    __shared__ SelBuf S;
+    __shared__ FinBuf S;
     extern __shared__ __align__(16) unsigned char dyn[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (int)blockDim.x / 32;
     const int FIN_NT = (int)blockDim.x;
@@ -1334,12 +1344,14 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     int *seg_end = cls + K;                            // K      by slot
     int *slot_of_rank = seg_end + K;                   // K
     int *rank_of_slot = slot_of_rank + K;              // K
-    u32 *supby = (u32 *)(rank_of_slot + K);            // K * nwK: [j][rb] = rows of slot block rb that would suppress slot j
-    u32 *begw = supby + (size_t)K * nwK;               // 32     by slot: first slot of a segment
+    u32 *begw = (u32 *)(rank_of_slot + K);             // 32     by slot: first slot of a segment
     u32 *keeps = begw + 32;                            // 32     by slot: survivors
     u32 *keepw = keeps + 32;                           // 32     by rank: survivors
     int *rb0 = (int *)(keepw + 32);                    // 32 (+4 pad): first slot block whose segments reach block cb
-    u64 *lbuf = (u64 *)(((uintptr_t)(rb0 + 36) + 15) & ~(uintptr_t)15);   // FIN_LCAP: a short candidate list, staged
+    // one region, two lives: the front end's scratch (FIN_LCAP keys: bin starts + scattered keys, or a staged list),
+    // then -- the front end is over by then -- the bit matrix of the tiled suppression path
+    u64 *lbuf = (u64 *)(((uintptr_t)(rb0 + 36) + 15) & ~(uintptr_t)15);
+    u32 *supby = (u32 *)lbuf;                          // K * nwK: [j][rb] = rows of slot block rb that would suppress slot j
 
     // ---- 1. exact top-K of the image's candidate list, sorted descending
     // streaming path: the streamed list, unless it was unusable and the rescue pass rebuilt g.list
@@ -1349,9 +1361,9 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     const u64 *list = use_s ? g.slist + (size_t)b * g.slist_cap : g.list + (size_t)b * pl.list_cap;
     if (tid == 0) { S.count = 0; S.flag = 0; S.thr = use_s ? ~g.sthr[b] : g.thr[b]; }
     if (tid < 32) keeps[tid] = 0u;
-    u64 *keyr = S.keys;                                 // the K best by rank (K <= SEL_KMAX <= SEL_CAP)
+    u64 *keyr = S.keys;                                 // the K best by rank (K <= FIN_NT_MAX)
     int m1 = -1;
-    if (n_list <= FIN_BK_KPT * FIN_NT && fp.lcap >= 2 * FIN_BK_BINS)
+    if (n_list <= FIN_BK_KPT * FIN_NT && fp.lcap >= FIN_BK_BINS)
         m1 = fin_front_buckets(S, list, n_list, K, (u32 *)cand, (u32 *)lbuf, lbuf + FIN_BK_BINS / 2, keyr);
     FIN_T(1);
     u64 mykey = 0ull;
@@ -1684,12 +1696,11 @@ static size_t fin_dyn_smem(int K, int *lcap) {
     const int nwK = (K + 31) / 32;
     size_t cp2 = 32;
     while (cp2 < (size_t)(K + FIN_SLACK)) cp2 <<= 1;
-    const size_t base = cp2 * 8 + (size_t)K * (16 + 4 + 4 + 4 + 4 + 4) + (size_t)K * nwK * 4 + 3 * 32 * 4 + 36 * 4 + 16;
-    const size_t budget = 227 * 1024 - sizeof(SelBuf) - 2048;        // per-CTA limit minus the static part
-    int cap = FIN_LCAP;
-    if (base + (size_t)cap * 8 > budget) cap = 0;
-    if (lcap) *lcap = cap;
-    return base + (size_t)cap * 8;
+    const size_t base = cp2 * 8 + (size_t)K * (16 + 4 + 4 + 4 + 4 + 4) + 3 * 32 * 4 + 36 * 4 + 16;
+    // front-end scratch and suppression bit matrix share one region (K <= 1024: at most 128 KB + 53 KB, within the CTA limit)
+    const size_t mat = (size_t)K * nwK * 4, scratch = (size_t)FIN_LCAP * 8;
+    if (lcap) *lcap = FIN_LCAP;
+    return base + (mat > scratch ? mat : scratch);
 }
 
 // CTAs that can be resident at once (SEL_CTAS_PER_SM per SM by __launch_bounds__)
@@ -1845,9 +1856,11 @@ static int launch_finalize(const VyHeads &hd, const RowParams &rp, const SelPlan
                            FinParams fp, int B, cudaStream_t st) {
     const size_t dyn = fin_dyn_smem(pl.K, &fp.lcap);
     if (pl.K > FIN_NT_MAX) VY_FAIL(VY_EINVAL, "finalize: K exceeds the CTA size");      // a thread per rank / slot
-    // 1024 threads: the kernel is a chain of short barrier-separated phases, more warps hide their latencies; but at
-    // 64 registers that is one CTA per SM, so a batch beyond one wave runs 512-thread CTAs, two to an SM (K permitting)
-    const int fin_nt = (pl.K <= FIN_NT_MAX / 2 && B > vy_sm_count()) ? FIN_NT_MAX / 2 : FIN_NT_MAX;
+    // a thread per rank / slot: 512 threads serve K <= 512 (the reference's nms_topk = 400).  Measured after the
+    // shared-memory diet (53 KB per CTA): against 1024 threads the one-stream step is 3 % slower at COCO 608 x 64 and
+    // faster everywhere else (one frame, 416^2 x 128, 320^2 x 256: two CTAs per SM), and independent batches on
+    // several streams gain 1-9 % (a small finalize CTA leaves the neighbouring stream's streaming CTAs resident)
+    const int fin_nt = pl.K <= FIN_NT_MAX / 2 ? FIN_NT_MAX / 2 : FIN_NT_MAX;
     if (fp.overlap_thresh > 0.0f && fp.overlap_thresh < 1e30f) {
         fp.thr_lo = fp.overlap_thresh * (1.0f - 9.5367431640625e-07f);      // 2^-20 (vy_nms_math.cuh)
         fp.thr_hi = fp.overlap_thresh * (1.0f + 9.5367431640625e-07f);
