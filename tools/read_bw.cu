@@ -83,6 +83,47 @@ __global__ void __launch_bounds__(128, 1) probe_c(const char *__restrict__ x, si
     if (acc != 0.f) out[0] = acc;
 }
 
+// D: the streaming kernel's geometry without its arithmetic: planes of HW floats, (b, a) blocks of P planes of which the
+// last C are read; a warp owns ROWS x 128 consecutive positions of PU consecutive planes and keeps 12 float4 per lane in
+// flight (12 / ROWS planes); consecutive warps own consecutive position chunks of the same plane group.
+template <int ROWS>
+__global__ void __launch_bounds__(256, 4) probe_d(const float *__restrict__ x, int HW, int P, int C, int PU, int n_ba, float *out) {
+    extern __shared__ float4 ring[];            // [8 warps][12][32]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float4 *mine = ring + (size_t)wid * 12 * 32 + lane;
+    const int chunks = (HW + 128 * ROWS - 1) / (128 * ROWS), groups = (C + PU - 1) / PU;
+    const long long n_units = (long long)n_ba * groups * chunks, n_warps = (long long)gridDim.x * 8;
+    constexpr int PF = 12 / ROWS;               // planes in flight
+    float acc = 0.f;
+    for (long long unit = (long long)blockIdx.x * 8 + wid; unit < n_units; unit += n_warps) {
+        const int chunk = (int)(unit % chunks);
+        const long long q = unit / chunks;
+        const int grp = (int)(q % groups);
+        const long long ba = q / groups;
+        const int c0 = grp * PU, np = min(PU, C - c0);
+        int pos = chunk * 128 * ROWS + lane * 4;
+        const float *base = x + ((size_t)ba * P + (P - C) + c0) * HW;
+        auto issue = [&](int pl_i, int slot) {
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const int pp = min(pos + r * 128, HW - 4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(mine + (slot * ROWS + r) * 32)), "l"(base + (size_t)pl_i * HW + pp) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int k = 0; k < PF; ++k) { if (k < np) issue(k, k); else asm volatile("cp.async.commit_group;" ::: "memory"); }
+        int slot = 0;
+        for (int k = 0; k < np; ++k) {
+            asm volatile("cp.async.wait_group %0;" :: "n"(PF - 1) : "memory");
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) acc += mine[(slot * ROWS + r) * 32].x > 1e30f ? 1.f : 0.f;
+            if (k + PF < np) issue(k + PF, slot); else asm volatile("cp.async.commit_group;" ::: "memory");
+            slot = slot + 1 == PF ? 0 : slot + 1;
+        }
+    }
+    if (acc != 0.f) out[0] = acc;
+}
+
 template <class F> static float timeit(F f, int n = 20) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     for (int i = 0; i < 3; ++i) f();
@@ -118,6 +159,22 @@ int main() {
         cudaFuncSetAttribute(probe_c<CH, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH * ST);
         ms = timeit([&] { probe_c<CH, ST><<<sms * 4, 128, CH * ST>>>(x, bytes, out); });
         printf("C bulk copy 4 KB x 12 stages, 4/SM : %.1f us -> %.0f GB/s\n", ms * 1e3, bytes / ms / 1e6);
+    }
+    {
+        // COCO 608 scale 2: 76 x 76 planes, 85 planes per (b, a) of which 80 are read, 64 x 3 blocks = 377 MB (354 MB read)
+        const int HW = 5776, P = 85, C = 80, n_ba = 192;
+        const double rd = (double)n_ba * C * HW * 4;
+        cudaFuncSetAttribute(probe_d<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 12 * 32 * 16);
+        cudaFuncSetAttribute(probe_d<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 12 * 32 * 16);
+        cudaFuncSetAttribute(probe_d<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 12 * 32 * 16);
+        for (int PU : {20, 40, 80}) {
+            ms = timeit([&] { probe_d<1><<<sms * 4, 256, 8 * 12 * 32 * 16>>>((const float *)x, HW, P, C, PU, n_ba, out); });
+            printf("D planes 76x76, warp = 128 pos x %2d planes, 12 planes in flight : %.1f us -> %.0f GB/s\n", PU, ms * 1e3, rd / ms / 1e6);
+            ms = timeit([&] { probe_d<2><<<sms * 4, 256, 8 * 12 * 32 * 16>>>((const float *)x, HW, P, C, PU, n_ba, out); });
+            printf("D planes 76x76, warp = 256 pos x %2d planes,  6 planes in flight : %.1f us -> %.0f GB/s\n", PU, ms * 1e3, rd / ms / 1e6);
+            ms = timeit([&] { probe_d<4><<<sms * 4, 256, 8 * 12 * 32 * 16>>>((const float *)x, HW, P, C, PU, n_ba, out); });
+            printf("D planes 76x76, warp = 512 pos x %2d planes,  3 planes in flight : %.1f us -> %.0f GB/s\n", PU, ms * 1e3, rd / ms / 1e6);
+        }
     }
     printf("last error: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
