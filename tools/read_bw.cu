@@ -124,6 +124,50 @@ __global__ void __launch_bounds__(256, 4) probe_d(const float *__restrict__ x, i
     if (acc != 0.f) out[0] = acc;
 }
 
+// E: the contiguous alternative WITH the streaming pass's arithmetic: every warp streams its own contiguous region
+// through a cp.async ring of DEPTH float4 per lane and tests each element against a per-position bound looked up in a
+// shared-memory table of HW floats (position = element index mod HW), 4 compares per float4.
+template <int DEPTH, int CTAS>
+__global__ void __launch_bounds__(256, CTAS) probe_e(const float4 *__restrict__ x, size_t n4, int HW, float *out) {
+    extern __shared__ float4 smem[];            // [8 warps][DEPTH][32] ring, then HW/4 float4 of bounds
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float4 *mine = smem + (size_t)wid * DEPTH * 32 + lane;
+    float4 *tab = smem + 8 * DEPTH * 32;
+    const int HW4 = HW / 4;
+    for (int i = threadIdx.x; i < HW4; i += 256) tab[i] = make_float4(1e30f, 1e30f, 1e30f, 1e30f);
+    __syncthreads();
+    const size_t nwarps = (size_t)gridDim.x * 8;
+    const size_t per = n4 / 32 / nwarps;        // rows of 32 float4 per warp
+    const size_t row0 = ((size_t)blockIdx.x * 8 + wid) * per;
+    const float4 *p = x + row0 * 32 + lane;
+    int tpos = (int)((row0 * 32 + lane) % HW4); // this lane's float4 index inside the plane
+    unsigned hits = 0;
+    constexpr int G = 4;                        // float4 rows per commit group
+    for (int u = 0; u < DEPTH && u < (int)per; ++u) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(mine + u * 32)), "l"(p + (size_t)u * 32) : "memory");
+        if ((u % G) == G - 1) asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    int slot = 0;
+    for (size_t r = 0; r + G <= per; r += G) {
+        asm volatile("cp.async.wait_group %0;" :: "n"(DEPTH / G - 1) : "memory");
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            const float4 v = mine[(slot + u) * 32];
+            const float4 t = tab[tpos];
+            hits |= (v.x >= t.x ? 1u : 0u) | (v.y >= t.y ? 2u : 0u) | (v.z >= t.z ? 4u : 0u) | (v.w >= t.w ? 8u : 0u);
+            tpos += 32; if (tpos >= HW4) tpos -= HW4;
+        }
+        if (r + DEPTH + G <= per) {
+#pragma unroll
+            for (int u = 0; u < G; ++u)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(mine + (slot + u) * 32)), "l"(p + (r + DEPTH + u) * 32) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        slot = slot + G == DEPTH ? 0 : slot + G;
+    }
+    if (hits) out[0] = (float)hits;
+}
+
 template <class F> static float timeit(F f, int n = 20) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     for (int i = 0; i < 3; ++i) f();
@@ -175,6 +219,16 @@ int main() {
             ms = timeit([&] { probe_d<4><<<sms * 4, 256, 8 * 12 * 32 * 16>>>((const float *)x, HW, P, C, PU, n_ba, out); });
             printf("D planes 76x76, warp = 512 pos x %2d planes,  3 planes in flight : %.1f us -> %.0f GB/s\n", PU, ms * 1e3, rd / ms / 1e6);
         }
+    }
+    {
+        const int HW = 5776;
+        const size_t sm12 = (size_t)8 * 12 * 32 * 16 + HW * 4, sm8 = (size_t)8 * 8 * 32 * 16 + HW * 4;
+        cudaFuncSetAttribute(probe_e<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm12);
+        ms = timeit([&] { probe_e<12, 3><<<sms * 3, 256, sm12>>>((const float4 *)x, bytes / 16, HW, out); });
+        printf("E contiguous + table lookup + compares, ring 12, 3 CTAs/SM : %.1f us -> %.0f GB/s\n", ms * 1e3, bytes / ms / 1e6);
+        cudaFuncSetAttribute(probe_e<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8);
+        ms = timeit([&] { probe_e<8, 4><<<sms * 4, 256, sm8>>>((const float4 *)x, bytes / 16, HW, out); });
+        printf("E contiguous + table lookup + compares, ring  8, 4 CTAs/SM : %.1f us -> %.0f GB/s\n", ms * 1e3, bytes / ms / 1e6);
     }
     printf("last error: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
