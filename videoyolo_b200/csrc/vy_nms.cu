@@ -55,10 +55,10 @@ struct SelGlobal {              // workspace views
     u64 *slots;                 // [B][G]     per-CTA ceil(K/G)-th largest
     u64 *list;                  // [B][list_cap]
     // streaming path only (see "sample + stream" below); null otherwise
-    u64 *sthr;                  // [B]        COMPLEMENT of the sample's bound (stream + finalize; may be optimistic, see below)
     int *scount;                // [B]        fill of the streamed candidate list
     int *sdone;                 // [B]        sample jobs finished
-    u64 *sslots;                // [B][Gs]    per-sample-job bounds
+    u64 *sslots;                // [B][Gs]    COMPLEMENT of every sample job's bound (each job stores its own: nothing to zero)
+    int Gs;
     u64 *slist;                 // [B][slist_cap]
     int slist_cap;
 };
@@ -72,7 +72,6 @@ static size_t sel_workspace_layout(int B, int G, int list_cap, SelGlobal *g, voi
     const size_t o_thr = off;   off = align_up(off + sizeof(u64) * (size_t)B, 256);
     const size_t o_cnt = off;   off = align_up(off + sizeof(int) * (size_t)B, 256);
     const size_t o_slot = off;  off = align_up(off + sizeof(u64) * (size_t)B * G, 256);
-    const size_t o_sthr = off;  off = align_up(off + sizeof(u64) * (size_t)B * (Gs ? 1 : 0), 256);
     const size_t o_scnt = off;  off = align_up(off + sizeof(int) * (size_t)B * (Gs ? 1 : 0), 256);
     const size_t o_sdone = off; off = align_up(off + sizeof(int) * (size_t)B * (Gs ? 1 : 0), 256);
     const size_t o_sslot = off; off = align_up(off + sizeof(u64) * (size_t)B * Gs, 256);
@@ -84,7 +83,7 @@ static size_t sel_workspace_layout(int B, int G, int list_cap, SelGlobal *g, voi
         g->count = (int *)((char *)base + o_cnt);
         g->slots = (u64 *)((char *)base + o_slot);
         g->list = (u64 *)((char *)base + o_list);
-        g->sthr = Gs ? (u64 *)((char *)base + o_sthr) : nullptr;
+        g->Gs = Gs;
         g->scount = Gs ? (int *)((char *)base + o_scnt) : nullptr;
         g->sdone = Gs ? (int *)((char *)base + o_sdone) : nullptr;
         g->sslots = Gs ? (u64 *)((char *)base + o_sslot) : nullptr;
@@ -99,9 +98,16 @@ static size_t sel_workspace_layout(int B, int G, int list_cap, SelGlobal *g, voi
 // ESTIMATE of a rank a few times K, not a guaranteed lower bound of the K-th largest score: with
 // probability ~1e-7 per image, or for adversarial layouts, it can be too high).  Those images are
 // redone exactly by vy_decode_select_kernel.
+// COMPLEMENT of the bound the streaming pass works with for image b = the minimum over the image's sample jobs (may be
+// optimistic, see below); ~0 = no bound
+__device__ __forceinline__ u64 stream_bound_compl(const SelGlobal &g, int b) {
+    u64 m = 0;
+    for (int j = 0; j < g.Gs; ++j) { const u64 v = g.sslots[(size_t)b * g.Gs + j]; m = v > m ? v : m; }
+    return m;
+}
 __device__ __forceinline__ bool stream_list_ok(const SelGlobal &g, int b, int K) {
     const int n = g.scount[b];
-    return n <= g.slist_cap && (n >= K || ~g.sthr[b] == 0ull);
+    return n <= g.slist_cap && (n >= K || ~stream_bound_compl(g, b) == 0ull);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -562,7 +568,13 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
     }
     // ---- publish: the image's bound is the MINIMUM over its jobs, kept as the maximum of the complements
     // (the workspace header starts at zero = "no job yet" = complement of the largest bound)
-    if (tid == 0) atomicMax(g.sthr + b, ~((u64)bound << 32));
+    if (tid == 0) g.sslots[(size_t)b * pl.Gs + gj] = ~((u64)bound << 32);
+    // the first job of an image also zeroes what the later kernels of the call accumulate into for that image (they
+    // all start after this grid has finished): no memset in front of the call
+    if (gj == 0) {
+        if (tid == 0) { g.scount[b] = 0; g.count[b] = 0; g.thr[b] = 0ull; }
+        if (tid < pl.G) g.slots[(size_t)b * pl.G + tid] = 0ull;
+    }
 }
 
 constexpr int STR_NT = 256;
@@ -877,7 +889,7 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
         un.n_s = (u32)sc.n_s; un.A = (u32)hd.A;
         un.valid_thresh = pl.valid_thresh;
         if (!dep_waited) { vy_grid_dep_wait(); dep_waited = true; }
-        un.thr = ~g.sthr[b];
+        un.thr = ~stream_bound_compl(g, b);
         const float smin = fmaxf(un.thr ? vy_key_score(un.thr) : pl.valid_thresh, pl.valid_thresh);
         {
             float to[4];
@@ -1359,7 +1371,7 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     const bool use_s = g.scount != nullptr && stream_list_ok(g, b, K);
     const int n_list = use_s ? g.scount[b] : min(g.count[b], pl.list_cap);
     const u64 *list = use_s ? g.slist + (size_t)b * g.slist_cap : g.list + (size_t)b * pl.list_cap;
-    if (tid == 0) { S.count = 0; S.flag = 0; S.thr = use_s ? ~g.sthr[b] : g.thr[b]; }
+    if (tid == 0) { S.count = 0; S.flag = 0; S.thr = use_s ? ~stream_bound_compl(g, b) : g.thr[b]; }
     if (tid < 32) keeps[tid] = 0u;
     u64 *keyr = S.keys;                                 // the K best by rank (K <= FIN_NT_MAX)
     int m1 = -1;
@@ -1911,7 +1923,7 @@ extern "C" int vy_decode_nms_f32(const float *const *head, const int *H, const i
     if (((uintptr_t)workspace & 255) != 0) VY_FAIL(VY_EALIGN, "workspace must be 256-byte aligned");
     for (int s = 0; s < n_scales; ++s)
         if (!head[s]) VY_FAIL(VY_EINVAL, "vy_decode_nms_f32: head[%d] is null", s);
-    VY_CUDA_CHECK(cudaMemsetAsync(workspace, 0, header, st));
+    if (!pl.stream) VY_CUDA_CHECK(cudaMemsetAsync(workspace, 0, header, st));     // (the sample kernel zeroes its images' state itself)
     if (pl.stream) {
         VY_KERNEL(VY_K_SAMPLE, st, (vy_decode_sample_kernel<<<B * pl.Gs, SAMP_NT, 0, st>>>(hd, pl, g)));
         VY_LAUNCH_CHECK("vy_decode_sample_kernel");
@@ -1939,10 +1951,14 @@ extern "C" int vy_decode_nms_f32(const float *const *head, const int *H, const i
     static const bool dbg = getenv("VY_DEBUG_LISTS") != nullptr;
     if (dbg && pl.stream && rc == VY_OK) {
         std::vector<int> cnt(B);
-        std::vector<u64> thr(B);
+        std::vector<u64> thr(B), slots((size_t)B * pl.Gs);
         cudaStreamSynchronize(st);
         cudaMemcpy(cnt.data(), g.scount, sizeof(int) * B, cudaMemcpyDeviceToHost);
-        cudaMemcpy(thr.data(), g.sthr, sizeof(u64) * B, cudaMemcpyDeviceToHost);
+        cudaMemcpy(slots.data(), g.sslots, sizeof(u64) * slots.size(), cudaMemcpyDeviceToHost);
+        for (int i = 0; i < B; ++i) {
+            thr[i] = 0;
+            for (int j = 0; j < pl.Gs; ++j) thr[i] = slots[(size_t)i * pl.Gs + j] > thr[i] ? slots[(size_t)i * pl.Gs + j] : thr[i];
+        }
         long long sum = 0; int mn = 1 << 30, mx = 0, bad = 0;
         for (int i = 0; i < B; ++i) {
             sum += cnt[i]; mn = cnt[i] < mn ? cnt[i] : mn; mx = cnt[i] > mx ? cnt[i] : mx;
