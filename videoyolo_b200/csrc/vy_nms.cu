@@ -1,13 +1,16 @@
 // vy_nms.cu -- candidate selection + box_nms kernels (fused-from-heads and generic-from-rows).
 //
-// Pipeline per call (two launches, no host sync):
-//   1. *_select_kernel  : streams the input ONCE (head maps: class/objectness planes only;
-//                         rows: the score column), keeps per-CTA top-K candidates in shared
-//                         memory under a rising threshold shared per image through global
-//                         memory, and appends the few survivors to a per-image list.
-//   2. nms_finalize     : one CTA per image: exact top-K + sort of the list, decode of the K
-//                         boxes, IoU suppression bitmask in warp tiles (ballot), greedy scan,
-//                         compaction, write of the (post_nms, W) rows + kept source rows.
+// Fused decode + box_nms from the head maps, large class-aware inputs (R >= 131072): four launches chained with
+// programmatic dependent launch, no memset, no host sync --
+//   1. vy_decode_sample_kernel  : 1/S of every image -> a per-image score bound (an ESTIMATE of the rank-4K score)
+//   2. vy_decode_stream_kernel  : the one pass over the class planes at that fixed bound; the few survivors are queued,
+//                                 scored 32 at a time and appended to a per-image candidate list
+//   3. vy_decode_select_kernel  : rescue pass for images whose list is unusable (normally exits at once)
+//   4. vy_nms_finalize_kernel   : one CTA per image: exact top-K of the list (bucket sort), regroup by class, decode of
+//                                 the K boxes, suppression (lane per reference slot, or 32 x 32 tiles for long
+//                                 segments), greedy resolution per segment, compaction, (post_nms, W) rows + kept rows
+// Small / class-agnostic inputs and materialised rows (vy_box_nms_f32, topk <= 1024): a memset, one adaptive
+// streaming select (*_select_kernel: per-CTA top-K under a rising threshold shared per image) and the same finalize.
 // Semantics follow MXNet _contrib_box_nms as called at yolo3.py:525-530.
 #include "vy_select.cuh"
 #include "vy_nms_math.cuh"
