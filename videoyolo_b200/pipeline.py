@@ -92,7 +92,7 @@ class HostDetector:
 
 class GraphedDetector:
     """Fused decode + box_nms for device-resident head maps of a FIXED shape, captured once in a CUDA graph:
-    a call is one ``cudaGraphLaunch`` instead of a memset and four kernel launches through ctypes.  Meant for
+    a call is one ``cudaGraphLaunch`` instead of four kernel launches through ctypes.  Meant for
     the launch-bound end of the path (small batches: BASELINE configs[0] is batch 1, where the kernels take
     tens of microseconds).  The library needs nothing special for this: it never allocates or synchronises
     and every launch goes to the stream it is handed, so its calls are capturable as they are.
