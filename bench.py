@@ -426,13 +426,15 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
 
-    # a fresh process on an idle GPU: keep the device busy for a moment before anything is timed, or a small config
-    # (one frame: the whole timed region is a few milliseconds) is over before the clocks have come up
-    t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < 0.5:
-        for i in range(8):
-            step(i, n_streams)
-        torch.cuda.synchronize()
+    # a fresh process on an idle GPU: a small config (one frame: inputs of a megabyte, the whole timed region a few
+    # milliseconds) is over before the clocks have come up, so keep the device busy for a moment first.  The large
+    # configs have just generated gigabytes of inputs on the device and go straight to their W warm-up steps.
+    if flush is not None:
+        t_spin = time.perf_counter()
+        while time.perf_counter() - t_spin < 0.5:
+            for i in range(8):
+                step(i, n_streams)
+            torch.cuda.synchronize()
 
     # ---- headline: device-resident
     c0 = _lib.launch_counts()
