@@ -14,6 +14,48 @@ from hypothesis import given, settings, strategies as st
 import oracle
 
 
+# ----------------------------------------------------------------------------- decode vs the reference's own code
+from conftest import DECODE_REF_NAMES, assert_decode_close, load_decode_ref  # noqa: E402
+
+
+@pytest.mark.parametrize("name", DECODE_REF_NAMES)
+def test_decode_oracle_matches_reference_execution(name):
+    """oracle.decode_c against what the REFERENCE'S OWN YOLOOutputV3.hybrid_forward (yolo3.py:130-199,
+    agnostic :184-188) + concat (:523) produced on the same head maps (tests/golden/make_golden.py,
+    reference_decode()).  Same rows in the same order; values to a few ulps (libm expf vs the
+    correctly rounded exp of the shim, then one rounding per fp32 op in identical order)."""
+    z = load_decode_ref(name)
+    mine = oracle.decode_c(z["heads"], z["C"], agnostic=z["agnostic"])
+    assert mine.shape == (z["B"], z["R"], 6)
+    assert_decode_close(mine[:, z["rows"]], z["dets_rows"], score_ulps=4, box_eps=2)
+    # every row, not just the stored ones: float64 column sums of the whole tensor
+    np.testing.assert_allclose(mine.astype(np.float64).sum(axis=1), z["col_sums"], rtol=1e-7)
+    # numpy twin, scale by scale
+    if not z["agnostic"]:
+        tw = np.concatenate([oracle.decode_numpy(h, a, s, z["C"]) for h, a, s in
+                             zip(z["heads"], oracle.ANCHORS[::-1], oracle.STRIDES[::-1])], axis=1)
+        assert_decode_close(tw[:, z["rows"]], z["dets_rows"], score_ulps=8, box_eps=4)
+
+
+@pytest.mark.parametrize("name", DECODE_REF_NAMES)
+def test_tail_oracle_matches_reference_execution(name):
+    """oracle.yolov3_postprocess against the (ids, scores, bboxes) the reference's own
+    YOLOV3.hybrid_forward (yolo3.py:448-534: concat, box_nms call with its arguments, slice_axis
+    post_nms, split) returned.  The box_nms step inside that run was oracle.box_nms_c (MXNet's
+    operator is not in /root/reference), so this pins the tail's plumbing, the argument values and
+    the decode feeding it -- not the NMS arithmetic (that: MXNet's documented vectors below)."""
+    z = load_decode_ref(name)
+    ids, scores, bboxes = oracle.yolov3_postprocess(z["heads"], z["C"], agnostic=z["agnostic"])
+    assert ids.shape == z["ids"].shape == (z["B"], 100, 1)
+    same = (ids == z["ids"]).all(axis=(1, 2))
+    assert same.all(), "kept classes differ in frames %s" % np.nonzero(~same)[0]
+    got = np.concatenate([ids, scores, bboxes], axis=-1)
+    ref = np.concatenate([z["ids"], z["scores"], z["bboxes"]], axis=-1)
+    live = ref[..., 0] >= 0
+    assert_decode_close(got[live], ref[live], score_ulps=4, box_eps=2)
+    assert (got[~live] == -1).all()
+
+
 # ----------------------------------------------------------------------------- box_nms
 def _cases(golden_dir=os.path.join(os.path.dirname(__file__), "golden")):
     with open(os.path.join(golden_dir, "box_nms_mxnet_doc.json")) as f:
