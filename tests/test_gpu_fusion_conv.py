@@ -65,6 +65,12 @@ def check(got, ref, name):
     (3, 3, 13, 13, 256, 128, (1, 1, 1)),      # the 1x1x1 cells (yolo3.py:229-230)
     (2, 1, 20, 20, 192, 64, (1, 3, 3)),       # 2-D conv after the 'cat' join: T=1, K*C channels
     (1, 5, 10, 10, 64, 64, (3, 3, 3)),        # window of 5
+    # the three shapes bench.py times (BASELINE configs[2], K=3 tip convs at 416^2; GEMM K = 13 824 / 6 912 / 3 456)
+    (2, 3, 13, 13, 512, 1024, (3, 3, 3)),
+    (2, 3, 26, 26, 256, 512, (3, 3, 3)),
+    (2, 3, 52, 52, 128, 256, (3, 3, 3)),
+    (2, 3, 13, 13, 1024, 512, (1, 1, 1)),     # first body cell of the stride-32 block at Darknet-53 width
+    (2, 1, 13, 13, 3072, 128, (1, 1, 1)),     # 'cat' join head conv: K = 3 * C_tip = 3072 (yolo3.py:1135-1136)
 ])
 def test_fusion_conv_matches_oracle(vy, B, T, H, W, Cin, Cout, k3):
     rng = np.random.RandomState(B * 100 + T + H + Cin)

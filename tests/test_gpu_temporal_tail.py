@@ -145,8 +145,8 @@ def test_upsample_concat(vy):
                                vy.ops.pack_p(torch.zeros(1, 1, 8, 9, 9).cuda(), "NTCHW"))
 
 
-@pytest.mark.parametrize("join,ctype", [("max", "3"), ("mean", "21")])
-def test_yolov3t_neck_matches_oracle_chain(vy, join, ctype):
+@pytest.mark.parametrize("join,ctype,widths", [("max", "3", "small"), ("mean", "21", "small"), ("max", "3", "darknet53")])
+def test_yolov3t_neck_matches_oracle_chain(vy, join, ctype, widths):
     """"next" row f2: the whole post-backbone part of YOLOV3T (detection blocks, transitions, upsample + concat, late
     join, outputs, NMS; yolo3.py:1126-1206) against the CPU oracle chain.  The block-body outputs (``route``) are compared
     scale by scale with a tolerance that grows with the depth of the bf16 chain; the NMS tail is exact on the GPU's own
@@ -155,6 +155,8 @@ def test_yolov3t_neck_matches_oracle_chain(vy, join, ctype):
     torch.manual_seed(7)
     B, K, C, size = 1, 3, 20, 96
     stage_channels, channels = (128, 64, 64), (64, 64, 64)
+    if widths == "darknet53":                              # the widths bench.py's temporal_neck leg runs (wrappers.py:91-103)
+        stage_channels, channels, size = (1024, 512, 256), (512, 256, 128), 128
     net = vy.YOLOV3TNeck(["c%d" % i for i in range(C)], k=K, k_join_type=join, block_conv_type=ctype,
                          stage_channels=stage_channels, channels=channels).cuda().eval()
     randomize_bn(net, rng)

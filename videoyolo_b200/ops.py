@@ -29,6 +29,22 @@ def _need_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
     return t.contiguous()
 
 
+def _check_result(t: Optional[torch.Tensor], name: str, shape, dtype, device) -> torch.Tensor:
+    """A caller-supplied result buffer is written through its raw pointer: it must be exactly what the kernel
+    expects (a copy made here would throw the results away, so nothing is converted -- it raises)."""
+    if t is None:
+        return torch.empty(shape, dtype=dtype, device=device)
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device != device:
+        raise RuntimeError("%s must be a CUDA tensor on %s (the device of the head maps)" % (name, device))
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous (it is written in place)" % name)
+    return t
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -134,10 +150,8 @@ def yolo3_decode_nms(heads, num_class: int, anchors, strides, nms_thresh: float 
         if h.shape[1] != A * (5 + num_class):
             raise ValueError("head has %d channels, expected A*(5+C)=%d" % (h.shape[1], A * (5 + num_class)))
     dev = heads[0].device
-    if out is None:
-        out = torch.empty((B, post_nms, 6), dtype=torch.float32, device=dev)
-    if kept is None:
-        kept = torch.empty((B, post_nms), dtype=torch.int32, device=dev)
+    out = _check_result(out, "out", (B, post_nms, 6), torch.float32, dev)
+    kept = _check_result(kept, "kept", (B, post_nms), torch.int32, dev)
     if B == 0:                                           # an empty batch is an empty result (MXNet operators agree)
         return out, kept
     L = _lib.lib()

@@ -53,10 +53,15 @@ class HostDetector:
         self.h2d_bytes = sum(h.numel() * 4 for h in heads)
         self.d2h_bytes = self._out_host.numel() * 4 + self._kept_host.numel() * 4
 
-    def __call__(self, heads: Sequence[torch.Tensor]):
+    def __call__(self, heads: Sequence[torch.Tensor], copy: bool = True):
         """heads: host tensors (B, A*(5+C), H, W) fp32 in network order (stride 32, 16, 8); pinned memory
         makes the copies asynchronous.  Returns host tensors ids (B,post,1), scores (B,post,1),
-        bboxes (B,post,4) and leaves the kept source rows in ``self.kept_rows`` (host, int32)."""
+        bboxes (B,post,4) and leaves the kept source rows in ``self.kept_rows`` (host, int32).
+
+        ``copy=True`` (default) returns FRESH host tensors, like the reference's ``as_numpy``
+        (utils/general.py:6-18): detect_yolo3.py:233-262 appends every batch's results to a list, which
+        must not alias the next batch.  ``copy=False`` returns views of the detector's persistent pinned
+        result buffer, which the next call overwrites (the zero-allocation loop of bench.py)."""
         for h in heads:
             if h.is_cuda or h.dtype != torch.float32 or not h.is_contiguous():
                 raise TypeError("HostDetector takes contiguous fp32 host tensors; device tensors go through YOLOV3")
@@ -85,8 +90,8 @@ class HostDetector:
             self._kept_host.copy_(self._kept_dev, non_blocking=True)
         self._compute.synchronize()                                     # as_numpy: the host needs the values
         start.wait_stream(self._compute)
-        self.kept_rows = self._kept_host
-        r = self._out_host
+        self.kept_rows = self._kept_host.clone() if copy else self._kept_host
+        r = self._out_host.clone() if copy else self._out_host
         return r[..., 0:1], r[..., 1:2], r[..., 2:6]
 
 
