@@ -183,6 +183,77 @@ def temporal_neck_leg(dev, B=8, K=3, C=30, size=416, iters=10):
             "library_kernel_ms_per_call": {k: round(v[0] / iters, 4) for k, v in prof.items()}}
 
 
+def voc_latency_leg(dev):
+    """BASELINE configs[0]: one VOC frame (20 cls, 416^2, batch 1) -- the call's latency, not a roofline: eager library
+    call and CUDA-graph replay, back to back and isolated (launch -> synchronize wall time, median)."""
+    import torch
+    import videoyolo_b200 as vy
+    from videoyolo_b200.pipeline import GraphedDetector
+    from videoyolo_b200.synth import random_heads_cuda
+    AN, ST = vy.ANCHORS[::-1], vy.STRIDES[::-1]
+    label, C, size, B = CONFIGS["voc416_b1"]
+    heads = random_heads_cuda(B, C, size, 3, dev)
+    det = GraphedDetector(C, AN, ST, [tuple(h.shape) for h in heads], dev)
+    det(heads)
+
+    def wall(fn, n=300):
+        for _ in range(30):
+            fn()
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e6
+
+    def one(fn, n=200):
+        ts = []
+        for _ in range(n):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e6)
+        return sorted(ts)[n // 2]
+
+    e = lambda: vy.yolo3_decode_nms(heads, C, AN, ST, out=det.out, kept=det.kept, workspace_buf=det.workspace, **NMS)
+    g = lambda: det()
+    r = {"workload": label, "unit": "us per frame",
+         "back_to_back_eager_us": round(wall(e), 2), "back_to_back_graph_us": round(wall(g), 2),
+         "isolated_eager_us": round(one(e), 2), "isolated_graph_us": round(one(g), 2)}
+    r["frames_per_s_graph"] = round(1e6 / r["back_to_back_graph_us"], 1)
+    return r
+
+
+def stress_nms_leg(dev, peak, B=128):
+    """BASELINE configs[3] with ITS arguments: 80 cls, 10 647 boxes (R = 851 760 rows per frame), batch 128,
+    valid_thresh = 0.001, topk = -1 (every valid row takes part), force_suppress off and on; the operator call of
+    yolo3.py:526-528 on the materialised (B, R, 6) tensor, full-size output (post_nms = -1).  Bytes per frame
+    (SURVEY.md 8d): the score/box read 24*R + the mandatory full-size output 24*R."""
+    import torch
+    import videoyolo_b200 as vy
+    from videoyolo_b200.synth import random_heads_cuda
+    AN, ST = vy.ANCHORS[::-1], vy.STRIDES[::-1]
+    heads = random_heads_cuda(B, 80, 416, 5, dev)
+    dets = vy.yolo3_decode(heads, 80, AN, ST)
+    del heads
+    R = dets.shape[1]
+    out = {"workload": CONFIGS["stress416_b128"][0].replace("reference NMS arguments", "valid_thresh 0.001, topk -1, full output"),
+           "rows_per_frame": R, "batch": B, "bytes_per_frame": 48 * R, "regime": "R: logits ~ N(0,1)"}
+    for force in (False, True):
+        fn = lambda: vy.box_nms(dets, 0.45, 0.001, -1, id_index=0, force_suppress=force)
+        o = fn(); torch.cuda.synchronize()
+        surv = float((o[..., 0] >= 0).sum()) / B
+        del o
+        ts = []
+        for _ in range(2):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); o = fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+            del o
+        ms = min(ts)
+        out["force_suppress_%s" % ("on" if force else "off")] = {
+            "ms_per_call": round(ms, 2), "frames_per_s": round(B / ms * 1e3, 1), "survivors_per_frame": round(surv, 1),
+            "hbm_frac": round(48.0 * R * B / (ms * 1e-3) / 1e9 / peak, 5)}
+    return out
+
+
 def load_traffic(config_name, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
     `ncu --set full` capture (profiles/roofline_traffic.json), or None."""
@@ -266,9 +337,24 @@ def cpu_port_fps(C, size, frames, seed, threads, steps=1, warmup=0):
     return frames / dt, dt
 
 
+def make_config(args, world, n_streams=None):
+    """The `config` object of the JSON line: the SAME dict for the native and the reference arm (the driver compares them)."""
+    label, C, size, B = CONFIGS[args.config]
+    in_bytes_frame, _ = frame_bytes(C, size, NMS["post_nms"])
+    in_bytes = in_bytes_frame * B
+    return {"workload": label, "classes": C, "input": size, "frames_per_gpu": B,
+            "global_frames_per_step": B * world, "boxes_per_frame": in_bytes_frame // (4 * (5 + C)),
+            "regime": args.regime + (": logits ~ N(0,1) (random-init weights)" if args.regime == "R" else ": trained-like"),
+            "nms": NMS, "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world,
+            "l2": ("inputs larger than L2 (%.0f MB per step)" % (in_bytes / 1e6)) if in_bytes >= (160 << 20)
+                  else "L2 flushed between steps (256 MiB write)",
+            "streams": args.streams if in_bytes >= (160 << 20) else 1}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path.  MXNet/GluonCV cannot be installed here (no wheel,
-    no network), so this is the oracle port, all host threads, on a bounded sample."""
+    no network), so this is the oracle port with all host threads; a step is the whole batch of the
+    config whenever K + W steps of that fit ~2.5 minutes (else a bounded sample of it, stated in cpu_baseline.sample)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -276,24 +362,36 @@ def run_reference(args):
     oracle.build()
     label, C, size, B = CONFIGS[args.config]
     cores = os.cpu_count() or 1
-    frames = min(B, max(cores, 8))
-    # calibrate so that K+W steps end within ~2.5 minutes
-    fps1, dt1 = cpu_port_fps(C, size, frames, 1236, cores)
+    frames = B
+    fps1, dt1 = cpu_port_fps(C, size, min(B, max(cores, 8)), 1236, cores)
     budget = 150.0
-    while frames > 1 and dt1 * (args.steps + args.warmup) > budget:
+    while frames > 1 and (frames / fps1) * (args.steps + args.warmup) > budget:
         frames = max(1, frames // 2)
-        fps1, dt1 = cpu_port_fps(C, size, frames, 1236, cores)
     fps, dt = cpu_port_fps(C, size, frames, 1236, cores, steps=args.steps, warmup=args.warmup)
     sample = "%d of %d frames per step, %d threads over frames (oracle/vy_oracle.c)" % (frames, B, cores)
     line = {"impl": "reference", "metric": "frames/sec decode+NMS", "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": label, "classes": C, "input": size, "frames_per_step": frames, "regime": "R",
-                       "nms": NMS},
+            "config": make_config(args, max(1, args.gpus)),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs nearest to its GPU (NVML's ideal affinity) BEFORE any pinned host buffer is
+    allocated: first-touch then places the buffers on that NUMA node, and eight ranks stop sharing node 0's memory."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -309,6 +407,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-conv", action="store_true", help="skip the fusion-conv (tensor-pipe) leg")
     ap.add_argument("--no-other", action="store_true", help="skip the short legs over the other BASELINE workloads")
+    ap.add_argument("--no-graph", action="store_true", help="headline steps as eager library calls instead of CUDA-graph replays")
     ap.add_argument("--streams", type=int, default=4,
                     help="CUDA streams the timed steps alternate over (1 = every step waits for the one before)")
     args = ap.parse_args()
@@ -316,16 +415,18 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpus = bind_to_gpu_numa(local)
+
     import torch
     import torch.distributed as dist
     import videoyolo_b200 as vy
     from videoyolo_b200 import _lib
-    from videoyolo_b200.pipeline import HostDetector
+    from videoyolo_b200.pipeline import GraphedDetector, HostDetector
     from videoyolo_b200.synth import random_heads_cuda
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -346,32 +447,9 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     _lib.lib()
-
-    label, C, size, B = CONFIGS[args.config]
     AN, ST = vy.ANCHORS[::-1], vy.STRIDES[::-1]
-    heads = random_heads_cuda(B, C, size, 1234 + 2 + rank, dev, regime=args.regime)
-    in_bytes_frame, out_bytes_frame = frame_bytes(C, size, NMS["post_nms"])
-    in_bytes = in_bytes_frame * B
-    out = torch.empty((B, NMS["post_nms"], 6), dtype=torch.float32, device=dev)
-    kept = torch.empty((B, NMS["post_nms"]), dtype=torch.int32, device=dev)
-    # inputs smaller than L2 (126 MB) are evicted between steps by writing a 256 MiB buffer
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if in_bytes < (160 << 20) else None
-
-    # Steps are independent batches, so consecutive steps may overlap: step i runs on stream i % n_streams
-    # with its own output buffers and workspace, which lets the latency-bound head (sample) and tail
-    # (finalize) of one step hide behind the bandwidth-bound streaming pass of its neighbour.  Configs that
-    # need an L2 flush between steps run on one stream.
-    n_streams = max(1, args.streams) if flush is None else 1
-    side = [torch.cuda.Stream(dev) for _ in range(n_streams)]
-    outs = [(out, kept)] + [(torch.empty_like(out), torch.empty_like(kept)) for _ in range(n_streams - 1)]
-
-    def step(i=0, n=1):
-        o, k = outs[i % n]
-        if n == 1:
-            vy.yolo3_decode_nms(heads, C, AN, ST, out=o, kept=k, **NMS)
-        else:
-            with torch.cuda.stream(side[i % n]):
-                vy.yolo3_decode_nms(heads, C, AN, ST, out=o, kept=k, **NMS)
+    peak, peak_src = load_peaks()
+    side = [torch.cuda.Stream(dev) for _ in range(max(1, args.streams))]
 
     def barrier():
         torch.cuda.synchronize()
@@ -386,42 +464,92 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(fn, steps, warmup, sampler=None, n=1):
-        """max-over-ranks milliseconds for `steps` calls of fn, device-timed."""
-        for i in range(warmup):
-            fn(i, n)
-        barrier()
-        if sampler:
-            sampler.active.set()
-        total = 0.0
-        if flush is None:
-            cur = torch.cuda.current_stream(dev)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(cur)
-            if n > 1:
-                for s_ in side[:n]:
-                    s_.wait_event(a)
-            for i in range(steps):
+    class Workload:
+        """One benchmarked config on this rank: ONE INPUT SET PER STREAM (own head maps, outputs and workspace), each
+        captured once in a CUDA graph (pipeline.GraphedDetector: the same library calls, replayed).  Steps are
+        independent batches: step i runs on stream i % n, so the latency-bound head (sample) and tail (finalize) of
+        one step hide behind the bandwidth-bound streaming pass of its neighbours.  Inputs smaller than L2 run on one
+        stream with a 256 MiB flush write between steps."""
+
+        def __init__(self, name, seed, regime, graph=True):
+            self.label, self.C, self.size, self.B = CONFIGS[name]
+            self.in_frame, self.out_frame = frame_bytes(self.C, self.size, NMS["post_nms"])
+            self.in_bytes = self.in_frame * self.B
+            self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if self.in_bytes < (160 << 20) else None
+            self.n = max(1, args.streams) if self.flush is None else 1
+            self.graph = graph
+            self.sets = []
+            for i in range(self.n):
+                heads = random_heads_cuda(self.B, self.C, self.size, seed + 1000 * i + rank, dev, regime=regime)
+                det = GraphedDetector(self.C, AN, ST, [tuple(h.shape) for h in heads], dev, **{
+                    "nms_thresh": NMS["nms_thresh"], "valid_thresh": NMS["valid_thresh"], "nms_topk": NMS["topk"],
+                    "post_nms": NMS["post_nms"]})
+                for dst, src in zip(det.heads, heads):
+                    dst.copy_(src)
+                del heads
+                self.sets.append(det)
+            torch.cuda.synchronize()
+
+        def step(self, i=0, n=1):
+            det = self.sets[i % len(self.sets)]
+            if n == 1:
+                det.graph.replay()
+            else:
+                with torch.cuda.stream(side[i % n]):
+                    det.graph.replay()
+
+        def step_eager(self, i=0, n=1):
+            det = self.sets[i % len(self.sets)]
+            if n == 1:
+                vy.yolo3_decode_nms(det.heads, self.C, AN, ST, out=det.out, kept=det.kept, workspace_buf=det.workspace, **NMS)
+            else:
+                with torch.cuda.stream(side[i % n]):
+                    vy.yolo3_decode_nms(det.heads, self.C, AN, ST, out=det.out, kept=det.kept, workspace_buf=det.workspace, **NMS)
+
+        def timed(self, fn, steps, warmup, sampler=None, n=1):
+            """max-over-ranks milliseconds for `steps` calls of fn, device-timed."""
+            for i in range(warmup):
                 fn(i, n)
-            if n > 1:
-                for s_ in side[:n]:
-                    cur.wait_event(s_.record_event())
-            b.record(cur)
-            torch.cuda.synchronize()
-            total = a.elapsed_time(b)
-        else:
-            evs = []
-            for i in range(steps):
-                flush.zero_()
+            barrier()
+            if sampler:
+                sampler.active.set()
+            if self.flush is None:
+                cur = torch.cuda.current_stream(dev)
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); fn(i, 1); b.record()
-                evs.append((a, b))
-            torch.cuda.synchronize()
-            total = sum(a.elapsed_time(b) for a, b in evs)
-        if sampler:
-            sampler.active.clear()
-        barrier()
-        return max_over_ranks(total)
+                a.record(cur)
+                if n > 1:
+                    for s_ in side[:n]:
+                        s_.wait_event(a)
+                for i in range(steps):
+                    fn(i, n)
+                if n > 1:
+                    for s_ in side[:n]:
+                        cur.wait_event(s_.record_event())
+                b.record(cur)
+                torch.cuda.synchronize()
+                total = a.elapsed_time(b)
+            else:
+                evs = []
+                for i in range(steps):
+                    self.flush.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); fn(i, 1); b.record()
+                    evs.append((a, b))
+                torch.cuda.synchronize()
+                total = sum(a.elapsed_time(b) for a, b in evs)
+            if sampler:
+                sampler.active.clear()
+            barrier()
+            return max_over_ranks(total)
+
+        def frac(self, ms_per_step):
+            return (self.in_bytes + self.out_frame * self.B) / (ms_per_step * 1e-3) / 1e9 / peak
+
+    label, C, size, B = CONFIGS[args.config]
+    wl = Workload(args.config, 1236, args.regime)
+    n_streams = wl.n
+    step = wl.step_eager if args.no_graph else wl.step
+    in_bytes = wl.in_bytes
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -429,7 +557,7 @@ def main():
     # a fresh process on an idle GPU: a small config (one frame: inputs of a megabyte, the whole timed region a few
     # milliseconds) is over before the clocks have come up, so keep the device busy for a moment first.  The large
     # configs have just generated gigabytes of inputs on the device and go straight to their W warm-up steps.
-    if flush is not None:
+    if wl.flush is not None:
         t_spin = time.perf_counter()
         while time.perf_counter() - t_spin < 0.5:
             for i in range(8):
@@ -437,25 +565,25 @@ def main():
             torch.cuda.synchronize()
 
     # ---- headline: device-resident
+    ms_total = wl.timed(step, args.steps, args.warmup, sampler, n_streams)
+    # the same steps strictly one after the other (reported beside the headline), and both as eager library calls
+    ms_serial = wl.timed(step, args.steps, 3, None, 1) if n_streams > 1 else ms_total
     c0 = _lib.launch_counts()
-    ms_total = timed(step, args.steps, args.warmup, sampler, n_streams)
+    ms_eager = wl.timed(wl.step_eager, args.steps, 3, None, n_streams)
     c1 = _lib.launch_counts()
-    # the same steps strictly one after the other (reported beside the headline)
-    ms_serial = timed(step, args.steps, 3, None, 1) if n_streams > 1 else ms_total
-    launches = {k: c1[k] - c0[k] for k in c1 if c1[k] - c0[k]}
-    # warm-up launches are not in the timed region
-    per_step = {k: v // (args.steps + args.warmup) for k, v in launches.items()}
+    ms_eager_serial = wl.timed(wl.step_eager, args.steps, 3, None, 1) if n_streams > 1 else ms_eager
+    # kernels per step: counted by the library on the eager launches (a graph replay launches the same kernels)
+    per_step = {k: (c1[k] - c0[k]) // (args.steps + 3) for k in c1 if c1[k] - c0[k]}
     gpu_launches = sum(per_step.values()) * args.steps
     ms_step = ms_total / args.steps
     fps = world * B * args.steps / (ms_total * 1e-3)
 
-    # ---- roofline pass: same steps with the library's per-kernel events switched on
+    # ---- roofline pass: same steps (eager, one stream) with the library's per-kernel events switched on
     _lib.prof_enable(True)
     _lib.prof_read()
-    ms_prof_total = timed(step, args.steps, 3, None, 1)
+    ms_prof_total = wl.timed(wl.step_eager, args.steps, 3, None, 1)
     prof = _lib.prof_read()
     _lib.prof_enable(False)
-    peak, peak_src = load_peaks()
     # the dominant kernel = the one with the largest share of the step (the warm-up launches of the
     # profiled pass are in the record too: average over all of them)
     kernel_ms = {k: v[0] / max(v[1], 1) * (v[1] / max(1, min(x[1] for x in prof.values()))) for k, v in prof.items()}
@@ -467,15 +595,18 @@ def main():
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": in_bytes,
                 "kernel_ms_per_step": {k: round(v, 5) for k, v in kernel_ms.items()},
                 "kernel_share_of_step": {k: round(v / sum(kernel_ms.values()), 4) for k, v in kernel_ms.items()},
-                "step_frac": round((in_bytes + out_bytes_frame * B) / (ms_step * 1e-3) / 1e9 / peak, 4),
-                "step_frac_single_stream": round((in_bytes + out_bytes_frame * B) / (ms_serial / args.steps * 1e-3) / 1e9 / peak, 4),
+                "step_frac": round(wl.frac(ms_step), 4),
+                "step_frac_single_stream": round(wl.frac(ms_serial / args.steps), 4),
+                "step_frac_eager": round(wl.frac(ms_eager / args.steps), 4),
+                "step_frac_single_stream_eager": round(wl.frac(ms_eager_serial / args.steps), 4),
                 "profiled_ms_per_step": round(ms_prof_total / args.steps, 5)}
 
     # ---- e2e: host buffers through the public host-facing call
     e2e = None
     if not args.no_e2e:
-        h_heads = [torch.empty(h.shape, dtype=torch.float32).pin_memory() for h in heads]
-        for hh, h in zip(h_heads, heads):
+        d0 = wl.sets[0]
+        h_heads = [torch.empty(h.shape, dtype=torch.float32).pin_memory() for h in d0.heads]
+        for hh, h in zip(h_heads, d0.heads):
             hh.copy_(h)
         torch.cuda.synchronize()
         det = HostDetector(C, AN, ST, dev, chunk=max(1, min(8, B)), **{"nms_thresh": NMS["nms_thresh"],
@@ -484,7 +615,7 @@ def main():
         last = {}
 
         def e2e_step():
-            last["r"] = det(h_heads)
+            last["r"] = det(h_heads, copy=False)
 
         for _ in range(3):
             e2e_step()
@@ -501,16 +632,19 @@ def main():
         sampler.active.clear()
         e2e_ms = max_over_ranks(max(a.elapsed_time(b), wall_ms))
         barrier()
-        # the host results of the last e2e step must be the device-resident results
-        ids_h = last["r"][0]
-        same = bool(torch.equal(ids_h[..., 0], out.cpu()[..., 0]))
+        # the host results of the last e2e step must be the device-resident results of the same input set
+        d0.graph.replay()
+        torch.cuda.synchronize()
+        same = bool(torch.equal(last["r"][0][..., 0], d0.out.cpu()[..., 0]))
         e2e = {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s",
                "h2d_bytes_per_step": det.h2d_bytes, "d2h_bytes_per_step": det.d2h_bytes, "steps": e2e_steps,
                "ms_per_step": e2e_ms / e2e_steps, "api": "videoyolo_b200.pipeline.HostDetector.__call__",
                "h2d_gbs": round(det.h2d_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9, 1),
                "bound": "PCIe host->device copy of the fp32 head maps (the kernels take ~1% of the step)",
+               "host_placement": ("process bound to the GPU's NUMA-local CPUs (%d cpus) before the pinned buffers were allocated" % len(cpus))
+                                 if cpus else "default placement (NVML affinity unavailable)",
                "matches_device_path": same}
-        del h_heads
+        del h_heads, det
     sampler.stop()
 
     # ---- temporal fusion conv: the tensor-core part of the path (rank 0 only; not part of `value`)
@@ -523,35 +657,41 @@ def main():
         except Exception as e:                     # the headline line must still be printed
             conv = {"error": str(e)[:200]}
 
-    # ---- the other device-resident workloads of BASELINE.json, same method, short (N=1 default run only): the metric's
-    # own 416^2 / 10647-box shape at batch 128 (configs[3]'s shape with the reference's NMS arguments) and configs[4]
+    # ---- the other device-resident workloads of BASELINE.json, same method, short, on EVERY rank (so the scaling run
+    # carries them too): the metric's own 416^2 / 10 647-box shape at batch 128 (configs[3]'s shape with the reference's
+    # NMS arguments), configs[4] (the config BASELINE names for scaling) and configs[2]'s decode + NMS part
     other = None
-    if rank == 0 and world == 1 and args.config == "coco608_b64" and flush is None and not args.no_other:
+    if args.config == "coco608_b64" and wl.flush is None and not args.no_other:
         other = {}
-        for name in ("stress416_b128", "vid320_b256"):
-            lbl2, C2, size2, B2 = CONFIGS[name]
-            h2 = random_heads_cuda(B2, C2, size2, 4321, dev, regime=args.regime)
-            o2 = [(torch.empty((B2, NMS["post_nms"], 6), dtype=torch.float32, device=dev),
-                   torch.empty((B2, NMS["post_nms"]), dtype=torch.int32, device=dev)) for _ in range(n_streams)]
-
-            def step2(i=0, n=1, h2=h2, C2=C2, o2=o2):
-                o, k = o2[i % n]
-                if n == 1:
-                    vy.yolo3_decode_nms(h2, C2, AN, ST, out=o, kept=k, **NMS)
-                else:
-                    with torch.cuda.stream(side[i % n]):
-                        vy.yolo3_decode_nms(h2, C2, AN, ST, out=o, kept=k, **NMS)
+        del wl.sets[1:]
+        for name in ("stress416_b128", "vid320_b256", "vid416_b32"):
+            w2 = Workload(name, 4321, args.regime)
             k2 = min(args.steps, 50)
-            ms_a = timed(step2, k2, 5, None, n_streams)
-            ms_b = timed(step2, k2, 3, None, 1)
-            inb2, outb2 = frame_bytes(C2, size2, NMS["post_nms"])
-            tot2 = (inb2 + outb2) * B2
-            other[name] = {"workload": lbl2, "steps": k2, "streams": n_streams,
-                           "value": round(B2 * k2 / (ms_a * 1e-3), 1), "value_single_stream": round(B2 * k2 / (ms_b * 1e-3), 1),
-                           "unit": "frames/s",
-                           "step_frac": round(tot2 / (ms_a / k2 * 1e-3) / 1e9 / peak, 4),
-                           "step_frac_single_stream": round(tot2 / (ms_b / k2 * 1e-3) / 1e9 / peak, 4)}
-            del h2, o2
+            ms_a = w2.timed(w2.step, k2, 5, None, w2.n)
+            ms_b = w2.timed(w2.step, k2, 3, None, 1) if w2.n > 1 else ms_a
+            other[name] = {"workload": w2.label, "steps": k2, "streams": w2.n, "n_gpus": world,
+                           "value": round(world * w2.B * k2 / (ms_a * 1e-3), 1),
+                           "value_single_stream": round(world * w2.B * k2 / (ms_b * 1e-3), 1),
+                           "unit": "frames/s", "step_frac": round(w2.frac(ms_a / k2), 4),
+                           "step_frac_single_stream": round(w2.frac(ms_b / k2), 4),
+                           "l2": "inputs larger than L2" if w2.flush is None else "L2 flushed between steps"}
+            del w2
+            torch.cuda.empty_cache()
+
+    # ---- configs[0]: one VOC frame, latency of the call (rank 0)
+    latency = None
+    if rank == 0 and not args.no_other:
+        try:
+            latency = voc_latency_leg(dev)
+        except Exception as e:
+            latency = {"error": str(e)[:200]}
+    # ---- configs[3] with ITS arguments: the box_nms operator at valid_thresh 0.001, topk -1, force_suppress off / on
+    stress = None
+    if rank == 0 and not args.no_other:
+        try:
+            stress = stress_nms_leg(dev, peak)
+        except Exception as e:
+            stress = {"error": str(e)[:200]}
 
     # ---- cpu baseline (rank 0, N=1 only): oracle port on a bounded sample of the same workload
     cpu = None
@@ -591,18 +731,19 @@ def main():
             cpu["graph_faithful"] = {"error": str(e)[:200]}
 
     if rank == 0:
+        cfg = make_config(args, world)
         line = {"metric": "frames/sec decode+NMS", "value": fps, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": label, "classes": C, "input": size, "frames_per_gpu": B,
-                           "global_frames_per_step": B * world, "boxes_per_frame": in_bytes_frame // (4 * (5 + C)),
-                           "regime": args.regime + (": logits ~ N(0,1) (random-init weights)" if args.regime == "R" else ": trained-like"),
-                           "nms": NMS, "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world,
-                           "l2": ("inputs larger than L2 (%.0f MB per step)" % (in_bytes / 1e6)) if flush is None
-                                 else "L2 flushed between steps (256 MiB write)",
-                           "streams": n_streams},
+                "config": cfg,
+                "launch_mode": ("eager library calls" if args.no_graph else
+                                "one CUDA graph per stream (the library's calls captured once: pipeline.GraphedDetector), "
+                                "one input set per stream"),
                 "value_single_stream": world * B * args.steps / (ms_serial * 1e-3),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fusion_conv": conv, "other_workloads": other, "gpu_launches": gpu_launches,
+                "value_eager": world * B * args.steps / (ms_eager * 1e-3),
+                "value_single_stream_eager": world * B * args.steps / (ms_eager_serial * 1e-3),
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fusion_conv": conv, "other_workloads": other,
+                "voc416_b1_latency": latency, "stress_nms": stress, "gpu_launches": gpu_launches,
                 "launches_per_step": per_step, "clocks": sampler.summary()}
         print(json.dumps(line))
     if world > 1:

@@ -63,7 +63,8 @@ const char *vy_last_error(void);
 #define VY_K_LAYOUT        9
 #define VY_K_SAMPLE       10
 #define VY_K_STREAM       11
-#define VY_K_COUNT        12
+#define VY_K_TABLE        12
+#define VY_K_COUNT        13
 const char *vy_kernel_name(int kernel_id);
 int vy_launch_counts(long long *host_counts, int n);     /* cumulative since load; returns VY_K_COUNT */
 int vy_prof_enable(int on);
@@ -122,6 +123,24 @@ int vy_decode_nms_f32(const float *const *host_head, const int *host_H, const in
                       float overlap_thresh, float valid_thresh, int topk, int force_suppress,
                       int post_nms, float *out, int32_t *kept_rows,
                       void *workspace, size_t workspace_bytes, vy_stream_t stream);
+
+/* The same call with everything that depends only on the shapes and arguments resolved ONCE (head description, job /
+ * tile / table plan, workspace layout): a hybridized Gluon block runs the same graph on the same shapes for every
+ * batch (YOLOV3.hybridize(), detect_yolo3.py:204), so the per-call host work should be a handful of launches.
+ *   create   host arrays as for vy_decode_nms_f32 (no head pointers); *plan is owned by the caller until destroy
+ *   launch   host_head[s] device pointers of this call's head maps; everything else as vy_decode_nms_f32.
+ *            A plan may be launched from several host threads / on several streams at once as long as every
+ *            concurrent launch has its own workspace and outputs.
+ * vy_decode_nms_f32 is create + launch on a stack plan (same kernels, same results). */
+typedef struct vy_decode_nms_plan vy_decode_nms_plan_t;
+int    vy_decode_nms_plan_create(const int *host_H, const int *host_W, const float *host_stride,
+                                 const float *host_anchors, int n_scales, int B, int A, int C, int agnostic,
+                                 float overlap_thresh, float valid_thresh, int topk, int force_suppress,
+                                 int post_nms, vy_decode_nms_plan_t **plan);
+size_t vy_decode_nms_plan_workspace_bytes(const vy_decode_nms_plan_t *plan);
+int    vy_decode_nms_plan_launch(const vy_decode_nms_plan_t *plan, const float *const *host_head, float *out,
+                                 int32_t *kept_rows, void *workspace, size_t workspace_bytes, vy_stream_t stream);
+void   vy_decode_nms_plan_destroy(vy_decode_nms_plan_t *plan);
 
 /* ---------------------------------------------------------------------------------------------
  * Pairwise IoU.  Replaces: utils/bbox.py:11-38 bbox_iou(bbox_a, bbox_b, offset).
@@ -193,6 +212,19 @@ int vy_unpack_p_to_f32(const void *y_p, int p_is_f32, int B, int C, int T, int H
  * e.g. the 1x1 `prediction` conv of YOLOOutputV3, yolo3.py:62, with A*(5+classes) = 75 / 105 / 255 outputs) */
 int vy_unpack_p_channels_to_f32(const void *y_p, int p_is_f32, int B, int Cp, int C, int T, int H, int W, float *x,
                                 long long stride_b, long long stride_c, long long stride_t, vy_stream_t stream);
+
+/* The 1x1 `prediction` conv of YOLOOutputV3 (yolo3.py:62,157: Conv2D with bias, fp32 in the reference) runs in the
+ * fusion-conv kernel with fp32-grade operands: a value v is carried as hi = bf16(v), lo = bf16(v - hi) in separate
+ * channels and w*v is accumulated in fp32 as w_hi*v_hi + w_lo*v_hi + w_hi*v_lo (dropped term ~2^-16 relative).
+ *   vy_pack_f32_split_to_p_bf16   fp32 tensor (strides as vy_pack_f32_to_p_bf16) -> P layout with 3*Cpad channels
+ *                                 [hi | hi | lo], channels C..Cpad of each third zero; pairs with weights [w_hi | w_lo | w_hi]
+ *   vy_cat_repeat_bf16            P layout (T, B, H+2, W+2, C) bf16 -> (1, B, H+2, W+2, rep*T*C): channel r*T*C + t*C + c
+ *                                 = frame t, channel c.  T = K, rep = 1 is the 'cat' late join (reshape (0,-3,-2),
+ *                                 yolo3.py:1135-1136); rep = 2 feeds a bf16 activation to split weights [w_hi | w_lo].
+ *   Both are accounted under VY_K_LAYOUT. */
+int vy_pack_f32_split_to_p_bf16(const float *x, long long stride_b, long long stride_c, long long stride_t,
+                                int B, int C, int Cpad, int T, int H, int W, void *y_p, vy_stream_t stream);
+int vy_cat_repeat_bf16(const void *x, int B, int T, int H, int W, int C, int rep, void *y, vy_stream_t stream);
 
 /* TemporalPooling 'direct' style (layers.py:201-205) on P-layout data: x (T, inner) -> y (inner),
  * inner = B*(H+2)*(W+2)*C, mode 0 = max, 1 = mean.  bf16 in/out. */

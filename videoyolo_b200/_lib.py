@@ -40,6 +40,12 @@ SIGNATURES = {
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "vy_decode_nms_plan_create": (ctypes.c_int, [c_i32p, c_i32p, c_f32p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "vy_decode_nms_plan_workspace_bytes": (ctypes.c_size_t, [c_vp]),
+    "vy_decode_nms_plan_launch": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "vy_decode_nms_plan_destroy": (None, [c_vp]),
     "vy_bbox_iou_f32": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_float, c_vp, c_vp]),
     "vy_bbox_iou_f64": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int,
@@ -58,6 +64,9 @@ SIGNATURES = {
     "vy_p_layout_elems": (ctypes.c_size_t, [ctypes.c_int] * 5),
     "vy_pack_f32_to_p_bf16": (ctypes.c_int, [c_vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong] +
                               [ctypes.c_int] * 5 + [c_vp, c_vp]),
+    "vy_pack_f32_split_to_p_bf16": (ctypes.c_int, [c_vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong] +
+                                    [ctypes.c_int] * 6 + [c_vp, c_vp]),
+    "vy_cat_repeat_bf16": (ctypes.c_int, [c_vp] + [ctypes.c_int] * 6 + [c_vp, c_vp]),
     "vy_unpack_p_to_f32": (ctypes.c_int, [c_vp] + [ctypes.c_int] * 6 + [c_vp, ctypes.c_longlong, ctypes.c_longlong,
                                                                         ctypes.c_longlong, c_vp]),
     "vy_unpack_p_channels_to_f32": (ctypes.c_int, [c_vp] + [ctypes.c_int] * 7 + [c_vp, ctypes.c_longlong, ctypes.c_longlong,
@@ -98,7 +107,7 @@ def check(rc: int) -> None:
         raise VyoloError(rc, lib().vy_last_error().decode("utf-8", "replace"))
 
 
-N_KERNEL_IDS = 12
+N_KERNEL_IDS = 13
 
 
 def launch_counts() -> dict:

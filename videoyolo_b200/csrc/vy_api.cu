@@ -22,7 +22,8 @@ extern "C" const char *vy_last_error(void) { return g_err; }
 static const char *const g_kernel_names[VY_K_COUNT] = {
     "vy_decode_kernel", "vy_decode_select_kernel", "vy_rows_select_kernel", "vy_nms_finalize_kernel",
     "vy_fill_kernel", "vy_bbox_iou_kernel", "vy_fusion_conv_kernel", "vy_temporal_pool_kernel",
-    "vy_nms_large_kernels", "vy_layout_kernels", "vy_decode_sample_kernel", "vy_decode_stream_kernel"};
+    "vy_nms_large_kernels", "vy_layout_kernels", "vy_decode_sample_kernel", "vy_decode_stream_kernel",
+    "vy_decode_table_kernel"};
 static std::atomic<long long> g_launches[VY_K_COUNT];
 static std::atomic<int> g_prof_on{0};
 struct ProfRec { int id; cudaEvent_t a, b; };
@@ -88,6 +89,21 @@ int vy_sm_count() {
     return cached[dev];
 }
 
+#include <map>
+cudaError_t vy_ensure_dyn_smem(const void *func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> set;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &cur = set[std::make_pair(func, dev)];
+    if (bytes <= cur) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
+
 int vy_fill_heads(VyHeads *h, const float *const *head, const int *H, const int *W, const float *stride,
                   const float *anchors, int n_scales, int B, int A, int C, int agnostic) {
     if (!h || !head || !H || !W || !stride || !anchors) VY_FAIL(VY_EINVAL, "null host array");
@@ -119,5 +135,9 @@ int vy_fill_heads(VyHeads *h, const float *const *head, const int *H, const int 
     h->R = (long long)h->Ceff * boxes;
     if (h->R > 0xfffffffeLL) VY_FAIL(VY_EINVAL, "R=%lld rows per image exceed the 32-bit row index", h->R);
     if ((long long)B * A * h->P > 0x7fffffffLL) VY_FAIL(VY_EINVAL, "B*A*P overflows int");
+    for (int s = 0; s < n_scales; ++s)        // SelBuf.it_off and the streaming pass's element indices are 32-bit per scale
+        if ((long long)B * A * h->P * h->sc[s].HW > 0xffffffffLL)
+            VY_FAIL(VY_EUNSUPPORTED, "scale %d holds %lld elements (>= 2^32): split the batch", s,
+                    (long long)B * A * h->P * h->sc[s].HW);
     return VY_OK;
 }

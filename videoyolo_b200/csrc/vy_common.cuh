@@ -20,6 +20,8 @@ void vy_set_error(const char *fmt, ...);
     vy_set_error("launch of %s failed: %s", name, cudaGetErrorString(e_)); return VY_ECUDA; } } while (0)
 
 int vy_sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel): only raises the limit, remembers what it set
+cudaError_t vy_ensure_dyn_smem(const void *func, size_t bytes);
 
 // ------------------------------------------------------------------ launch accounting (vyolo.h: vy_prof_*)
 // Every kernel launch of the library goes through VY_KERNEL: it is counted always and, while

@@ -273,7 +273,9 @@ constexpr int LY_C = 64, LY_P = 128, LY_NT = 256;
 
 __global__ void __launch_bounds__(LY_NT)
 vy_pack_kernel(const float *__restrict__ x, long long sb, long long sc, long long st, int B, int C,
-               int T, int H, int W, __nv_bfloat16 *__restrict__ y) {
+               int T, int H, int W, __nv_bfloat16 *__restrict__ y, int Ctot, int split) {
+    // split > 0 (vy_pack_f32_split_to_p_bf16): every value v goes out as hi = bf16(v) at channel c and split + c and as
+    // lo = bf16(v - hi) at 2*split + c of a pixel of Ctot = 3*split channels
     __shared__ float tile[LY_C][LY_P + 1];
     const int HW = H * W, Wp = W + 2;
     const int p0 = blockIdx.x * LY_P, c0 = blockIdx.y * LY_C;
@@ -295,7 +297,21 @@ vy_pack_kernel(const float *__restrict__ x, long long sb, long long sc, long lon
         }
     }
     __syncthreads();
-    __nv_bfloat16 *dst = y + ((size_t)t * B + b) * (size_t)(H + 2) * Wp * C;
+    __nv_bfloat16 *dst = y + ((size_t)t * B + b) * (size_t)(H + 2) * Wp * Ctot;
+    if (split > 0) {
+        for (int i = threadIdx.x; i < LY_P * LY_C; i += LY_NT) {
+            const int p = i / LY_C, c = i % LY_C;
+            const int pos = p0 + p;
+            if (pos >= HW || c0 + c >= C) continue;
+            const int h = pos / W, w = pos % W;
+            const float v = tile[c][p];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            __nv_bfloat16 *o = dst + ((size_t)(h + 1) * Wp + (w + 1)) * Ctot + c0 + c;
+            o[0] = hi; o[split] = hi; o[2 * split] = lo;
+        }
+        return;
+    }
     if ((C & 7) == 0) {                                    // 8 channels = one 16-byte store
         for (int i = threadIdx.x; i < LY_P * (LY_C / 8); i += LY_NT) {
             const int p = i / (LY_C / 8), c = (i % (LY_C / 8)) * 8;
@@ -499,8 +515,53 @@ extern "C" int vy_pack_f32_to_p_bf16(const float *x, long long stride_b, long lo
     VY_LAUNCH_CHECK("vy_zero_border_kernel");
     const dim3 grid((H * W + LY_P - 1) / LY_P, (C + LY_C - 1) / LY_C, T * B);
     VY_KERNEL(VY_K_LAYOUT, st, (vy_pack_kernel<<<grid, LY_NT, 0, st>>>(x, stride_b, stride_c, stride_t, B, C, T, H, W,
-                                                                     (__nv_bfloat16 *)y_p)));
+                                                                     (__nv_bfloat16 *)y_p, C, 0)));
     VY_LAUNCH_CHECK("vy_pack_kernel");
+    return VY_OK;
+}
+
+extern "C" int vy_pack_f32_split_to_p_bf16(const float *x, long long stride_b, long long stride_c, long long stride_t,
+                                           int B, int C, int Cpad, int T, int H, int W, void *y_p, vy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x || !y_p || B < 1 || C < 1 || Cpad < C || T < 1 || H < 1 || W < 1) VY_FAIL(VY_EINVAL, "vy_pack_f32_split_to_p_bf16: bad arguments");
+    if ((long long)T * B > 65535) VY_FAIL(VY_EUNSUPPORTED, "vy_pack_f32_split_to_p_bf16: T*B must be <= 65535");
+    // channels C .. Cpad of every third and the border stay zero: the whole tensor is cleared first
+    VY_CUDA_CHECK(cudaMemsetAsync(y_p, 0, (size_t)T * B * (H + 2) * (W + 2) * 3 * Cpad * sizeof(__nv_bfloat16), st));
+    const dim3 grid((H * W + LY_P - 1) / LY_P, (C + LY_C - 1) / LY_C, T * B);
+    VY_KERNEL(VY_K_LAYOUT, st, (vy_pack_kernel<<<grid, LY_NT, 0, st>>>(x, stride_b, stride_c, stride_t, B, C, T, H, W,
+                                                                     (__nv_bfloat16 *)y_p, 3 * Cpad, Cpad)));
+    VY_LAUNCH_CHECK("vy_pack_kernel");
+    return VY_OK;
+}
+
+// y[b][hp][wp][r*(T*C) + t*C + c] = x[t][b][hp][wp][c]: the 'cat' join (reshape (0,-3,-2), yolo3.py:1136) on P-layout
+// data, repeated `rep` times along the channels (rep = 2 feeds the split-weight prediction conv).  One thread per
+// 16-byte vector of the output; the zero border is copied with the rest.
+__global__ void vy_cat_repeat_kernel(const uint4 *__restrict__ x, long long frame8, int T, int C8, int rep, long long npix,
+                                     uint4 *__restrict__ y) {
+    const int Co8 = rep * T * C8;
+    const long long total = npix * Co8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % Co8);
+        const long long pix = i / Co8;
+        const int tc = v % (T * C8), t = tc / C8, c = tc - t * C8;
+        y[i] = x[(long long)t * frame8 + pix * C8 + c];
+    }
+}
+
+extern "C" int vy_cat_repeat_bf16(const void *x, int B, int T, int H, int W, int C, int rep, void *y, vy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x || !y || B < 1 || T < 1 || H < 1 || W < 1 || C < 1 || rep < 1) VY_FAIL(VY_EINVAL, "vy_cat_repeat_bf16: bad arguments");
+    if (C % 8 != 0 || (((uintptr_t)x | (uintptr_t)y) & 15) != 0)
+        VY_FAIL(VY_EALIGN, "vy_cat_repeat_bf16: C must be a multiple of 8 and x, y 16-byte aligned");
+    const long long npix = (long long)B * (H + 2) * (W + 2);
+    const long long total = npix * rep * T * (C / 8);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)vy_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    VY_KERNEL(VY_K_LAYOUT, st, (vy_cat_repeat_kernel<<<(unsigned)blocks, 256, 0, st>>>((const uint4 *)x, npix * (C / 8), T, C / 8, rep,
+                                                                                        npix, (uint4 *)y)));
+    VY_LAUNCH_CHECK("vy_cat_repeat_kernel");
     return VY_OK;
 }
 

@@ -50,6 +50,21 @@ struct SelPlan {
     int unit_begin[VY_MAX_SCALES + 1];
     int units_per_image;
     long long n_units;
+    // ---- tile streaming (stream2): every (b, scale, anchor) block of class planes is one contiguous array of C*HW
+    // floats, cut into tiles of S2_TILE bytes; the global tile sequence (b, s, a, t) is dealt to the CTAs in equal
+    // contiguous ranges.  The per-position logit bounds come from a table built by vy_decode_table_kernel.
+    int tiles_blk[VY_MAX_SCALES];           // tiles per (b, s, a) block
+    int tile_tpp[VY_MAX_SCALES];            // planes of >= S2_TILE bytes: tiles per plane (else 0)
+    int tile_ppt[VY_MAX_SCALES];            // smaller planes: whole planes per tile (else 0)
+    int tile_begin[VY_MAX_SCALES + 1];      // first tile of scale s within an image (order: s, a, t)
+    int tiles_per_image;
+    long long n_tiles;
+    int tab_hwp[VY_MAX_SCALES];             // floats per (s, a) table segment: HW + 3 wrap-around copies, rounded up to 4
+    int tab_off[VY_MAX_SCALES + 1];         // first float of scale s in an image's table
+    int tab_floats;                         // table floats per image (multiple of 4)
+    int tabblk_begin[VY_MAX_SCALES + 1];    // vy_decode_table_kernel: first CTA of scale s within an image
+    int tabblk_per_image;
+    int tab_max;                            // largest segment (floats)
 };
 
 struct SelGlobal {              // workspace views
@@ -64,13 +79,15 @@ struct SelGlobal {              // workspace views
     int Gs;
     u64 *slist;                 // [B][slist_cap]
     int slist_cap;
+    float *tab;                 // [B][tab_floats]  per-box logit bound of the tile-streaming pass
+    u64 *sthr;                  // [B]              the bound key the table was built for
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Gs == 0: no streaming-path arrays
 static size_t sel_workspace_layout(int B, int G, int list_cap, SelGlobal *g, void *base, size_t *header,
-                                   int Gs = 0, int slist_cap = 0) {
+                                   int Gs = 0, int slist_cap = 0, int tab_floats = 0) {
     size_t off = 0;
     const size_t o_thr = off;   off = align_up(off + sizeof(u64) * (size_t)B, 256);
     const size_t o_cnt = off;   off = align_up(off + sizeof(int) * (size_t)B, 256);
@@ -81,7 +98,11 @@ static size_t sel_workspace_layout(int B, int G, int list_cap, SelGlobal *g, voi
     if (header) *header = off;  // the part that must be zeroed per call
     const size_t o_list = off;  off = align_up(off + sizeof(u64) * (size_t)B * (size_t)list_cap, 256);
     const size_t o_slist = off; off = align_up(off + sizeof(u64) * (size_t)B * (size_t)slist_cap, 256);
+    const size_t o_tab = off;   off = align_up(off + sizeof(float) * (size_t)B * (size_t)tab_floats, 256);
+    const size_t o_sthr = off;  off = align_up(off + sizeof(u64) * (size_t)B * (tab_floats ? 1 : 0), 256);
     if (g && base) {
+        g->tab = tab_floats ? (float *)((char *)base + o_tab) : nullptr;
+        g->sthr = tab_floats ? (u64 *)((char *)base + o_sthr) : nullptr;
         g->thr = (u64 *)((char *)base + o_thr);
         g->count = (int *)((char *)base + o_cnt);
         g->slots = (u64 *)((char *)base + o_slot);
@@ -915,6 +936,456 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
         }
     }
     vy_grid_dep_trigger();                              // (a trigger at the start lets the dependents crowd the tail: measured slower)
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile streaming (the bandwidth pass, second generation).
+//
+//   vy_decode_table_kernel    per box the logit bound the streaming pass tests against: t_c >= logit(s_min / sigma(t_obj))
+//                             (vy_tcmin) for the image's bound s_min, as ONE table in global memory (4 bytes per box; it
+//                             stays in L2).  One thread per entry, after the sample kernel.  The old pass recomputed these
+//                             bounds in the prologue of every unit (objectness load, sigmoid, division, logarithm per 128
+//                             positions x ~27 planes): up to half of its instructions, and most of them at C = 30.
+//   vy_decode_stream2_kernel  every (b, scale, anchor) block of class planes is ONE contiguous array of C*HW floats
+//                             (channel a*P+5+c, yolo3.py:158-160).  It is cut into tiles of S2_TILE bytes; the global
+//                             tile sequence is dealt to the CTAs in equal contiguous ranges (each CTA streams ~one block's
+//                             worth of contiguous memory).  A producer warp brings tiles into a shared-memory ring with
+//                             1-D bulk copies (cp.async.bulk, one elected lane, mbarrier complete_tx) and, when the range
+//                             enters a new block, that block's slice of the table (same barrier).  Eight consumer warps test
+//                             float4 against float4 of the table (position = element index mod HW), queue the rare hits as
+//                             element indices and score them 32 at a time (str_hq-style), exactly as before.
+//                             Planes whose size is not a multiple of 4 floats (13^2, 19^2 grids) go through the same ring:
+//                             the copy starts at the 16-byte boundary below the tile and the consumers shift.
+// ------------------------------------------------------------------------------------------------
+#ifndef S2_TILE
+#define S2_TILE 24576                               // bytes per tile (one consumer warp tests a whole tile)
+#endif
+#ifndef S2_WARPS
+#define S2_WARPS 8                                  // consumer warps; ring stage s (tiles s, s + n_stages, ...) belongs to warp s
+#endif
+constexpr int S2_MAX_STAGES = S2_WARPS;             // ring depth is chosen at launch from the shared-memory budget (one warp per stage)
+constexpr int S2_NT = S2_WARPS * 32 + 32;           // + the producer warp
+constexpr int S2_STAGE_BYTES = S2_TILE + 256;       // a tile lands at the same offset inside a 128-byte line as its source (+ <= 12 bytes of shift)
+constexpr int S2_K = S2_TILE / 16 / 32;             // float4 per lane and tile
+static_assert(S2_K % 4 == 0 && S2_K < 64, "tile size");
+
+// what the producer tells the consumers about a tile: one 16-byte word
+//   x = e0      first element of the tile inside its (b, s, a) block (the hit path turns element indices into rows)
+//   y = n       floats in the tile
+//   z = zpos    position (inside its plane) of the tile's first element: 0 unless the plane is longer than a tile
+//   w = b:16 | s:2 | a:3 | tab:1 | tpar:1 | aligned:1 | shift:2 | tail:2 | doff:3
+//       tab / tpar = table buffer of the block and the parity of its load (what bar_tab completes); shift = floats in
+//       front of the tile in the stage (the copy starts at the 16-byte boundary below it); tail = floats of the tile that
+//       are NOT in the stage (the copy must not run past the end of the tensor: the last <= 3 floats of a tensor whose
+//       end is not 16-byte aligned); doff = 16-byte units between the stage base and the copy: source and destination of
+//       a bulk copy sit at the same offset inside their 128-byte lines
+constexpr u32 S2_BLK_MASK = 0x7fffffu;             // b, s, a, tab, tpar: equal for the tiles of one block
+struct S2Tile { int b, s, a, tab, tpar, aligned, shift, tail, doff; };
+__device__ __forceinline__ u32 s2_pack(const S2Tile &t) {
+    return (u32)t.b | ((u32)t.s << 16) | ((u32)t.a << 18) | ((u32)t.tab << 21) | ((u32)t.tpar << 22) |
+           ((u32)t.aligned << 23) | ((u32)t.shift << 24) | ((u32)t.tail << 26) | ((u32)t.doff << 28);
+}
+
+__device__ __forceinline__ u32 s2_smem(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void s2_mbar_init(u64 *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(s2_smem(bar)), "r"(count) : "memory");
+}
+// (a wait that has not come true after ~2^24 polls -- seconds -- is a protocol error: trap instead of hanging the device)
+__device__ __forceinline__ void s2_mbar_wait(u64 *bar, u32 parity) {
+    u32 ok = 0, spins = 0;
+    const u32 a = s2_smem(bar);
+    while (!ok) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void s2_mbar_arrive(u64 *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(s2_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void s2_mbar_expect(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(s2_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void s2_bulk(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(s2_smem(dst)), "l"(src), "r"(bytes), "r"(s2_smem(bar)) : "memory");
+}
+
+constexpr int TAB_PER_CTA = 1024;                   // table entries per CTA (4 per thread), all of one (b, s, a) segment
+__global__ void __launch_bounds__(256)
+vy_decode_table_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl, SelGlobal g) {
+    // block -> (image, scale, anchor, chunk of the segment): small loops and one division per CTA, none per entry
+    const int b = blockIdx.x / pl.tabblk_per_image;
+    int r = blockIdx.x - b * pl.tabblk_per_image;
+    int s = 0;
+    while (s + 1 < hd.n_scales && r >= pl.tabblk_begin[s + 1]) ++s;
+    r -= pl.tabblk_begin[s];
+    const int bps = (pl.tab_hwp[s] + TAB_PER_CTA - 1) / TAB_PER_CTA;
+    const int a = r / bps, chunk = r - a * bps;
+    const VyScale &sc = hd.sc[s];
+    const int HW = sc.HW, hwp = pl.tab_hwp[s];
+    const float *obj = sc.head + ((size_t)(b * hd.A + a) * hd.P + 4) * (size_t)HW;
+    float *out = g.tab + (size_t)b * pl.tab_floats + pl.tab_off[s] + (size_t)a * hwp;
+    float to[TAB_PER_CTA / 256];
+#pragma unroll
+    for (int k = 0; k < TAB_PER_CTA / 256; ++k) {         // the head maps do not depend on the sample kernel: load first
+        int pos = chunk * TAB_PER_CTA + k * 256 + threadIdx.x;
+        if (pos >= HW) pos -= HW;                         // entries HW .. HW+2 repeat 0 .. 2 (a shifted float4 may wrap)
+        to[k] = pos < HW ? vy_ldg32(obj + pos) : 0.0f;
+    }
+    vy_grid_dep_wait();                                   // the sample kernel's bounds
+    // the image's bound = minimum over its sample jobs (kept as complements): every warp reduces the <= 32 slots itself
+    u64 m = (threadIdx.x & 31) < g.Gs ? g.sslots[(size_t)b * g.Gs + (threadIdx.x & 31)] : 0ull;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { const u64 o = sel_shfl_xor_u64(m, off); m = o > m ? o : m; }
+    const u64 thr = ~m;
+    const float smin = fmaxf(thr ? vy_key_score(thr) : pl.valid_thresh, pl.valid_thresh);
+#pragma unroll
+    for (int k = 0; k < TAB_PER_CTA / 256; ++k) {
+        const int pos = chunk * TAB_PER_CTA + k * 256 + threadIdx.x;
+        if (pos < hwp) out[pos] = pos < HW + 3 ? vy_tcmin(smin, vy_sigmoid(to[k])) : CUDART_INF_F;   // (padding can never pass)
+    }
+    if (blockIdx.x == b * pl.tabblk_per_image && threadIdx.x == 0) g.sthr[b] = thr;
+    vy_grid_dep_trigger();
+}
+
+// score up to 32 queued hits, one per lane (entry = element index inside the block named by the metadata word w),
+// survivors -> wbuf -> image list.  Everything about the block is worked out HERE, on the rare path.
+__device__ __forceinline__ void s2_score(const VyHeads &hd, float valid_thresh, u32 w, const u32 *hq, int n, u64 *wbuf,
+                                         int &cnt, const SelGlobal &g, int lane, u32 lt_mask) {
+    const int b = (int)(w & 0xffffu), s = (int)((w >> 16) & 3u), a = (int)((w >> 18) & 7u);
+    const VyScale &sc = hd.sc[s];
+    const u32 HW = (u32)sc.HW;
+    const float *pc0 = sc.head + ((size_t)(b * hd.A + a) * hd.P + 5) * (size_t)HW;       // class plane 0 of the block
+    bool ok = false;
+    u64 key = 0;
+    if (lane < n) {
+        const u32 e = hq[lane];
+        const u32 plane = e / HW, pos = e - plane * HW;
+        const float tv = vy_ldg32(pc0 + e);
+        const float to = vy_ldg32(pc0 + pos - HW);                   // the objectness plane sits right below class plane 0
+        const float sv = vy_score(tv, vy_sigmoid(to));
+        if (sv > valid_thresh) {
+            key = vy_make_key(sv, (u32)(sc.row_off + a) + plane * (u32)sc.n_s + pos * (u32)hd.A);
+            ok = key >= g.sthr[b];
+        }
+    }
+    const u32 bal = __ballot_sync(0xffffffffu, ok);
+    if (bal) {
+        if (ok) wbuf[cnt + __popc(bal & lt_mask)] = key;
+        cnt += __popc(bal);
+        __syncwarp();
+        if (cnt >= 32) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(g.scount + b, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const u64 k0 = wbuf[lane], k1 = wbuf[32 + lane];
+            if (base + lane < g.slist_cap) g.slist[(size_t)b * g.slist_cap + base + lane] = k0;
+            __syncwarp();
+            wbuf[lane] = k1;
+            cnt -= 32;
+            __syncwarp();
+        }
+    }
+}
+// queue the elements of every lane's flagged float4 (bit k = float4 k of the lane = elements ebase + k*estep + 0..3 of the
+// block; those outside [e0, e0 + n) -- a shifted tile's first / last float4 -- are dropped); warp-uniform entry.  The scorer
+// recomputes every queued element's score exactly, so the three elements of a float4 that did not pass cost a lookup each
+// and nothing else.  (returns qn | cnt << 16: the two counters live in registers of the caller)
+__device__ __noinline__ int s2_push(const VyHeads &hd, float valid_thresh, u32 w, u64 mask, u32 ebase, u32 estep, u32 e0, int n,
+                                    u32 *hq, int qn, u64 *wbuf, int cnt, const SelGlobal &g) {
+    const int lane = threadIdx.x & 31;
+    const u32 lt_mask = (1u << lane) - 1u;
+    u32 left = __ballot_sync(0xffffffffu, mask != 0ull);
+    while (left) {
+        u32 eb = 0;
+        if (mask) {
+            const int k = __ffsll((long long)mask) - 1;
+            mask &= mask - 1;
+            eb = ebase + (u32)k * estep;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            // element eb + q of lanes that hold a flagged float4 this round (inside the tile: an unsigned compare)
+            const bool in = ((left >> lane) & 1u) && (eb + (u32)q - e0) < (u32)n;
+            const u32 bal = __ballot_sync(0xffffffffu, in);
+            if (in) hq[qn + __popc(bal & lt_mask)] = eb + (u32)q;
+            qn += __popc(bal);
+            __syncwarp();
+            if (qn >= 32) {
+                s2_score(hd, valid_thresh, w, hq, 32, wbuf, cnt, g, lane, lt_mask);
+                const u32 rest = hq[32 + lane];
+                __syncwarp();
+                hq[lane] = rest;
+                qn -= 32;
+                __syncwarp();
+            }
+        }
+        left = __ballot_sync(0xffffffffu, mask != 0ull);
+    }
+    return qn | (cnt << 16);
+}
+// end of a block: score what is still queued, hand the warp's keys to the image's list
+__device__ __noinline__ void s2_flush(const VyHeads &hd, float valid_thresh, u32 w, u32 *hq, int qn, u64 *wbuf, int cnt,
+                                      const SelGlobal &g) {
+    const int lane = threadIdx.x & 31;
+    const u32 lt_mask = (1u << lane) - 1u;
+    if (qn > 0) { s2_score(hd, valid_thresh, w, hq, qn, wbuf, cnt, g, lane, lt_mask); qn = 0; }
+    if (cnt > 0) {
+        const int b = (int)(w & 0xffffu);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(g.scount + b, cnt);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < cnt && base + lane < g.slist_cap) g.slist[(size_t)b * g.slist_cap + base + lane] = wbuf[lane];
+        __syncwarp();
+    }
+}
+
+// One CTA per SM (its ring and two table buffers take ~150 KB), but registers capped as if two were resident: a
+// finalize or sample CTA of a neighbouring stream still fits beside it.
+//   barriers   full[stage]   the tile's bytes have landed (producer: expect_tx; waited for by the owning warp)
+//              empty[stage]  the owning warp has tested the tile (one arrival)
+//              tab[buf]      the block's table slice has landed in buffer buf (producer: expect_tx; every warp waits for
+//                            it once per block it meets)
+//   A table buffer is reused by the block after next.  Tiles are issued in order and issuing tile i waits for the release
+//   of tile i - n_stages, so when tile i goes out every tile <= i - n_stages has been tested; the producer waits for the
+//   last tile of the buffer's previous block explicitly only when that is more recent (runs of one-tile blocks).
+__global__ void __launch_bounds__(S2_NT, 2)
+vy_decode_stream2_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl,
+                         const __grid_constant__ SelGlobal g, int n_stages) {
+    extern __shared__ __align__(128) unsigned char s2_dyn[];          // ring [n_stages][S2_STAGE_BYTES], tables [2][tab_max]
+    __shared__ __align__(8) u64 bar_full[S2_MAX_STAGES], bar_empty[S2_MAX_STAGES], bar_tab[2];
+    __shared__ int4 meta[S2_MAX_STAGES];
+    __shared__ u64 wbuf_all[S2_WARPS][64];
+    __shared__ u32 hq_all[S2_WARPS][STR_HQ];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned char *ring = s2_dyn;
+    float *tabs = (float *)(s2_dyn + (size_t)n_stages * S2_STAGE_BYTES);
+    if (tid == 0) {
+        for (int i = 0; i < n_stages; ++i) { s2_mbar_init(&bar_full[i], 1); s2_mbar_init(&bar_empty[i], 1); }
+        s2_mbar_init(&bar_tab[0], 1); s2_mbar_init(&bar_tab[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long t_begin = pl.n_tiles * (long long)blockIdx.x / gridDim.x;
+    const long long t_end = pl.n_tiles * (long long)(blockIdx.x + 1) / gridDim.x;
+    const int n_mine = (int)(t_end - t_begin);
+    vy_grid_dep_wait();                                   // the table (and through it the sample's bounds)
+
+    if (wid == S2_WARPS) {
+        // ------------------------------------------------------------------ producer warp
+        // A batch = 32 consecutive tiles, one per lane.  The lanes work out their tiles side by side (the integer
+        // divisions of the decode cost one lane as much as 32) and keep the descriptors in registers; then the tiles are
+        // issued in order, each by its own lane: wait for the stage, one 16-byte word of metadata, expect_tx, bulk copy
+        // (+ the block's table slice).  The ring covers the pause of the next batch's decode.
+        const int b0 = (int)(t_begin / pl.tiles_per_image);
+        const int r0 = (int)(t_begin - (long long)b0 * pl.tiles_per_image);
+        int blocks_before = 0;                            // blocks this CTA's range has entered so far
+        int carry1 = 0, carry2 = 0;                       // first tiles of the two most recent blocks entered before this batch
+        for (int i0 = 0; i0 < n_mine; i0 += 32) {
+            const int it = i0 + lane;                     // tile index inside the CTA's range
+            const bool act = it < n_mine;
+            int b = b0, s = 0, a = 0, t = 0;
+            if (act) {
+                int r = r0 + it;
+                const int db = r / pl.tiles_per_image;
+                b += db; r -= db * pl.tiles_per_image;
+                while (s + 1 < hd.n_scales && r >= pl.tile_begin[s + 1]) ++s;
+                r -= pl.tile_begin[s];
+                a = r / pl.tiles_blk[s]; t = r - a * pl.tiles_blk[s];
+            }
+            const bool first = act && (t == 0 || it == 0);
+            const u32 fb = __ballot_sync(0xffffffffu, first);
+            const u32 below = fb & ((1u << lane) - 1u);
+            const int ord = blocks_before + __popc(below) + (first ? 1 : 0) - 1;      // which block of the range this tile is in
+            // first tiles of the two blocks BEFORE this lane's (meaningful for a `first` lane): the block before last
+            // [p2, p1) used this lane's table buffer before
+            int p1 = carry1, p2 = carry2;
+            if (below) {
+                p1 = i0 + 31 - __clz(below);
+                const u32 below2 = below & ~(0x80000000u >> __clz(below));
+                p2 = below2 ? i0 + 31 - __clz(below2) : carry1;
+            }
+            if (fb) {
+                const u32 fb2 = fb & ~(0x80000000u >> __clz(fb));
+                carry2 = fb2 ? i0 + 31 - __clz(fb2) : carry1;
+                carry1 = i0 + 31 - __clz(fb);
+            }
+            blocks_before += __popc(fb);
+            const VyScale &sc = hd.sc[s];
+            int e0, n, zpos;
+            if (pl.tile_tpp[s] > 0) {                     // long planes: tiles inside one plane
+                const int c = t / pl.tile_tpp[s], part = t - c * pl.tile_tpp[s];
+                zpos = part * (S2_TILE / 4);
+                e0 = c * sc.HW + zpos;
+                n = min(S2_TILE / 4, sc.HW - zpos);
+            } else {                                      // whole planes per tile
+                const int c0 = t * pl.tile_ppt[s];
+                zpos = 0;
+                e0 = c0 * sc.HW;
+                n = min(pl.tile_ppt[s], hd.C - c0) * sc.HW;
+            }
+            const float *src = sc.head + ((size_t)(b * hd.A + a) * hd.P + 5) * (size_t)sc.HW + e0;
+            const uintptr_t addr = (uintptr_t)src;
+            S2Tile ti;
+            ti.b = b; ti.s = s; ti.a = a; ti.tab = ord & 1; ti.tpar = (ord >> 1) & 1;
+            ti.shift = (int)((addr & 15) >> 2);
+            const uintptr_t src_al = addr - (uintptr_t)ti.shift * 4;
+            ti.doff = (int)((src_al & 127) >> 4);
+            long long bytes = ((long long)(ti.shift + n) * 4 + 15) & ~15LL;
+            const uintptr_t end_al = ((uintptr_t)(sc.head + (size_t)hd.B * hd.A * hd.P * (size_t)sc.HW)) & ~(uintptr_t)15;
+            if (src_al + (uintptr_t)bytes > end_al) bytes = end_al > src_al ? (long long)(end_al - src_al) : 0;
+            int n_smem = (int)(bytes / 4) - ti.shift;
+            n_smem = n_smem < 0 ? 0 : (n_smem > n ? n : n_smem);
+            ti.tail = n - n_smem;                         // <= 3
+            ti.aligned = (ti.shift == 0 && (sc.HW & 3) == 0) ? 1 : 0;
+            const int4 word = make_int4(e0, n, zpos, (int)s2_pack(ti));
+            const u32 tbytes = (u32)pl.tab_hwp[s] * 4u;
+            const float *tsrc = g.tab + (size_t)b * pl.tab_floats + pl.tab_off[s] + (size_t)a * pl.tab_hwp[s];
+            const int stage = it % n_stages, round = it / n_stages;
+            const u32 dst = s2_smem(ring + (size_t)stage * S2_STAGE_BYTES + ti.doff * 16);
+            const u32 tdst = s2_smem(tabs + (size_t)ti.tab * pl.tab_max);
+            // the table buffer's previous block (ord - 2) = tiles [p2, p1): those of the last ring round may still be under
+            // test (tiles are tested by different warps, in any order), everything older has been released
+            const int tw_lo = max(p2, it - n_stages + 1), tw_hi = (first && ord >= 2) ? p1 : 0;
+            const int n_batch = min(32, n_mine - i0);
+            for (int i = 0; i < n_batch; ++i) {           // in tile order
+                if (lane == i) {
+                    if (round > 0) s2_mbar_wait(&bar_empty[stage], (u32)((round - 1) & 1));
+                    for (int tw = tw_lo; tw < tw_hi; ++tw) s2_mbar_wait(&bar_empty[tw % n_stages], (u32)((tw / n_stages) & 1));
+                    if (first) {
+                        s2_mbar_expect(&bar_tab[ti.tab], tbytes);
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     :: "r"(tdst), "l"(tsrc), "r"(tbytes), "r"(s2_smem(&bar_tab[ti.tab])) : "memory");
+                    }
+                    meta[stage] = word;
+                    s2_mbar_expect(&bar_full[stage], (u32)bytes);
+                    if (bytes)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     :: "r"(dst), "l"((const void *)src_al), "r"((u32)bytes), "r"(s2_smem(&bar_full[stage])) : "memory");
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ consumer warps
+        // Warp `wid` owns ring stage `wid`, i.e. tiles wid, wid + n_stages, ... of the range, whole (a stage's rounds must be
+        // waited for in order by ONE warp: a parity wait cannot tell round r from round r - 2): lane l tests float4 l,
+        // l + 32, ... of a tile.
+        // Where those sit in the block's table: tiles start at position 0 of a plane (or -- planes longer than a tile --
+        // at zpos), so the first index is the same for every tile of a block and the rest follow by adding 32 (mod the
+        // plane size).
+        const u32 lt_mask = (1u << lane) - 1u;
+        u64 *wbuf = wbuf_all[wid];
+        u32 *hq = hq_all[wid];
+        int qn = 0, cnt = 0;
+        const float valid_thresh = pl.valid_thresh;
+        const int tab_max = pl.tab_max;
+        u32 cur_w = 0xffffffffu;                          // metadata word of the block this warp is in
+        int idx0 = 0, plane = 4;                          // first table index of this lane; plane size (float4, or floats when shifted)
+        const int stage = wid;
+        u32 phase = 0;
+        for (int it = wid; it < n_mine && wid < n_stages; it += n_stages, phase ^= 1u) {
+            s2_mbar_wait(&bar_full[stage], phase);
+            const int4 word = meta[stage];
+            const u32 w = (u32)word.w;
+            const int n = word.y;
+            if ((w ^ cur_w) & S2_BLK_MASK) {              // the warp enters another block
+                if (qn > 0 || cnt > 0) { s2_flush(hd, valid_thresh, cur_w, hq, qn, wbuf, cnt, g); qn = 0; cnt = 0; }
+                s2_mbar_wait(&bar_tab[(w >> 21) & 1u], (w >> 22) & 1u);
+                const int HW = hd.sc[(w >> 16) & 3u].HW;
+                if ((w >> 23) & 1u) { plane = HW >> 2; idx0 = lane % plane; }
+                else { plane = HW; idx0 = (4 * lane) % plane; }
+            }
+            cur_w = w;
+            const float *tab = tabs + ((w >> 21) & 1u) * tab_max;
+            const unsigned char *st = ring + (size_t)stage * S2_STAGE_BYTES + (w >> 28) * 16;
+            u64 hits = 0;                                 // bit k: this lane's float4 k has an element at or above its bound
+#ifndef S2_DBG_NOCOMPARE
+            if ((w >> 23) & 1u) {
+                // aligned: float4 of the tile against float4 of the table
+                const int nf4 = n >> 2;
+                const float4 *d4 = (const float4 *)st + lane;
+                const float4 *t4 = (const float4 *)tab + (word.z >> 2);
+                const int step = 32 % plane;
+                int idx = idx0;
+                const int kmax = (nf4 + 31) >> 5;         // float4 rows of 32 lanes in this tile (<= S2_K)
+                // four rows at a time: the eight loads first, then branch-free compares.  Rows past the end of the tile
+                // are read all the same (stale bytes of the stage, a valid table index) and masked out.
+                for (int k0 = 0; k0 < kmax; k0 += 4) {
+                    float4 v[4], t[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        v[u] = d4[32 * (k0 + u)];
+                        t[u] = t4[idx];
+                        idx += step;
+                        if (idx >= plane) idx -= plane;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        u32 h;
+                        asm("{\n\t.reg .pred p;\n\t"
+                            "setp.ge.f32 p, %1, %5;\n\t"
+                            "setp.ge.or.f32 p, %2, %6, p;\n\t"
+                            "setp.ge.or.f32 p, %3, %7, p;\n\t"
+                            "setp.ge.or.f32 p, %4, %8, p;\n\t"
+                            "selp.u32 %0, 1, 0, p;\n\t}"
+                            : "=r"(h) : "f"(v[u].x), "f"(v[u].y), "f"(v[u].z), "f"(v[u].w), "f"(t[u].x), "f"(t[u].y), "f"(t[u].z), "f"(t[u].w));
+                        h &= (lane + 32 * (k0 + u) < nf4) ? 1u : 0u;
+                        hits |= (u64)h << (k0 + u);
+                    }
+                }
+            } else {
+                // shifted / odd plane size: stage float (shift + el) is element e0 + el of the block
+                const int shift = (int)((w >> 24) & 3u), n_smem = n - (int)((w >> 26) & 3u);
+                const int nf4 = (shift + n + 3) >> 2;
+                const float4 *d4 = (const float4 *)st;
+                const float *pc0e = nullptr;
+                if (n_smem < n) {
+                    const int b = (int)(w & 0xffffu), a = (int)((w >> 18) & 7u);
+                    pc0e = hd.sc[(w >> 16) & 3u].head + ((size_t)(b * hd.A + a) * hd.P + 5) * (size_t)plane + word.x;
+                }
+                const int step = 128 % plane;
+                int pb = idx0 + word.z - shift;           // position of stage float 4*lane (zpos > 0 only in planes longer than a tile)
+                if (pb < 0) pb += plane;
+                if (pb >= plane) pb -= plane;
+                const int kmax = (nf4 + 31) >> 5;
+                for (int k = 0; k < kmax; ++k) {
+                    const int j = lane + 32 * k;
+                    const float4 v4 = d4[j];              // (rows past the end: stale bytes of the stage, masked below)
+                    const float t0 = tab[pb], t1 = tab[pb + 1], t2 = tab[pb + 2], t3 = tab[pb + 3];
+                    const int el = 4 * j - shift;         // element of v4.x
+                    float x0 = v4.x, x1 = v4.y, x2 = v4.z, x3 = v4.w;
+                    if (n_smem < n) {                     // the tensor's last <= 3 floats are not in the stage
+                        if (el >= n_smem && el < n) x0 = vy_ldg32(pc0e + el);
+                        if (el + 1 >= n_smem && el + 1 < n) x1 = vy_ldg32(pc0e + el + 1);
+                        if (el + 2 >= n_smem && el + 2 < n) x2 = vy_ldg32(pc0e + el + 2);
+                        if (el + 3 >= n_smem && el + 3 < n) x3 = vy_ldg32(pc0e + el + 3);
+                    }
+                    const u32 h = ((x0 >= t0) & (el >= 0) & (el < n)) | ((x1 >= t1) & (el + 1 >= 0) & (el + 1 < n)) |
+                                  ((x2 >= t2) & (el + 2 >= 0) & (el + 2 < n)) | ((x3 >= t3) & (el + 3 >= 0) & (el + 3 < n));
+                    hits |= (u64)(h & 1u) << k;
+                    pb += step;
+                    if (pb >= plane) pb -= plane;
+                }
+            }
+#endif
+            // the stage is free as soon as it has been TESTED: hand it back before looking after the hits -- scoring them is
+            // a round trip to L2 that must not hold up the ring
+            __syncwarp();
+            if (lane == 0) s2_mbar_arrive(&bar_empty[stage]);
+            if (__any_sync(0xffffffffu, hits != 0ull)) {
+                // rare: which elements of the flagged float4 passed is worked out from global memory by the scorer, which
+                // takes ELEMENT indices: queue all four elements of a flagged float4 (the scorer drops what fails)
+                const int shift = ((w >> 23) & 1u) ? 0 : (int)((w >> 24) & 3u);
+                const int r = s2_push(hd, valid_thresh, w, hits, (u32)(word.x + 4 * lane - shift), 128u, (u32)word.x, n, hq, qn,
+                                      wbuf, cnt, g);
+                qn = r & 0xffff; cnt = r >> 16;
+            }
+        }
+        if (qn > 0 || cnt > 0) s2_flush(hd, valid_thresh, cur_w, hq, qn, wbuf, cnt, g);
+    }
+    vy_grid_dep_trigger();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1760,6 +2231,7 @@ static int plan_heads(const VyHeads &hd, int topk, float valid_thresh, SelPlan *
 static void plan_stream(const VyHeads &hd, SelPlan *pl) {
     pl->stream = 0;
     if (hd.agnostic || hd.R < 131072 || hd.C < 1) return;
+    if (hd.B > 0xffff || hd.A > 8 || hd.n_scales > 4) return;             // fields of the tile-streaming pass's metadata word
     // sampled fraction 1/S
     long long S = hd.R / (40LL * pl->K);
     if (S < 4) return;
@@ -1837,7 +2309,52 @@ static void plan_stream(const VyHeads &hd, SelPlan *pl) {
     for (int s = hd.n_scales; s <= VY_MAX_SCALES; ++s) pl->unit_begin[s] = units;
     pl->units_per_image = units;
     pl->n_units = (long long)units * hd.B;
+    // tile streaming: tiles per block, table segments
+    int tiles = 0, tf = 0;
+    pl->tab_max = 0;
+    for (int s = 0; s < hd.n_scales; ++s) {
+        // a tile never starts in the middle of a plane unless the plane is longer than a tile (then at multiples of
+        // the tile size): the table index of a lane's elements is then the same for every tile of a block
+        const int TF = S2_TILE / 4, HWs = hd.sc[s].HW;
+        if (HWs >= TF) {
+            pl->tile_tpp[s] = (HWs + TF - 1) / TF; pl->tile_ppt[s] = 0;
+            pl->tiles_blk[s] = hd.C * pl->tile_tpp[s];
+        } else {
+            pl->tile_tpp[s] = 0; pl->tile_ppt[s] = TF / HWs;
+            pl->tiles_blk[s] = (hd.C + pl->tile_ppt[s] - 1) / pl->tile_ppt[s];
+        }
+        pl->tile_begin[s] = tiles;
+        tiles += pl->tiles_blk[s] * hd.A;
+        pl->tab_hwp[s] = (hd.sc[s].HW + 3 + 3) & ~3;
+        pl->tab_off[s] = tf;
+        tf += pl->tab_hwp[s] * hd.A;
+        if (pl->tab_hwp[s] > pl->tab_max) pl->tab_max = pl->tab_hwp[s];
+    }
+    for (int s = hd.n_scales; s <= VY_MAX_SCALES; ++s) { pl->tile_begin[s] = tiles; pl->tab_off[s] = tf; }
+    int tb = 0;
+    for (int s = 0; s < hd.n_scales; ++s) {
+        pl->tabblk_begin[s] = tb;
+        tb += hd.A * ((pl->tab_hwp[s] + TAB_PER_CTA - 1) / TAB_PER_CTA);
+    }
+    for (int s = hd.n_scales; s <= VY_MAX_SCALES; ++s) pl->tabblk_begin[s] = tb;
+    pl->tabblk_per_image = tb;
+    pl->tiles_per_image = tiles;
+    pl->n_tiles = (long long)tiles * hd.B;
+    pl->tab_floats = tf;
     pl->stream = 1;
+}
+
+// ring depth and dynamic shared memory of the tile-streaming kernel: the ring gets what the two table buffers leave of
+// the budget (VY_S2_SMEM_KB, default 150 KB: a finalize / sample CTA of a neighbouring stream still fits on the SM)
+static int stream2_stages(const SelPlan &pl, size_t *dyn_bytes) {
+    static const int budget_kb = getenv("VY_S2_SMEM_KB") ? atoi(getenv("VY_S2_SMEM_KB")) : 200;
+    const size_t tabs = 2 * (size_t)pl.tab_max * sizeof(float);
+    const size_t budget = (size_t)(budget_kb < 48 ? 48 : (budget_kb > 210 ? 210 : budget_kb)) << 10;
+    long long n = budget > tabs ? (long long)((budget - tabs) / S2_STAGE_BYTES) : 0;
+    if (n > S2_MAX_STAGES) n = S2_MAX_STAGES;
+    if (n < 2) n = 2;
+    if (dyn_bytes) *dyn_bytes = (size_t)n * S2_STAGE_BYTES + tabs;
+    return (int)n;
 }
 
 // keys per image in the streamed list: 4x the expected K*S, never more than the image has rows
@@ -1883,73 +2400,97 @@ static int launch_finalize(const VyHeads &hd, const RowParams &rp, const SelPlan
         fp.thr_lo = -INFINITY;
         fp.thr_hi = INFINITY;
     }
-    VY_CUDA_CHECK(cudaFuncSetAttribute(vy_nms_finalize_kernel<SRC>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    VY_CUDA_CHECK(vy_ensure_dyn_smem((const void *)vy_nms_finalize_kernel<SRC>, dyn));
     VY_KERNEL(VY_K_FINALIZE, st, (vy_launch(vy_nms_finalize_kernel<SRC>, dim3(B), dim3(fin_nt), dyn, st, true, hd, rp, pl, g, fp)));
     VY_LAUNCH_CHECK("vy_nms_finalize_kernel");
     return VY_OK;
 }
 
-extern "C" size_t vy_decode_nms_workspace_bytes(const int *H, const int *W, int n_scales, int B, int A,
-                                                int C, int agnostic, int topk) {
-    VyHeads hd;
-    const float *fake[VY_MAX_SCALES] = {nullptr, nullptr, nullptr, nullptr};
-    float st[VY_MAX_SCALES] = {1, 1, 1, 1};
-    float an[VY_MAX_SCALES * VY_MAX_ANCHORS * 2] = {0};
-    if (vy_fill_heads(&hd, fake, H, W, st, an, n_scales, B, A, C, agnostic) != VY_OK) return 0;
+// ------------------------------------------------------------------------------------------------
+// plan handle of the fused path: everything that depends only on the shapes and arguments -- head description, job /
+// tile / table plan, workspace layout -- is resolved once; a launch fills in the pointers and enqueues the kernels.
+// ------------------------------------------------------------------------------------------------
+struct vy_decode_nms_plan {
+    VyHeads hd;                  // head pointers null; vec decided per launch from the real pointers
     SelPlan pl;
-    if (plan_heads(hd, topk, 0.0f, &pl) != VY_OK) { vy_set_error("topk out of range for the fused path"); return 0; }
-    return sel_workspace_layout(B, pl.G, pl.list_cap, nullptr, nullptr, nullptr, pl.stream ? pl.Gs : 0,
-                                pl.stream ? stream_list_cap(hd, pl) : 0);
+    int slist_cap;
+    size_t ws_bytes, header;
+    float overlap_thresh;
+    int force_suppress, post_nms, topk;
+};
+
+static int plan_init(vy_decode_nms_plan *P, const int *H, const int *W, const float *stride, const float *anchors,
+                     int n_scales, int B, int A, int C, int agnostic, float overlap_thresh, float valid_thresh, int topk,
+                     int force_suppress, int post_nms) {
+    const float *fake[VY_MAX_SCALES] = {nullptr, nullptr, nullptr, nullptr};
+    int rc = vy_fill_heads(&P->hd, fake, H, W, stride, anchors, n_scales, B, A, C, agnostic);
+    if (rc != VY_OK) return rc;
+    if (post_nms < 1) VY_FAIL(VY_EINVAL, "vy_decode_nms: post_nms must be >= 1");
+    rc = plan_heads(P->hd, topk, valid_thresh, &P->pl);
+    if (rc != VY_OK) VY_FAIL(rc, "vy_decode_nms: min(topk,R)=%d outside [1,%d]; use vy_decode_f32 + vy_box_nms_f32",
+                             topk, SEL_KMAX);
+    P->slist_cap = P->pl.stream ? stream_list_cap(P->hd, P->pl) : 0;
+    P->ws_bytes = sel_workspace_layout(B, P->pl.G, P->pl.list_cap, nullptr, nullptr, &P->header, P->pl.stream ? P->pl.Gs : 0,
+                                       P->slist_cap, P->pl.stream ? P->pl.tab_floats : 0);
+    P->overlap_thresh = overlap_thresh; P->force_suppress = force_suppress; P->post_nms = post_nms; P->topk = topk;
+    return VY_OK;
 }
 
-extern "C" int vy_decode_nms_f32(const float *const *head, const int *H, const int *W, const float *stride,
-                                 const float *anchors, int n_scales, int B, int A, int C, int agnostic,
-                                 float overlap_thresh, float valid_thresh, int topk, int force_suppress,
-                                 int post_nms, float *out, int32_t *kept_rows, void *workspace,
-                                 size_t workspace_bytes, vy_stream_t stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    VyHeads hd;
-    int rc = vy_fill_heads(&hd, head, H, W, stride, anchors, n_scales, B, A, C, agnostic);
-    if (rc != VY_OK) return rc;
-    if (post_nms < 1 || !out) VY_FAIL(VY_EINVAL, "vy_decode_nms_f32: post_nms must be >= 1 and out non-null");
-    SelPlan pl;
-    rc = plan_heads(hd, topk, valid_thresh, &pl);
-    if (rc != VY_OK) VY_FAIL(rc, "vy_decode_nms_f32: min(topk,R)=%d outside [1,%d]; use vy_decode_f32 + vy_box_nms_f32",
-                             topk, SEL_KMAX);
-    SelGlobal g;
-    size_t header = 0;
-    const size_t need = sel_workspace_layout(B, pl.G, pl.list_cap, &g, workspace, &header, pl.stream ? pl.Gs : 0,
-                                             pl.stream ? stream_list_cap(hd, pl) : 0);
-    if (!workspace || workspace_bytes < need)
-        VY_FAIL(VY_EWORKSPACE, "vy_decode_nms_f32: workspace %zu < %zu bytes", workspace_bytes, need);
+static int plan_launch(const vy_decode_nms_plan *P, const float *const *head, float *out, int32_t *kept_rows,
+                       void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (!out) VY_FAIL(VY_EINVAL, "vy_decode_nms: out is null");
+    if (!workspace || workspace_bytes < P->ws_bytes)
+        VY_FAIL(VY_EWORKSPACE, "vy_decode_nms: workspace %zu < %zu bytes", workspace_bytes, P->ws_bytes);
     if (((uintptr_t)workspace & 255) != 0) VY_FAIL(VY_EALIGN, "workspace must be 256-byte aligned");
-    for (int s = 0; s < n_scales; ++s)
-        if (!head[s]) VY_FAIL(VY_EINVAL, "vy_decode_nms_f32: head[%d] is null", s);
-    if (!pl.stream) VY_CUDA_CHECK(cudaMemsetAsync(workspace, 0, header, st));     // (the sample kernel zeroes its images' state itself)
+    VyHeads hd = P->hd;
+    const SelPlan &pl = P->pl;
+    const int B = hd.B;
+    for (int s = 0; s < hd.n_scales; ++s) {
+        if (!head || !head[s]) VY_FAIL(VY_EINVAL, "vy_decode_nms: head[%d] is null", s);
+        if (((uintptr_t)head[s] & 3) != 0) VY_FAIL(VY_EALIGN, "head[%d] not 4-byte aligned", s);
+        hd.sc[s].head = head[s];
+        hd.sc[s].vec = (hd.sc[s].HW % 4 == 0 && (((uintptr_t)head[s]) & 15) == 0) ? 4 : 1;
+    }
+    SelGlobal g;
+    sel_workspace_layout(B, pl.G, pl.list_cap, &g, workspace, nullptr, pl.stream ? pl.Gs : 0, P->slist_cap,
+                         pl.stream ? pl.tab_floats : 0);
+    if (!pl.stream) VY_CUDA_CHECK(cudaMemsetAsync(workspace, 0, P->header, st));     // (the sample kernel zeroes its images' state itself)
     if (pl.stream) {
         VY_KERNEL(VY_K_SAMPLE, st, (vy_decode_sample_kernel<<<B * pl.Gs, SAMP_NT, 0, st>>>(hd, pl, g)));
         VY_LAUNCH_CHECK("vy_decode_sample_kernel");
-        long long ctas = (pl.n_units + STR_NT / 32 - 1) / (STR_NT / 32);
-        const long long resident = (long long)STR_CTAS_PER_SM * vy_sm_count();
-        if (ctas > resident) ctas = resident;
-        // PDL on this launch only in the latency regime (grid below one wave): on a full machine the early
-        // CTAs crowd the sample kernel's tail (measured: -4 % at COCO 608 x 64, +15 % at VOC 416 x 1)
-        const size_t ring_bytes = (size_t)(STR_NT / 32) * STR_RING * 32 * sizeof(float4);
-        VY_CUDA_CHECK(cudaFuncSetAttribute(vy_decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
-        VY_KERNEL(VY_K_STREAM, st, (vy_launch(vy_decode_stream_kernel, dim3((unsigned)ctas), dim3(STR_NT), ring_bytes, st, ctas < resident, hd, pl, g)));
-        VY_LAUNCH_CHECK("vy_decode_stream_kernel");
+        static const bool stream_v1 = getenv("VY_STREAM_V1") != nullptr;        // A/B: the unit-streaming pass of round 1
+        if (stream_v1) {
+            long long ctas = (pl.n_units + STR_NT / 32 - 1) / (STR_NT / 32);
+            const long long resident = (long long)STR_CTAS_PER_SM * vy_sm_count();
+            if (ctas > resident) ctas = resident;
+            // PDL on this launch only in the latency regime (grid below one wave): on a full machine the early
+            // CTAs crowd the sample kernel's tail (measured: -4 % at COCO 608 x 64, +15 % at VOC 416 x 1)
+            const size_t ring_bytes = (size_t)(STR_NT / 32) * STR_RING * 32 * sizeof(float4);
+            VY_CUDA_CHECK(vy_ensure_dyn_smem((const void *)vy_decode_stream_kernel, ring_bytes));
+            VY_KERNEL(VY_K_STREAM, st, (vy_launch(vy_decode_stream_kernel, dim3((unsigned)ctas), dim3(STR_NT), ring_bytes, st, ctas < resident, hd, pl, g)));
+            VY_LAUNCH_CHECK("vy_decode_stream_kernel");
+        } else {
+            VY_KERNEL(VY_K_TABLE, st, (vy_launch(vy_decode_table_kernel, dim3((unsigned)(B * pl.tabblk_per_image)), dim3(256), 0, st, true, hd, pl, g)));
+            VY_LAUNCH_CHECK("vy_decode_table_kernel");
+            size_t dyn = 0;
+            const int nst = stream2_stages(pl, &dyn);
+            long long ctas = vy_sm_count();
+            if (ctas > pl.n_tiles) ctas = pl.n_tiles;
+            VY_CUDA_CHECK(vy_ensure_dyn_smem((const void *)vy_decode_stream2_kernel, dyn));
+            VY_KERNEL(VY_K_STREAM, st, (vy_launch(vy_decode_stream2_kernel, dim3((unsigned)ctas), dim3(S2_NT), dyn, st, true, hd, pl, g, nst)));
+            VY_LAUNCH_CHECK("vy_decode_stream2_kernel");
+        }
     }
     VY_KERNEL(VY_K_SELECT_HEADS, st, (vy_launch(vy_decode_select_kernel, dim3(select_grid(pl.n_jobs)), dim3(SEL_NT), 0, st, true, hd, pl, g)));
     VY_LAUNCH_CHECK("vy_decode_select_kernel");
     FinParams fp;
-    fp.K = pl.K; fp.post_rows = post_nms; fp.out_stride_rows = post_nms;
-    fp.overlap_thresh = overlap_thresh; fp.force_suppress = force_suppress;
+    fp.K = pl.K; fp.post_rows = P->post_nms; fp.out_stride_rows = P->post_nms;
+    fp.overlap_thresh = P->overlap_thresh; fp.force_suppress = P->force_suppress;
     fp.in_format = VY_FMT_CORNER; fp.out_format = VY_FMT_CORNER; fp.W = 6; fp.fill_rest = 1;
     fp.out = out; fp.kept_rows = kept_rows;
     RowParams rp;
     memset(&rp, 0, sizeof(rp));
-    rc = launch_finalize<0>(hd, rp, pl, g, fp, B, st);
+    int rc = launch_finalize<0>(hd, rp, pl, g, fp, B, st);
     // VY_DEBUG_LISTS=1: (debugging aid, synchronises) print the fill of the streamed candidate lists
     static const bool dbg = getenv("VY_DEBUG_LISTS") != nullptr;
     if (dbg && pl.stream && rc == VY_OK) {
@@ -1971,6 +2512,49 @@ extern "C" int vy_decode_nms_f32(const float *const *head, const int *H, const i
                 pl.K, pl.samp_stride, pl.Gs, pl.Ksq, g.slist_cap, (double)sum / B, mn, mx, bad, B);
     }
     return rc;
+}
+
+extern "C" int vy_decode_nms_plan_create(const int *H, const int *W, const float *stride, const float *anchors,
+                                         int n_scales, int B, int A, int C, int agnostic, float overlap_thresh,
+                                         float valid_thresh, int topk, int force_suppress, int post_nms,
+                                         vy_decode_nms_plan_t **plan) {
+    if (!plan) VY_FAIL(VY_EINVAL, "vy_decode_nms_plan_create: plan is null");
+    *plan = nullptr;
+    vy_decode_nms_plan *P = (vy_decode_nms_plan *)calloc(1, sizeof(vy_decode_nms_plan));
+    if (!P) VY_FAIL(VY_EINVAL, "vy_decode_nms_plan_create: out of host memory");
+    const int rc = plan_init(P, H, W, stride, anchors, n_scales, B, A, C, agnostic, overlap_thresh, valid_thresh, topk,
+                             force_suppress, post_nms);
+    if (rc != VY_OK) { free(P); return rc; }
+    *plan = P;
+    return VY_OK;
+}
+extern "C" size_t vy_decode_nms_plan_workspace_bytes(const vy_decode_nms_plan_t *plan) { return plan ? plan->ws_bytes : 0; }
+extern "C" int vy_decode_nms_plan_launch(const vy_decode_nms_plan_t *plan, const float *const *head, float *out,
+                                         int32_t *kept_rows, void *workspace, size_t workspace_bytes, vy_stream_t stream) {
+    if (!plan) VY_FAIL(VY_EINVAL, "vy_decode_nms_plan_launch: plan is null");
+    return plan_launch(plan, head, out, kept_rows, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+extern "C" void vy_decode_nms_plan_destroy(vy_decode_nms_plan_t *plan) { free(plan); }
+
+extern "C" size_t vy_decode_nms_workspace_bytes(const int *H, const int *W, int n_scales, int B, int A,
+                                                int C, int agnostic, int topk) {
+    vy_decode_nms_plan P;
+    float st[VY_MAX_SCALES] = {1, 1, 1, 1};
+    float an[VY_MAX_SCALES * VY_MAX_ANCHORS * 2] = {0};
+    if (plan_init(&P, H, W, st, an, n_scales, B, A, C, agnostic, 0.5f, 0.0f, topk, 0, 1) != VY_OK) return 0;
+    return P.ws_bytes;
+}
+
+extern "C" int vy_decode_nms_f32(const float *const *head, const int *H, const int *W, const float *stride,
+                                 const float *anchors, int n_scales, int B, int A, int C, int agnostic,
+                                 float overlap_thresh, float valid_thresh, int topk, int force_suppress,
+                                 int post_nms, float *out, int32_t *kept_rows, void *workspace,
+                                 size_t workspace_bytes, vy_stream_t stream) {
+    vy_decode_nms_plan P;
+    const int rc = plan_init(&P, H, W, stride, anchors, n_scales, B, A, C, agnostic, overlap_thresh, valid_thresh, topk,
+                             force_suppress, post_nms);
+    if (rc != VY_OK) return rc;
+    return plan_launch(&P, head, out, kept_rows, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 // implemented in vy_nms_large.cu: topk < 0 or min(topk,R) > SEL_KMAX

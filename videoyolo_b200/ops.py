@@ -59,6 +59,24 @@ def workspace(nbytes: int, device) -> torch.Tensor:
     return buf
 
 
+class workspace_scope:
+    """Route ``workspace()`` to a caller-owned store for the duration of the block: an object that captures library
+    calls in a CUDA graph keeps the scratch buffers its kernels write to (pipeline.GraphedModule)."""
+
+    def __init__(self, store: dict):
+        self.store = store
+
+    def __enter__(self):
+        global _WS_CACHE
+        self._prev, _WS_CACHE = _WS_CACHE, self.store
+        return self
+
+    def __exit__(self, *exc):
+        global _WS_CACHE
+        _WS_CACHE = self._prev
+        return False
+
+
 def _head_args(heads: Sequence[torch.Tensor], anchors, strides):
     n = len(heads)
     if n < 1 or n > 4 or len(anchors) != n or len(strides) != n:
@@ -66,6 +84,9 @@ def _head_args(heads: Sequence[torch.Tensor], anchors, strides):
     heads = [_need_cuda(h, "heads[%d]" % i) for i, h in enumerate(heads)]
     B = heads[0].shape[0]
     A = len(anchors[0]) // 2
+    for a in anchors:
+        if len(a) != 2 * A:
+            raise ValueError("every scale needs the same number of anchors (%d), got %d values" % (A, len(a)))
     for h in heads:
         if h.dim() != 4 or h.shape[0] != B or h.device != heads[0].device:
             raise ValueError("heads must be (B, A*(5+C), H, W) on one device")
@@ -91,12 +112,7 @@ def yolo3_decode(heads, num_class: int, anchors, strides, agnostic: bool = False
         if h.shape[1] != A * (5 + num_class):
             raise ValueError("head has %d channels, expected A*(5+C)=%d" % (h.shape[1], A * (5 + num_class)))
     R = n_rows(heads, num_class, A, agnostic)
-    if out is None:
-        out = torch.empty((B, R, 6), dtype=torch.float32, device=heads[0].device)
-    else:
-        out = _need_cuda(out, "out")
-        if tuple(out.shape) != (B, R, 6):
-            raise ValueError("out must be (B, R, 6) = %s" % ((B, R, 6),))
+    out = _check_result(out, "out", (B, R, 6), torch.float32, heads[0].device)
     if B == 0:
         return out
     with torch.cuda.device(heads[0].device):
@@ -140,30 +156,100 @@ def box_nms(data: torch.Tensor, overlap_thresh: float = 0.5, valid_thresh: float
     return (out, kept) if return_kept else out
 
 
+class DecodeNmsPlan:
+    """Owns a ``vy_decode_nms_plan_t`` (include/vyolo.h): the fused call's shape-dependent planning done once, like the
+    cached graph of a hybridized Gluon block (detect_yolo3.py:204).  ``launch`` only fills in this call's pointers."""
+
+    def __init__(self, shapes, num_class, anchors, strides, nms_thresh, valid_thresh, topk, post_nms, force_suppress,
+                 agnostic):
+        n = len(shapes)
+        if n < 1 or n > 4 or len(anchors) != n or len(strides) != n:
+            raise ValueError("need 1..4 scales with matching anchors/strides")
+        A = len(anchors[0]) // 2
+        for a in anchors:
+            if len(a) != 2 * A:
+                raise ValueError("every scale needs the same number of anchors (%d), got %d values" % (A, len(a)))
+        B = shapes[0][0]
+        for sh in shapes:
+            if len(sh) != 4 or sh[0] != B:
+                raise ValueError("heads must be (B, A*(5+C), H, W)")
+            if sh[1] != A * (5 + num_class):
+                raise ValueError("head has %d channels, expected A*(5+C)=%d" % (sh[1], A * (5 + num_class)))
+        self.B, self.A, self.n, self.post_nms = B, A, n, int(post_nms)
+        H = (ctypes.c_int * n)(*[sh[2] for sh in shapes])
+        W = (ctypes.c_int * n)(*[sh[3] for sh in shapes])
+        st = (ctypes.c_float * n)(*[float(v) for v in strides])
+        flat = [float(v) for a in anchors for v in a]
+        an = (ctypes.c_float * len(flat))(*flat)
+        L = _lib.lib()
+        h = ctypes.c_void_p()
+        _lib.check(L.vy_decode_nms_plan_create(H, W, st, an, n, B, A, num_class, int(agnostic), float(nms_thresh),
+                                               float(valid_thresh), int(topk), int(bool(force_suppress)), int(post_nms),
+                                               ctypes.byref(h)))
+        self._h, self._destroy = h, L.vy_decode_nms_plan_destroy
+        self._launch = L.vy_decode_nms_plan_launch
+        self.workspace_bytes = int(L.vy_decode_nms_plan_workspace_bytes(h))
+        self._ptrs = (ctypes.c_void_p * n)()
+
+    def launch(self, heads, out, kept, ws, stream: int):
+        for i, t in enumerate(heads):
+            self._ptrs[i] = t.data_ptr()
+        _lib.check(self._launch(self._h, self._ptrs, out.data_ptr(), kept.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._destroy(h)
+
+
+_PLANS = {}
+
+
+def decode_nms_plan(shapes, num_class, anchors, strides, nms_thresh=0.45, valid_thresh=0.01, topk=400, post_nms=100,
+                    force_suppress=False, agnostic=False) -> DecodeNmsPlan:
+    """The (cached) plan of a fused call on head maps of these shapes with these arguments."""
+    key = (tuple(tuple(int(v) for v in sh) for sh in shapes), int(num_class), tuple(tuple(a) for a in anchors),
+           tuple(strides), float(nms_thresh), float(valid_thresh), int(topk), int(post_nms), bool(force_suppress),
+           bool(agnostic))
+    p = _PLANS.get(key)
+    if p is None:
+        if len(_PLANS) > 256:
+            _PLANS.clear()
+        p = _PLANS[key] = DecodeNmsPlan(key[0], num_class, anchors, strides, nms_thresh, valid_thresh, topk, post_nms,
+                                        force_suppress, agnostic)
+    return p
+
+
 def yolo3_decode_nms(heads, num_class: int, anchors, strides, nms_thresh: float = 0.45,
                      valid_thresh: float = 0.01, topk: int = 400, post_nms: int = 100,
                      force_suppress: bool = False, agnostic: bool = False,
-                     out: Optional[torch.Tensor] = None, kept: Optional[torch.Tensor] = None):
-    """Fused decode + box_nms + post_nms slice.  Returns (out (B, post_nms, 6), kept (B, post_nms))."""
-    heads, ptrs, H, W, st, an, n, B, A = _head_args(heads, anchors, strides)
-    for h in heads:
-        if h.shape[1] != A * (5 + num_class):
-            raise ValueError("head has %d channels, expected A*(5+C)=%d" % (h.shape[1], A * (5 + num_class)))
+                     out: Optional[torch.Tensor] = None, kept: Optional[torch.Tensor] = None,
+                     workspace_buf: Optional[torch.Tensor] = None):
+    """Fused decode + box_nms + post_nms slice.  Returns (out (B, post_nms, 6), kept (B, post_nms)).
+    ``workspace_buf``: a caller-owned uint8 CUDA scratch tensor (a captured CUDA graph must own the buffer its
+    kernels write to); default: the per-(device, stream) cached one."""
+    if len(heads) < 1:
+        raise ValueError("need 1..4 scales with matching anchors/strides")
+    heads = [_need_cuda(h, "heads[%d]" % i) for i, h in enumerate(heads)]
     dev = heads[0].device
+    for h in heads:
+        if h.dim() != 4 or h.device != dev:
+            raise ValueError("heads must be (B, A*(5+C), H, W) on one device")
+    B = heads[0].shape[0]
     out = _check_result(out, "out", (B, post_nms, 6), torch.float32, dev)
     kept = _check_result(kept, "kept", (B, post_nms), torch.int32, dev)
     if B == 0:                                           # an empty batch is an empty result (MXNet operators agree)
         return out, kept
-    L = _lib.lib()
+    plan = decode_nms_plan([h.shape for h in heads], num_class, anchors, strides, nms_thresh, valid_thresh, topk,
+                           post_nms, force_suppress, agnostic)
     with torch.cuda.device(dev):
-        need = L.vy_decode_nms_workspace_bytes(H, W, n, B, A, num_class, int(agnostic), int(topk))
-        if need == 0:
-            raise _lib.VyoloError(-5, L.vy_last_error().decode())
-        ws = workspace(need, dev)
-        _lib.check(L.vy_decode_nms_f32(ptrs, H, W, st, an, n, B, A, num_class, int(agnostic),
-                                       float(nms_thresh), float(valid_thresh), int(topk),
-                                       int(bool(force_suppress)), int(post_nms), out.data_ptr(),
-                                       kept.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        if workspace_buf is None:
+            ws = workspace(plan.workspace_bytes, dev)
+        else:
+            ws = workspace_buf
+            if not ws.is_cuda or ws.device != dev or ws.dtype != torch.uint8 or ws.numel() < plan.workspace_bytes:
+                raise ValueError("workspace_buf must be a uint8 CUDA tensor of >= %d bytes on %s" % (plan.workspace_bytes, dev))
+        plan.launch(heads, out, kept, ws, _stream())
     return out, kept
 
 
@@ -264,6 +350,52 @@ def pack_p(x: torch.Tensor, layout: str = "NCDHW") -> PTensor:
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().vy_pack_f32_to_p_bf16(x.data_ptr(), sb, sc, st, B, C, T, H, W, out.data_ptr(), _stream()))
     return PTensor(out, B, T, H, W, C)
+
+
+def pack_p_split(x: torch.Tensor, layout: str = "NCHW") -> PTensor:
+    """fp32 CUDA tensor -> P layout bf16 with 3*Cpad channels [hi | hi | lo] (hi = bf16(v), lo = bf16(v - hi), Cpad = C
+    rounded up to 64, padding zero): the activation operand of a split-precision 1x1 conv (``split_weight(w, 3)``)."""
+    x = _need_cuda(x, "x")
+    if layout == "NCHW":
+        B, C, H, W = x.shape
+        T, sb, sc, st = 1, C * H * W, H * W, 0
+    elif layout == "NTCHW":
+        B, T, C, H, W = x.shape
+        sb, st, sc = T * C * H * W, C * H * W, H * W
+    else:
+        raise ValueError("layout must be NCHW or NTCHW")
+    Cpad = (C + 63) // 64 * 64
+    out = torch.empty((T, B, H + 2, W + 2, 3 * Cpad), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vy_pack_f32_split_to_p_bf16(x.data_ptr(), sb, sc, st, B, C, Cpad, T, H, W, out.data_ptr(), _stream()))
+    return PTensor(out, B, T, H, W, 3 * Cpad)
+
+
+def cat_repeat(x: PTensor, rep: int = 1) -> PTensor:
+    """The 'cat' late join (reshape (0,-3,-2), yolo3.py:1135-1136) of a P-layout activation: (T, B, ., ., C) ->
+    (1, B, ., ., rep*T*C), channel r*T*C + t*C + c = frame t, channel c; ``rep`` repeats the joined channels
+    (rep = 2 pairs with ``split_weight(w, 2)``)."""
+    if not isinstance(x, PTensor) or x.data.dtype != torch.bfloat16:
+        raise TypeError("cat_repeat takes a bf16 PTensor")
+    y = torch.empty((1, x.B, x.H + 2, x.W + 2, rep * x.T * x.C), dtype=torch.bfloat16, device=x.data.device)
+    with torch.cuda.device(x.data.device):
+        _lib.check(_lib.lib().vy_cat_repeat_bf16(x.data.data_ptr(), x.B, x.T, x.H, x.W, x.C, int(rep), y.data_ptr(), _stream()))
+    return PTensor(y, x.B, 1, x.H, x.W, rep * x.T * x.C)
+
+
+def split_weight(w: torch.Tensor, parts: int) -> torch.Tensor:
+    """1x1 conv weight (Cout, Cin[, 1, 1]) fp32 -> the fusion-conv operand (Cout_pad, 1, 1, 1, parts*Cin_pad) bf16 that
+    carries it at fp32 grade: [w_hi | w_lo] against an activation repeated twice (``cat_repeat(x, 2)``), or
+    [w_hi | w_lo | w_hi] against ``pack_p_split``'s [hi | hi | lo].  Cout / Cin are zero-padded to multiples of 64."""
+    w = w.reshape(w.shape[0], -1).float()
+    n, cin = w.shape
+    npad, cpad = (n + 63) // 64 * 64, (cin + 63) // 64 * 64
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    out = torch.zeros((npad, 1, 1, 1, parts * cpad), dtype=torch.bfloat16, device=w.device)
+    for i, part in enumerate([hi, lo, hi][:parts]):
+        out[:n, 0, 0, 0, i * cpad: i * cpad + cin] = part
+    return out
 
 
 def unpack_p(p: PTensor, layout: str = "NCDHW", channels: Optional[int] = None) -> torch.Tensor:

@@ -104,7 +104,8 @@ class GraphedDetector:
 
     ``det(heads)`` copies the heads into the graph's static inputs (device-to-device) and replays;
     ``det()`` replays on whatever ``det.heads`` currently hold.  Returns ``(out (B, post_nms, 6), kept)``,
-    static tensors that the next replay overwrites.
+    static tensors that the next replay overwrites.  The replay is enqueued on the CALLER's current stream; one
+    object = one workspace = one replay in flight at a time (use one object per stream for concurrent batches).
     """
 
     def __init__(self, num_class: int, anchors, strides, shapes: Sequence[Sequence[int]], device,
@@ -116,9 +117,15 @@ class GraphedDetector:
         self.out = torch.empty((B, post_nms, 6), dtype=torch.float32, device=self.device)
         self.kept = torch.empty((B, post_nms), dtype=torch.int32, device=self.device)
         kw = dict(nms_thresh=nms_thresh, valid_thresh=valid_thresh, topk=nms_topk, post_nms=post_nms, agnostic=agnostic)
+        # the graph's kernels write to THIS buffer: owned here, not the per-stream cache of ops (which another caller
+        # on the same stream handle may outgrow and replace while the graph still points at it)
+        plan = ops.decode_nms_plan([h.shape for h in self.heads], num_class, anchors, strides, nms_thresh, valid_thresh,
+                                   nms_topk, post_nms, False, agnostic)
+        self.workspace = torch.empty(max(plan.workspace_bytes, 256), dtype=torch.uint8, device=self.device)
+        kw["workspace_buf"] = self.workspace
         self._stream = torch.cuda.Stream(self.device)
         self._stream.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(self._stream):                 # warm-up: sizes the cached workspace of this stream
+        with torch.cuda.stream(self._stream):                 # warm-up: loads the kernels, sets their attributes
             ops.yolo3_decode_nms(self.heads, num_class, anchors, strides, out=self.out, kept=self.kept, **kw)
         self._stream.synchronize()
         self.graph = torch.cuda.CUDAGraph()
@@ -148,13 +155,15 @@ class GraphedModule:
         dev = self.inputs[0].device
         self._stream = torch.cuda.Stream(dev)
         self._stream.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(self._stream), torch.no_grad():
-            for _ in range(max(1, warmup)):                    # sizes cached workspaces, packs weights, folds BN
-                module(*self.inputs)
-        self._stream.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=self._stream), torch.no_grad():
-            self.outputs = module(*self.inputs)
+        self._workspaces = {}                                  # scratch buffers the captured kernels write to: owned here
+        with ops.workspace_scope(self._workspaces):
+            with torch.cuda.stream(self._stream), torch.no_grad():
+                for _ in range(max(1, warmup)):                # sizes the workspaces, packs weights, folds BN
+                    module(*self.inputs)
+            self._stream.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self._stream), torch.no_grad():
+                self.outputs = module(*self.inputs)
 
     def __call__(self, *inputs):
         if inputs:

@@ -20,11 +20,56 @@ STRIDES = [8, 16, 32]
 CHANNELS = [512, 256, 128]
 
 
+class Prediction(torch.nn.Module):
+    """The 1x1 ``prediction`` conv of YOLOOutputV3 (``nn.Conv2D(all_pred, kernel_size=1, padding=0, strides=1)``,
+    yolo3.py:62, applied at :157): weight (all_pred, in_channels, 1, 1) + bias, MXNet's default initialisation
+    (Uniform(0.07) weight, zero bias).  It runs in the library's tcgen05 fusion-conv kernel -- no cuDNN / cuBLAS -- with
+    SPLIT operands so that it keeps the reference's fp32 grade: a value is carried as hi = bf16(v) and lo = bf16(v - hi)
+    in separate channels and the products w_hi*v_hi + w_lo*v_hi + w_hi*v_lo are accumulated in fp32 in TMEM (what is
+    dropped is ~2^-16 relative).  Inputs: an fp32 NCHW tensor (the tip of a 2-D model), or a bf16 ``ops.PTensor`` (the
+    tip of the temporal models: exact in bf16 already, so only the weight is split; K frames are joined 'cat'-wise,
+    yolo3.py:1135-1136).  Returns the fp32 NCHW head map (B, all_pred, H, W)."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.weight = torch.nn.Parameter(torch.empty((out_channels, in_channels, 1, 1)).uniform_(-0.07, 0.07))
+        self.bias = torch.nn.Parameter(torch.zeros(out_channels))
+        self._packed = {}
+
+    def _operands(self, parts: int):
+        key = (self.weight._version, self.bias._version, self.weight.device)
+        hit = self._packed.get(parts)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                w = ops.split_weight(self.weight.detach(), parts)
+                npad = w.shape[0]
+                shift = torch.zeros(npad, dtype=torch.float32, device=w.device)
+                shift[: self.bias.numel()] = self.bias.detach().float()
+                hit = (key, w, torch.ones(npad, dtype=torch.float32, device=w.device), shift)
+            self._packed[parts] = hit
+        return hit[1:]
+
+    def forward(self, x):
+        n, cin = self.weight.shape[0], self.weight.shape[1]
+        if isinstance(x, ops.PTensor):
+            if x.T * x.C != cin:
+                raise ValueError("prediction conv expects %d input channels, got %d x %d frames" % (cin, x.C, x.T))
+            w, scale, shift = self._operands(2)
+            xp = ops.cat_repeat(x, 2)
+        else:
+            if x.dim() != 4 or x.shape[1] != cin:
+                raise ValueError("prediction conv expects (B, %d, H, W)" % cin)
+            w, scale, shift = self._operands(3)
+            xp = ops.pack_p_split(x, "NCHW")
+        pred = ops.fusion_conv(xp, w, scale, shift, slope=1.0, out_f32=True)      # identity activation, bias as shift
+        return ops.unpack_p(pred, "NCHW", channels=n)
+
+
 class YOLOOutputV3(torch.nn.Module):
     """YOLO output layer V3 (yolo3.py:25-199), inference branch.
 
-    ``__call__(x)`` applies the 1x1 ``prediction`` conv (yolo3.py:62,157; a library conv) to the tip
-    feature map and decodes it with the CUDA kernel into ``(B, C*H*W*A, 6)`` detections in the
+    ``__call__(x)`` applies the 1x1 ``prediction`` conv (yolo3.py:62,157; ``Prediction``: the library's own kernel) to
+    the tip feature map and decodes it with the CUDA kernel into ``(B, C*H*W*A, 6)`` detections in the
     reference's row order.  ``decode(pred)`` skips the conv for an already computed head map.
     """
 
@@ -41,8 +86,7 @@ class YOLOOutputV3(torch.nn.Module):
         self._alloc_size = tuple(alloc_size)
         self._anchors = [float(v) for v in anchors.reshape(-1)]
         all_pred = self._num_pred * self._num_anchors                       # :57
-        self.prediction = (torch.nn.Conv2d(in_channels, all_pred, kernel_size=1, padding=0, stride=1)
-                           if in_channels else None)                        # :62
+        self.prediction = Prediction(in_channels, all_pred) if in_channels else None     # :62
 
     def _check(self, pred: torch.Tensor):
         if pred.shape[2] > self._alloc_size[0] or pred.shape[3] > self._alloc_size[1]:
@@ -162,17 +206,18 @@ class YOLOV3T(torch.nn.Module):
     ``net(x32, x16, x8)`` takes the three block-body outputs, each (B, K, channel_i, H_i, W_i) fp32 on a CUDA
     device (network order, channel_i = 512, 256, 128: wrappers.py:91-103).  The reference asserts that 3-D /
     2+1-D blocks need k > 1 and a late join (yolo3.py:979-985); so does this class.  The tip convs run in the
-    tcgen05 fusion-conv kernel (bf16 operands, fp32 accumulation); the 1x1 prediction conv is a library conv
-    (fp32) as in YOLOOutputV3; decode + box_nms is the fused kernel path of YOLOV3.
+    tcgen05 fusion-conv kernel (bf16 operands and activations, fp32 accumulation); the 1x1 prediction conv runs in the
+    same kernel on the joined bf16 tip with split, fp32-grade weights (``Prediction``) for all three join types -- there
+    is no cuDNN / cuBLAS call on this path; decode + box_nms is the fused kernel path of YOLOV3.  Against the fp32
+    reference the head logits therefore differ by what the bf16 ACTIVATIONS of the fusion conv cost (the stated fusion-conv
+    tolerance, 1e-2 of the tensor's range), not by the prediction conv.
     """
 
     def __init__(self, classes: Sequence[str], k: int = 3, k_join_type: str = "max", block_conv_type: str = "3",
                  channels: Sequence[int] = (512, 256, 128), anchors=None, strides=None,
-                 nms_thresh=0.45, nms_topk=400, post_nms=100, agnostic=False, native_head=True, **kwargs):
+                 nms_thresh=0.45, nms_topk=400, post_nms=100, agnostic=False, **kwargs):
         super().__init__()
         from .layers import Conv, TemporalPooling
-        self._native_head = bool(native_head)
-        self._head_cache = None
         assert k > 1, "3-D and 2+1-D convolutions need a temporal window (yolo3.py:981-983)"
         assert k_join_type in ("max", "mean", "cat")                      # yolo3.py:984
         assert block_conv_type in ("3", "21")
@@ -216,38 +261,14 @@ class YOLOV3T(torch.nn.Module):
                 feats.append(ops.unpack_p(self.pools[i](tip), "NCHW"))
         return feats
 
-    def _head_weights(self):
-        """the 1x1 prediction convs (yolo3.py:62: Conv2D with bias) as fusion-conv operands: weight padded to a
-        multiple of 64 output channels in the kernel's (Cout, 1, 1, 1, Cin) bf16 layout, scale 1, shift = bias."""
-        convs = [o.prediction for o in self.tail.yolo_outputs]
-        key = tuple((c.weight._version, c.bias._version, c.weight.device) for c in convs)
-        if self._head_cache is None or self._head_cache[0] != key:
-            packed = []
-            with torch.no_grad():
-                for c in convs:
-                    n, cin = c.weight.shape[0], c.weight.shape[1]
-                    npad = (n + 63) // 64 * 64
-                    w = torch.zeros((npad, 1, 1, 1, cin), dtype=torch.bfloat16, device=c.weight.device)
-                    w[:n, 0, 0, 0] = c.weight.detach()[:, :, 0, 0].to(torch.bfloat16)
-                    shift = torch.zeros(npad, dtype=torch.float32, device=c.weight.device)
-                    shift[:n] = c.bias.detach().float()
-                    packed.append((w, torch.ones(npad, dtype=torch.float32, device=c.weight.device), shift, n))
-            self._head_cache = (key, packed)
-        return self._head_cache[1]
-
     def head_maps(self, *xs):
-        """the three NCHW head maps (B, A*(5+C), H, W) fp32 = outputs of the prediction convs (yolo3.py:157).
-        native_head: the prediction conv runs in the fusion-conv kernel directly on the joined bf16 tip (identity
-        activation, bias as shift, fp32 output) and only the head map is converted to NCHW; otherwise the joined
-        tip is unpacked to fp32 and goes through the library conv of YOLOOutputV3."""
-        if not self._native_head or self._join == "cat":
-            feats = self.tip_features(*xs)
-            return [o.prediction(f) for o, f in zip(self.tail.yolo_outputs, feats)]
+        """the three NCHW head maps (B, A*(5+C), H, W) fp32 = outputs of the prediction convs (yolo3.py:157), computed
+        by ``Prediction`` directly on the joined bf16 tip ('max' / 'mean': the pooled frame; 'cat': the K frames side by
+        side in the channels); only the head map is converted to NCHW."""
         heads = []
         for i, tip in enumerate(self._tips(xs)):
-            w, scale, shift, n = self._head_weights()[i]
-            pred = ops.fusion_conv(self.pools[i](tip), w, scale, shift, slope=1.0, out_f32=True)
-            heads.append(ops.unpack_p(pred, "NCHW", channels=n))
+            joined = tip if self._join == "cat" else self.pools[i](tip)
+            heads.append(self.tail.yolo_outputs[i].prediction(joined))
         return heads
 
     def forward(self, *xs):
