@@ -175,6 +175,31 @@ int vy_bbox_batch_iou_f32(const float *a, const float *b, int B, int N, int M, f
 int vy_detect_consume_f32(const float *dets, int B, int P, float clip_hi, float norm, float *clipped,
                           float *normed, int32_t *counts, vy_stream_t stream);
 
+/* hierarchical_nms on the device ("next" row f3).
+ * Replaces: hierarchical_nms(predictions, dataset, ov_thresh, conf_thresh, level_thresh) with its iou() helper,
+ *           detect_yolo3.py:712-789 -- per image, the python double loop over the detections.
+ *   boxes   (B, N, 6) rows [cls, conf, x1, y1, x2, y2] in the order detect() collected them; rows with cls < 0 = padding
+ *   lifted  (n_cls) int32: the class the `while levels[cls] > level_thresh` walk (:766-767) ends at, per class
+ *   branch  (n_cls, n_cls) uint8: dataset.on_branch(i, j) (:743-747)
+ *   out     (B, N, 6) the new prediction rows in the order the reference appends them, -1 padded; counts (B) rows kept
+ *   float32 arithmetic in the reference's operation order (detect() hands iou() np.float32 values).  N <= 1024. */
+int vy_hier_nms_f32(const float *boxes, int B, int N, const int32_t *lifted, const unsigned char *branch, int n_cls,
+                    float ov_thresh, float conf_thresh, float *out, int32_t *counts, vy_stream_t stream);
+
+/* The per-image part of the VOC metric update on the device ("next" row f3).
+ * Replaces: VOCMApMetric.update, metrics/pascalvoc.py:116-184 (strip padding, per class: sort by score, bbox_iou against
+ *           the class's ground truths, greedy true-positive assignment), i.e. what validate() calls per batch
+ *           (train_yolov3.py:473-488).
+ *   dets      (B, P, 6) rows [id, score, x1, y1, x2, y2], -1 padded (vy_decode_nms_f32 / vy_box_nms_f32 output)
+ *   gt_boxes  (B, M, 4); gt_labels (B, M) (< 0 = padding); gt_difficult (B, M) or NULL
+ *   out_label / out_score / out_match (B, P): the valid predictions ordered by (class ascending, score descending, later
+ *             row first among equal scores), match in {1 true positive, 0 false positive, -1 difficult}; -2 padded
+ *   counts (B) valid predictions; n_pos (B, n_class) non-difficult ground truths per class
+ *   The host then only extends its per-class lists.  P <= 1024, M <= 512. */
+int vy_voc_match_f32(const float *dets, const float *gt_boxes, const float *gt_labels, const float *gt_difficult,
+                     int B, int P, int M, int n_class, float iou_thresh, int32_t *out_label, float *out_score,
+                     int32_t *out_match, int32_t *counts, int32_t *n_pos, vy_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Temporal fusion convolution: LeakyReLU(BN(ConvND(x))), use_bias=False, stride 1, groups 1.
  * Replaces: Conv / _conv2d / _conv3d / _conv21d cells, models/definitions/layers.py:63-89,135-158,

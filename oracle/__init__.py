@@ -395,3 +395,108 @@ def detect_consume(ids: np.ndarray, bboxes: np.ndarray, size: float):
         valid = np.where(ids[i].flat >= 0)[0]                              # :256
         per_image.append((valid, (clipped[i, valid, :] / np.float32(size)).astype(np.float32)))   # :257
     return clipped, per_image
+
+
+# --------------------------------------------------------------------------- device-side consumers
+def voc_match(pred_bboxes, pred_labels, pred_scores, gt_bboxes, gt_labels, gt_difficults=None, iou_thresh=0.5):
+    """What ``VOCMApMetric.update`` appends for ONE image (metrics/pascalvoc.py:116-184, class_map = None), as arrays
+    instead of per-class python lists: the valid predictions ordered by (class ascending, score descending -- ties in the
+    order ``argsort()[::-1]`` of a stable sort gives: later row first), each with its ``match`` value (1 true positive,
+    0 false positive, -1 matched to a difficult ground truth), and the number of non-difficult ground truths per class.
+    Returns (labels (n,), scores (n,), match (n,), n_pos {class: count})."""
+    pred_bboxes, gt_bboxes = np.asarray(pred_bboxes, dtype=np.float32), np.asarray(gt_bboxes, dtype=np.float32)
+    pred_label, pred_score = np.asarray(pred_labels).reshape(-1), np.asarray(pred_scores, dtype=np.float32).reshape(-1)
+    gt_label = np.asarray(gt_labels).reshape(-1)
+    valid_pred = np.where(pred_label >= 0)[0]                         # :118
+    pred_bbox = pred_bboxes[valid_pred, :]
+    pred_label = pred_label[valid_pred].astype(int)
+    pred_score = pred_score[valid_pred]
+    valid_gt = np.where(gt_label >= 0)[0]                             # :127
+    gt_bbox = gt_bboxes[valid_gt, :]
+    gt_label = gt_label[valid_gt].astype(int)
+    gt_difficult = np.zeros(gt_bbox.shape[0]) if gt_difficults is None else np.asarray(gt_difficults).reshape(-1)[valid_gt]
+    out_l, out_s, out_m, n_pos = [], [], [], {}
+    for l in np.unique(np.concatenate((pred_label, gt_label)).astype(int)):                        # :136
+        pred_mask_l = pred_label == l
+        pred_bbox_l, pred_score_l = pred_bbox[pred_mask_l], pred_score[pred_mask_l]
+        order = pred_score_l.argsort(kind="stable")[::-1]             # :141 (stable: what the default gives for <= 16 rows)
+        pred_bbox_l, pred_score_l = pred_bbox_l[order], pred_score_l[order]
+        gt_mask_l = gt_label == l
+        gt_bbox_l, gt_difficult_l = gt_bbox[gt_mask_l], gt_difficult[gt_mask_l]
+        n_pos[int(l)] = n_pos.get(int(l), 0) + int(np.logical_not(gt_difficult_l).sum())           # :149
+        out_l.extend([l] * len(pred_score_l)); out_s.extend(pred_score_l)                           # :150
+        if len(pred_bbox_l) == 0:
+            continue
+        if len(gt_bbox_l) == 0:
+            out_m.extend((0,) * pred_bbox_l.shape[0])                 # :155
+            continue
+        iou = bbox_iou_f32(pred_bbox_l, gt_bbox_l)                    # :166 (gluoncv bbox_iou == utils/bbox.py:11-38, fp32 in)
+        gt_index = iou.argmax(axis=1)
+        gt_index[iou.max(axis=1) < iou_thresh] = -1                   # :169
+        selec = np.zeros(gt_bbox_l.shape[0], dtype=bool)
+        for gt_idx in gt_index:                                       # :173-184
+            if gt_idx >= 0:
+                if gt_difficult_l[gt_idx]:
+                    out_m.append(-1)
+                else:
+                    out_m.append(0 if selec[gt_idx] else 1)
+                selec[gt_idx] = True
+            else:
+                out_m.append(0)
+    return (np.array(out_l, dtype=np.int32), np.array(out_s, dtype=np.float32), np.array(out_m, dtype=np.int32), n_pos)
+
+
+def bbox_iou_f32(bbox_a, bbox_b, offset=0):
+    """utils/bbox.py:11-38 evaluated in the dtype numpy gives float32 inputs (what the metric feeds it)."""
+    a, b = np.asarray(bbox_a, dtype=np.float32), np.asarray(bbox_b, dtype=np.float32)
+    tl = np.maximum(a[:, None, :2], b[:, :2])
+    br = np.minimum(a[:, None, 2:4], b[:, 2:4])
+    area_i = np.prod(br - tl + np.float32(offset), axis=2) * (tl < br).all(axis=2)
+    area_a = np.prod(a[:, 2:4] - a[:, :2] + np.float32(offset), axis=1)
+    area_b = np.prod(b[:, 2:4] - b[:, :2] + np.float32(offset), axis=1)
+    with np.errstate(all="ignore"):
+        return (area_i / (area_a[:, None] + area_b - area_i)).astype(np.float32)
+
+
+def hier_iou_f32(bb, bbgt):
+    """``iou`` of detect_yolo3.py:712-733 on float32 boxes (detect() hands it np.float32 scalars; the +1 / +1. are weak
+    python scalars, so every operation rounds to float32)."""
+    f = np.float32
+    ov = f(0)
+    iw = f(f(min(bb[2], bbgt[2]) - max(bb[0], bbgt[0])) + f(1))
+    ih = f(f(min(bb[3], bbgt[3]) - max(bb[1], bbgt[1])) + f(1))
+    if iw > 0 and ih > 0:
+        intersect = f(iw * ih)
+        ua = f(f(f(f(f(bb[2] - bb[0]) + f(1)) * f(f(bb[3] - bb[1]) + f(1))) +
+                 f(f(f(bbgt[2] - bbgt[0]) + f(1)) * f(f(bbgt[3] - bbgt[1]) + f(1)))) - intersect)
+        ov = f(intersect / ua)
+    return ov
+
+
+def hierarchical_nms(boxes, lifted, branch, ov_thresh=0.5, conf_thresh=0.0):
+    """``hierarchical_nms`` of detect_yolo3.py:736-789 for ONE image.  ``boxes`` (n, 6) float32 rows [cls, conf, x1, y1,
+    x2, y2] in the order detect() collected them; ``lifted[c]`` = the class the ``while levels[cls] > level_thresh``
+    loop (:766-767) ends at for class c; ``branch[i][j]`` = ``dataset.on_branch(i, j)`` (:743-747).  Returns the new
+    prediction rows (m, 6) in the order they were appended."""
+    boxes = np.asarray(boxes, dtype=np.float32)
+    order = sorted(range(len(boxes)), key=lambda i: boxes[i][0], reverse=True)      # :758 (stable: ties keep their order)
+    new = []
+    for i in order:
+        cls, conf, coords = int(boxes[i][0]), boxes[i][1], boxes[i][2:6]
+        if conf < conf_thresh:                                        # :763
+            continue
+        cls = int(lifted[cls])                                        # :766-767
+        max_ov, max_idx = np.float32(0), -1
+        for idx, boxb in enumerate(new):                              # :772-776
+            overlap = hier_iou_f32(coords, boxb[2:6])
+            if overlap > ov_thresh and overlap > max_ov:
+                max_ov, max_idx = overlap, idx
+        if max_idx == -1:
+            new.append([cls, conf] + list(coords))                    # :779
+        else:
+            boxb = new[max_idx]
+            if not branch[cls][int(boxb[0])]:                         # :783
+                new.append([cls, conf] + list(coords))
+            elif cls == int(boxb[0]):                                 # :786
+                new[max_idx][1] = max(new[max_idx][1], conf)
+    return np.array(new, dtype=np.float32).reshape(-1, 6)

@@ -23,6 +23,12 @@ Three kinds of fixture, provenance stated per file:
                            tensors are 5-44 MB per frame, so those files hold every `row_step`-th
                            row + float64 column sums; the head maps are regenerated from the
                            stored seed (legacy numpy RandomState stream) and checked by checksum.
+  consumer_ref.npz         outputs of the REFERENCE ITSELF for the device-side consumer step:
+                           `hierarchical_nms` + `iou` (detect_yolo3.py:712-789; their source text is cut out of
+                           the file and executed as is, with a stand-in dataset object for levels / parents /
+                           on_branch) and `VOCMApMetric.update` (metrics/pascalvoc.py:85-184, imported under
+                           the mxnet stub; its `bbox_iou` is the reference's own utils/bbox.py -- gluoncv's is the
+                           same function) on seeded detections.
   postproc_regress_*.npz   outputs of OUR ORACLE (oracle/) on small seeded head maps: regression
                            pins so that neither the oracle nor the CUDA path can drift silently.
                            (Not reference outputs.)
@@ -233,6 +239,125 @@ def reference_decode():
               % (name, dets.shape, len(rows), int((ids.a[0] >= 0).sum())))
 
 
+def reference_consumers():
+    """hierarchical_nms and the VOC metric update, executed from the reference's own source (module docstring)."""
+    import ast
+    import importlib
+    import types
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, "/root/reference")
+    import mx_shim
+    mx_shim.install()
+    out = {}
+    rng = np.random.RandomState(20261018)
+
+    def boxes(n, scale, wh=0.4):
+        xy = rng.uniform(0, scale, size=(n, 2))
+        return np.concatenate([xy, xy + rng.uniform(0.02 * scale, wh * scale, size=(n, 2))], axis=1).astype(np.float32)
+
+    # ---- hierarchical_nms: cut `iou` and `hierarchical_nms` out of detect_yolo3.py (the module itself needs absl flags,
+    # cv2, the datasets ...) and run them on float32 detections, as detect() collects them (:254-265)
+    src = open("/root/reference/detect_yolo3.py").read()
+    tree = ast.parse(src)
+    ns = {"tqdm": lambda it, **kw: it}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("iou", "hierarchical_nms"):
+            exec(compile(ast.Module([node], []), "/root/reference/detect_yolo3.py", "exec"), ns)
+    # a small hierarchy: 0 root; 1, 2 children of 0; 3, 4 children of 1; 5 child of 2; 6 child of 5
+    parent = {0: None, 1: 0, 2: 0, 3: 1, 4: 1, 5: 2, 6: 5}
+    level = {0: 0, 1: 1, 2: 1, 3: 2, 4: 2, 5: 2, 6: 3}
+    names = ["n%d" % i for i in range(7)]
+
+    class FakeDataset:
+        wn_classes = names
+        parents = {names[c]: (names[p] if p is not None else None) for c, p in parent.items()}
+
+        def get_levels(self):
+            return [level[i] for i in range(7)]
+
+        def on_branch(self, i, j):          # is j on the branch of i (i itself, an ancestor or a descendant)?
+            def anc(x):
+                r = set()
+                while x is not None:
+                    r.add(x); x = parent[x]
+                return r
+            return i in anc(j) or j in anc(i)
+
+    ds = FakeDataset()
+    for case, (n_img, n_box, level_thresh, ov, conf) in {"a": (6, 40, 2, 0.5, 0.0), "b": (4, 60, 1, 0.3, 0.2),
+                                                         "c": (3, 25, 10, 0.5, 0.0)}.items():
+        preds, raw = {}, []
+        for i in range(n_img):
+            centres = boxes(6, 1.0, 0.3)
+            rows = []
+            for _ in range(n_box):
+                c = centres[rng.randint(6)] + rng.normal(0, 0.01, 4).astype(np.float32)      # clusters -> real overlaps
+                rows.append([int(rng.randint(7)), np.float32(rng.uniform(0, 1))] + list(c.astype(np.float32)))
+            preds["img%d" % i] = rows
+            raw.append(np.array([[r[0], r[1]] + [float(v) for v in r[2:]] for r in rows], dtype=np.float32))
+        new = ns["hierarchical_nms"](preds, ds, ov_thresh=ov, conf_thresh=conf, level_thresh=level_thresh)
+        lifted = []
+        for c in range(7):
+            x = c
+            while level[x] > max(0, level_thresh):
+                x = parent[x]
+            lifted.append(x)
+        out["hier_%s_in" % case] = np.stack(raw)
+        res = np.full((n_img, n_box, 6), -1, dtype=np.float32)
+        cnt = np.zeros(n_img, dtype=np.int32)
+        for i in range(n_img):
+            r = np.array([[b[0], b[1]] + [float(v) for v in b[2:]] for b in new["img%d" % i]], dtype=np.float32).reshape(-1, 6)
+            res[i, : len(r)] = r
+            cnt[i] = len(r)
+        out["hier_%s_out" % case], out["hier_%s_count" % case] = res, cnt
+        out["hier_%s_lifted" % case] = np.array(lifted, dtype=np.int32)
+        out["hier_%s_branch" % case] = np.array([[ds.on_branch(i, j) for j in range(7)] for i in range(7)], dtype=np.uint8)
+        out["hier_%s_args" % case] = np.array([ov, conf], dtype=np.float64)
+
+    # ---- VOCMApMetric.update
+    ref_bbox = importlib.util.spec_from_file_location("ref_bbox2", "/root/reference/utils/bbox.py")
+    ref_bbox_mod = importlib.util.module_from_spec(ref_bbox)
+    ref_bbox.loader.exec_module(ref_bbox_mod)
+    sys.modules["gluoncv.utils.bbox"] = types.ModuleType("gluoncv.utils.bbox")
+    sys.modules["gluoncv.utils.bbox"].bbox_iou = ref_bbox_mod.bbox_iou
+    sys.modules["mxnet"].metric = types.ModuleType("mxnet.metric")
+
+    class EvalMetric:
+        def __init__(self, name, **kw):
+            self.name = name
+
+    sys.modules["mxnet"].metric.EvalMetric = EvalMetric
+    sys.modules["mxnet"].nd.NDArray = mx_shim.NDArray
+    voc = importlib.import_module("metrics.pascalvoc")
+    B, P, M, ncls = 5, 100, 12, 6
+    gtb = np.stack([boxes(M, 416.0) for _ in range(B)])
+    gtl = rng.randint(-1, ncls, size=(B, M)).astype(np.float32)
+    gtd = rng.randint(0, 2, size=(B, M)).astype(np.float32)
+    pb = np.empty((B, P, 4), dtype=np.float32)
+    for b in range(B):
+        for p in range(P):
+            pb[b, p] = gtb[b, rng.randint(M)] + rng.normal(0, 6, 4) if rng.rand() < 0.6 else boxes(1, 416.0)[0]
+    pl = rng.randint(0, ncls, size=(B, P)).astype(np.float32)
+    ps = np.round(rng.uniform(0, 1, size=(B, P)) * 64).astype(np.float32) / 64          # ties on purpose
+    nvalid = rng.randint(5, P, size=B)
+    for b in range(B):                                                                   # -1 padding after the survivors
+        pl[b, nvalid[b]:] = -1; ps[b, nvalid[b]:] = -1; pb[b, nvalid[b]:] = -1
+    out.update(voc_pb=pb, voc_pl=pl, voc_ps=ps, voc_gtb=gtb, voc_gtl=gtl, voc_gtd=gtd)
+    for with_diff in (0, 1):
+        m = voc.VOCMApMetric(iou_thresh=0.5)
+        m.update(pb, pl[..., None], ps[..., None], gtb, gtl[..., None], gtd[..., None] if with_diff else None)
+        classes = sorted(set(m._n_pos) | set(m._score))
+        out["voc%d_classes" % with_diff] = np.array(classes, dtype=np.int32)
+        out["voc%d_npos" % with_diff] = np.array([m._n_pos[c] for c in classes], dtype=np.int64)
+        out["voc%d_score" % with_diff] = np.concatenate([np.array(m._score[c], dtype=np.float32) for c in classes])
+        out["voc%d_match" % with_diff] = np.concatenate([np.array(m._match[c], dtype=np.int32) for c in classes])
+        out["voc%d_len" % with_diff] = np.array([len(m._score[c]) for c in classes], dtype=np.int32)
+        out["voc%d_map" % with_diff] = np.array(m.get()[1], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "consumer_ref.npz"), **out)
+    print("consumer_ref: hierarchical_nms cases a/b/c kept", [int(out["hier_%s_count" % c].sum()) for c in "abc"],
+          "| VOC mAP", float(out["voc0_map"]), float(out["voc1_map"]))
+
+
 if __name__ == "__main__":
     with open(os.path.join(HERE, "box_nms_mxnet_doc.json"), "w") as f:
         json.dump({"provenance": "hand-transcribed from MXNet public box_nms docs + test_box_nms_op; "
@@ -240,4 +365,5 @@ if __name__ == "__main__":
     ref_bbox_iou()
     oracle_regress()
     reference_decode()
+    reference_consumers()
     print("golden fixtures written to", HERE)

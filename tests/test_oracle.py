@@ -307,3 +307,56 @@ def test_decode_torch_graph_equals_numpy_graph():
     assert got.shape == ref.shape
     np.testing.assert_array_equal(got[..., 0], ref[..., 0])
     np.testing.assert_allclose(got[..., 1:], ref[..., 1:], rtol=1e-5, atol=1e-5 * size)      # libm vs torch exp
+
+
+# ----------------------------------------------------------------------------- device-side consumers vs the reference's own code
+def _consumer_ref(golden_dir=os.path.join(os.path.dirname(__file__), "golden")):
+    return np.load(os.path.join(golden_dir, "consumer_ref.npz"))
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_hierarchical_nms_oracle_matches_reference_execution(case):
+    """oracle.hierarchical_nms against the reference's own `hierarchical_nms` / `iou` (detect_yolo3.py:712-789), executed
+    from its source on seeded float32 detections (tests/golden/make_golden.py:reference_consumers)."""
+    z = _consumer_ref()
+    ov, conf = z["hier_%s_args" % case]
+    for i, boxes in enumerate(z["hier_%s_in" % case]):
+        got = oracle.hierarchical_nms(boxes, z["hier_%s_lifted" % case], z["hier_%s_branch" % case], ov, conf)
+        n = int(z["hier_%s_count" % case][i])
+        assert len(got) == n
+        np.testing.assert_array_equal(got, z["hier_%s_out" % case][i, :n])
+
+
+@pytest.mark.parametrize("with_diff", [0, 1])
+def test_voc_match_oracle_matches_reference_execution(with_diff):
+    """oracle.voc_match against what the reference's own VOCMApMetric.update (metrics/pascalvoc.py:85-184) accumulated."""
+    z = _consumer_ref()
+    B = z["voc_pb"].shape[0]
+    score, match, npos = {}, {}, {}
+    for b in range(B):
+        l, s, m, n = oracle.voc_match(z["voc_pb"][b], z["voc_pl"][b], z["voc_ps"][b], z["voc_gtb"][b], z["voc_gtl"][b],
+                                      z["voc_gtd"][b] if with_diff else None)
+        for c in np.unique(l):
+            score.setdefault(int(c), []).extend(s[l == c]); match.setdefault(int(c), []).extend(m[l == c])
+        for c, v in n.items():
+            npos[c] = npos.get(c, 0) + v
+            score.setdefault(c, []); match.setdefault(c, [])
+    classes = list(z["voc%d_classes" % with_diff])
+    assert sorted(set(npos) | set(score)) == classes
+    np.testing.assert_array_equal([npos.get(c, 0) for c in classes], z["voc%d_npos" % with_diff])
+    np.testing.assert_array_equal(np.concatenate([np.array(score[c], dtype=np.float32) for c in classes]), z["voc%d_score" % with_diff])
+    # match values: identical wherever the order is defined.  Among EQUAL scores of one (image, class) the reference's
+    # order is whatever numpy's default (unstable, platform-dependent) argsort returns (metrics/pascalvoc.py:141), and
+    # the greedy TP assignment follows that order; the oracle and the CUDA kernel define it (later row first), so within
+    # a run of equal scores the match values are compared as multisets.  (The fixture quantises scores to force ties.)
+    got_m = np.concatenate([np.array(match[c], dtype=np.int32) for c in classes])
+    ref_m, ref_s = z["voc%d_match" % with_diff], z["voc%d_score" % with_diff]
+    cls_of = np.repeat(np.arange(len(classes)), z["voc%d_len" % with_diff])
+    i = 0
+    while i < len(ref_m):
+        j = i
+        while j + 1 < len(ref_m) and ref_s[j + 1] == ref_s[i] and cls_of[j + 1] == cls_of[i]:
+            j += 1
+        assert sorted(got_m[i:j + 1]) == sorted(ref_m[i:j + 1]), (i, j)
+        i = j + 1
+    assert (got_m == ref_m).mean() > 0.97

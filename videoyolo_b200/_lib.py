@@ -58,6 +58,9 @@ SIGNATURES = {
     "vy_upsample_concat_bf16": (ctypes.c_int, [c_vp, c_vp] + [ctypes.c_int] * 8 + [c_vp, c_vp]),
     "vy_detect_consume_f32": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, c_vp, c_vp,
                                              c_vp, c_vp]),
+    "vy_hier_nms_f32": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                       c_vp, c_vp, c_vp]),
+    "vy_voc_match_f32": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp] + [ctypes.c_int] * 4 + [ctypes.c_float] + [c_vp] * 6),
     "vy_temporal_pool_bf16": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_long, ctypes.c_int, c_vp, c_vp]),
     "vy_temporal_dwconv_bf16": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),

@@ -961,9 +961,12 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
 #define S2_TILE 24576                               // bytes per tile (one consumer warp tests a whole tile)
 #endif
 #ifndef S2_WARPS
-#define S2_WARPS 8                                  // consumer warps; ring stage s (tiles s, s + n_stages, ...) belongs to warp s
+#define S2_WARPS 24                                 // consumer warps: S2_WPS per ring stage (tiles s, s + n_stages, ... of stage s)
 #endif
-constexpr int S2_MAX_STAGES = S2_WARPS;             // ring depth is chosen at launch from the shared-memory budget (one warp per stage)
+#ifndef S2_WPS
+#define S2_WPS 4                                    // warps sharing a tile: warp h of a stage tests the row groups g = h (mod S2_WPS)
+#endif
+constexpr int S2_MAX_STAGES = S2_WARPS / S2_WPS;    // ring depth is chosen at launch from the shared-memory budget
 constexpr int S2_NT = S2_WARPS * 32 + 32;           // + the producer warp
 constexpr int S2_STAGE_BYTES = S2_TILE + 256;       // a tile lands at the same offset inside a 128-byte line as its source (+ <= 12 bytes of shift)
 constexpr int S2_K = S2_TILE / 16 / 32;             // float4 per lane and tile
@@ -1049,33 +1052,44 @@ vy_decode_table_kernel(const __grid_constant__ VyHeads hd, const __grid_constant
     vy_grid_dep_trigger();
 }
 
-// score up to 32 queued hits, one per lane (entry = element index inside the block named by the metadata word w),
-// survivors -> wbuf -> image list.  Everything about the block is worked out HERE, on the rare path.
-__device__ __forceinline__ void s2_score(const VyHeads &hd, float valid_thresh, u32 w, const u32 *hq, int n, u64 *wbuf,
-                                         int &cnt, const SelGlobal &g, int lane, u32 lt_mask) {
+// ---- the rare path of a consumer warp.  Hits are QUEUED as element indices of the block (warp-private queue in shared
+// memory); full batches of 32 are scored one per lane: logit and objectness come back from L2 (the bulk copy left them
+// there), the score is the decode kernel's, the key is tested against the image's bound and survivors go to the warp's key
+// buffer (one atomic + one 256-byte store per 32 keys).  Scoring is SPLIT: a batch's loads are issued and the warp goes
+// on with the next tile; the batch is completed (scores, keys) when the next one is ready or the block ends, so the L2
+// round trip hides behind a tile's worth of compares.
+struct S2Warp {
+    int qn, cnt;                 // entries waiting in hq, keys waiting in wbuf (warp-uniform)
+    int pn;                      // lanes of the pending batch (0: none)
+    u32 pe;                      // pending: this lane's element, its logit and objectness logit
+    float ptv, pto;
+};
+constexpr int S2_HQ = 160;                              // queue entries per warp (a batch leaves at 32; a round of hits adds <= 128)
+
+__device__ __forceinline__ void s2_complete(const VyHeads &hd, float valid_thresh, u32 w, S2Warp &S, u64 *wbuf, const SelGlobal &g) {
+    if (S.pn == 0) return;
+    const int lane = threadIdx.x & 31;
+    const u32 lt_mask = (1u << lane) - 1u;
     const int b = (int)(w & 0xffffu), s = (int)((w >> 16) & 3u), a = (int)((w >> 18) & 7u);
     const VyScale &sc = hd.sc[s];
     const u32 HW = (u32)sc.HW;
-    const float *pc0 = sc.head + ((size_t)(b * hd.A + a) * hd.P + 5) * (size_t)HW;       // class plane 0 of the block
     bool ok = false;
     u64 key = 0;
-    if (lane < n) {
-        const u32 e = hq[lane];
-        const u32 plane = e / HW, pos = e - plane * HW;
-        const float tv = vy_ldg32(pc0 + e);
-        const float to = vy_ldg32(pc0 + pos - HW);                   // the objectness plane sits right below class plane 0
-        const float sv = vy_score(tv, vy_sigmoid(to));
+    if (lane < S.pn) {
+        const u32 plane = S.pe / HW, pos = S.pe - plane * HW;
+        const float sv = vy_score(S.ptv, vy_sigmoid(S.pto));
         if (sv > valid_thresh) {
             key = vy_make_key(sv, (u32)(sc.row_off + a) + plane * (u32)sc.n_s + pos * (u32)hd.A);
             ok = key >= g.sthr[b];
         }
     }
+    S.pn = 0;
     const u32 bal = __ballot_sync(0xffffffffu, ok);
     if (bal) {
-        if (ok) wbuf[cnt + __popc(bal & lt_mask)] = key;
-        cnt += __popc(bal);
+        if (ok) wbuf[S.cnt + __popc(bal & lt_mask)] = key;
+        S.cnt += __popc(bal);
         __syncwarp();
-        if (cnt >= 32) {
+        if (S.cnt >= 32) {
             int base = 0;
             if (lane == 0) base = atomicAdd(g.scount + b, 32);
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -1083,88 +1097,146 @@ __device__ __forceinline__ void s2_score(const VyHeads &hd, float valid_thresh, 
             if (base + lane < g.slist_cap) g.slist[(size_t)b * g.slist_cap + base + lane] = k0;
             __syncwarp();
             wbuf[lane] = k1;
-            cnt -= 32;
+            S.cnt -= 32;
             __syncwarp();
         }
     }
 }
-// queue the elements of every lane's flagged float4 (bit k = float4 k of the lane = elements ebase + k*estep + 0..3 of the
-// block; those outside [e0, e0 + n) -- a shifted tile's first / last float4 -- are dropped); warp-uniform entry.  The scorer
-// recomputes every queued element's score exactly, so the three elements of a float4 that did not pass cost a lookup each
-// and nothing else.  (returns qn | cnt << 16: the two counters live in registers of the caller)
-__device__ __noinline__ int s2_push(const VyHeads &hd, float valid_thresh, u32 w, u64 mask, u32 ebase, u32 estep, u32 e0, int n,
-                                    u32 *hq, int qn, u64 *wbuf, int cnt, const SelGlobal &g) {
+// issue the loads of the first n (<= 32) queued entries and take them off the queue
+__device__ __forceinline__ void s2_issue(const VyHeads &hd, u32 w, S2Warp &S, u32 *hq, int n) {
     const int lane = threadIdx.x & 31;
-    const u32 lt_mask = (1u << lane) - 1u;
-    u32 left = __ballot_sync(0xffffffffu, mask != 0ull);
-    while (left) {
-        u32 eb = 0;
-        if (mask) {
-            const int k = __ffsll((long long)mask) - 1;
-            mask &= mask - 1;
-            eb = ebase + (u32)k * estep;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            // element eb + q of lanes that hold a flagged float4 this round (inside the tile: an unsigned compare)
-            const bool in = ((left >> lane) & 1u) && (eb + (u32)q - e0) < (u32)n;
-            const u32 bal = __ballot_sync(0xffffffffu, in);
-            if (in) hq[qn + __popc(bal & lt_mask)] = eb + (u32)q;
-            qn += __popc(bal);
-            __syncwarp();
-            if (qn >= 32) {
-                s2_score(hd, valid_thresh, w, hq, 32, wbuf, cnt, g, lane, lt_mask);
-                const u32 rest = hq[32 + lane];
-                __syncwarp();
-                hq[lane] = rest;
-                qn -= 32;
-                __syncwarp();
-            }
-        }
-        left = __ballot_sync(0xffffffffu, mask != 0ull);
+    const int b = (int)(w & 0xffffu), s = (int)((w >> 16) & 3u), a = (int)((w >> 18) & 7u);
+    const VyScale &sc = hd.sc[s];
+    const u32 HW = (u32)sc.HW;
+    const float *pc0 = sc.head + ((size_t)(b * hd.A + a) * hd.P + 5) * (size_t)HW;       // class plane 0 of the block
+    if (lane < n) {
+        const u32 e = hq[lane];
+        const u32 plane = e / HW, pos = e - plane * HW;
+        S.pe = e;
+        S.ptv = vy_ldg32(pc0 + e);
+        S.pto = vy_ldg32(pc0 + pos - HW);                // the objectness plane sits right below class plane 0
     }
-    return qn | (cnt << 16);
+    S.pn = n;
+    // what is left moves to the front (in rounds of 32, front to back: a round's sources lie at or behind its targets)
+    const int rest = S.qn - n;
+    for (int r = 0; r < rest; r += 32) {
+        u32 v = 0;
+        if (r + lane < rest) v = hq[n + r + lane];
+        __syncwarp();
+        if (r + lane < rest) hq[r + lane] = v;
+        __syncwarp();
+    }
+    S.qn = rest;
 }
-// end of a block: score what is still queued, hand the warp's keys to the image's list
-__device__ __noinline__ void s2_flush(const VyHeads &hd, float valid_thresh, u32 w, u32 *hq, int qn, u64 *wbuf, int cnt,
-                                      const SelGlobal &g) {
+__device__ __noinline__ void s2_drain32(const VyHeads &hd, float valid_thresh, u32 w, S2Warp &S, u32 *hq, u64 *wbuf, const SelGlobal &g) {
+    s2_complete(hd, valid_thresh, w, S, wbuf, g);
+    s2_issue(hd, w, S, hq, 32);
+}
+// end of a block: score everything that is pending or queued, hand the warp's keys to the image's list
+__device__ __noinline__ void s2_flush(const VyHeads &hd, float valid_thresh, u32 w, S2Warp &S, u32 *hq, u64 *wbuf, const SelGlobal &g) {
     const int lane = threadIdx.x & 31;
-    const u32 lt_mask = (1u << lane) - 1u;
-    if (qn > 0) { s2_score(hd, valid_thresh, w, hq, qn, wbuf, cnt, g, lane, lt_mask); qn = 0; }
-    if (cnt > 0) {
+    s2_complete(hd, valid_thresh, w, S, wbuf, g);
+    while (S.qn > 0) {
+        s2_issue(hd, w, S, hq, min(S.qn, 32));
+        s2_complete(hd, valid_thresh, w, S, wbuf, g);
+    }
+    if (S.cnt > 0) {
         const int b = (int)(w & 0xffffu);
         int base = 0;
-        if (lane == 0) base = atomicAdd(g.scount + b, cnt);
+        if (lane == 0) base = atomicAdd(g.scount + b, S.cnt);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (lane < cnt && base + lane < g.slist_cap) g.slist[(size_t)b * g.slist_cap + base + lane] = wbuf[lane];
+        if (lane < S.cnt && base + lane < g.slist_cap) g.slist[(size_t)b * g.slist_cap + base + lane] = wbuf[lane];
         __syncwarp();
+        S.cnt = 0;
+    }
+}
+// A tile has flagged float4 (bit k of `hits` = float4 lane + 32k of the tile): find which of their elements pass (the
+// stage and the table are still the tile's: this runs BEFORE the stage is handed back) and queue those.  Warp-uniform
+// entry.  st4 / tab as in the caller; t_first = table index (float4 units when aligned, else floats) of this lane's
+// float4 0, t_step / t_mod = what 32 float4 further means in the table.
+__device__ __noinline__ void s2_queue_hits(const VyHeads &hd, float valid_thresh, u32 w, S2Warp &S, u32 *hq, u64 *wbuf,
+                                           const SelGlobal &g, u64 hits, const float4 *st4, const float *tab, int t_first,
+                                           int t_mod, u32 e0, int n) {
+    const int lane = threadIdx.x & 31;
+    const u32 lt_mask = (1u << lane) - 1u;
+    const bool aligned = (w >> 23) & 1u;
+    const int shift = aligned ? 0 : (int)((w >> 24) & 3u);
+    u32 left = __ballot_sync(0xffffffffu, hits != 0ull);
+    while (left) {
+        u32 pass = 0, eb = 0;
+        if (hits) {
+            const int k = __ffsll((long long)hits) - 1;
+            hits &= hits - 1;
+            const int j = lane + 32 * k;
+            const float4 v = st4[j];
+            const int el = 4 * j - shift;                // element (inside the tile) of v.x
+            eb = e0 + (u32)el;
+            int ti = t_first + (aligned ? 32 : 128) * k; // table index of the float4: wraps at the plane size
+            if (ti >= t_mod) { if (t_mod >= 2048) { ti -= t_mod; if (ti >= t_mod) ti -= t_mod; if (ti >= t_mod) ti -= t_mod; } else ti %= t_mod; }
+            float t0, t1, t2, t3;
+            if (aligned) {
+                const float4 t = ((const float4 *)tab)[ti];
+                t0 = t.x; t1 = t.y; t2 = t.z; t3 = t.w;
+            } else {
+                t0 = tab[ti]; t1 = tab[ti + 1]; t2 = tab[ti + 2]; t3 = tab[ti + 3];
+            }
+            // (the tensor's last <= 3 floats, which a shifted copy may not hold, are flagged conservatively: the
+            // scorer reads them from global memory)
+            const int n_smem = n - (int)((w >> 26) & 3u);
+            pass = ((v.x >= t0 || el >= n_smem) && el >= 0 && el < n ? 1u : 0u) |
+                   ((v.y >= t1 || el + 1 >= n_smem) && el + 1 >= 0 && el + 1 < n ? 2u : 0u) |
+                   ((v.z >= t2 || el + 2 >= n_smem) && el + 2 >= 0 && el + 2 < n ? 4u : 0u) |
+                   ((v.w >= t3 || el + 3 >= n_smem) && el + 3 >= 0 && el + 3 < n ? 8u : 0u);
+        }
+        // every lane's <= 4 entries go to the queue behind those of the lanes before it: one warp scan per round
+        const int mine = __popc(pass);
+        int incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += o;
+        }
+        int at = S.qn + incl - mine;
+        while (pass) {
+            const int q = __ffs(pass) - 1;
+            pass &= pass - 1;
+            hq[at++] = eb + (u32)q;
+        }
+        S.qn += __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        while (S.qn > S2_HQ - 128) s2_drain32(hd, valid_thresh, w, S, hq, wbuf, g);       // (dense hits: make room for a round)
+        left = __ballot_sync(0xffffffffu, hits != 0ull);
     }
 }
 
 // One CTA per SM (its ring and two table buffers take ~150 KB), but registers capped as if two were resident: a
 // finalize or sample CTA of a neighbouring stream still fits beside it.
-//   barriers   full[stage]   the tile's bytes have landed (producer: expect_tx; waited for by the owning warp)
-//              empty[stage]  the owning warp has tested the tile (one arrival)
+//   barriers   full[stage]   the tile's bytes have landed (producer: expect_tx; waited for by the stage's warps)
+//              empty[stage]  the stage's warps have tested the tile (S2_WPS arrivals)
 //              tab[buf]      the block's table slice has landed in buffer buf (producer: expect_tx; every warp waits for
 //                            it once per block it meets)
-//   A table buffer is reused by the block after next.  Tiles are issued in order and issuing tile i waits for the release
-//   of tile i - n_stages, so when tile i goes out every tile <= i - n_stages has been tested; the producer waits for the
-//   last tile of the buffer's previous block explicitly only when that is more recent (runs of one-tile blocks).
-__global__ void __launch_bounds__(S2_NT, 2)
+//   Tiles go to WHICHEVER stage is free (a warp that is scoring hits or flushing a block holds its stage for a few
+//   microseconds; with tiles bound to stages in order the whole ring would wait behind it).  A stage's warps take what
+//   arrives, one round after the other, and stop at a tile of zero floats.  A table buffer is reused by the block after
+//   next: the producer counts the buffer's tiles that are out and loads the next table when none is left.
+__global__ void __launch_bounds__(S2_NT, 1)
 vy_decode_stream2_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl,
                          const __grid_constant__ SelGlobal g, int n_stages) {
     extern __shared__ __align__(128) unsigned char s2_dyn[];          // ring [n_stages][S2_STAGE_BYTES], tables [2][tab_max]
     __shared__ __align__(8) u64 bar_full[S2_MAX_STAGES], bar_empty[S2_MAX_STAGES], bar_tab[2];
     __shared__ int4 meta[S2_MAX_STAGES];
+    __shared__ int p_busy[S2_MAX_STAGES], p_par[S2_MAX_STAGES], p_buf[S2_MAX_STAGES], p_out[2], p_next;   // producer's books
     __shared__ u64 wbuf_all[S2_WARPS][64];
-    __shared__ u32 hq_all[S2_WARPS][STR_HQ];
+    __shared__ u32 hq_all[S2_WARPS][S2_HQ];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     unsigned char *ring = s2_dyn;
     float *tabs = (float *)(s2_dyn + (size_t)n_stages * S2_STAGE_BYTES);
     if (tid == 0) {
-        for (int i = 0; i < n_stages; ++i) { s2_mbar_init(&bar_full[i], 1); s2_mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < n_stages; ++i) { s2_mbar_init(&bar_full[i], 1); s2_mbar_init(&bar_empty[i], S2_WPS); }
         s2_mbar_init(&bar_tab[0], 1); s2_mbar_init(&bar_tab[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < n_stages; ++i) { p_busy[i] = 0; p_par[i] = 0; p_buf[i] = 0; }
+        p_out[0] = p_out[1] = 0; p_next = 0;
     }
     __syncthreads();
     const long long t_begin = pl.n_tiles * (long long)blockIdx.x / gridDim.x;
@@ -1181,7 +1253,6 @@ vy_decode_stream2_kernel(const __grid_constant__ VyHeads hd, const __grid_consta
         const int b0 = (int)(t_begin / pl.tiles_per_image);
         const int r0 = (int)(t_begin - (long long)b0 * pl.tiles_per_image);
         int blocks_before = 0;                            // blocks this CTA's range has entered so far
-        int carry1 = 0, carry2 = 0;                       // first tiles of the two most recent blocks entered before this batch
         for (int i0 = 0; i0 < n_mine; i0 += 32) {
             const int it = i0 + lane;                     // tile index inside the CTA's range
             const bool act = it < n_mine;
@@ -1198,19 +1269,6 @@ vy_decode_stream2_kernel(const __grid_constant__ VyHeads hd, const __grid_consta
             const u32 fb = __ballot_sync(0xffffffffu, first);
             const u32 below = fb & ((1u << lane) - 1u);
             const int ord = blocks_before + __popc(below) + (first ? 1 : 0) - 1;      // which block of the range this tile is in
-            // first tiles of the two blocks BEFORE this lane's (meaningful for a `first` lane): the block before last
-            // [p2, p1) used this lane's table buffer before
-            int p1 = carry1, p2 = carry2;
-            if (below) {
-                p1 = i0 + 31 - __clz(below);
-                const u32 below2 = below & ~(0x80000000u >> __clz(below));
-                p2 = below2 ? i0 + 31 - __clz(below2) : carry1;
-            }
-            if (fb) {
-                const u32 fb2 = fb & ~(0x80000000u >> __clz(fb));
-                carry2 = fb2 ? i0 + 31 - __clz(fb2) : carry1;
-                carry1 = i0 + 31 - __clz(fb);
-            }
             blocks_before += __popc(fb);
             const VyScale &sc = hd.sc[s];
             int e0, n, zpos;
@@ -1242,29 +1300,61 @@ vy_decode_stream2_kernel(const __grid_constant__ VyHeads hd, const __grid_consta
             const int4 word = make_int4(e0, n, zpos, (int)s2_pack(ti));
             const u32 tbytes = (u32)pl.tab_hwp[s] * 4u;
             const float *tsrc = g.tab + (size_t)b * pl.tab_floats + pl.tab_off[s] + (size_t)a * pl.tab_hwp[s];
-            const int stage = it % n_stages, round = it / n_stages;
-            const u32 dst = s2_smem(ring + (size_t)stage * S2_STAGE_BYTES + ti.doff * 16);
             const u32 tdst = s2_smem(tabs + (size_t)ti.tab * pl.tab_max);
-            // the table buffer's previous block (ord - 2) = tiles [p2, p1): those of the last ring round may still be under
-            // test (tiles are tested by different warps, in any order), everything older has been released
-            const int tw_lo = max(p2, it - n_stages + 1), tw_hi = (first && ord >= 2) ? p1 : 0;
             const int n_batch = min(32, n_mine - i0);
-            for (int i = 0; i < n_batch; ++i) {           // in tile order
+            for (int i = 0; i < n_batch; ++i) {           // in tile order, each tile by its own lane
                 if (lane == i) {
-                    if (round > 0) s2_mbar_wait(&bar_empty[stage], (u32)((round - 1) & 1));
-                    for (int tw = tw_lo; tw < tw_hi; ++tw) s2_mbar_wait(&bar_empty[tw % n_stages], (u32)((tw / n_stages) & 1));
+                    // a stage whose warps have arrived goes back on the books as free; its tile no longer uses its table
+                    auto reap = [&](int st) {
+                        if (p_busy[st]) {
+                            u32 ok;
+                            asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                         : "=r"(ok) : "r"(s2_smem(&bar_empty[st])), "r"((u32)p_par[st]) : "memory");
+                            if (ok) { p_busy[st] = 0; p_par[st] ^= 1; p_out[p_buf[st]] -= 1; }
+                        }
+                        return !p_busy[st];
+                    };
                     if (first) {
+                        // the buffer's previous block must be through (every one of its tiles tested and released)
+                        u32 spins = 0;
+                        while (p_out[ti.tab] > 0) {
+                            for (int st = 0; st < n_stages; ++st) reap(st);
+                            if (++spins > (1u << 24)) __trap();
+                        }
                         s2_mbar_expect(&bar_tab[ti.tab], tbytes);
                         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                      :: "r"(tdst), "l"(tsrc), "r"(tbytes), "r"(s2_smem(&bar_tab[ti.tab])) : "memory");
                     }
-                    meta[stage] = word;
-                    s2_mbar_expect(&bar_full[stage], (u32)bytes);
+                    int st = p_next;
+                    for (u32 spins = 0; !reap(st); ) {    // the next free stage, starting behind the last one used
+                        if (++st == n_stages) st = 0;
+                        if (++spins > (1u << 26)) __trap();
+                    }
+                    p_next = st + 1 == n_stages ? 0 : st + 1;
+                    p_busy[st] = 1; p_buf[st] = ti.tab; p_out[ti.tab] += 1;
+                    meta[st] = word;
+                    s2_mbar_expect(&bar_full[st], (u32)bytes);
                     if (bytes)
                         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     :: "r"(dst), "l"((const void *)src_al), "r"((u32)bytes), "r"(s2_smem(&bar_full[stage])) : "memory");
+                                     :: "r"(s2_smem(ring + (size_t)st * S2_STAGE_BYTES + ti.doff * 16)), "l"((const void *)src_al),
+                                        "r"((u32)bytes), "r"(s2_smem(&bar_full[st])) : "memory");
                 }
                 __syncwarp();
+            }
+        }
+        // every stage gets a last message: a tile of zero floats
+        if (lane == 0) {
+            for (int st = 0; st < n_stages; ++st) {
+                u32 spins = 0;
+                while (p_busy[st]) {
+                    u32 ok;
+                    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(ok) : "r"(s2_smem(&bar_empty[st])), "r"((u32)p_par[st]) : "memory");
+                    if (ok) { p_busy[st] = 0; p_par[st] ^= 1; }
+                    if (++spins > (1u << 26)) __trap();
+                }
+                meta[st] = make_int4(0, 0, 0, -1);
+                s2_mbar_arrive(&bar_full[st]);
             }
         }
     } else {
@@ -1275,44 +1365,46 @@ vy_decode_stream2_kernel(const __grid_constant__ VyHeads hd, const __grid_consta
         // Where those sit in the block's table: tiles start at position 0 of a plane (or -- planes longer than a tile --
         // at zpos), so the first index is the same for every tile of a block and the rest follow by adding 32 (mod the
         // plane size).
-        const u32 lt_mask = (1u << lane) - 1u;
         u64 *wbuf = wbuf_all[wid];
         u32 *hq = hq_all[wid];
-        int qn = 0, cnt = 0;
+        S2Warp S;
+        S.qn = 0; S.cnt = 0; S.pn = 0; S.pe = 0; S.ptv = 0.0f; S.pto = 0.0f;
         const float valid_thresh = pl.valid_thresh;
         const int tab_max = pl.tab_max;
         u32 cur_w = 0xffffffffu;                          // metadata word of the block this warp is in
-        int idx0 = 0, plane = 4;                          // first table index of this lane; plane size (float4, or floats when shifted)
-        const int stage = wid;
-        u32 phase = 0;
-        for (int it = wid; it < n_mine && wid < n_stages; it += n_stages, phase ^= 1u) {
+        int idx0 = 0, idx0h = 0, plane = 4;                          // first table index of this lane; plane size (float4, or floats when shifted)
+        const int stage = wid % n_stages, half = wid / n_stages;        // warps beyond S2_WPS * n_stages have no stage
+        for (u32 phase = 0; half < S2_WPS; phase ^= 1u) {
             s2_mbar_wait(&bar_full[stage], phase);
             const int4 word = meta[stage];
             const u32 w = (u32)word.w;
             const int n = word.y;
+            if (n == 0) break;                            // the producer's last message
             if ((w ^ cur_w) & S2_BLK_MASK) {              // the warp enters another block
-                if (qn > 0 || cnt > 0) { s2_flush(hd, valid_thresh, cur_w, hq, qn, wbuf, cnt, g); qn = 0; cnt = 0; }
+                if (S.qn > 0 || S.cnt > 0 || S.pn > 0) s2_flush(hd, valid_thresh, cur_w, S, hq, wbuf, g);
                 s2_mbar_wait(&bar_tab[(w >> 21) & 1u], (w >> 22) & 1u);
                 const int HW = hd.sc[(w >> 16) & 3u].HW;
-                if ((w >> 23) & 1u) { plane = HW >> 2; idx0 = lane % plane; }
+                if ((w >> 23) & 1u) { plane = HW >> 2; idx0 = lane % plane; idx0h = (idx0 + 128 * half) % plane; }
                 else { plane = HW; idx0 = (4 * lane) % plane; }
             }
             cur_w = w;
             const float *tab = tabs + ((w >> 21) & 1u) * tab_max;
             const unsigned char *st = ring + (size_t)stage * S2_STAGE_BYTES + (w >> 28) * 16;
             u64 hits = 0;                                 // bit k: this lane's float4 k has an element at or above its bound
+            int t_first = 0;                              // table index of this lane's float4 0 (for the rare path)
 #ifndef S2_DBG_NOCOMPARE
             if ((w >> 23) & 1u) {
                 // aligned: float4 of the tile against float4 of the table
                 const int nf4 = n >> 2;
                 const float4 *d4 = (const float4 *)st + lane;
                 const float4 *t4 = (const float4 *)tab + (word.z >> 2);
-                const int step = 32 % plane;
-                int idx = idx0;
+                const int step = 32 % plane, skip = (128 * (S2_WPS - 1)) % plane;
+                t_first = idx0;
+                int idx = idx0h;                          // this warp's first group of four rows starts at row 4 * half
                 const int kmax = (nf4 + 31) >> 5;         // float4 rows of 32 lanes in this tile (<= S2_K)
                 // four rows at a time: the eight loads first, then branch-free compares.  Rows past the end of the tile
                 // are read all the same (stale bytes of the stage, a valid table index) and masked out.
-                for (int k0 = 0; k0 < kmax; k0 += 4) {
+                for (int k0 = 4 * half; k0 < kmax; k0 += 4 * S2_WPS) {
                     float4 v[4], t[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -1321,6 +1413,8 @@ vy_decode_stream2_kernel(const __grid_constant__ VyHeads hd, const __grid_consta
                         idx += step;
                         if (idx >= plane) idx -= plane;
                     }
+                    idx += skip;                          // over the other warps' groups
+                    if (idx >= plane) idx -= plane;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         u32 h;
@@ -1345,12 +1439,15 @@ vy_decode_stream2_kernel(const __grid_constant__ VyHeads hd, const __grid_consta
                     const int b = (int)(w & 0xffffu), a = (int)((w >> 18) & 7u);
                     pc0e = hd.sc[(w >> 16) & 3u].head + ((size_t)(b * hd.A + a) * hd.P + 5) * (size_t)plane + word.x;
                 }
-                const int step = 128 % plane;
                 int pb = idx0 + word.z - shift;           // position of stage float 4*lane (zpos > 0 only in planes longer than a tile)
                 if (pb < 0) pb += plane;
                 if (pb >= plane) pb -= plane;
+                t_first = pb;
                 const int kmax = (nf4 + 31) >> 5;
-                for (int k = 0; k < kmax; ++k) {
+                const int step_w = (128 * S2_WPS) % plane;
+                pb += 128 * half;
+                if (pb >= plane) pb %= plane;
+                for (int k = half; k < kmax; k += S2_WPS) {
                     const int j = lane + 32 * k;
                     const float4 v4 = d4[j];              // (rows past the end: stale bytes of the stage, masked below)
                     const float t0 = tab[pb], t1 = tab[pb + 1], t2 = tab[pb + 2], t3 = tab[pb + 3];
@@ -1365,25 +1462,24 @@ vy_decode_stream2_kernel(const __grid_constant__ VyHeads hd, const __grid_consta
                     const u32 h = ((x0 >= t0) & (el >= 0) & (el < n)) | ((x1 >= t1) & (el + 1 >= 0) & (el + 1 < n)) |
                                   ((x2 >= t2) & (el + 2 >= 0) & (el + 2 < n)) | ((x3 >= t3) & (el + 3 >= 0) & (el + 3 < n));
                     hits |= (u64)(h & 1u) << k;
-                    pb += step;
+                    pb += step_w;
                     if (pb >= plane) pb -= plane;
                 }
             }
 #endif
-            // the stage is free as soon as it has been TESTED: hand it back before looking after the hits -- scoring them is
-            // a round trip to L2 that must not hold up the ring
+            // rare: which elements of the flagged float4 passed -> the warp's queue (shared memory only)
+            if (__any_sync(0xffffffffu, hits != 0ull)) {
+                const bool al = (w >> 23) & 1u;          // (aligned: the table pointer includes zpos; indices wrap at the plane size)
+                s2_queue_hits(hd, valid_thresh, w, S, hq, wbuf, g, hits, (const float4 *)st,
+                              al ? (const float *)((const float4 *)tab + (word.z >> 2)) : tab, t_first, plane, (u32)word.x, n);
+            }
+            // the stage is free as soon as it has been tested and its hits are queued: hand it back before scoring them --
+            // that is a round trip to L2 which must not hold up the ring
             __syncwarp();
             if (lane == 0) s2_mbar_arrive(&bar_empty[stage]);
-            if (__any_sync(0xffffffffu, hits != 0ull)) {
-                // rare: which elements of the flagged float4 passed is worked out from global memory by the scorer, which
-                // takes ELEMENT indices: queue all four elements of a flagged float4 (the scorer drops what fails)
-                const int shift = ((w >> 23) & 1u) ? 0 : (int)((w >> 24) & 3u);
-                const int r = s2_push(hd, valid_thresh, w, hits, (u32)(word.x + 4 * lane - shift), 128u, (u32)word.x, n, hq, qn,
-                                      wbuf, cnt, g);
-                qn = r & 0xffff; cnt = r >> 16;
-            }
+            if (S.qn >= 32) s2_drain32(hd, valid_thresh, w, S, hq, wbuf, g);
         }
-        if (qn > 0 || cnt > 0) s2_flush(hd, valid_thresh, cur_w, hq, qn, wbuf, cnt, g);
+        if (S.qn > 0 || S.cnt > 0 || S.pn > 0) s2_flush(hd, valid_thresh, cur_w, S, hq, wbuf, g);
     }
     vy_grid_dep_trigger();
 }

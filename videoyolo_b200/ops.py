@@ -315,6 +315,60 @@ def detect_consume(dets: torch.Tensor, size: float):
     return clipped, normed, counts
 
 
+def hierarchical_nms(boxes: torch.Tensor, lifted, branch, ov_thresh: float = 0.5, conf_thresh: float = 0.0):
+    """``hierarchical_nms`` of detect_yolo3.py:736-789 on the device.  ``boxes`` (B, N, 6) float32 CUDA rows
+    [cls, conf, x1, y1, x2, y2] (cls < 0 = padding); ``lifted`` (n_cls,) the class every class is raised to by the
+    ``level_thresh`` walk (:766-767); ``branch`` (n_cls, n_cls) ``dataset.on_branch(i, j)``.  Returns
+    (new rows (B, N, 6) in the reference's append order, -1 padded; rows kept per image (B,) int32)."""
+    boxes = _need_cuda(boxes, "boxes")
+    if boxes.dim() != 3 or boxes.shape[2] != 6:
+        raise ValueError("boxes must be (B, N, 6)")
+    dev = boxes.device
+    lifted = torch.as_tensor(lifted, dtype=torch.int32, device=dev).contiguous()
+    branch = torch.as_tensor(branch, device=dev).to(torch.uint8).contiguous()
+    n_cls = lifted.numel()
+    if tuple(branch.shape) != (n_cls, n_cls):
+        raise ValueError("branch must be (n_cls, n_cls)")
+    B, N = boxes.shape[0], boxes.shape[1]
+    out = torch.empty_like(boxes)
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    if B == 0 or N == 0:
+        return out, counts
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().vy_hier_nms_f32(boxes.data_ptr(), B, N, lifted.data_ptr(), branch.data_ptr(), n_cls,
+                                              float(ov_thresh), float(conf_thresh), out.data_ptr(), counts.data_ptr(), _stream()))
+    return out, counts
+
+
+def voc_match(dets: torch.Tensor, gt_bboxes: torch.Tensor, gt_labels: torch.Tensor, gt_difficults: Optional[torch.Tensor] = None,
+              n_class: int = 1, iou_thresh: float = 0.5):
+    """The per-image part of ``VOCMApMetric.update`` (metrics/pascalvoc.py:116-184) on the device.  ``dets`` (B, P, 6) as
+    returned by the fused tail; ``gt_bboxes`` (B, M, 4), ``gt_labels`` (B, M[, 1]) (< 0 = padding), ``gt_difficults``
+    (B, M[, 1]) or None.  Returns (labels (B, P) int32, scores (B, P), match (B, P) int32 in {1, 0, -1}; -2 padding;
+    valid predictions per image (B,), n_pos (B, n_class)): per image the valid predictions in the metric's order
+    (class ascending, score descending, later row first among equal scores)."""
+    dets = _need_cuda(dets, "dets")
+    gb = _need_cuda(gt_bboxes, "gt_bboxes")
+    gl = _need_cuda(gt_labels.reshape(gt_labels.shape[0], -1).float(), "gt_labels")
+    gd = _need_cuda(gt_difficults.reshape(gt_difficults.shape[0], -1).float(), "gt_difficults") if gt_difficults is not None else None
+    if dets.dim() != 3 or dets.shape[2] != 6 or gb.dim() != 3 or gb.shape[2] != 4 or gb.shape[0] != dets.shape[0]:
+        raise ValueError("dets (B, P, 6) and gt_bboxes (B, M, 4) expected")
+    B, P, M = dets.shape[0], dets.shape[1], gb.shape[1]
+    if tuple(gl.shape) != (B, M) or (gd is not None and tuple(gd.shape) != (B, M)):
+        raise ValueError("gt_labels / gt_difficults must be (B, M)")
+    dev = dets.device
+    lab = torch.empty((B, P), dtype=torch.int32, device=dev)
+    sc = torch.empty((B, P), dtype=torch.float32, device=dev)
+    mt = torch.empty((B, P), dtype=torch.int32, device=dev)
+    cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+    npos = torch.empty((B, n_class), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().vy_voc_match_f32(dets.data_ptr(), gb.data_ptr(), gl.data_ptr(), gd.data_ptr() if gd is not None else None,
+                                               B, P, M, int(n_class), float(iou_thresh), lab.data_ptr(), sc.data_ptr(),
+                                               mt.data_ptr(), cnt.data_ptr(), npos.data_ptr(), _stream()))
+    return lab, sc, mt, cnt, npos
+
+
 # ----------------------------------------------------------------------------------- temporal fusion conv
 class PTensor:
     """An activation in the library's P layout: ``data`` is a bf16 (or fp32) CUDA tensor of shape
