@@ -872,7 +872,7 @@ __device__ __forceinline__ void str_unit_async(const StrUnit &un, float4 *ring_l
 }
 
 __global__ void __launch_bounds__(STR_NT, STR_CTAS_PER_SM)
-vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl, SelGlobal g) {
+vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl, SelGlobal g, int use_tab) {
     __shared__ u64 wbuf_all[STR_NT / 32][64];
     __shared__ u32 hq_all[STR_NT / 32][STR_HQ];
     extern __shared__ __align__(16) unsigned char str_dyn[];          // [STR_NT/32][STR_RING][32] float4
@@ -913,6 +913,15 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
         un.n_s = (u32)sc.n_s; un.A = (u32)hd.A;
         un.valid_thresh = pl.valid_thresh;
         if (!dep_waited) { vy_grid_dep_wait(); dep_waited = true; }
+        if (use_tab && vec) {
+            // the per-box logit bounds were worked out once, by vy_decode_table_kernel: one 16-byte load instead of the
+            // objectness load, four sigmoids, four divisions and four logarithms per unit
+            un.thr = g.sthr[b];
+            const float4 tq = *(const float4 *)(g.tab + (size_t)b * pl.tab_floats + pl.tab_off[s] + (size_t)a * pl.tab_hwp[s] + pos0);
+            un.tcmin[0] = nv > 0 ? tq.x : CUDART_INF_F; un.tcmin[1] = nv > 1 ? tq.y : CUDART_INF_F;
+            un.tcmin[2] = nv > 2 ? tq.z : CUDART_INF_F; un.tcmin[3] = nv > 3 ? tq.w : CUDART_INF_F;
+            un.conf[0] = un.conf[1] = un.conf[2] = un.conf[3] = 0.0f;      // (only the scalar path scores from registers)
+        } else {
         un.thr = ~stream_bound_compl(g, b);
         const float smin = fmaxf(un.thr ? vy_key_score(un.thr) : pl.valid_thresh, pl.valid_thresh);
         {
@@ -923,6 +932,7 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
                 un.conf[v] = vy_sigmoid(to[v]);
                 un.tcmin[v] = v < nv ? vy_tcmin(smin, un.conf[v]) : CUDART_INF_F;
             }
+        }
         }
         int cnt = 0;                                       // keys waiting in wbuf (warp-uniform)
         if (vec) str_unit_async(un, ring_lane, hq_all[wid], wbuf, cnt, b, g, lane, lt_mask);
@@ -1468,7 +1478,11 @@ vy_decode_stream2_kernel(const __grid_constant__ VyHeads hd, const __grid_consta
             }
 #endif
             // rare: which elements of the flagged float4 passed -> the warp's queue (shared memory only)
+#ifdef S2_DBG_NOQUEUE
+            if (false) {
+#else
             if (__any_sync(0xffffffffu, hits != 0ull)) {
+#endif
                 const bool al = (w >> 23) & 1u;          // (aligned: the table pointer includes zpos; indices wrap at the plane size)
                 s2_queue_hits(hd, valid_thresh, w, S, hq, wbuf, g, hits, (const float4 *)st,
                               al ? (const float *)((const float4 *)tab + (word.z >> 2)) : tab, t_first, plane, (u32)word.x, n);
@@ -1477,7 +1491,11 @@ vy_decode_stream2_kernel(const __grid_constant__ VyHeads hd, const __grid_consta
             // that is a round trip to L2 which must not hold up the ring
             __syncwarp();
             if (lane == 0) s2_mbar_arrive(&bar_empty[stage]);
+#ifdef S2_DBG_NOSCORE
+            if (S.qn >= 32) S.qn -= 32;
+#else
             if (S.qn >= 32) s2_drain32(hd, valid_thresh, w, S, hq, wbuf, g);
+#endif
         }
         if (S.qn > 0 || S.cnt > 0 || S.pn > 0) s2_flush(hd, valid_thresh, cur_w, S, hq, wbuf, g);
     }
@@ -2554,8 +2572,14 @@ static int plan_launch(const vy_decode_nms_plan *P, const float *const *head, fl
     if (pl.stream) {
         VY_KERNEL(VY_K_SAMPLE, st, (vy_decode_sample_kernel<<<B * pl.Gs, SAMP_NT, 0, st>>>(hd, pl, g)));
         VY_LAUNCH_CHECK("vy_decode_sample_kernel");
-        static const bool stream_v1 = getenv("VY_STREAM_V1") != nullptr;        // A/B: the unit-streaming pass of round 1
-        if (stream_v1) {
+        // VY_STREAM_MODE (A/B): "v1" the unit-streaming pass of round 1, "v1t" the same with the bound table, "v2" tile streaming
+        static const char *mode_env = getenv("VY_STREAM_MODE");
+        static const int mode = !mode_env ? 0 : (!strcmp(mode_env, "v1t") ? 1 : (!strcmp(mode_env, "v2") ? 2 : 0));
+        if (mode < 2) {
+            if (mode == 1) {
+                VY_KERNEL(VY_K_TABLE, st, (vy_launch(vy_decode_table_kernel, dim3((unsigned)(B * pl.tabblk_per_image)), dim3(256), 0, st, true, hd, pl, g)));
+                VY_LAUNCH_CHECK("vy_decode_table_kernel");
+            }
             long long ctas = (pl.n_units + STR_NT / 32 - 1) / (STR_NT / 32);
             const long long resident = (long long)STR_CTAS_PER_SM * vy_sm_count();
             if (ctas > resident) ctas = resident;
@@ -2563,7 +2587,7 @@ static int plan_launch(const vy_decode_nms_plan *P, const float *const *head, fl
             // CTAs crowd the sample kernel's tail (measured: -4 % at COCO 608 x 64, +15 % at VOC 416 x 1)
             const size_t ring_bytes = (size_t)(STR_NT / 32) * STR_RING * 32 * sizeof(float4);
             VY_CUDA_CHECK(vy_ensure_dyn_smem((const void *)vy_decode_stream_kernel, ring_bytes));
-            VY_KERNEL(VY_K_STREAM, st, (vy_launch(vy_decode_stream_kernel, dim3((unsigned)ctas), dim3(STR_NT), ring_bytes, st, ctas < resident, hd, pl, g)));
+            VY_KERNEL(VY_K_STREAM, st, (vy_launch(vy_decode_stream_kernel, dim3((unsigned)ctas), dim3(STR_NT), ring_bytes, st, ctas < resident || mode == 1, hd, pl, g, mode)));
             VY_LAUNCH_CHECK("vy_decode_stream_kernel");
         } else {
             VY_KERNEL(VY_K_TABLE, st, (vy_launch(vy_decode_table_kernel, dim3((unsigned)(B * pl.tabblk_per_image)), dim3(256), 0, st, true, hd, pl, g)));
