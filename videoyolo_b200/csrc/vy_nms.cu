@@ -61,10 +61,8 @@ struct SelPlan {
     long long n_tiles;
     int tab_hwp[VY_MAX_SCALES];             // floats per (s, a) table segment: HW + 3 wrap-around copies, rounded up to 4
     int tab_off[VY_MAX_SCALES + 1];         // first float of scale s in an image's table
-    int tab_floats;                         // table floats per image (multiple of 4)
-    int tabblk_begin[VY_MAX_SCALES + 1];    // vy_decode_table_kernel: first CTA of scale s within an image
-    int tabblk_per_image;
     int tab_max;                            // largest segment (floats)
+    int s3_groups[VY_MAX_SCALES];           // segment streaming: warp groups per CTA (each with its own table) at scale s
 };
 
 struct SelGlobal {              // workspace views
@@ -79,15 +77,13 @@ struct SelGlobal {              // workspace views
     int Gs;
     u64 *slist;                 // [B][slist_cap]
     int slist_cap;
-    float *tab;                 // [B][tab_floats]  per-box logit bound of the tile-streaming pass
-    u64 *sthr;                  // [B]              the bound key the table was built for
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Gs == 0: no streaming-path arrays
 static size_t sel_workspace_layout(int B, int G, int list_cap, SelGlobal *g, void *base, size_t *header,
-                                   int Gs = 0, int slist_cap = 0, int tab_floats = 0) {
+                                   int Gs = 0, int slist_cap = 0) {
     size_t off = 0;
     const size_t o_thr = off;   off = align_up(off + sizeof(u64) * (size_t)B, 256);
     const size_t o_cnt = off;   off = align_up(off + sizeof(int) * (size_t)B, 256);
@@ -98,11 +94,7 @@ static size_t sel_workspace_layout(int B, int G, int list_cap, SelGlobal *g, voi
     if (header) *header = off;  // the part that must be zeroed per call
     const size_t o_list = off;  off = align_up(off + sizeof(u64) * (size_t)B * (size_t)list_cap, 256);
     const size_t o_slist = off; off = align_up(off + sizeof(u64) * (size_t)B * (size_t)slist_cap, 256);
-    const size_t o_tab = off;   off = align_up(off + sizeof(float) * (size_t)B * (size_t)tab_floats, 256);
-    const size_t o_sthr = off;  off = align_up(off + sizeof(u64) * (size_t)B * (tab_floats ? 1 : 0), 256);
     if (g && base) {
-        g->tab = tab_floats ? (float *)((char *)base + o_tab) : nullptr;
-        g->sthr = tab_floats ? (u64 *)((char *)base + o_sthr) : nullptr;
         g->thr = (u64 *)((char *)base + o_thr);
         g->count = (int *)((char *)base + o_cnt);
         g->slots = (u64 *)((char *)base + o_slot);
@@ -358,9 +350,6 @@ vy_decode_select_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
     vy_grid_dep_wait();
     for (int job = blockIdx.x; job < pl.n_jobs; job += gridDim.x) {
         const int b = job / pl.G;
-        // streaming path: this kernel is the rescue pass and only serves images whose streamed
-        // candidate list overflowed (the sample misjudged the score distribution)
-        if (g.scount && stream_list_ok(g, b, pl.K)) continue;
         SelJob jb;
         jb.G = pl.G; jb.g = job % pl.G; jb.K = pl.K; jb.Kq = pl.Kq;
         jb.g_thr_b = g.thr + b;
@@ -872,7 +861,7 @@ __device__ __forceinline__ void str_unit_async(const StrUnit &un, float4 *ring_l
 }
 
 __global__ void __launch_bounds__(STR_NT, STR_CTAS_PER_SM)
-vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl, SelGlobal g, int use_tab) {
+vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl, SelGlobal g) {
     __shared__ u64 wbuf_all[STR_NT / 32][64];
     __shared__ u32 hq_all[STR_NT / 32][STR_HQ];
     extern __shared__ __align__(16) unsigned char str_dyn[];          // [STR_NT/32][STR_RING][32] float4
@@ -913,15 +902,6 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
         un.n_s = (u32)sc.n_s; un.A = (u32)hd.A;
         un.valid_thresh = pl.valid_thresh;
         if (!dep_waited) { vy_grid_dep_wait(); dep_waited = true; }
-        if (use_tab && vec) {
-            // the per-box logit bounds were worked out once, by vy_decode_table_kernel: one 16-byte load instead of the
-            // objectness load, four sigmoids, four divisions and four logarithms per unit
-            un.thr = g.sthr[b];
-            const float4 tq = *(const float4 *)(g.tab + (size_t)b * pl.tab_floats + pl.tab_off[s] + (size_t)a * pl.tab_hwp[s] + pos0);
-            un.tcmin[0] = nv > 0 ? tq.x : CUDART_INF_F; un.tcmin[1] = nv > 1 ? tq.y : CUDART_INF_F;
-            un.tcmin[2] = nv > 2 ? tq.z : CUDART_INF_F; un.tcmin[3] = nv > 3 ? tq.w : CUDART_INF_F;
-            un.conf[0] = un.conf[1] = un.conf[2] = un.conf[3] = 0.0f;      // (only the scalar path scores from registers)
-        } else {
         un.thr = ~stream_bound_compl(g, b);
         const float smin = fmaxf(un.thr ? vy_key_score(un.thr) : pl.valid_thresh, pl.valid_thresh);
         {
@@ -932,7 +912,6 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
                 un.conf[v] = vy_sigmoid(to[v]);
                 un.tcmin[v] = v < nv ? vy_tcmin(smin, un.conf[v]) : CUDART_INF_F;
             }
-        }
         }
         int cnt = 0;                                       // keys waiting in wbuf (warp-uniform)
         if (vec) str_unit_async(un, ring_lane, hq_all[wid], wbuf, cnt, b, g, lane, lt_mask);
@@ -948,559 +927,9 @@ vy_decode_stream_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
     vy_grid_dep_trigger();                              // (a trigger at the start lets the dependents crowd the tail: measured slower)
 }
 
-// ------------------------------------------------------------------------------------------------
-// Tile streaming (the bandwidth pass, second generation).
-//
-//   vy_decode_table_kernel    per box the logit bound the streaming pass tests against: t_c >= logit(s_min / sigma(t_obj))
-//                             (vy_tcmin) for the image's bound s_min, as ONE table in global memory (4 bytes per box; it
-//                             stays in L2).  One thread per entry, after the sample kernel.  The old pass recomputed these
-//                             bounds in the prologue of every unit (objectness load, sigmoid, division, logarithm per 128
-//                             positions x ~27 planes): up to half of its instructions, and most of them at C = 30.
-//   vy_decode_stream2_kernel  every (b, scale, anchor) block of class planes is ONE contiguous array of C*HW floats
-//                             (channel a*P+5+c, yolo3.py:158-160).  It is cut into tiles of S2_TILE bytes; the global
-//                             tile sequence is dealt to the CTAs in equal contiguous ranges (each CTA streams ~one block's
-//                             worth of contiguous memory).  A producer warp brings tiles into a shared-memory ring with
-//                             1-D bulk copies (cp.async.bulk, one elected lane, mbarrier complete_tx) and, when the range
-//                             enters a new block, that block's slice of the table (same barrier).  Eight consumer warps test
-//                             float4 against float4 of the table (position = element index mod HW), queue the rare hits as
-//                             element indices and score them 32 at a time (str_hq-style), exactly as before.
-//                             Planes whose size is not a multiple of 4 floats (13^2, 19^2 grids) go through the same ring:
-//                             the copy starts at the 16-byte boundary below the tile and the consumers shift.
-// ------------------------------------------------------------------------------------------------
-#ifndef S2_TILE
-#define S2_TILE 24576                               // bytes per tile (one consumer warp tests a whole tile)
+#ifdef VY_STREAM_ALT
+#include "vy_stream_alt.cuh"
 #endif
-#ifndef S2_WARPS
-#define S2_WARPS 24                                 // consumer warps: S2_WPS per ring stage (tiles s, s + n_stages, ... of stage s)
-#endif
-#ifndef S2_WPS
-#define S2_WPS 4                                    // warps sharing a tile: warp h of a stage tests the row groups g = h (mod S2_WPS)
-#endif
-constexpr int S2_MAX_STAGES = S2_WARPS / S2_WPS;    // ring depth is chosen at launch from the shared-memory budget
-constexpr int S2_NT = S2_WARPS * 32 + 32;           // + the producer warp
-constexpr int S2_STAGE_BYTES = S2_TILE + 256;       // a tile lands at the same offset inside a 128-byte line as its source (+ <= 12 bytes of shift)
-constexpr int S2_K = S2_TILE / 16 / 32;             // float4 per lane and tile
-static_assert(S2_K % 4 == 0 && S2_K < 64, "tile size");
-
-// what the producer tells the consumers about a tile: one 16-byte word
-//   x = e0      first element of the tile inside its (b, s, a) block (the hit path turns element indices into rows)
-//   y = n       floats in the tile
-//   z = zpos    position (inside its plane) of the tile's first element: 0 unless the plane is longer than a tile
-//   w = b:16 | s:2 | a:3 | tab:1 | tpar:1 | aligned:1 | shift:2 | tail:2 | doff:3
-//       tab / tpar = table buffer of the block and the parity of its load (what bar_tab completes); shift = floats in
-//       front of the tile in the stage (the copy starts at the 16-byte boundary below it); tail = floats of the tile that
-//       are NOT in the stage (the copy must not run past the end of the tensor: the last <= 3 floats of a tensor whose
-//       end is not 16-byte aligned); doff = 16-byte units between the stage base and the copy: source and destination of
-//       a bulk copy sit at the same offset inside their 128-byte lines
-constexpr u32 S2_BLK_MASK = 0x7fffffu;             // b, s, a, tab, tpar: equal for the tiles of one block
-struct S2Tile { int b, s, a, tab, tpar, aligned, shift, tail, doff; };
-__device__ __forceinline__ u32 s2_pack(const S2Tile &t) {
-    return (u32)t.b | ((u32)t.s << 16) | ((u32)t.a << 18) | ((u32)t.tab << 21) | ((u32)t.tpar << 22) |
-           ((u32)t.aligned << 23) | ((u32)t.shift << 24) | ((u32)t.tail << 26) | ((u32)t.doff << 28);
-}
-
-__device__ __forceinline__ u32 s2_smem(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void s2_mbar_init(u64 *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(s2_smem(bar)), "r"(count) : "memory");
-}
-// (a wait that has not come true after ~2^24 polls -- seconds -- is a protocol error: trap instead of hanging the device)
-__device__ __forceinline__ void s2_mbar_wait(u64 *bar, u32 parity) {
-    u32 ok = 0, spins = 0;
-    const u32 a = s2_smem(bar);
-    while (!ok) {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-        if (!ok && ++spins > (1u << 24)) __trap();
-    }
-}
-__device__ __forceinline__ void s2_mbar_arrive(u64 *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(s2_smem(bar)) : "memory");
-}
-__device__ __forceinline__ void s2_mbar_expect(u64 *bar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(s2_smem(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void s2_bulk(void *dst, const void *src, u32 bytes, u64 *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(s2_smem(dst)), "l"(src), "r"(bytes), "r"(s2_smem(bar)) : "memory");
-}
-
-constexpr int TAB_PER_CTA = 1024;                   // table entries per CTA (4 per thread), all of one (b, s, a) segment
-__global__ void __launch_bounds__(256)
-vy_decode_table_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl, SelGlobal g) {
-    // block -> (image, scale, anchor, chunk of the segment): small loops and one division per CTA, none per entry
-    const int b = blockIdx.x / pl.tabblk_per_image;
-    int r = blockIdx.x - b * pl.tabblk_per_image;
-    int s = 0;
-    while (s + 1 < hd.n_scales && r >= pl.tabblk_begin[s + 1]) ++s;
-    r -= pl.tabblk_begin[s];
-    const int bps = (pl.tab_hwp[s] + TAB_PER_CTA - 1) / TAB_PER_CTA;
-    const int a = r / bps, chunk = r - a * bps;
-    const VyScale &sc = hd.sc[s];
-    const int HW = sc.HW, hwp = pl.tab_hwp[s];
-    const float *obj = sc.head + ((size_t)(b * hd.A + a) * hd.P + 4) * (size_t)HW;
-    float *out = g.tab + (size_t)b * pl.tab_floats + pl.tab_off[s] + (size_t)a * hwp;
-    float to[TAB_PER_CTA / 256];
-#pragma unroll
-    for (int k = 0; k < TAB_PER_CTA / 256; ++k) {         // the head maps do not depend on the sample kernel: load first
-        int pos = chunk * TAB_PER_CTA + k * 256 + threadIdx.x;
-        if (pos >= HW) pos -= HW;                         // entries HW .. HW+2 repeat 0 .. 2 (a shifted float4 may wrap)
-        to[k] = pos < HW ? vy_ldg32(obj + pos) : 0.0f;
-    }
-    vy_grid_dep_wait();                                   // the sample kernel's bounds
-    // the image's bound = minimum over its sample jobs (kept as complements): every warp reduces the <= 32 slots itself
-    u64 m = (threadIdx.x & 31) < g.Gs ? g.sslots[(size_t)b * g.Gs + (threadIdx.x & 31)] : 0ull;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) { const u64 o = sel_shfl_xor_u64(m, off); m = o > m ? o : m; }
-    const u64 thr = ~m;
-    const float smin = fmaxf(thr ? vy_key_score(thr) : pl.valid_thresh, pl.valid_thresh);
-#pragma unroll
-    for (int k = 0; k < TAB_PER_CTA / 256; ++k) {
-        const int pos = chunk * TAB_PER_CTA + k * 256 + threadIdx.x;
-        if (pos < hwp) out[pos] = pos < HW + 3 ? vy_tcmin(smin, vy_sigmoid(to[k])) : CUDART_INF_F;   // (padding can never pass)
-    }
-    if (blockIdx.x == b * pl.tabblk_per_image && threadIdx.x == 0) g.sthr[b] = thr;
-    vy_grid_dep_trigger();
-}
-
-// ---- the rare path of a consumer warp.  Hits are QUEUED as element indices of the block (warp-private queue in shared
-// memory); full batches of 32 are scored one per lane: logit and objectness come back from L2 (the bulk copy left them
-// there), the score is the decode kernel's, the key is tested against the image's bound and survivors go to the warp's key
-// buffer (one atomic + one 256-byte store per 32 keys).  Scoring is SPLIT: a batch's loads are issued and the warp goes
-// on with the next tile; the batch is completed (scores, keys) when the next one is ready or the block ends, so the L2
-// round trip hides behind a tile's worth of compares.
-struct S2Warp {
-    int qn, cnt;                 // entries waiting in hq, keys waiting in wbuf (warp-uniform)
-    int pn;                      // lanes of the pending batch (0: none)
-    u32 pe;                      // pending: this lane's element, its logit and objectness logit
-    float ptv, pto;
-};
-constexpr int S2_HQ = 160;                              // queue entries per warp (a batch leaves at 32; a round of hits adds <= 128)
-
-__device__ __forceinline__ void s2_complete(const VyHeads &hd, float valid_thresh, u32 w, S2Warp &S, u64 *wbuf, const SelGlobal &g) {
-    if (S.pn == 0) return;
-    const int lane = threadIdx.x & 31;
-    const u32 lt_mask = (1u << lane) - 1u;
-    const int b = (int)(w & 0xffffu), s = (int)((w >> 16) & 3u), a = (int)((w >> 18) & 7u);
-    const VyScale &sc = hd.sc[s];
-    const u32 HW = (u32)sc.HW;
-    bool ok = false;
-    u64 key = 0;
-    if (lane < S.pn) {
-        const u32 plane = S.pe / HW, pos = S.pe - plane * HW;
-        const float sv = vy_score(S.ptv, vy_sigmoid(S.pto));
-        if (sv > valid_thresh) {
-            key = vy_make_key(sv, (u32)(sc.row_off + a) + plane * (u32)sc.n_s + pos * (u32)hd.A);
-            ok = key >= g.sthr[b];
-        }
-    }
-    S.pn = 0;
-    const u32 bal = __ballot_sync(0xffffffffu, ok);
-    if (bal) {
-        if (ok) wbuf[S.cnt + __popc(bal & lt_mask)] = key;
-        S.cnt += __popc(bal);
-        __syncwarp();
-        if (S.cnt >= 32) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(g.scount + b, 32);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const u64 k0 = wbuf[lane], k1 = wbuf[32 + lane];
-            if (base + lane < g.slist_cap) g.slist[(size_t)b * g.slist_cap + base + lane] = k0;
-            __syncwarp();
-            wbuf[lane] = k1;
-            S.cnt -= 32;
-            __syncwarp();
-        }
-    }
-}
-// issue the loads of the first n (<= 32) queued entries and take them off the queue
-__device__ __forceinline__ void s2_issue(const VyHeads &hd, u32 w, S2Warp &S, u32 *hq, int n) {
-    const int lane = threadIdx.x & 31;
-    const int b = (int)(w & 0xffffu), s = (int)((w >> 16) & 3u), a = (int)((w >> 18) & 7u);
-    const VyScale &sc = hd.sc[s];
-    const u32 HW = (u32)sc.HW;
-    const float *pc0 = sc.head + ((size_t)(b * hd.A + a) * hd.P + 5) * (size_t)HW;       // class plane 0 of the block
-    if (lane < n) {
-        const u32 e = hq[lane];
-        const u32 plane = e / HW, pos = e - plane * HW;
-        S.pe = e;
-        S.ptv = vy_ldg32(pc0 + e);
-        S.pto = vy_ldg32(pc0 + pos - HW);                // the objectness plane sits right below class plane 0
-    }
-    S.pn = n;
-    // what is left moves to the front (in rounds of 32, front to back: a round's sources lie at or behind its targets)
-    const int rest = S.qn - n;
-    for (int r = 0; r < rest; r += 32) {
-        u32 v = 0;
-        if (r + lane < rest) v = hq[n + r + lane];
-        __syncwarp();
-        if (r + lane < rest) hq[r + lane] = v;
-        __syncwarp();
-    }
-    S.qn = rest;
-}
-__device__ __noinline__ void s2_drain32(const VyHeads &hd, float valid_thresh, u32 w, S2Warp &S, u32 *hq, u64 *wbuf, const SelGlobal &g) {
-    s2_complete(hd, valid_thresh, w, S, wbuf, g);
-    s2_issue(hd, w, S, hq, 32);
-}
-// end of a block: score everything that is pending or queued, hand the warp's keys to the image's list
-__device__ __noinline__ void s2_flush(const VyHeads &hd, float valid_thresh, u32 w, S2Warp &S, u32 *hq, u64 *wbuf, const SelGlobal &g) {
-    const int lane = threadIdx.x & 31;
-    s2_complete(hd, valid_thresh, w, S, wbuf, g);
-    while (S.qn > 0) {
-        s2_issue(hd, w, S, hq, min(S.qn, 32));
-        s2_complete(hd, valid_thresh, w, S, wbuf, g);
-    }
-    if (S.cnt > 0) {
-        const int b = (int)(w & 0xffffu);
-        int base = 0;
-        if (lane == 0) base = atomicAdd(g.scount + b, S.cnt);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (lane < S.cnt && base + lane < g.slist_cap) g.slist[(size_t)b * g.slist_cap + base + lane] = wbuf[lane];
-        __syncwarp();
-        S.cnt = 0;
-    }
-}
-// A tile has flagged float4 (bit k of `hits` = float4 lane + 32k of the tile): find which of their elements pass (the
-// stage and the table are still the tile's: this runs BEFORE the stage is handed back) and queue those.  Warp-uniform
-// entry.  st4 / tab as in the caller; t_first = table index (float4 units when aligned, else floats) of this lane's
-// float4 0, t_step / t_mod = what 32 float4 further means in the table.
-__device__ __noinline__ void s2_queue_hits(const VyHeads &hd, float valid_thresh, u32 w, S2Warp &S, u32 *hq, u64 *wbuf,
-                                           const SelGlobal &g, u64 hits, const float4 *st4, const float *tab, int t_first,
-                                           int t_mod, u32 e0, int n) {
-    const int lane = threadIdx.x & 31;
-    const u32 lt_mask = (1u << lane) - 1u;
-    const bool aligned = (w >> 23) & 1u;
-    const int shift = aligned ? 0 : (int)((w >> 24) & 3u);
-    u32 left = __ballot_sync(0xffffffffu, hits != 0ull);
-    while (left) {
-        u32 pass = 0, eb = 0;
-        if (hits) {
-            const int k = __ffsll((long long)hits) - 1;
-            hits &= hits - 1;
-            const int j = lane + 32 * k;
-            const float4 v = st4[j];
-            const int el = 4 * j - shift;                // element (inside the tile) of v.x
-            eb = e0 + (u32)el;
-            int ti = t_first + (aligned ? 32 : 128) * k; // table index of the float4: wraps at the plane size
-            if (ti >= t_mod) { if (t_mod >= 2048) { ti -= t_mod; if (ti >= t_mod) ti -= t_mod; if (ti >= t_mod) ti -= t_mod; } else ti %= t_mod; }
-            float t0, t1, t2, t3;
-            if (aligned) {
-                const float4 t = ((const float4 *)tab)[ti];
-                t0 = t.x; t1 = t.y; t2 = t.z; t3 = t.w;
-            } else {
-                t0 = tab[ti]; t1 = tab[ti + 1]; t2 = tab[ti + 2]; t3 = tab[ti + 3];
-            }
-            // (the tensor's last <= 3 floats, which a shifted copy may not hold, are flagged conservatively: the
-            // scorer reads them from global memory)
-            const int n_smem = n - (int)((w >> 26) & 3u);
-            pass = ((v.x >= t0 || el >= n_smem) && el >= 0 && el < n ? 1u : 0u) |
-                   ((v.y >= t1 || el + 1 >= n_smem) && el + 1 >= 0 && el + 1 < n ? 2u : 0u) |
-                   ((v.z >= t2 || el + 2 >= n_smem) && el + 2 >= 0 && el + 2 < n ? 4u : 0u) |
-                   ((v.w >= t3 || el + 3 >= n_smem) && el + 3 >= 0 && el + 3 < n ? 8u : 0u);
-        }
-        // every lane's <= 4 entries go to the queue behind those of the lanes before it: one warp scan per round
-        const int mine = __popc(pass);
-        int incl = mine;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += o;
-        }
-        int at = S.qn + incl - mine;
-        while (pass) {
-            const int q = __ffs(pass) - 1;
-            pass &= pass - 1;
-            hq[at++] = eb + (u32)q;
-        }
-        S.qn += __shfl_sync(0xffffffffu, incl, 31);
-        __syncwarp();
-        while (S.qn > S2_HQ - 128) s2_drain32(hd, valid_thresh, w, S, hq, wbuf, g);       // (dense hits: make room for a round)
-        left = __ballot_sync(0xffffffffu, hits != 0ull);
-    }
-}
-
-// One CTA per SM (its ring and two table buffers take ~150 KB), but registers capped as if two were resident: a
-// finalize or sample CTA of a neighbouring stream still fits beside it.
-//   barriers   full[stage]   the tile's bytes have landed (producer: expect_tx; waited for by the stage's warps)
-//              empty[stage]  the stage's warps have tested the tile (S2_WPS arrivals)
-//              tab[buf]      the block's table slice has landed in buffer buf (producer: expect_tx; every warp waits for
-//                            it once per block it meets)
-//   Tiles go to WHICHEVER stage is free (a warp that is scoring hits or flushing a block holds its stage for a few
-//   microseconds; with tiles bound to stages in order the whole ring would wait behind it).  A stage's warps take what
-//   arrives, one round after the other, and stop at a tile of zero floats.  A table buffer is reused by the block after
-//   next: the producer counts the buffer's tiles that are out and loads the next table when none is left.
-__global__ void __launch_bounds__(S2_NT, 1)
-vy_decode_stream2_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ SelPlan pl,
-                         const __grid_constant__ SelGlobal g, int n_stages) {
-    extern __shared__ __align__(128) unsigned char s2_dyn[];          // ring [n_stages][S2_STAGE_BYTES], tables [2][tab_max]
-    __shared__ __align__(8) u64 bar_full[S2_MAX_STAGES], bar_empty[S2_MAX_STAGES], bar_tab[2];
-    __shared__ int4 meta[S2_MAX_STAGES];
-    __shared__ int p_busy[S2_MAX_STAGES], p_par[S2_MAX_STAGES], p_buf[S2_MAX_STAGES], p_out[2], p_next;   // producer's books
-    __shared__ u64 wbuf_all[S2_WARPS][64];
-    __shared__ u32 hq_all[S2_WARPS][S2_HQ];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    unsigned char *ring = s2_dyn;
-    float *tabs = (float *)(s2_dyn + (size_t)n_stages * S2_STAGE_BYTES);
-    if (tid == 0) {
-        for (int i = 0; i < n_stages; ++i) { s2_mbar_init(&bar_full[i], 1); s2_mbar_init(&bar_empty[i], S2_WPS); }
-        s2_mbar_init(&bar_tab[0], 1); s2_mbar_init(&bar_tab[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int i = 0; i < n_stages; ++i) { p_busy[i] = 0; p_par[i] = 0; p_buf[i] = 0; }
-        p_out[0] = p_out[1] = 0; p_next = 0;
-    }
-    __syncthreads();
-    const long long t_begin = pl.n_tiles * (long long)blockIdx.x / gridDim.x;
-    const long long t_end = pl.n_tiles * (long long)(blockIdx.x + 1) / gridDim.x;
-    const int n_mine = (int)(t_end - t_begin);
-    vy_grid_dep_wait();                                   // the table (and through it the sample's bounds)
-
-    if (wid == S2_WARPS) {
-        // ------------------------------------------------------------------ producer warp
-        // A batch = 32 consecutive tiles, one per lane.  The lanes work out their tiles side by side (the integer
-        // divisions of the decode cost one lane as much as 32) and keep the descriptors in registers; then the tiles are
-        // issued in order, each by its own lane: wait for the stage, one 16-byte word of metadata, expect_tx, bulk copy
-        // (+ the block's table slice).  The ring covers the pause of the next batch's decode.
-        const int b0 = (int)(t_begin / pl.tiles_per_image);
-        const int r0 = (int)(t_begin - (long long)b0 * pl.tiles_per_image);
-        int blocks_before = 0;                            // blocks this CTA's range has entered so far
-        for (int i0 = 0; i0 < n_mine; i0 += 32) {
-            const int it = i0 + lane;                     // tile index inside the CTA's range
-            const bool act = it < n_mine;
-            int b = b0, s = 0, a = 0, t = 0;
-            if (act) {
-                int r = r0 + it;
-                const int db = r / pl.tiles_per_image;
-                b += db; r -= db * pl.tiles_per_image;
-                while (s + 1 < hd.n_scales && r >= pl.tile_begin[s + 1]) ++s;
-                r -= pl.tile_begin[s];
-                a = r / pl.tiles_blk[s]; t = r - a * pl.tiles_blk[s];
-            }
-            const bool first = act && (t == 0 || it == 0);
-            const u32 fb = __ballot_sync(0xffffffffu, first);
-            const u32 below = fb & ((1u << lane) - 1u);
-            const int ord = blocks_before + __popc(below) + (first ? 1 : 0) - 1;      // which block of the range this tile is in
-            blocks_before += __popc(fb);
-            const VyScale &sc = hd.sc[s];
-            int e0, n, zpos;
-            if (pl.tile_tpp[s] > 0) {                     // long planes: tiles inside one plane
-                const int c = t / pl.tile_tpp[s], part = t - c * pl.tile_tpp[s];
-                zpos = part * (S2_TILE / 4);
-                e0 = c * sc.HW + zpos;
-                n = min(S2_TILE / 4, sc.HW - zpos);
-            } else {                                      // whole planes per tile
-                const int c0 = t * pl.tile_ppt[s];
-                zpos = 0;
-                e0 = c0 * sc.HW;
-                n = min(pl.tile_ppt[s], hd.C - c0) * sc.HW;
-            }
-            const float *src = sc.head + ((size_t)(b * hd.A + a) * hd.P + 5) * (size_t)sc.HW + e0;
-            const uintptr_t addr = (uintptr_t)src;
-            S2Tile ti;
-            ti.b = b; ti.s = s; ti.a = a; ti.tab = ord & 1; ti.tpar = (ord >> 1) & 1;
-            ti.shift = (int)((addr & 15) >> 2);
-            const uintptr_t src_al = addr - (uintptr_t)ti.shift * 4;
-            ti.doff = (int)((src_al & 127) >> 4);
-            long long bytes = ((long long)(ti.shift + n) * 4 + 15) & ~15LL;
-            const uintptr_t end_al = ((uintptr_t)(sc.head + (size_t)hd.B * hd.A * hd.P * (size_t)sc.HW)) & ~(uintptr_t)15;
-            if (src_al + (uintptr_t)bytes > end_al) bytes = end_al > src_al ? (long long)(end_al - src_al) : 0;
-            int n_smem = (int)(bytes / 4) - ti.shift;
-            n_smem = n_smem < 0 ? 0 : (n_smem > n ? n : n_smem);
-            ti.tail = n - n_smem;                         // <= 3
-            ti.aligned = (ti.shift == 0 && (sc.HW & 3) == 0) ? 1 : 0;
-            const int4 word = make_int4(e0, n, zpos, (int)s2_pack(ti));
-            const u32 tbytes = (u32)pl.tab_hwp[s] * 4u;
-            const float *tsrc = g.tab + (size_t)b * pl.tab_floats + pl.tab_off[s] + (size_t)a * pl.tab_hwp[s];
-            const u32 tdst = s2_smem(tabs + (size_t)ti.tab * pl.tab_max);
-            const int n_batch = min(32, n_mine - i0);
-            for (int i = 0; i < n_batch; ++i) {           // in tile order, each tile by its own lane
-                if (lane == i) {
-                    // a stage whose warps have arrived goes back on the books as free; its tile no longer uses its table
-                    auto reap = [&](int st) {
-                        if (p_busy[st]) {
-                            u32 ok;
-                            asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                                         : "=r"(ok) : "r"(s2_smem(&bar_empty[st])), "r"((u32)p_par[st]) : "memory");
-                            if (ok) { p_busy[st] = 0; p_par[st] ^= 1; p_out[p_buf[st]] -= 1; }
-                        }
-                        return !p_busy[st];
-                    };
-                    if (first) {
-                        // the buffer's previous block must be through (every one of its tiles tested and released)
-                        u32 spins = 0;
-                        while (p_out[ti.tab] > 0) {
-                            for (int st = 0; st < n_stages; ++st) reap(st);
-                            if (++spins > (1u << 24)) __trap();
-                        }
-                        s2_mbar_expect(&bar_tab[ti.tab], tbytes);
-                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     :: "r"(tdst), "l"(tsrc), "r"(tbytes), "r"(s2_smem(&bar_tab[ti.tab])) : "memory");
-                    }
-                    int st = p_next;
-                    for (u32 spins = 0; !reap(st); ) {    // the next free stage, starting behind the last one used
-                        if (++st == n_stages) st = 0;
-                        if (++spins > (1u << 26)) __trap();
-                    }
-                    p_next = st + 1 == n_stages ? 0 : st + 1;
-                    p_busy[st] = 1; p_buf[st] = ti.tab; p_out[ti.tab] += 1;
-                    meta[st] = word;
-                    s2_mbar_expect(&bar_full[st], (u32)bytes);
-                    if (bytes)
-                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     :: "r"(s2_smem(ring + (size_t)st * S2_STAGE_BYTES + ti.doff * 16)), "l"((const void *)src_al),
-                                        "r"((u32)bytes), "r"(s2_smem(&bar_full[st])) : "memory");
-                }
-                __syncwarp();
-            }
-        }
-        // every stage gets a last message: a tile of zero floats
-        if (lane == 0) {
-            for (int st = 0; st < n_stages; ++st) {
-                u32 spins = 0;
-                while (p_busy[st]) {
-                    u32 ok;
-                    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                                 : "=r"(ok) : "r"(s2_smem(&bar_empty[st])), "r"((u32)p_par[st]) : "memory");
-                    if (ok) { p_busy[st] = 0; p_par[st] ^= 1; }
-                    if (++spins > (1u << 26)) __trap();
-                }
-                meta[st] = make_int4(0, 0, 0, -1);
-                s2_mbar_arrive(&bar_full[st]);
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ consumer warps
-        // Warp `wid` owns ring stage `wid`, i.e. tiles wid, wid + n_stages, ... of the range, whole (a stage's rounds must be
-        // waited for in order by ONE warp: a parity wait cannot tell round r from round r - 2): lane l tests float4 l,
-        // l + 32, ... of a tile.
-        // Where those sit in the block's table: tiles start at position 0 of a plane (or -- planes longer than a tile --
-        // at zpos), so the first index is the same for every tile of a block and the rest follow by adding 32 (mod the
-        // plane size).
-        u64 *wbuf = wbuf_all[wid];
-        u32 *hq = hq_all[wid];
-        S2Warp S;
-        S.qn = 0; S.cnt = 0; S.pn = 0; S.pe = 0; S.ptv = 0.0f; S.pto = 0.0f;
-        const float valid_thresh = pl.valid_thresh;
-        const int tab_max = pl.tab_max;
-        u32 cur_w = 0xffffffffu;                          // metadata word of the block this warp is in
-        int idx0 = 0, idx0h = 0, plane = 4;                          // first table index of this lane; plane size (float4, or floats when shifted)
-        const int stage = wid % n_stages, half = wid / n_stages;        // warps beyond S2_WPS * n_stages have no stage
-        for (u32 phase = 0; half < S2_WPS; phase ^= 1u) {
-            s2_mbar_wait(&bar_full[stage], phase);
-            const int4 word = meta[stage];
-            const u32 w = (u32)word.w;
-            const int n = word.y;
-            if (n == 0) break;                            // the producer's last message
-            if ((w ^ cur_w) & S2_BLK_MASK) {              // the warp enters another block
-                if (S.qn > 0 || S.cnt > 0 || S.pn > 0) s2_flush(hd, valid_thresh, cur_w, S, hq, wbuf, g);
-                s2_mbar_wait(&bar_tab[(w >> 21) & 1u], (w >> 22) & 1u);
-                const int HW = hd.sc[(w >> 16) & 3u].HW;
-                if ((w >> 23) & 1u) { plane = HW >> 2; idx0 = lane % plane; idx0h = (idx0 + 128 * half) % plane; }
-                else { plane = HW; idx0 = (4 * lane) % plane; }
-            }
-            cur_w = w;
-            const float *tab = tabs + ((w >> 21) & 1u) * tab_max;
-            const unsigned char *st = ring + (size_t)stage * S2_STAGE_BYTES + (w >> 28) * 16;
-            u64 hits = 0;                                 // bit k: this lane's float4 k has an element at or above its bound
-            int t_first = 0;                              // table index of this lane's float4 0 (for the rare path)
-#ifndef S2_DBG_NOCOMPARE
-            if ((w >> 23) & 1u) {
-                // aligned: float4 of the tile against float4 of the table
-                const int nf4 = n >> 2;
-                const float4 *d4 = (const float4 *)st + lane;
-                const float4 *t4 = (const float4 *)tab + (word.z >> 2);
-                const int step = 32 % plane, skip = (128 * (S2_WPS - 1)) % plane;
-                t_first = idx0;
-                int idx = idx0h;                          // this warp's first group of four rows starts at row 4 * half
-                const int kmax = (nf4 + 31) >> 5;         // float4 rows of 32 lanes in this tile (<= S2_K)
-                // four rows at a time: the eight loads first, then branch-free compares.  Rows past the end of the tile
-                // are read all the same (stale bytes of the stage, a valid table index) and masked out.
-                for (int k0 = 4 * half; k0 < kmax; k0 += 4 * S2_WPS) {
-                    float4 v[4], t[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        v[u] = d4[32 * (k0 + u)];
-                        t[u] = t4[idx];
-                        idx += step;
-                        if (idx >= plane) idx -= plane;
-                    }
-                    idx += skip;                          // over the other warps' groups
-                    if (idx >= plane) idx -= plane;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        u32 h;
-                        asm("{\n\t.reg .pred p;\n\t"
-                            "setp.ge.f32 p, %1, %5;\n\t"
-                            "setp.ge.or.f32 p, %2, %6, p;\n\t"
-                            "setp.ge.or.f32 p, %3, %7, p;\n\t"
-                            "setp.ge.or.f32 p, %4, %8, p;\n\t"
-                            "selp.u32 %0, 1, 0, p;\n\t}"
-                            : "=r"(h) : "f"(v[u].x), "f"(v[u].y), "f"(v[u].z), "f"(v[u].w), "f"(t[u].x), "f"(t[u].y), "f"(t[u].z), "f"(t[u].w));
-                        h &= (lane + 32 * (k0 + u) < nf4) ? 1u : 0u;
-                        hits |= (u64)h << (k0 + u);
-                    }
-                }
-            } else {
-                // shifted / odd plane size: stage float (shift + el) is element e0 + el of the block
-                const int shift = (int)((w >> 24) & 3u), n_smem = n - (int)((w >> 26) & 3u);
-                const int nf4 = (shift + n + 3) >> 2;
-                const float4 *d4 = (const float4 *)st;
-                const float *pc0e = nullptr;
-                if (n_smem < n) {
-                    const int b = (int)(w & 0xffffu), a = (int)((w >> 18) & 7u);
-                    pc0e = hd.sc[(w >> 16) & 3u].head + ((size_t)(b * hd.A + a) * hd.P + 5) * (size_t)plane + word.x;
-                }
-                int pb = idx0 + word.z - shift;           // position of stage float 4*lane (zpos > 0 only in planes longer than a tile)
-                if (pb < 0) pb += plane;
-                if (pb >= plane) pb -= plane;
-                t_first = pb;
-                const int kmax = (nf4 + 31) >> 5;
-                const int step_w = (128 * S2_WPS) % plane;
-                pb += 128 * half;
-                if (pb >= plane) pb %= plane;
-                for (int k = half; k < kmax; k += S2_WPS) {
-                    const int j = lane + 32 * k;
-                    const float4 v4 = d4[j];              // (rows past the end: stale bytes of the stage, masked below)
-                    const float t0 = tab[pb], t1 = tab[pb + 1], t2 = tab[pb + 2], t3 = tab[pb + 3];
-                    const int el = 4 * j - shift;         // element of v4.x
-                    float x0 = v4.x, x1 = v4.y, x2 = v4.z, x3 = v4.w;
-                    if (n_smem < n) {                     // the tensor's last <= 3 floats are not in the stage
-                        if (el >= n_smem && el < n) x0 = vy_ldg32(pc0e + el);
-                        if (el + 1 >= n_smem && el + 1 < n) x1 = vy_ldg32(pc0e + el + 1);
-                        if (el + 2 >= n_smem && el + 2 < n) x2 = vy_ldg32(pc0e + el + 2);
-                        if (el + 3 >= n_smem && el + 3 < n) x3 = vy_ldg32(pc0e + el + 3);
-                    }
-                    const u32 h = ((x0 >= t0) & (el >= 0) & (el < n)) | ((x1 >= t1) & (el + 1 >= 0) & (el + 1 < n)) |
-                                  ((x2 >= t2) & (el + 2 >= 0) & (el + 2 < n)) | ((x3 >= t3) & (el + 3 >= 0) & (el + 3 < n));
-                    hits |= (u64)(h & 1u) << k;
-                    pb += step_w;
-                    if (pb >= plane) pb -= plane;
-                }
-            }
-#endif
-            // rare: which elements of the flagged float4 passed -> the warp's queue (shared memory only)
-#ifdef S2_DBG_NOQUEUE
-            if (false) {
-#else
-            if (__any_sync(0xffffffffu, hits != 0ull)) {
-#endif
-                const bool al = (w >> 23) & 1u;          // (aligned: the table pointer includes zpos; indices wrap at the plane size)
-                s2_queue_hits(hd, valid_thresh, w, S, hq, wbuf, g, hits, (const float4 *)st,
-                              al ? (const float *)((const float4 *)tab + (word.z >> 2)) : tab, t_first, plane, (u32)word.x, n);
-            }
-            // the stage is free as soon as it has been tested and its hits are queued: hand it back before scoring them --
-            // that is a round trip to L2 which must not hold up the ring
-            __syncwarp();
-            if (lane == 0) s2_mbar_arrive(&bar_empty[stage]);
-#ifdef S2_DBG_NOSCORE
-            if (S.qn >= 32) S.qn -= 32;
-#else
-            if (S.qn >= 32) s2_drain32(hd, valid_thresh, w, S, hq, wbuf, g);
-#endif
-        }
-        if (S.qn > 0 || S.cnt > 0 || S.pn > 0) s2_flush(hd, valid_thresh, cur_w, S, hq, wbuf, g);
-    }
-    vy_grid_dep_trigger();
-}
 
 // ------------------------------------------------------------------------------------------------
 // source 2: materialised detection rows (generic box_nms).  Iteration = SEL_NT consecutive rows.
@@ -1920,9 +1349,107 @@ static __device__ __noinline__ int fin_front_general(FinBuf &S, const u64 *list,
 // is one contiguous segment still ordered by rank.  Suppression only ever happens inside a segment, so the
 // IoU tests run over (segment length)^2 pairs instead of K^2, and segments that share no 32-slot block are
 // resolved by different warps.
+// ---- exact rescue of an image whose streamed candidate list is unusable (overflow, or fewer than K keys under a
+// non-trivial bound: the sample misjudged the score distribution; probability ~1e-7 per image with random-init or
+// trained-like logits, certain for adversarial inputs such as all-equal scores).  The image's CTA redoes the selection
+// alone: MSB-first radix select over the 64-bit keys of EVERY (box, class) of the image, keys recomputed from the head
+// maps in each pass (same arithmetic as the streaming pass: vy_score(t_c, sigmoid(t_obj)), row = the reference's), until
+// the keys at or above the prefix fit the list; one more pass collects them.  Slow (a pass reads the whole image with
+// one CTA) and rare; it replaces a separate rescue launch that sat on the critical path of every call.
+template <class F>
+__device__ __forceinline__ void fin_for_each_key(const VyHeads &hd, const SelPlan &pl, int b, F f) {
+    for (int idx = threadIdx.x; idx < pl.items_per_frame; idx += blockDim.x) {
+        int s = 0;
+        while (s + 1 < hd.n_scales && idx >= pl.item_begin[s + 1]) ++s;
+        const VyScale &sc = hd.sc[s];
+        const int rel = idx - pl.item_begin[s];
+        const int a = rel / pl.items_per_plane[s];
+        const int pos0 = (rel - a * pl.items_per_plane[s]) * 4;
+        const int nv = min(4, sc.HW - pos0);
+        const float *p = sc.head + ((size_t)(b * hd.A + a) * hd.P) * (size_t)sc.HW + pos0;
+        const u32 row0 = (u32)(sc.row_off + (long long)pos0 * hd.A + a);
+        float conf[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) conf[v] = v < nv ? vy_sigmoid(vy_ldg32(p + 4 * (size_t)sc.HW + v)) : 0.0f;
+        for (int c = 0; c < hd.C; ++c) {
+            const float *q = p + (size_t)(5 + c) * (size_t)sc.HW;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                if (v < nv) {
+                    const float sv = vy_score(vy_ldg32(q + v), conf[v]);
+                    if (sv > pl.valid_thresh) f(vy_make_key(sv, row0 + (u32)c * (u32)sc.n_s + (u32)v * (u32)hd.A));
+                }
+            }
+        }
+    }
+}
+// returns the number of keys written to out[0 .. cap); *lower = a lower bound of the image's K-th largest key (0: none)
+static __device__ __noinline__ int fin_rescue_heads(const VyHeads &hd, const SelPlan &pl, int b, int K, u64 *out, int cap,
+                                                    u32 *hist /* 256 + 4 words of shared memory */, u64 *lower) {
+    const int tid = threadIdx.x;
+    const int limit = cap < 4096 ? cap : 4096;           // (<= 4096 keys keep the finalize on its bucket-sort front end)
+    u64 prefix = 0;
+    int kk = K;
+    int shift = 56;
+    for (;; shift -= 8) {
+        for (int i = tid; i < 260; i += blockDim.x) hist[i] = 0u;
+        __syncthreads();
+        {
+            // run-length aggregation: neighbouring keys of a thread mostly share the leading digits
+            u32 cur = 0xffffffffu, run = 0;
+            const int sh = shift;
+            const u64 pf = prefix;
+            fin_for_each_key(hd, pl, b, [&](u64 key) {
+                if (sh == 56 || ((key ^ pf) >> (sh + 8)) == 0ull) {
+                    const u32 d = (u32)(key >> sh) & 255u;
+                    if (d != cur) { if (run) atomicAdd(&hist[cur], run); cur = d; run = 0; }
+                    ++run;
+                }
+            });
+            if (run) atomicAdd(&hist[cur], run);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            u32 above = 0;
+            int dig = -1;
+            for (int d = 255; d >= 0; --d) {
+                if (above + hist[d] >= (u32)kk) { dig = d; break; }
+                above += hist[d];
+            }
+            hist[256] = (u32)dig; hist[257] = above; hist[258] = dig >= 0 ? hist[dig] : 0u;
+        }
+        __syncthreads();
+        const int dig = (int)hist[256];
+        if (dig < 0) { prefix = 0; break; }              // (first pass only) fewer than K valid keys in the image: take them all
+        const u32 above = hist[257], inb = hist[258];
+        prefix |= (u64)dig << shift;
+        kk -= (int)above;
+        const long long ge = (long long)(K - kk) + inb;  // keys at or above the prefix (its lower bits zero)
+        __syncthreads();
+        if (ge <= limit || shift == 0) break;
+    }
+    // collect
+    if (tid == 0) hist[259] = 0u;
+    __syncthreads();
+    {
+        const u64 pf = prefix;
+        fin_for_each_key(hd, pl, b, [&](u64 key) {
+            if (key >= pf) {
+                const u32 at = atomicAdd(&hist[259], 1u);
+                if (at < (u32)cap) out[at] = key;
+            }
+        });
+    }
+    __syncthreads();
+    const u32 n = hist[259];
+    *lower = prefix;
+    return (int)(n < (u32)cap ? n : (u32)cap);
+}
+
 template <int SRC>   // 0: head maps, 1: rows
 __global__ void __launch_bounds__(FIN_NT_MAX)
-vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinParams fp) {
+vy_nms_finalize_kernel(const __grid_constant__ VyHeads hd, const __grid_constant__ RowParams rp, const __grid_constant__ SelPlan pl,
+                       const __grid_constant__ SelGlobal g, const __grid_constant__ FinParams fp) {
     __shared__ FinBuf S;
     extern __shared__ __align__(16) unsigned char dyn[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (int)blockDim.x / 32;
@@ -1956,10 +1483,16 @@ vy_nms_finalize_kernel(VyHeads hd, RowParams rp, SelPlan pl, SelGlobal g, FinPar
     // ---- 1. exact top-K of the image's candidate list, sorted descending
     // streaming path: the streamed list, unless it was unusable and the rescue pass rebuilt g.list
     vy_grid_dep_wait();
-    const bool use_s = g.scount != nullptr && stream_list_ok(g, b, K);
-    const int n_list = use_s ? g.scount[b] : min(g.count[b], pl.list_cap);
+    const bool use_s = g.scount != nullptr;
+    int n_list = use_s ? g.scount[b] : min(g.count[b], pl.list_cap);
     const u64 *list = use_s ? g.slist + (size_t)b * g.slist_cap : g.list + (size_t)b * pl.list_cap;
-    if (tid == 0) { S.count = 0; S.flag = 0; S.thr = use_s ? ~stream_bound_compl(g, b) : g.thr[b]; }
+    u64 thr0 = use_s ? ~stream_bound_compl(g, b) : g.thr[b];
+    if (SRC == 0 && use_s && !stream_list_ok(g, b, K)) {
+        // unusable streamed list: this CTA redoes the image's selection exactly (fin_rescue_heads), into the same list
+        n_list = fin_rescue_heads(hd, pl, b, K, g.slist + (size_t)b * g.slist_cap, g.slist_cap, (u32 *)lbuf, &thr0);
+        __syncthreads();
+    }
+    if (tid == 0) { S.count = 0; S.flag = 0; S.thr = thr0; }
     if (tid < 32) keeps[tid] = 0u;
     u64 *keyr = S.keys;                                 // the K best by rank (K <= FIN_NT_MAX)
     int m1 = -1;
@@ -2345,7 +1878,9 @@ static int plan_heads(const VyHeads &hd, int topk, float valid_thresh, SelPlan *
 static void plan_stream(const VyHeads &hd, SelPlan *pl) {
     pl->stream = 0;
     if (hd.agnostic || hd.R < 131072 || hd.C < 1) return;
+#ifdef VY_STREAM_ALT
     if (hd.B > 0xffff || hd.A > 8 || hd.n_scales > 4) return;             // fields of the tile-streaming pass's metadata word
+#endif
     // sampled fraction 1/S
     long long S = hd.R / (40LL * pl->K);
     if (S < 4) return;
@@ -2423,6 +1958,7 @@ static void plan_stream(const VyHeads &hd, SelPlan *pl) {
     for (int s = hd.n_scales; s <= VY_MAX_SCALES; ++s) pl->unit_begin[s] = units;
     pl->units_per_image = units;
     pl->n_units = (long long)units * hd.B;
+#ifdef VY_STREAM_ALT
     // tile streaming: tiles per block, table segments
     int tiles = 0, tf = 0;
     pl->tab_max = 0;
@@ -2445,31 +1981,38 @@ static void plan_stream(const VyHeads &hd, SelPlan *pl) {
         if (pl->tab_hwp[s] > pl->tab_max) pl->tab_max = pl->tab_hwp[s];
     }
     for (int s = hd.n_scales; s <= VY_MAX_SCALES; ++s) { pl->tile_begin[s] = tiles; pl->tab_off[s] = tf; }
-    int tb = 0;
-    for (int s = 0; s < hd.n_scales; ++s) {
-        pl->tabblk_begin[s] = tb;
-        tb += hd.A * ((pl->tab_hwp[s] + TAB_PER_CTA - 1) / TAB_PER_CTA);
+    for (int s = 0; s < hd.n_scales; ++s) {               // as many groups as tables of this scale fit beside each other
+        static const int divs[] = {12, 6, 4, 3, 2, 1};
+        int ng = 1;
+        for (int d : divs) if (S3_WARPS % d == 0 && (long long)d * pl->tab_hwp[s] <= pl->tab_max) { ng = d; break; }
+        pl->s3_groups[s] = ng;
     }
-    for (int s = hd.n_scales; s <= VY_MAX_SCALES; ++s) pl->tabblk_begin[s] = tb;
-    pl->tabblk_per_image = tb;
     pl->tiles_per_image = tiles;
     pl->n_tiles = (long long)tiles * hd.B;
-    pl->tab_floats = tf;
+#endif
     pl->stream = 1;
 }
 
+#ifdef VY_STREAM_ALT
 // ring depth and dynamic shared memory of the tile-streaming kernel: the ring gets what the two table buffers leave of
 // the budget (VY_S2_SMEM_KB, default 150 KB: a finalize / sample CTA of a neighbouring stream still fits on the SM)
 static int stream2_stages(const SelPlan &pl, size_t *dyn_bytes) {
-    static const int budget_kb = getenv("VY_S2_SMEM_KB") ? atoi(getenv("VY_S2_SMEM_KB")) : 200;
+    static const int budget_kb = getenv("VY_S2_SMEM_KB") ? atoi(getenv("VY_S2_SMEM_KB")) : 0;
+    static size_t static_bytes = 0;
+    if (!static_bytes) {
+        cudaFuncAttributes fa;
+        static_bytes = cudaFuncGetAttributes(&fa, (const void *)vy_decode_stream2_kernel) == cudaSuccess ? fa.sharedSizeBytes : 48 << 10;
+    }
     const size_t tabs = 2 * (size_t)pl.tab_max * sizeof(float);
-    const size_t budget = (size_t)(budget_kb < 48 ? 48 : (budget_kb > 210 ? 210 : budget_kb)) << 10;
+    size_t budget = (size_t)(227 << 10) - static_bytes - 1024;         // what a CTA may have beside the static arrays
+    if (budget_kb >= 48 && ((size_t)budget_kb << 10) < budget) budget = (size_t)budget_kb << 10;
     long long n = budget > tabs ? (long long)((budget - tabs) / S2_STAGE_BYTES) : 0;
     if (n > S2_MAX_STAGES) n = S2_MAX_STAGES;
     if (n < 2) n = 2;
     if (dyn_bytes) *dyn_bytes = (size_t)n * S2_STAGE_BYTES + tabs;
     return (int)n;
 }
+#endif
 
 // keys per image in the streamed list: 4x the expected K*S, never more than the image has rows
 static int stream_list_cap(const VyHeads &hd, const SelPlan &pl) {
@@ -2545,7 +2088,7 @@ static int plan_init(vy_decode_nms_plan *P, const int *H, const int *W, const fl
                              topk, SEL_KMAX);
     P->slist_cap = P->pl.stream ? stream_list_cap(P->hd, P->pl) : 0;
     P->ws_bytes = sel_workspace_layout(B, P->pl.G, P->pl.list_cap, nullptr, nullptr, &P->header, P->pl.stream ? P->pl.Gs : 0,
-                                       P->slist_cap, P->pl.stream ? P->pl.tab_floats : 0);
+                                       P->slist_cap);
     P->overlap_thresh = overlap_thresh; P->force_suppress = force_suppress; P->post_nms = post_nms; P->topk = topk;
     return VY_OK;
 }
@@ -2566,43 +2109,48 @@ static int plan_launch(const vy_decode_nms_plan *P, const float *const *head, fl
         hd.sc[s].vec = (hd.sc[s].HW % 4 == 0 && (((uintptr_t)head[s]) & 15) == 0) ? 4 : 1;
     }
     SelGlobal g;
-    sel_workspace_layout(B, pl.G, pl.list_cap, &g, workspace, nullptr, pl.stream ? pl.Gs : 0, P->slist_cap,
-                         pl.stream ? pl.tab_floats : 0);
+    sel_workspace_layout(B, pl.G, pl.list_cap, &g, workspace, nullptr, pl.stream ? pl.Gs : 0, P->slist_cap);
     if (!pl.stream) VY_CUDA_CHECK(cudaMemsetAsync(workspace, 0, P->header, st));     // (the sample kernel zeroes its images' state itself)
     if (pl.stream) {
         VY_KERNEL(VY_K_SAMPLE, st, (vy_decode_sample_kernel<<<B * pl.Gs, SAMP_NT, 0, st>>>(hd, pl, g)));
         VY_LAUNCH_CHECK("vy_decode_sample_kernel");
-        // VY_STREAM_MODE (A/B): "v1" the unit-streaming pass of round 1, "v1t" the same with the bound table, "v2" tile streaming
+        long long ctas = (pl.n_units + STR_NT / 32 - 1) / (STR_NT / 32);
+        const long long resident = (long long)STR_CTAS_PER_SM * vy_sm_count();
+        if (ctas > resident) ctas = resident;
+        // PDL on this launch only in the latency regime (grid below one wave): on a full machine the early
+        // CTAs crowd the sample kernel's tail (measured: -4 % at COCO 608 x 64, +15 % at VOC 416 x 1)
+        const size_t ring_bytes = (size_t)(STR_NT / 32) * STR_RING * 32 * sizeof(float4);
+#ifdef VY_STREAM_ALT
+        // development build: VY_STREAM_MODE=v2 (tile streaming) / v3 (segment streaming) select the alternates
         static const char *mode_env = getenv("VY_STREAM_MODE");
-        static const int mode = !mode_env ? 0 : (!strcmp(mode_env, "v1t") ? 1 : (!strcmp(mode_env, "v2") ? 2 : 0));
-        if (mode < 2) {
-            if (mode == 1) {
-                VY_KERNEL(VY_K_TABLE, st, (vy_launch(vy_decode_table_kernel, dim3((unsigned)(B * pl.tabblk_per_image)), dim3(256), 0, st, true, hd, pl, g)));
-                VY_LAUNCH_CHECK("vy_decode_table_kernel");
-            }
-            long long ctas = (pl.n_units + STR_NT / 32 - 1) / (STR_NT / 32);
-            const long long resident = (long long)STR_CTAS_PER_SM * vy_sm_count();
-            if (ctas > resident) ctas = resident;
-            // PDL on this launch only in the latency regime (grid below one wave): on a full machine the early
-            // CTAs crowd the sample kernel's tail (measured: -4 % at COCO 608 x 64, +15 % at VOC 416 x 1)
-            const size_t ring_bytes = (size_t)(STR_NT / 32) * STR_RING * 32 * sizeof(float4);
-            VY_CUDA_CHECK(vy_ensure_dyn_smem((const void *)vy_decode_stream_kernel, ring_bytes));
-            VY_KERNEL(VY_K_STREAM, st, (vy_launch(vy_decode_stream_kernel, dim3((unsigned)ctas), dim3(STR_NT), ring_bytes, st, ctas < resident || mode == 1, hd, pl, g, mode)));
-            VY_LAUNCH_CHECK("vy_decode_stream_kernel");
-        } else {
-            VY_KERNEL(VY_K_TABLE, st, (vy_launch(vy_decode_table_kernel, dim3((unsigned)(B * pl.tabblk_per_image)), dim3(256), 0, st, true, hd, pl, g)));
-            VY_LAUNCH_CHECK("vy_decode_table_kernel");
+        static const int mode = !mode_env ? 0 : (!strcmp(mode_env, "v3") ? 3 : (!strcmp(mode_env, "v2") ? 2 : 0));
+        if (mode == 3) {
+            const size_t dyn = (size_t)S3_WARPS * S3_RING_BYTES + (size_t)pl.tab_max * sizeof(float);
+            long long c3 = (long long)S3_CTAS_PER_SM * vy_sm_count();
+            if (c3 > pl.n_tiles) c3 = pl.n_tiles;
+            VY_CUDA_CHECK(vy_ensure_dyn_smem((const void *)vy_decode_stream3_kernel, dyn));
+            VY_KERNEL(VY_K_STREAM, st, (vy_launch(vy_decode_stream3_kernel, dim3((unsigned)c3), dim3(S3_NT), dyn, st, true, hd, pl, g)));
+            VY_LAUNCH_CHECK("vy_decode_stream3_kernel");
+        } else if (mode == 2) {
             size_t dyn = 0;
             const int nst = stream2_stages(pl, &dyn);
-            long long ctas = vy_sm_count();
-            if (ctas > pl.n_tiles) ctas = pl.n_tiles;
+            long long c2 = vy_sm_count();
+            if (c2 > pl.n_tiles) c2 = pl.n_tiles;
             VY_CUDA_CHECK(vy_ensure_dyn_smem((const void *)vy_decode_stream2_kernel, dyn));
-            VY_KERNEL(VY_K_STREAM, st, (vy_launch(vy_decode_stream2_kernel, dim3((unsigned)ctas), dim3(S2_NT), dyn, st, true, hd, pl, g, nst)));
+            VY_KERNEL(VY_K_STREAM, st, (vy_launch(vy_decode_stream2_kernel, dim3((unsigned)c2), dim3(S2_NT), dyn, st, true, hd, pl, g, nst)));
             VY_LAUNCH_CHECK("vy_decode_stream2_kernel");
+        } else
+#endif
+        {
+            VY_CUDA_CHECK(vy_ensure_dyn_smem((const void *)vy_decode_stream_kernel, ring_bytes));
+            VY_KERNEL(VY_K_STREAM, st, (vy_launch(vy_decode_stream_kernel, dim3((unsigned)ctas), dim3(STR_NT), ring_bytes, st, ctas < resident, hd, pl, g)));
+            VY_LAUNCH_CHECK("vy_decode_stream_kernel");
         }
     }
-    VY_KERNEL(VY_K_SELECT_HEADS, st, (vy_launch(vy_decode_select_kernel, dim3(select_grid(pl.n_jobs)), dim3(SEL_NT), 0, st, true, hd, pl, g)));
-    VY_LAUNCH_CHECK("vy_decode_select_kernel");
+    if (!pl.stream) {        // small / class-agnostic inputs: the adaptive select IS the selection
+        VY_KERNEL(VY_K_SELECT_HEADS, st, (vy_launch(vy_decode_select_kernel, dim3(select_grid(pl.n_jobs)), dim3(SEL_NT), 0, st, true, hd, pl, g)));
+        VY_LAUNCH_CHECK("vy_decode_select_kernel");
+    }
     FinParams fp;
     fp.K = pl.K; fp.post_rows = P->post_nms; fp.out_stride_rows = P->post_nms;
     fp.overlap_thresh = P->overlap_thresh; fp.force_suppress = P->force_suppress;
