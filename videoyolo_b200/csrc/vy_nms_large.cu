@@ -36,6 +36,9 @@ constexpr int LG_WORDS = LG_TILE / 32;
 constexpr int LG_CHUNK = 2048;       // ranks per compaction chunk
 constexpr int LG_CNT = 256;          // threads per compaction CTA (8 flags each)
 constexpr int LA_NT = 256;           // threads per CTA of the adjacency kernel
+#ifndef LA_CTAS
+#define LA_CTAS 5
+#endif
 constexpr int LA_E = 4;              // edge slots per candidate (average over a segment)
 
 struct LgLayout {
@@ -480,7 +483,7 @@ __device__ unsigned long long la_stats[8];     // visits, lower positions, area-
 #define LA_COUNT(i, v) do { } while (0)
 #endif
 template <int FMT>
-__global__ void __launch_bounds__(LA_NT) lg_adj_kernel(const __grid_constant__ LgNms p) {
+__global__ void __launch_bounds__(LA_NT, LA_CTAS) lg_adj_kernel(const __grid_constant__ LgNms p) {
     __shared__ long long sh_len;
     __shared__ int sh_flag, sh_ne, sh_done, sh_nreg;
     __shared__ u32 sh_scan[LA_NT];
@@ -621,30 +624,33 @@ __global__ void __launch_bounds__(LA_NT) lg_adj_kernel(const __grid_constant__ L
                 const float mc = fmaxf(gc.w, gc.h);
                 // sizes a suppressor can have: (t*mc, mc/t), with slack; thr >= 0.05 on this path
                 const int l_lo = lg_level(p.thr * mc * 0.999f), l_hi = lg_level(mc / p.thr * 1.001f);
-                bool scan_all = l_hi - l_lo > 7;
-                // the probe windows, level by level (warp-uniform): first cell, cells per row, cells
-                int wx0[8], wy0[8], wnx[8], wn[8];
-                int total = 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    wx0[i] = wy0[i] = wnx[i] = wn[i] = 0;
-                    const int L = l_lo + i;
-                    if (L <= l_hi && !scan_all) {
-                        const float cs = lg_pow2(L - sh), inv = lg_pow2(sh - L);
-                        const float rx = gc.w * reach, ry = gc.h * reach;
-                        const float mx = rx + cs * 1e-3f + (fabsf(gc.cx) + rx) * 1e-6f;
-                        const float my = ry + cs * 1e-3f + (fabsf(gc.cy) + ry) * 1e-6f;
-                        const float fx0 = floorf((gc.cx - mx) * inv), fx1 = floorf((gc.cx + mx) * inv);
-                        const float fy0 = floorf((gc.cy - my) * inv), fy1 = floorf((gc.cy + my) * inv);
-                        if (!(fabsf(fx0) < 1.0e9f && fabsf(fx1) < 1.0e9f && fabsf(fy0) < 1.0e9f && fabsf(fy1) < 1.0e9f) ||
-                            fx1 - fx0 > 31.0f || fy1 - fy0 > 31.0f) scan_all = true;
-                        else {
-                            wx0[i] = (int)fx0; wy0[i] = (int)fy0; wnx[i] = (int)fx1 - (int)fx0 + 1;
-                            wn[i] = wnx[i] * ((int)fy1 - (int)fy0 + 1);
-                            total += wn[i];
-                        }
+                // the probe windows: lane i works out level l_lo + i (first cell, cells per row, cells); prefix over the levels
+                const int nlev = l_hi - l_lo + 1;
+                int my_x0 = 0, my_y0 = 0, my_nx = 1, my_n = 0;
+                bool bad = false;
+                if (lane < nlev && nlev <= 8) {
+                    const int L = l_lo + lane;
+                    const float cs = lg_pow2(L - sh), inv = lg_pow2(sh - L);
+                    const float rx = gc.w * reach, ry = gc.h * reach;
+                    const float mx = rx + cs * 1e-3f + (fabsf(gc.cx) + rx) * 1e-6f;
+                    const float my = ry + cs * 1e-3f + (fabsf(gc.cy) + ry) * 1e-6f;
+                    const float fx0 = floorf((gc.cx - mx) * inv), fx1 = floorf((gc.cx + mx) * inv);
+                    const float fy0 = floorf((gc.cy - my) * inv), fy1 = floorf((gc.cy + my) * inv);
+                    if (!(fabsf(fx0) < 1.0e9f && fabsf(fx1) < 1.0e9f && fabsf(fy0) < 1.0e9f && fabsf(fy1) < 1.0e9f) ||
+                        fx1 - fx0 > 31.0f || fy1 - fy0 > 31.0f) bad = true;
+                    else {
+                        my_x0 = (int)fx0; my_y0 = (int)fy0; my_nx = (int)fx1 - (int)fx0 + 1;
+                        my_n = my_nx * ((int)fy1 - (int)fy0 + 1);
                     }
                 }
+                const bool scan_all = nlev > 8 || __any_sync(0xffffffffu, bad);
+                int my_end = my_n;                                   // inclusive prefix over the levels (lanes 0..7)
+#pragma unroll
+                for (int off = 1; off < 8; off <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, my_end, off);
+                    if (lane >= off) my_end += v;
+                }
+                const int total = __shfl_sync(0xffffffffu, my_end, 7);
                 if (scan_all) {                                      // (awkward geometry: every member, 32 at a time)
                     for (int r = lane; r < nreg; r += 32) test(r, sap[r]);
                 } else {
@@ -652,13 +658,17 @@ __global__ void __launch_bounds__(LA_NT) lg_adj_kernel(const __grid_constant__ L
                         // this lane's cell of the round: member range, trimmed to the chunks at or below the candidate's
                         int r0 = 0, n = 0;
                         const int q = q0 + lane;
+                        // level of cell q: the first level whose prefix exceeds q (<= 8 levels: a few shuffles, all lanes)
+                        int i = 0;
+#pragma unroll
+                        for (int j = 0; j < 7; ++j) {
+                            const int e = __shfl_sync(0xffffffffu, my_end, j);
+                            if (q >= e) i = j + 1;
+                        }
+                        const int lv_end = __shfl_sync(0xffffffffu, my_end, i), lv_n = __shfl_sync(0xffffffffu, my_n, i);
+                        const int nx = __shfl_sync(0xffffffffu, my_nx, i), x0 = __shfl_sync(0xffffffffu, my_x0, i), y0 = __shfl_sync(0xffffffffu, my_y0, i);
                         if (q < total) {
-                            int i = 0, qq = q;
-#pragma unroll
-                            for (int j = 0; j < 7; ++j) if (i == j && qq >= wn[j]) { qq -= wn[j]; i = j + 1; }
-                            int nx = wnx[0], x0 = wx0[0], y0 = wy0[0];
-#pragma unroll
-                            for (int j = 1; j < 8; ++j) if (i == j) { nx = wnx[j]; x0 = wx0[j]; y0 = wy0[j]; }
+                            const int qq = q - (lv_end - lv_n);
                             const int iy = qq / nx, ix = qq - iy * nx;
                             const u32 c = lg_hash(l_lo + i, x0 + ix, y0 + iy) & hmask;
                             LA_COUNT(4, 1);
@@ -674,6 +684,8 @@ __global__ void __launch_bounds__(LA_NT) lg_adj_kernel(const __grid_constant__ L
                             }
                             n = r1 - r0;
                         }
+                        const int nmax = __reduce_max_sync(0xffffffffu, n);
+                        if (nmax == 0) continue;
                         // flatten: member t of the round belongs to the lane whose running offset covers it
                         int inc = n;
 #pragma unroll
@@ -683,21 +695,27 @@ __global__ void __launch_bounds__(LA_NT) lg_adj_kernel(const __grid_constant__ L
                         }
                         const int exc = inc - n;
                         const int T = __shfl_sync(0xffffffffu, inc, 31);
-                        for (int t0 = 0; t0 < T; t0 += 32) {
-                            const int t = t0 + lane;
-                            // owner = the last lane with exc <= t (binary search over the 32 offsets)
-                            int own = 0;
+                        if (((T + 31) >> 5) * 3 >= nmax * 2) {
+                            // short lists: lane by lane, member m of every cell at once (no owner search)
+                            for (int m = 0; m < nmax; ++m)
+                                if (m < n) test(r0 + m, sap[r0 + m]);
+                        } else {
+                            for (int t0 = 0; t0 < T; t0 += 32) {
+                                const int t = t0 + lane;
+                                // owner = the last lane with exc <= t (binary search over the 32 offsets)
+                                int own = 0;
 #pragma unroll
-                            for (int step = 16; step > 0; step >>= 1) {
-                                const int cand = own + step;
-                                const int e = __shfl_sync(0xffffffffu, exc, cand & 31);
-                                if (cand < 32 && e <= t) own = cand;
-                            }
-                            const int o_exc = __shfl_sync(0xffffffffu, exc, own);
-                            const int o_r0 = __shfl_sync(0xffffffffu, r0, own);
-                            if (t < T) {
-                                const int r = o_r0 + (t - o_exc);
-                                test(r, sap[r]);
+                                for (int step = 16; step > 0; step >>= 1) {
+                                    const int cand = own + step;
+                                    const int e = __shfl_sync(0xffffffffu, exc, cand & 31);
+                                    if (cand < 32 && e <= t) own = cand;
+                                }
+                                const int o_exc = __shfl_sync(0xffffffffu, exc, own);
+                                const int o_r0 = __shfl_sync(0xffffffffu, r0, own);
+                                if (t < T) {
+                                    const int r = o_r0 + (t - o_exc);
+                                    test(r, sap[r]);
+                                }
                             }
                         }
                     }
