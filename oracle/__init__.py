@@ -5,17 +5,23 @@ post-processing path (anchor decode -> temporal fusion conv -> box_nms).  Only
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import this package; ``videoyolo_b200`` never does.
 
-PARITY UNPINNED by the reference itself: /root/reference holds no tests or golden
-vectors and its arithmetic runs in un-vendored, un-pinned ``mxnet-cu100`` /
-``gluoncv`` (requirements.txt:1-2), neither of which is installable here.  The
-oracle is pinned instead by:
-  * tests/golden/box_nms_mxnet_doc.json  - known answers from MXNet's public
-    ``box_nms`` documentation / unit test (hand transcribed, provenance flagged);
-  * oracle.box_nms_py - an independently structured python twin;
-  * torchvision.ops.nms per class (same IoU formula);
-  * tests/golden/bbox_iou_ref.npz - outputs of the reference's own
-    utils/bbox.py:bbox_iou, imported in the build container
-    (tests/golden/make_golden.py is the generating script).
+PARITY: /root/reference holds no tests or golden vectors of its own, and its
+arithmetic runs in un-vendored, un-pinned ``mxnet-cu100`` / ``gluoncv``
+(requirements.txt:1-2), neither installable here.  What pins the oracle:
+  * decode, the YOLOV3 tail, bbox_iou, hierarchical_nms, VOCMApMetric.update:
+    PINNED BY THE REFERENCE'S OWN CODE, executed in the build container --
+    tests/golden/make_golden.py imports /root/reference's yolo3.py /
+    utils/bbox.py / metrics/pascalvoc.py unmodified (and cuts hierarchical_nms
+    out of detect_yolo3.py) under a numpy-fp32 stand-in for the few MXNet array
+    ops they call (tests/golden/mx_shim.py); outputs committed as
+    tests/golden/decode_ref_*.npz, bbox_iou_ref.npz, consumer_ref.npz;
+  * box_nms: PARITY UNPINNED by the reference (the operator's source lives in
+    MXNet, absent from /root/reference).  Restated from MXNet's published
+    algorithm, anchored on the reference's call site
+    (yolo3.py:526-528) and pinned by tests/golden/box_nms_mxnet_doc.json (known
+    answers of MXNet's public documentation / unit test, hand transcribed), an
+    independently structured python twin (box_nms_py) and torchvision.ops.nms
+    per class (same IoU formula).
 
 Functions and what they follow:
   decode_numpy        models/definitions/yolo/yolo3.py:151-199 op for op (numpy fp32)

@@ -6,14 +6,18 @@
  * cpu_baseline / --impl reference legs may load this library; the product
  * (videoyolo_b200/) never does.
  *
- * PARITY UNPINNED BY THE REFERENCE: /root/reference has no tests, fixtures or
- * golden vectors, and the arithmetic lives in un-vendored, un-pinned third-
- * party packages (mxnet-cu100, gluoncv; requirements.txt:1-2).  This oracle is
- * pinned instead against (a) the known-answer vectors of MXNet's public
- * box_nms documentation / unit test (tests/golden/box_nms_mxnet_doc.json),
- * (b) an independent python twin (oracle/box_nms_py.py), (c) torchvision's
- * per-class nms, and (d) for bbox_iou, outputs of the reference's own
- * utils/bbox.py imported in the build container (tests/golden/bbox_iou_ref.npz).
+ * PARITY: /root/reference has no tests, fixtures or golden vectors of its own, and
+ * its arithmetic lives in un-vendored, un-pinned third-party packages
+ * (mxnet-cu100, gluoncv; requirements.txt:1-2).  The decode (and the YOLOV3 tail
+ * around it) is PINNED BY THE REFERENCE'S OWN CODE: yolo3.py imported unmodified
+ * under a numpy-fp32 stand-in for MXNet's array ops and run in the build container
+ * (tests/golden/make_golden.py -> tests/golden/decode_ref_*.npz); bbox_iou by
+ * outputs of the reference's utils/bbox.py (tests/golden/bbox_iou_ref.npz).
+ * box_nms stays PARITY UNPINNED by the reference (the operator's source is in
+ * MXNet, not in /root/reference): restated from MXNet's published algorithm and
+ * pinned by (a) the known-answer vectors of MXNet's public box_nms documentation
+ * / unit test (tests/golden/box_nms_mxnet_doc.json), (b) an independent python
+ * twin (oracle.box_nms_py), (c) torchvision's per-class nms.
  *
  * What each function follows:
  *   vy_oracle_decode_f32   models/definitions/yolo/yolo3.py:151-199
