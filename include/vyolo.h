@@ -63,7 +63,7 @@ const char *vy_last_error(void);
 #define VY_K_LAYOUT        9
 #define VY_K_SAMPLE       10
 #define VY_K_STREAM       11
-#define VY_K_TABLE        12
+#define VY_K_TABLE        12      /* (development builds with -DVY_STREAM_ALT only) */
 #define VY_K_COUNT        13
 const char *vy_kernel_name(int kernel_id);
 int vy_launch_counts(long long *host_counts, int n);     /* cumulative since load; returns VY_K_COUNT */
