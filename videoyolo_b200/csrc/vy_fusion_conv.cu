@@ -20,6 +20,7 @@
 // overlaps the MMAs of tile i+1.  Epilogue: tcgen05.ld -> scale/shift (folded BN) -> LeakyReLU ->
 // border zeroing -> bf16 (or fp32) -> global.
 #include "vy_common.cuh"
+#include <stdlib.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <string.h>
@@ -478,6 +479,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+#ifndef CV_REL128
+#define CV_REL128 1.43     // time per output column of a 128-wide tile relative to a 256-wide one (measured at equal wave
+#define CV_REL64 2.36      // counts, tools/conv_bench.py with VY_CONV_BN: 0.112 / 0.185 ms against 0.078 ms at 26^2 256->512)
+#endif
+
 EncodeTiledFn encode_fn() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -613,7 +619,29 @@ extern "C" int vy_fusion_conv_bf16(const void *x, const void *w, const float *sc
     const int Hp = H + 2, Wp = W + 2;
     const long long rows = (long long)B * Hp * Wp;
     if (rows > 0x7fffff00LL) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16: B*Hp*Wp too large");
-    const int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    // N tile: the widest one wastes the least operand traffic, but the persistent grid runs ceil(tiles / SMs) waves of
+    // whole tiles -- 180 tiles of 128 x 256 at 13^2 x 8 windows are two waves, the second 22 % full.  Pick the width
+    // with the lowest estimated time = waves x width x (measured relative cost per column of the narrower tiles).  With
+    // the measured costs (a 128 x 128 MMA tile re-reads A twice as often: 1.43x per column) the widest width that divides
+    // Cout wins at every benchmarked shape, 13^2 included (0.114 ms against 0.148 ms); the estimate only moves to a narrower
+    // tile when it saves more than a third of the waves.
+    int BN = 64;
+    {
+        static const char *force = getenv("VY_CONV_BN");          // (A/B runs)
+        const long long mt = (long long)T * ((rows + CV_BM - 1) / CV_BM);
+        const int sms = vy_sm_count();
+        double best = 1e300;
+        const int cand[3] = {256, 128, 64};
+        const double rel[3] = {1.0, CV_REL128, CV_REL64};
+        for (int i = 0; i < 3; ++i) {
+            if (Cout % cand[i] != 0) continue;
+            if (force && atoi(force) != cand[i] && Cout % atoi(force) == 0) continue;
+            const long long tiles = mt * (Cout / cand[i]);
+            const long long waves = (tiles + sms - 1) / sms;
+            const double cost = (double)waves * cand[i] * rel[i];
+            if (cost < best) { best = cost; BN = cand[i]; }
+        }
+    }
     const long long Ktot = (long long)kt * kh * kw * Cin;
 
     CUtensorMap mx, mw;
