@@ -30,6 +30,9 @@
 
 namespace {
 
+#ifndef LG_SH
+#define LG_SH 1                   // tiled kernel: cells of 2^(L - LG_SH); measured at configs[3] force_suppress: 0 -> 336 ms, 1 -> 332 ms, 2 -> 490 ms, 3 -> 1303 ms (the lockstep cell loop pays per probed cell)
+#endif
 constexpr int LG_NT = 1024;          // threads per NMS CTA
 constexpr int LG_TILE = 1024;        // candidates per tile (== LG_NT)
 constexpr int LG_WORDS = LG_TILE / 32;
@@ -226,6 +229,8 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
     const u32 lt_mask = (1u << lane) - 1u;
     const long long R = p.rp.R, N = (long long)p.B * R;
     const int n_seg = p.all_pairs ? p.B : *p.n_seg;
+    const float reach = fmaxf(1.0f - p.thr, 0.5f / p.thr - 0.5f) * 1.01f;       // (GRID: thr >= 0.05)
+    const int sh = p.thr >= 0.3f ? LG_SH : (p.thr >= 0.15f ? 1 : 0);
 
     for (int seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
         long long seg0, len = 0;
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
         }
         const size_t img = (size_t)b * (size_t)R;
         u32 hmask = 0;
-        u32 *hhead = nullptr;
+        u32 *hhead = nullptr, *htail = nullptr;
         if (GRID) {
             // the segment's hash region: [2*seg0, 2*seg0 + hsize), hsize the largest power of two <= 2*len
             if (!p.all_pairs) {
@@ -255,10 +260,15 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
                 len = sh_len;
             }
             if (tid == 0) sh_irr = LG_EMPTY;
-            u32 hsize = 2;
-            while ((long long)hsize * 2 <= 2 * len) hsize *= 2;
+            // hsize = the largest power of two <= len: heads in the first half of the region, TAILS in the second (a chain is
+            // walked oldest = highest-ranked kept box first: that is the likely suppressor, and a candidate stops at the
+            // first one it finds; with the newest box at the head a candidate walked most of a chain before it met its
+            // suppressor -- 2.8 k warp instructions per candidate, most of them here)
+            u32 hsize = 1;
+            while ((long long)hsize * 2 <= len) hsize *= 2;
             hmask = hsize - 1;
             hhead = p.hash_head + 2 * (size_t)seg0;
+            htail = hhead + hsize;
             __syncthreads();
         }
         int m = 0;                                  // boxes kept so far (CTA-uniform)
@@ -321,16 +331,34 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
                 int hn = 0;
                 u32 cur = LG_EMPTY;
                 if (probing && !fallback) cur = sh_irr;      // irregular kept boxes: everyone checks them
-                int budget = 2 * m + 64;                     // chain-walk steps (a corrupted table cannot hang the GPU)
+                int budget = 8 * m + 256;                    // chain-walk steps (a corrupted table cannot hang the GPU)
+                // (the walk is a chain of dependent loads -- an L2 round trip per kept box -- and the tile waits for its
+                // longest walk: four chains are followed side by side, so four round trips overlap)
                 auto drain = [&]() {
+                    u32 c0 = cur, c1 = LG_EMPTY, c2 = LG_EMPTY, c3 = LG_EMPTY;
                     for (;;) {
-                        if (cur == LG_EMPTY && hn > 0) cur = hb[--hn];
-                        const bool busy = alive && !fallback && cur != LG_EMPTY && budget > 0;
+                        if (c0 == LG_EMPTY && hn > 0) c0 = hb[--hn];
+                        if (c1 == LG_EMPTY && hn > 0) c1 = hb[--hn];
+                        if (c2 == LG_EMPTY && hn > 0) c2 = hb[--hn];
+                        if (c3 == LG_EMPTY && hn > 0) c3 = hb[--hn];
+                        const bool busy = alive && !fallback && budget > 0 &&
+                                          (c0 != LG_EMPTY || c1 != LG_EMPTY || c2 != LG_EMPTY || c3 != LG_EMPTY);
                         if (!__any_sync(0xffffffffu, busy)) break;
                         if (busy) {
-                            --budget;
-                            if (nms_suppresses_fast(p.kept_box[cur], p.kept_area[cur], bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT)) alive = false;
-                            else cur = p.next[cur];
+                            budget -= 4;
+                            // all the loads first
+                            const u32 q0 = c0 != LG_EMPTY ? c0 : 0u, q1 = c1 != LG_EMPTY ? c1 : 0u;
+                            const u32 q2 = c2 != LG_EMPTY ? c2 : 0u, q3 = c3 != LG_EMPTY ? c3 : 0u;
+                            const u32 n0 = p.next[q0], n1 = p.next[q1], n2 = p.next[q2], n3 = p.next[q3];
+                            const float4 b0 = p.kept_box[q0], b1 = p.kept_box[q1], b2 = p.kept_box[q2], b3 = p.kept_box[q3];
+                            const float a0 = p.kept_area[q0], a1 = p.kept_area[q1], a2 = p.kept_area[q2], a3 = p.kept_area[q3];
+                            bool hit = c0 != LG_EMPTY && nms_suppresses_fast(b0, a0, bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT);
+                            hit |= c1 != LG_EMPTY && nms_suppresses_fast(b1, a1, bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT);
+                            hit |= c2 != LG_EMPTY && nms_suppresses_fast(b2, a2, bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT);
+                            hit |= c3 != LG_EMPTY && nms_suppresses_fast(b3, a3, bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT);
+                            if (hit) alive = false;
+                            c0 = c0 != LG_EMPTY ? n0 : LG_EMPTY; c1 = c1 != LG_EMPTY ? n1 : LG_EMPTY;
+                            c2 = c2 != LG_EMPTY ? n2 : LG_EMPTY; c3 = c3 != LG_EMPTY ? n3 : LG_EMPTY;
                         }
                     }
                     hn = 0; cur = LG_EMPTY;
@@ -340,14 +368,16 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
                 for (int L = wl_lo; L <= wl_hi; ++L) {
                     int x0 = 0, y0 = 0, nx = 0, ncell = 0;
                     if (probing && !fallback && alive && L >= l_lo && L <= l_hi) {
-                        const float cs = lg_pow2(L), inv = lg_pow2(-L);
-                        const float rx = (gc.w + cs) * 0.5f, ry = (gc.h + cs) * 0.5f;
-                        const float mx = rx * 1.001f + cs * 1e-3f + (fabsf(gc.cx) + rx) * 1e-6f;
-                        const float my = ry * 1.001f + cs * 1e-3f + (fabsf(gc.cy) + ry) * 1e-6f;
+                        // centres of two boxes with IoU > t are closer than reach * (own extent) per axis (derivation at
+                        // lg_adj_kernel); kept boxes are registered by centre in cells of 2^(L - sh)
+                        const float cs = lg_pow2(L - sh), inv = lg_pow2(sh - L);
+                        const float rx = gc.w * reach, ry = gc.h * reach;
+                        const float mx = rx + cs * 1e-3f + (fabsf(gc.cx) + rx) * 1e-6f;
+                        const float my = ry + cs * 1e-3f + (fabsf(gc.cy) + ry) * 1e-6f;
                         const float fx0 = floorf((gc.cx - mx) * inv), fx1 = floorf((gc.cx + mx) * inv);
                         const float fy0 = floorf((gc.cy - my) * inv), fy1 = floorf((gc.cy + my) * inv);
                         if (!(fabsf(fx0) < 1.0e9f && fabsf(fx1) < 1.0e9f && fabsf(fy0) < 1.0e9f && fabsf(fy1) < 1.0e9f) ||
-                            fx1 - fx0 > 15.0f || fy1 - fy0 > 15.0f) {
+                            fx1 - fx0 > 31.0f || fy1 - fy0 > 31.0f) {
                             fallback = true;
                         } else {
                             x0 = (int)fx0; y0 = (int)fy0; nx = (int)fx1 - x0 + 1;
@@ -439,10 +469,16 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
                             bool placed = false;
                             if (gk.kind == 0) {
                                 const int L = lg_level(fmaxf(gk.w, gk.h));
-                                const float inv = lg_pow2(-L);
+                                const float inv = lg_pow2(sh - L);
                                 const float fx = floorf(gk.cx * inv), fy = floorf(gk.cy * inv);
                                 if (fabsf(fx) < 1.0e9f && fabsf(fy) < 1.0e9f) {
-                                    p.next[idx] = atomicExch(&hhead[lg_hash(L, (int)fx, (int)fy) & hmask], idx);
+                                    // append at the tail (the exchanges on the tail word order concurrent appends; the
+                                    // link of the previous tail is written by its successor)
+                                    const u32 hb_ = lg_hash(L, (int)fx, (int)fy) & hmask;
+                                    p.next[idx] = LG_EMPTY;
+                                    __threadfence_block();
+                                    const u32 prev = atomicExch(&htail[hb_], idx);
+                                    if (prev == LG_EMPTY) hhead[hb_] = idx; else p.next[prev] = idx;
                                     placed = true;
                                 }
                             }
