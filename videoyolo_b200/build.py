@@ -66,7 +66,8 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), variant: s
     objs = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in srcs]
     if force or jobs or _stale(SO, objs):
         cmd = [nvcc, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                    "--cudart", "static"]
+                                                    "--cudart", "static",
+                                                    "-Xlinker", "--version-script=" + os.path.join(CSRC, "exports.map")]
         # static cudart: no dependence on which libcudart the host process (torch) brings; driver
         # entry points (cuTensorMapEncode*) are resolved at run time through cudaGetDriverEntryPoint,
         # so the library also loads on a box without libcuda.so.1 (the CPU-only build container).
