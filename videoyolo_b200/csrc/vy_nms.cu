@@ -482,8 +482,16 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
     const int jl = tid % pl.samp_ipj, lanep = tid / pl.samp_ipj;
     const int j = ib * pl.samp_ipj + jl;
     const int c_lo = pb * pl.samp_ppj, c_hi = min(hd.C, c_lo + pl.samp_ppj);
+    // The CTA wants its Ksq-th largest key, and Ksq is small against the thread count (13 at COCO 608^2, 145 at VID 320^2):
+    // a thread's two best keys stand for its <= 16 (the Ksq-th largest of a subset is <= that of the whole set, so the
+    // bound can only come out lower = more careful, and it does only when one thread holds three of the CTA's Ksq
+    // best: ~0.5 % of the threads at Ksq = 145).  The radix passes then walk 2 keys per thread instead of 16.
+    const bool full = pl.Ksq > SAMP_NT / 2;            // (CTA-uniform) large Ksq: every key takes part
+    if (full) {
 #pragma unroll
-    for (int k = 0; k < SAMP_MAXK; ++k) skey[k][tid] = 0u;
+        for (int k = 0; k < SAMP_MAXK; ++k) skey[k][tid] = 0u;
+    }
+    u32 top0 = 0u, top1 = 0u;
     int n_mine = 0;
     ItemRef r;
     if (lanep < pl.samp_pls && j < pl.samp_items &&
@@ -518,7 +526,13 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
                     float best = 0.0f;
 #pragma unroll
                     for (int v = 0; v < 4; ++v) if (v < r.nv) best = fmaxf(best, samp_sigmoid(tc[k][v]) * cf[v]);
-                    if (best > pl.valid_thresh) { skey[k0 + k][tid] = vy_f2ord(best); ++n_mine; }
+                    if (best > pl.valid_thresh) {
+                        const u32 key = vy_f2ord(best);
+                        if (full) skey[k0 + k][tid] = key;
+                        top1 = max(top1, min(top0, key));
+                        top0 = max(top0, key);
+                        ++n_mine;
+                    }
                 }
             }
         }
@@ -536,15 +550,20 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
             __syncthreads();
             // run-length aggregation: neighbouring keys of a thread mostly share the leading digits
             u32 cur = 0xffffffffu, run = 0;
+            auto visit = [&](u32 k) {
+                if (k != 0u && (shift == 24 || ((k ^ prefix) >> (shift + 8)) == 0u)) {
+                    const u32 d = (k >> shift) & 255u;
+                    if (d != cur) { if (run) atomicAdd(&hist[cur], run); cur = d; run = 0; }
+                    ++run;
+                }
+            };
             if (n_mine) {
+                if (full) {
 #pragma unroll
-                for (int i = 0; i < SAMP_MAXK; ++i) {
-                    const u32 k = skey[i][tid];
-                    if (k != 0u && (shift == 24 || ((k ^ prefix) >> (shift + 8)) == 0u)) {
-                        const u32 d = (k >> shift) & 255u;
-                        if (d != cur) { if (run) atomicAdd(&hist[cur], run); cur = d; run = 0; }
-                        ++run;
-                    }
+                    for (int i = 0; i < SAMP_MAXK; ++i) visit(skey[i][tid]);
+                } else {
+                    visit(top0);
+                    visit(top1);
                 }
             }
             if (run) atomicAdd(&hist[cur], run);
