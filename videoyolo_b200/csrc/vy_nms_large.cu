@@ -565,6 +565,7 @@ __global__ void __launch_bounds__(LA_NT, LA_CTAS) lg_adj_kernel(const __grid_con
         volatile unsigned char *status = p.status + seg0;
         u64 *edges = p.edges + (size_t)LA_E * (size_t)seg0;
         const long long cap = (long long)LA_E * len;
+        const int cap_i = (int)(cap < 0x3fffffffLL ? cap : 0x3fffffffLL);       // edge slots of the segment (the counter is an int)
         // ---- 1. boxes by position; members per (level, cell) bucket
         for (u32 i = tid; i < hsize; i += LA_NT) cell[i] = 0u;
         __syncthreads();
@@ -633,6 +634,7 @@ __global__ void __launch_bounds__(LA_NT, LA_CTAS) lg_adj_kernel(const __grid_con
         {
             const int lane = tid & 31, warp = tid >> 5;
             for (int sl = warp; sl < nreg; sl += LA_NT / 32) {
+                if (*(volatile int *)&sh_ne > cap_i) break;          // overflowed: the tiled kernel takes the segment
                 const float4 bx = sbox[sl];
                 const uint2 me = sap[sl];
                 const float ar = __uint_as_float(me.x);
@@ -652,8 +654,11 @@ __global__ void __launch_bounds__(LA_NT, LA_CTAS) lg_adj_kernel(const __grid_con
                     LA_COUNT(2, 1);
                     if (nms_suppresses_fast(sbox[r], ak, bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT)) {
                         LA_COUNT(3, 1);
-                        const int at = atomicAdd(&sh_ne, 1);
-                        if (at < cap) edges[at] = ((u64)k << 32) | (u64)pos;
+                        // (once the region has overflowed nobody counts on: the counter stays within a CTA's worth of cap)
+                        if (*(volatile int *)&sh_ne <= cap_i) {
+                            const int at = atomicAdd(&sh_ne, 1);
+                            if (at < cap_i) edges[at] = ((u64)k << 32) | (u64)pos;
+                        }
                         ++found;
                     }
                 };
@@ -763,7 +768,7 @@ __global__ void __launch_bounds__(LA_NT, LA_CTAS) lg_adj_kernel(const __grid_con
         }
         __syncthreads();
         const int ne = sh_ne;
-        if (ne > cap) { if (tid == 0) p.seg_starts_rw[seg] = (u32)seg0 | 0x80000000u; continue; }
+        if (ne > cap_i) { if (tid == 0) p.seg_starts_rw[seg] = (u32)seg0 | 0x80000000u; continue; }
         // ---- 3. resolution: rounds over the open edges
         for (int done = 0; done < ne; ) {
             for (int e = tid; e < ne; e += LA_NT) {
