@@ -1,3 +1,4 @@
+"""One class-agnostic box_nms call at BASELINE configs[3] arguments (for ncu captures of lg_nms_kernel): force_only.py [B]"""
 import sys, os
 sys.path.insert(0, os.getcwd())
 import torch

@@ -1,5 +1,5 @@
 # A/B of the streaming pass: parity tests of the fused path (default mode), then per-kernel times per mode / variant build
-# usage: bash tools/r2_variants.sh <tag> <mode[:variant]> ...
+# usage: bash tools/stream_ab.sh <tag> <mode[:variant]> ...
 tag=${1:-r2}; shift
 timeout 400 python -m pytest tests/test_gpu_postproc.py -m gpu -x -q -k "fused or full_size or finalize or reference_execution or empty or graph" 2>&1 | tail -15 > gpurun_out/${tag}_tests.log
 tail -3 gpurun_out/${tag}_tests.log
