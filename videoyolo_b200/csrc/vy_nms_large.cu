@@ -39,9 +39,12 @@ constexpr int LG_WORDS = LG_TILE / 32;
 constexpr int LG_CHUNK = 2048;       // ranks per compaction chunk
 constexpr int LG_CNT = 256;          // threads per compaction CTA (8 flags each)
 constexpr int LA_NT = 256;           // threads per CTA of the adjacency kernel
-#ifndef LA_CTAS
-#define LA_CTAS 5
+#ifndef LA_SH
+#define LA_SH 1                   // adjacency kernel: cells of 2^(L - LA_SH); measured at configs[3] class-aware: 0 -> 289 ms, 1 -> 239 ms, 2 -> 270 ms, 3 -> 494 ms
 #endif
+#ifndef LA_CTAS
+#define LA_CTAS 8                  // CTAs per SM (= 32 registers per thread): the kernel is latency-bound, measured at configs[3]
+#endif                           // class-aware: 4 -> 231 ms, 5 -> 217 ms, 6 -> 199 ms, 8 -> 183 ms; the grid is exactly the resident CTAs
 constexpr int LA_E = 4;              // edge slots per candidate (average over a segment)
 
 struct LgLayout {
@@ -533,7 +536,7 @@ __global__ void __launch_bounds__(LA_NT, LA_CTAS) lg_adj_kernel(const __grid_con
     // arithmetic; the fp32 predicate's roundings are relative 2^-23, the probes carry a 1 % slack.)  Boxes are registered by
     // centre in cells of 2^(L - sh), finer where the reach is short, so a probe window is a few cells wide.
     const float reach = fmaxf(1.0f - p.thr, 0.5f / p.thr - 0.5f) * 1.01f;
-    const int sh = p.thr >= 0.3f ? 2 : (p.thr >= 0.15f ? 1 : 0);
+    const int sh = p.thr >= 0.3f ? LA_SH : (p.thr >= 0.15f ? 1 : 0);
     const float atl = p.thr * 0.99f;
     for (int seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
         const long long seg0 = p.seg_starts[seg];
@@ -738,8 +741,12 @@ __global__ void __launch_bounds__(LA_NT, LA_CTAS) lg_adj_kernel(const __grid_con
                         const int T = __shfl_sync(0xffffffffu, inc, 31);
                         if (((T + 31) >> 5) * 3 >= nmax * 2) {
                             // short lists: lane by lane, member m of every cell at once (no owner search)
-                            for (int m = 0; m < nmax; ++m)
-                                if (m < n) test(r0 + m, sap[r0 + m]);
+                            for (int m = 0; m < nmax; m += 2) {          // (two members per round: their loads overlap)
+                                const uint2 q0 = m < n ? sap[r0 + m] : make_uint2(0u, 0xffffffffu);
+                                const uint2 q1 = m + 1 < n ? sap[r0 + m + 1] : make_uint2(0u, 0xffffffffu);
+                                test(r0 + m, q0);                         // (position 0xffffffff is never below the candidate's)
+                                test(r0 + m + 1, q1);
+                            }
                         } else {
                             for (int t0 = 0; t0 < T; t0 += 32) {
                                 const int t = t0 + lane;
@@ -969,8 +976,8 @@ int vy_box_nms_large(const RowParams &rp, int B, long long K, float overlap_thre
     // variant: the hash arrays hold the adjacency kernel's chains)
     const bool use_adj = use_grid && !all_pairs;
     if (use_adj) {
-        if (in_format == VY_FMT_CORNER) VY_KERNEL(VY_K_NMS_LARGE, st, (lg_adj_kernel<VY_FMT_CORNER><<<sms * 8, LA_NT, 0, st>>>(p)));
-        else VY_KERNEL(VY_K_NMS_LARGE, st, (lg_adj_kernel<VY_FMT_CENTER><<<sms * 8, LA_NT, 0, st>>>(p)));
+        if (in_format == VY_FMT_CORNER) VY_KERNEL(VY_K_NMS_LARGE, st, (lg_adj_kernel<VY_FMT_CORNER><<<sms * LA_CTAS, LA_NT, 0, st>>>(p)));
+        else VY_KERNEL(VY_K_NMS_LARGE, st, (lg_adj_kernel<VY_FMT_CENTER><<<sms * LA_CTAS, LA_NT, 0, st>>>(p)));
         VY_LAUNCH_CHECK("lg_adj_kernel");
         p.only_flagged = 1;
     }
