@@ -226,6 +226,14 @@ int vy_fusion_conv_bf16(const void *x, const void *w, const float *scale, const 
                         int kt, int kh, int kw, void *y, int y_is_f32,
                         void *workspace, size_t workspace_bytes, vy_stream_t stream);
 
+/* The same cell for T = 1 with the result written in the reference's own layout: y is the fp32 (B, out_channels, H, W)
+ * tensor (NCHW), the first out_channels <= Cout channels, interior pixels only -- the 1x1 `prediction` conv of
+ * YOLOOutputV3 (yolo3.py:62,157; Cout = all_pred padded to a multiple of 64, leaky_slope = 1, bias as shift) hands its
+ * head maps to vy_decode_nms_f32 without a layout pass in between. */
+int vy_fusion_conv_bf16_nchw(const void *x, const void *w, const float *scale, const float *shift,
+                             float leaky_slope, int B, int H, int W, int Cin, int Cout, int kh, int kw,
+                             float *y, int out_channels, vy_stream_t stream);
+
 /* Layout conversion between the reference's fp32 tensors and the P layout.  Element (b, c, t, h, w)
  * of the fp32 tensor lives at x[b*stride_b + c*stride_c + t*stride_t + h*W + w], which covers both
  * NCDHW (after the swapaxes of yolo3.py:256-262) and (B, K, C, H, W) (before it), and T = 1 NCHW. */

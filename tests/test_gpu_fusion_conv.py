@@ -99,6 +99,27 @@ def test_fusion_conv_fp32_output_and_chain(vy):
     check(got, ref, "conv21d")
 
 
+def test_fusion_conv_nchw_output_equals_unpacked_p_output(vy):
+    """vy_fusion_conv_bf16_nchw (the prediction conv's epilogue writes the reference's NCHW head map itself) == the P-layout
+    fp32 output of the same cell unpacked, bit for bit; channel counts that are not a multiple of 64 (all_pred = 75, 105,
+    255), odd grids, 1x1 and 3x3 kernels."""
+    ops = vy.ops
+    rng = np.random.RandomState(5)
+    for B, H, W, Cin, Cout, C, k in ((3, 13, 13, 128, 128, 75, 1), (2, 19, 19, 192, 256, 255, 1), (2, 10, 10, 64, 128, 105, 1),
+                                     (1, 26, 26, 64, 64, 64, 3), (2, 7, 5, 64, 64, 33, 3)):
+        x = torch.from_numpy(bf16_round(rng.normal(0, 1, size=(B, Cin, H, W)).astype(np.float32))).cuda()
+        w = torch.from_numpy(bf16_round(rng.uniform(-0.07, 0.07, size=(Cout, Cin, k, k)).astype(np.float32))).cuda()
+        scale = torch.from_numpy(rng.uniform(0.5, 1.5, Cout).astype(np.float32)).cuda()
+        shift = torch.from_numpy(rng.normal(0, 0.2, Cout).astype(np.float32)).cuda()
+        xp = ops.pack_p(x, "NCHW")
+        wt = ops.conv_weight(w)
+        for slope in (1.0, 0.1):
+            ref = ops.unpack_p(ops.fusion_conv(xp, wt, scale, shift, slope, out_f32=True), "NCHW", channels=C)
+            got = ops.fusion_conv_nchw(xp, wt, scale, shift, slope, channels=C)
+            assert got.shape == (B, C, H, W)
+            assert torch.equal(got, ref), (B, H, W, Cin, Cout, C, k, slope)
+
+
 def test_inflated_weights_identity(vy):
     """three_darknet.py:335-347: a clip of identical frames through a 3x3x3 conv whose weights are the
     2-D weights / kt in every temporal tap equals the 2-D conv (interior frames)."""

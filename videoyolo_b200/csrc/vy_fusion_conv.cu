@@ -42,6 +42,7 @@ struct ConvParams {
     const float *scale, *shift;
     void *y;
     int y_is_f32;
+    int nchw_C, nchw_H, nchw_W;  // nchw_C > 0: y is the reference's fp32 (B, nchw_C, H, W) tensor (T == 1): interior pixels, first nchw_C channels
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -235,7 +236,20 @@ vy_fusion_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                         x = x > 0.0f ? x : x * cp.slope;                                                   // layers.py:69,78
                         o[i] = interior ? x : 0.0f;
                     }
-                    if (cp.y_is_f32) {
+                    if (cp.nchw_C > 0) {
+                        // the head maps of YOLOOutputV3 leave the GEMM in the reference's own layout (yolo3.py:157-158):
+                        // consecutive lanes hold consecutive pixels, so every channel is one 128-byte run per warp
+                        if (interior) {
+                            const int bimg = r / plane;
+                            float *dst = (float *)cp.y + ((size_t)bimg * cp.nchw_C * cp.nchw_H + (size_t)(hp - 1)) * cp.nchw_W + (wp - 1);
+                            const size_t cstride = (size_t)cp.nchw_H * cp.nchw_W;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const int n = n0 + ch * 32 + i;
+                                if (n < cp.nchw_C) dst[(size_t)n * cstride] = o[i];
+                            }
+                        }
+                    } else if (cp.y_is_f32) {
                         float4 *dst = (float4 *)((float *)cp.y + out_off + ch * 32);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
@@ -599,11 +613,9 @@ extern "C" size_t vy_fusion_conv_workspace_bytes(int B, int T, int H, int W, int
     return 0;      // operands are read in place through TMA; nothing is staged in global memory
 }
 
-extern "C" int vy_fusion_conv_bf16(const void *x, const void *w, const float *scale, const float *shift,
-                                   float leaky_slope, int B, int T, int H, int W, int Cin, int Cout,
-                                   int kt, int kh, int kw, void *y, int y_is_f32, void *workspace,
-                                   size_t workspace_bytes, vy_stream_t stream) {
-    (void)workspace; (void)workspace_bytes;
+static int conv_launch(const void *x, const void *w, const float *scale, const float *shift,
+                       float leaky_slope, int B, int T, int H, int W, int Cin, int Cout,
+                       int kt, int kh, int kw, void *y, int y_is_f32, int nchw_C, vy_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!x || !w || !scale || !shift || !y) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16: null pointer");
     if (B < 1 || T < 1 || H < 1 || W < 1) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16: bad shape");
@@ -672,9 +684,26 @@ extern "C" int vy_fusion_conv_bf16(const void *x, const void *w, const float *sc
     cp.cin_blocks = Cin / CV_BK;
     cp.n_tiles_total = (long long)T * cp.m_tiles * cp.n_tiles;
     cp.slope = leaky_slope; cp.scale = scale; cp.shift = shift; cp.y = y; cp.y_is_f32 = y_is_f32;
+    cp.nchw_C = nchw_C; cp.nchw_H = H; cp.nchw_W = W;
     if (BN == 256) return launch_conv<256>(mx, mw, cp, st);
     if (BN == 128) return launch_conv<128>(mx, mw, cp, st);
     return launch_conv<64>(mx, mw, cp, st);
+}
+
+extern "C" int vy_fusion_conv_bf16(const void *x, const void *w, const float *scale, const float *shift,
+                                   float leaky_slope, int B, int T, int H, int W, int Cin, int Cout,
+                                   int kt, int kh, int kw, void *y, int y_is_f32, void *workspace,
+                                   size_t workspace_bytes, vy_stream_t stream) {
+    (void)workspace; (void)workspace_bytes;
+    return conv_launch(x, w, scale, shift, leaky_slope, B, T, H, W, Cin, Cout, kt, kh, kw, y, y_is_f32, 0, stream);
+}
+
+extern "C" int vy_fusion_conv_bf16_nchw(const void *x, const void *w, const float *scale, const float *shift,
+                                        float leaky_slope, int B, int H, int W, int Cin, int Cout, int kh, int kw,
+                                        float *y, int out_channels, vy_stream_t stream) {
+    if (out_channels < 1 || out_channels > Cout) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16_nchw: out_channels must be in [1, Cout]");
+    if (((uintptr_t)y & 3) != 0) VY_FAIL(VY_EALIGN, "vy_fusion_conv_bf16_nchw: y must be 4-byte aligned");
+    return conv_launch(x, w, scale, shift, leaky_slope, B, 1, H, W, Cin, Cout, 1, kh, kw, y, 1, out_channels, stream);
 }
 
 extern "C" int vy_temporal_pool_bf16(const void *x, int T, long inner, int mode, void *y, vy_stream_t stream) {

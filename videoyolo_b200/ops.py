@@ -503,6 +503,36 @@ def fusion_conv(x: PTensor, weight: torch.Tensor, scale: torch.Tensor, shift: to
     return PTensor(y, x.B, x.T, x.H, x.W, Cout)
 
 
+def fusion_conv_nchw(x: PTensor, weight: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
+                     slope: float = 1.0, channels: Optional[int] = None) -> torch.Tensor:
+    """The same cell for a 2-D input (T == 1, (1, kh, kw) weight) with the result in the reference's own layout: the fp32
+    (B, channels, H, W) tensor, first ``channels`` of the Cout output channels.  The 1x1 ``prediction`` conv uses it
+    (slope 1 = no activation, bias as shift): its head maps go to the decode without a layout pass."""
+    if not isinstance(x, PTensor):
+        raise TypeError("fusion_conv_nchw takes a PTensor (ops.pack_p)")
+    if x.T != 1:
+        raise ValueError("fusion_conv_nchw needs T == 1")
+    w = _need_cuda(weight, "weight", torch.bfloat16)
+    scale = _need_cuda(scale, "scale")
+    shift = _need_cuda(shift, "shift")
+    Cout, kt, kh, kw, Cin = w.shape
+    if kt != 1:
+        raise ValueError("fusion_conv_nchw takes a (Cout, 1, kh, kw, Cin) weight")
+    if Cin != x.C:
+        raise ValueError("weight has %d input channels, activation has %d" % (Cin, x.C))
+    if scale.numel() != Cout or shift.numel() != Cout:
+        raise ValueError("scale/shift must have Cout elements")
+    C = Cout if channels is None else int(channels)
+    if not 1 <= C <= Cout:
+        raise ValueError("channels must be in [1, %d]" % Cout)
+    y = torch.empty((x.B, C, x.H, x.W), dtype=torch.float32, device=x.data.device)
+    with torch.cuda.device(x.data.device):
+        _lib.check(_lib.lib().vy_fusion_conv_bf16_nchw(x.data.data_ptr(), w.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                                       float(slope), x.B, x.H, x.W, Cin, Cout, kh, kw,
+                                                       y.data_ptr(), C, _stream()))
+    return y
+
+
 def conv_weight(w_ref: torch.Tensor) -> torch.Tensor:
     """The reference's conv weight (Cout, Cin, [kt,] kh, kw) fp32 -> (Cout, kt, kh, kw, Cin) bf16 CUDA."""
     if w_ref.dim() == 4:

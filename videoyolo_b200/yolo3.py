@@ -61,8 +61,8 @@ class Prediction(torch.nn.Module):
                 raise ValueError("prediction conv expects (B, %d, H, W)" % cin)
             w, scale, shift = self._operands(3)
             xp = ops.pack_p_split(x, "NCHW")
-        pred = ops.fusion_conv(xp, w, scale, shift, slope=1.0, out_f32=True)      # identity activation, bias as shift
-        return ops.unpack_p(pred, "NCHW", channels=n)
+        # identity activation, bias as shift; the GEMM's epilogue writes the reference's NCHW head map itself
+        return ops.fusion_conv_nchw(xp, w, scale, shift, slope=1.0, channels=n)
 
 
 class YOLOOutputV3(torch.nn.Module):
