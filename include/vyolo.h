@@ -152,6 +152,17 @@ int vy_bbox_iou_f64(const double *a, int N, int lda, const double *b, int M, int
                     double offset, double *out, vy_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Anchor matching of the prefetch target generator ("next" row f4).
+ * Replaces: models/definitions/yolo/yolo_target.py:86-94 -- shift_gt_boxes / shift_anchor_boxes, nd.contrib.box_iou
+ *           (MXNet, corner format) and `ious.argmax(axis=1)`: for every ground-truth box the anchor whose zero-centred
+ *           box overlaps its zero-centred box best.
+ *   gt_boxes (B, M, 4) corner boxes (padding rows of -1 get match 0, as the reference computes before it skips them),
+ *   16-byte aligned; anchors (A, 2) = all_anchors (:63) as (w, h), A <= 32; matches (B, M) int32;
+ *   ious (B, A, M) or NULL = `ious` after the transpose at :92.  Accounted under VY_K_IOU. */
+int vy_anchor_match_f32(const float *gt_boxes, int B, int M, const float *anchors, int A, int32_t *matches,
+                        float *ious, vy_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Batched pairwise IoU of the dynamic-target step ("next" row f4).
  * Replaces: gluoncv.nn.bbox.BBoxBatchIOU as called at models/definitions/yolo/yolo_target.py:171,202
  *           (defaults: corner format, offset 0, eps 1e-15), fused with `ious.max(axis=-1)` (:203) and the

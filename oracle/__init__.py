@@ -31,6 +31,7 @@ Functions and what they follow:
   bbox_iou            utils/bbox.py:11-38
   conv_bn_leaky       models/definitions/layers.py:63-89,135-158 (torch CPU fp32 engine)
   bbox_batch_iou      gluoncv BBoxBatchIOU as called at models/definitions/yolo/yolo_target.py:171,202
+  anchor_match        yolo_target.py:86-94 (nd.contrib.box_iou of zero-centred anchors / ground truths + argmax)
   decode_torch_graph  the Gluon graph of yolo3.py:158-197,:523 op by op on torch CPU (bench.py's graph-faithful CPU figure)
 """
 from __future__ import annotations
@@ -353,6 +354,53 @@ def bbox_batch_iou(a: np.ndarray, b: np.ndarray, offset=0.0, eps=1e-15) -> np.nd
     area_b = ((br - bl + off) * (bb - bt + off))[..., None, :]
     union = (area_a + area_b) - i
     return (i / (union + e)).astype(np.float32)
+
+
+def box_iou_mxnet(lhs: np.ndarray, rhs: np.ndarray) -> np.ndarray:
+    """MXNet ``nd.contrib.box_iou(lhs, rhs, format='corner')`` -> lhs.shape[:-1] + rhs.shape[:-1].  The operator's source
+    is in MXNet (un-vendored, requirements.txt:1), not in /root/reference: restated from its published algorithm
+    (src/operator/contrib/bounding_box-inl.h: Intersect / BoxArea / compute_overlap) -- per axis
+    w = min(right) - max(left), 0 if negative; i = w_x * w_y; 0 if i <= 0 else i / (area_l + area_r - i), area = 0 for a
+    negative extent -- fp32 op for op.  PARITY UNPINNED by the reference (no MXNet here)."""
+    lhs = np.asarray(lhs, np.float32)
+    rhs = np.asarray(rhs, np.float32)
+    L = lhs.reshape(-1, 4)[:, None, :]
+    Rr = rhs.reshape(-1, 4)[None, :, :]
+    z = np.float32(0)
+    wx = np.minimum(L[..., 2], Rr[..., 2]) - np.maximum(L[..., 0], Rr[..., 0])
+    wx = np.where(wx < z, z, wx).astype(np.float32)
+    wy = np.minimum(L[..., 3], Rr[..., 3]) - np.maximum(L[..., 1], Rr[..., 1])
+    wy = np.where(wy < z, z, wy).astype(np.float32)
+    inter = (wx * wy).astype(np.float32)
+
+    def area(b):
+        w, h = b[..., 2] - b[..., 0], b[..., 3] - b[..., 1]
+        return np.where((w < z) | (h < z), z, w * h).astype(np.float32)
+
+    union = ((area(L) + area(Rr)).astype(np.float32) - inter).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = np.where(inter > z, inter / union, z).astype(np.float32)
+    return out.reshape(lhs.shape[:-1] + rhs.shape[:-1])
+
+
+def anchor_match(gt_boxes: np.ndarray, anchors: np.ndarray):
+    """The anchor matching of YOLOV3PrefetchTargetGenerator.forward, models/definitions/yolo/yolo_target.py:86-94, line for
+    line in numpy fp32: bbox2center = gluoncv BBoxCornerToCenter (width = xmax - xmin, height = ymax - ymin), bbox2corner
+    = BBoxCenterToCorner (x -+ w/2), ``nd.contrib.box_iou`` = box_iou_mxnet, argmax = first maximum.
+    gt_boxes (B, M, 4), anchors (A, 2) = all_anchors -> matches (B, M) int32, ious (B, A, M)."""
+    gt = np.asarray(gt_boxes, np.float32)
+    all_anchors = np.asarray(anchors, np.float32).reshape(-1, 2)
+    gtw = (gt[..., 2:3] - gt[..., 0:1]).astype(np.float32)                                        # :86 bbox2center
+    gth = (gt[..., 3:4] - gt[..., 1:2]).astype(np.float32)
+    h = np.float32(0.5)
+    shift_gt_boxes = np.concatenate([-h * gtw, -h * gth, h * gtw, h * gth], axis=-1).astype(np.float32)      # :89
+    anchor_boxes = np.concatenate([np.float32(0) * all_anchors, all_anchors], axis=-1)            # :90 zero center anchors
+    hw, hh = anchor_boxes[:, 2:3] / np.float32(2), anchor_boxes[:, 3:4] / np.float32(2)           # :91 bbox2corner
+    shift_anchor_boxes = np.concatenate([anchor_boxes[:, 0:1] - hw, anchor_boxes[:, 1:2] - hh,
+                                         anchor_boxes[:, 0:1] + hw, anchor_boxes[:, 1:2] + hh], axis=-1).astype(np.float32)
+    ious = box_iou_mxnet(shift_anchor_boxes, shift_gt_boxes).transpose((1, 0, 2))                 # :92  (B, A, M)
+    matches = ious.argmax(axis=1).astype(np.int32)                                                # :94  (B, M)
+    return matches, ious
 
 
 def conv_bn_leaky(x, w, gamma, beta, mean, var, padding, stride=1, eps=1e-5, slope=0.1, groups=1):

@@ -360,3 +360,18 @@ def test_voc_match_oracle_matches_reference_execution(with_diff):
         assert sorted(got_m[i:j + 1]) == sorted(ref_m[i:j + 1]), (i, j)
         i = j + 1
     assert (got_m == ref_m).mean() > 0.97
+
+
+def test_anchor_match_known_answers():
+    """yolo_target.py:86-94 restated (oracle.anchor_match): a box of exactly an anchor's size matches it with IoU 1
+    wherever it lies; IoU of zero-centred boxes = min-area / max-area when one contains the other; padding rows give 0."""
+    an = np.array([[10, 13], [16, 30], [33, 23]], np.float32)
+    gt = np.array([[[100, 200, 116, 230], [5, 5, 6, 6], [-1, -1, -1, -1], [0, 0, 66, 46]]], np.float32)
+    m, iou = oracle.anchor_match(gt, an)
+    assert m.tolist() == [[1, 0, 0, 2]]
+    assert iou.shape == (1, 3, 4) and iou[0, 1, 0] == 1.0
+    np.testing.assert_allclose(iou[0, :, 1], [1 / 130, 1 / 480, 1 / 759], rtol=1e-6)       # 1x1 box inside every anchor
+    assert (iou[0, :, 2] == 0).all()                                                     # the -1 row: zero extent
+    np.testing.assert_allclose(iou[0, 2, 3], 0.25, rtol=1e-6)                            # anchor 2 scaled by 2 per side
+    np.testing.assert_allclose(oracle.box_iou_mxnet(np.array([[0, 0, 2, 2]], np.float32), np.array([[1, 1, 3, 3]], np.float32)),
+                               [[1 / 7]], rtol=1e-6)

@@ -55,6 +55,7 @@ SIGNATURES = {
                             [c_vp, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp]),
     "vy_fusion_conv_bf16_nchw": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_float] + [ctypes.c_int] * 7 +
                                  [c_vp, ctypes.c_int, c_vp]),
+    "vy_anchor_match_f32": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, c_vp, c_vp, c_vp]),
     "vy_bbox_batch_iou_f32": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                              ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp, c_vp]),
     "vy_upsample_concat_bf16": (ctypes.c_int, [c_vp, c_vp] + [ctypes.c_int] * 8 + [c_vp, c_vp]),

@@ -154,3 +154,64 @@ extern "C" int vy_detect_consume_f32(const float *dets, int B, int P, float clip
     VY_LAUNCH_CHECK("vy_detect_consume_kernel");
     return VY_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Anchor matching of the prefetch target generator (yolo_target.py:86-93): every ground-truth box, moved to the
+// origin (shift_gt_boxes :89), against the zero-centred anchors (anchor_boxes / bbox2corner :90-91) with
+// nd.contrib.box_iou (:92), then argmax over the anchors (:94).  MXNet's box_iou (corner format): per axis
+// w = min(right) - max(left), 0 if negative; i = w_x * w_y; 0 if i <= 0, else i / (area_l + area_r - i) with
+// area = 0 for a negative extent (bounding_box-inl.h: Intersect / BoxArea / compute_overlap); argmax = first maximum.
+// One thread per ground-truth box; fp32, un-contracted, in that operation order.
+// ------------------------------------------------------------------------------------------------
+constexpr int AM_MAX_A = 32;
+__global__ void __launch_bounds__(128)
+vy_anchor_match_kernel(const float *__restrict__ gt, long long n, int M, const float *__restrict__ anchors, int A,
+                       int32_t *__restrict__ matches, float *__restrict__ ious) {
+    __shared__ float aw[AM_MAX_A], ah[AM_MAX_A];
+    if (threadIdx.x < A) { aw[threadIdx.x] = anchors[2 * threadIdx.x]; ah[threadIdx.x] = anchors[2 * threadIdx.x + 1]; }
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 g = *(const float4 *)(gt + 4 * i);
+    // bbox2center (BBoxCornerToCenter): width = xmax - xmin, height = ymax - ymin; the shifted box is (-w/2, -h/2, w/2, h/2)
+    const float gw = __fsub_rn(g.z, g.x), gh = __fsub_rn(g.w, g.y);
+    const float gl = __fmul_rn(-0.5f, gw), gt_ = __fmul_rn(-0.5f, gh), gr = __fmul_rn(0.5f, gw), gb = __fmul_rn(0.5f, gh);
+    const float gwx = __fsub_rn(gr, gl), ghy = __fsub_rn(gb, gt_);
+    const float garea = (gwx < 0.0f || ghy < 0.0f) ? 0.0f : __fmul_rn(gwx, ghy);
+    const long long b = i / M, m = i - b * M;
+    int best = 0;
+    float best_v = -CUDART_INF_F;
+    for (int a = 0; a < A; ++a) {
+        // bbox2corner (BBoxCenterToCorner) of (0, 0, aw, ah): (-aw/2, -ah/2, aw/2, ah/2)
+        const float hw = __fdiv_rn(aw[a], 2.0f), hh = __fdiv_rn(ah[a], 2.0f);
+        const float al = __fsub_rn(0.0f, hw), at = __fsub_rn(0.0f, hh), ar = __fadd_rn(0.0f, hw), ab = __fadd_rn(0.0f, hh);
+        float wx = __fsub_rn(fminf(ar, gr), fmaxf(al, gl));
+        wx = wx < 0.0f ? 0.0f : wx;
+        float wy = __fsub_rn(fminf(ab, gb), fmaxf(at, gt_));
+        wy = wy < 0.0f ? 0.0f : wy;
+        const float inter = __fmul_rn(wx, wy);
+        float v = 0.0f;
+        if (inter > 0.0f) {
+            const float awx = __fsub_rn(ar, al), ahy = __fsub_rn(ab, at);
+            const float aarea = (awx < 0.0f || ahy < 0.0f) ? 0.0f : __fmul_rn(awx, ahy);
+            v = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, garea), inter));
+        }
+        if (ious) ious[(b * A + a) * M + m] = v;              // (B, A, M): ious.transpose((1, 0, 2)) of the (A, B, M) result
+        if (v > best_v) { best_v = v; best = a; }             // first maximum (NaN never wins)
+    }
+    matches[i] = best;
+}
+
+extern "C" int vy_anchor_match_f32(const float *gt_boxes, int B, int M, const float *anchors, int A, int32_t *matches,
+                                   float *ious, vy_stream_t st) {
+    if (B < 0 || M < 0 || A < 1 || A > AM_MAX_A) VY_FAIL(VY_EINVAL, "anchor_match: need B, M >= 0 and 1 <= A <= %d", AM_MAX_A);
+    if (B == 0 || M == 0) return VY_OK;
+    if (!gt_boxes || !anchors || !matches) VY_FAIL(VY_EINVAL, "anchor_match: null pointer");
+    if (((uintptr_t)gt_boxes) & 15) VY_FAIL(VY_EALIGN, "anchor_match: gt_boxes must be 16-byte aligned");
+    const long long n = (long long)B * M;
+    VY_KERNEL(VY_K_IOU, (cudaStream_t)st,
+              (vy_anchor_match_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)st>>>(gt_boxes, n, M, anchors, A,
+                                                                                                  matches, ious)));
+    VY_LAUNCH_CHECK("vy_anchor_match_kernel");
+    return VY_OK;
+}

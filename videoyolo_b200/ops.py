@@ -298,6 +298,24 @@ def bbox_batch_iou(a: torch.Tensor, b: torch.Tensor, offset=0, eps=1e-15, ignore
     return (ious, imax, obj) if fused else ious
 
 
+def anchor_match(gt_boxes: torch.Tensor, anchors, return_ious: bool = False):
+    """The anchor matching of YOLOV3PrefetchTargetGenerator (yolo_target.py:86-94): ``nd.contrib.box_iou`` of the
+    zero-centred anchors against the zero-centred ground-truth boxes and ``argmax`` over the anchors, one kernel.
+    gt_boxes (B, M, 4) corner boxes (fp32 CUDA), anchors: the (A, 2) ``all_anchors`` as (w, h).
+    Returns matches (B, M) int32 [, ious (B, A, M)]."""
+    gt = _need_cuda(gt_boxes, "gt_boxes")
+    if gt.dim() != 3 or gt.shape[2] != 4:
+        raise ValueError("anchor_match: gt_boxes (B, M, 4) expected")
+    an = torch.as_tensor(anchors, dtype=torch.float32).reshape(-1, 2).to(gt.device).contiguous()
+    B, M, A = gt.shape[0], gt.shape[1], an.shape[0]
+    matches = torch.empty((B, M), dtype=torch.int32, device=gt.device)
+    ious = torch.empty((B, A, M), dtype=torch.float32, device=gt.device) if return_ious else None
+    with torch.cuda.device(gt.device):
+        _lib.check(_lib.lib().vy_anchor_match_f32(gt.data_ptr(), B, M, an.data_ptr(), A, matches.data_ptr(),
+                                                  ious.data_ptr() if return_ious else None, _stream()))
+    return (matches, ious) if return_ious else matches
+
+
 def detect_consume(dets: torch.Tensor, size: float):
     """The device part of what detect()/validate() do with net(x)'s output (detect_yolo3.py:226,254-258):
     returns (bboxes clipped to [0, size] (B,P,4), normalised boxes of the valid rows (B,P,4; -1 elsewhere),
