@@ -197,6 +197,84 @@ def test_yolov3t_neck_matches_oracle_chain(vy, join, ctype, widths):
     np.testing.assert_array_equal(bboxes.cpu().numpy(), o_bb)
 
 
+@pytest.mark.parametrize("join", ["max", "mean", "cat"])
+def test_yolov3t_neck_early_join(vy, join):
+    """Early join (yolo3.py:1107-1123): every stage output joined over the window first ('cat' reshape (0,-3,-2) or
+    TemporalPooling), then the 2-D neck.  Routes against the oracle chain on the joined inputs, NMS tail exact on the
+    GPU's own head maps."""
+    rng = np.random.RandomState(77 + len(join))
+    torch.manual_seed(9)
+    B, K, C, size = 2, 3, 20, 96
+    stage_channels, channels = (128, 64, 64), (64, 64, 64)
+    net = vy.YOLOV3TNeck(["c%d" % i for i in range(C)], k=K, k_join_type=join, block_conv_type="2", k_join_pos="early",
+                         stage_channels=stage_channels, channels=channels).cuda().eval()
+    randomize_bn(net, rng)
+    rs = [bf16_round(rng.normal(0, 1, size=(B, K, c, g, g))) for c, g in zip(stage_channels, oracle.grid_sizes(size))]
+    with torch.no_grad():
+        routes = net.routes(*[torch.from_numpy(r).cuda() for r in rs])
+        ids, scores, bboxes = net(*[torch.from_numpy(r).cuda() for r in rs])
+
+    def joined(r):                                         # (B, K, C, H, W) -> (B, C', 1, H, W)
+        if join == "cat":
+            j = r.reshape(r.shape[0], -1, r.shape[3], r.shape[4])                       # yolo3.py:1110
+        else:
+            j = bf16_round(oracle.temporal_pool(r, join).astype(np.float32))            # yolo3.py:1112
+        return j[:, :, None]
+
+    def run_conv(conv, y):
+        for cell in conv.cells:
+            y = oracle_cell(cell, y)
+        return y
+
+    x = joined(rs[0])
+    for i, block in enumerate(net.blocks):
+        for conv in block.body:
+            x = run_conv(conv, x)
+        assert routes[i].T == 1
+        got = vy.ops.unpack_p(routes[i], "NCDHW").cpu().numpy()
+        scale = np.abs(x).max()
+        assert np.abs(got - x).max() <= 2e-2 * (i + 1) * scale, ("route %d" % i, np.abs(got - x).max(), scale)
+        if i + 1 < len(net.blocks):
+            t = run_conv(net.transitions[i].model, x)
+            g = rs[i + 1].shape[-1]
+            up = t.repeat(2, axis=-1).repeat(2, axis=-2)[..., :g, :g]
+            x = np.concatenate([up, joined(rs[i + 1])], axis=1)
+    with torch.no_grad():
+        heads = net.head.head_maps(*routes)
+    AN, ST = oracle.ANCHORS[::-1], oracle.STRIDES[::-1]
+    dets = vy.yolo3_decode(heads, C, AN, ST).cpu().numpy()
+    o_ids, o_sc, o_bb, o_rec = oracle.yolov3_tail(dets, return_record=True)
+    np.testing.assert_array_equal(net.last_kept_rows.cpu().numpy(), o_rec)
+    np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
+    np.testing.assert_array_equal(bboxes.cpu().numpy(), o_bb)
+
+
+def test_yolov3temporal_tail_over_the_window(vy):
+    """YOLOV3Temporal with t_out (yolo3_temporal.py:468, 540-552): TimeDistributed output layers, box_nms over
+    (B, T, R, 6) with every leading dimension as batch, slice on axis -2: (B, T, post_nms, .) outputs, each frame's
+    result bit-exact against the oracle tail on that frame's decoded rows."""
+    rng = np.random.RandomState(12)
+    B, T, C, size = 2, 3, 20, 160
+    net = vy.YOLOV3Temporal(classes=["c%d" % i for i in range(C)])
+    heads = [rng.normal(0, 1, size=(B, T, 3 * (5 + C), g, g)).astype(np.float32) for g in oracle.grid_sizes(size)]
+    ids, scores, bboxes = net(*[torch.from_numpy(h).cuda() for h in heads])
+    assert ids.shape == (B, T, 100, 1) and scores.shape == (B, T, 100, 1) and bboxes.shape == (B, T, 100, 4)
+    assert net.last_kept_rows.shape == (B, T, 100)
+    AN, ST = oracle.ANCHORS[::-1], oracle.STRIDES[::-1]
+    for b in range(B):
+        for t in range(T):
+            frame = [torch.from_numpy(h[b:b + 1, t]).cuda() for h in heads]
+            dets = vy.yolo3_decode(frame, C, AN, ST).cpu().numpy()
+            o_ids, o_sc, o_bb, o_rec = oracle.yolov3_tail(dets, return_record=True)
+            np.testing.assert_array_equal(net.last_kept_rows[b, t].cpu().numpy(), o_rec[0])
+            np.testing.assert_array_equal(ids[b, t].cpu().numpy(), o_ids[0])
+            np.testing.assert_array_equal(scores[b, t].cpu().numpy(), o_sc[0])
+            np.testing.assert_array_equal(bboxes[b, t].cpu().numpy(), o_bb[0])
+    # a 4-D input is the 2-D model
+    i2, s2, b2 = net(*[torch.from_numpy(h[:, 0]).cuda() for h in heads])
+    assert i2.shape == (B, 100, 1) and torch.equal(i2, ids[:, 0])
+
+
 def test_graphed_module_equals_eager(vy):
     """The neck captured in a CUDA graph (pipeline.GraphedModule) replays to exactly the eager results, also on new inputs."""
     from videoyolo_b200.pipeline import GraphedModule

@@ -7,8 +7,9 @@ PyTorch supplies device buffers, streams and torch.distributed only.  No CPU fal
 from . import _lib, ops, parallel
 from .ops import bbox_batch_iou, bbox_iou, box_nms, yolo3_decode, yolo3_decode_nms
 from .layers import Conv, Conv1D, TemporalPooling, TimeDistributed, YOLODetectionBlockV3
-from .yolo3 import ANCHORS, STRIDES, YOLOOutputV3, YOLOV3, YOLOV3T, YOLOV3TNeck, YOLOV3_noback, get_yolov3_postprocess
+from .yolo3 import (ANCHORS, STRIDES, YOLOOutputV3, YOLOV3, YOLOV3T, YOLOV3Temporal, YOLOV3TNeck, YOLOV3_noback,
+                    get_yolov3_postprocess)
 
 __all__ = ["bbox_batch_iou", "bbox_iou", "box_nms", "yolo3_decode", "yolo3_decode_nms", "YOLOOutputV3", "YOLOV3",
-           "YOLOV3_noback", "YOLOV3T", "YOLOV3TNeck", "YOLODetectionBlockV3", "Conv", "Conv1D", "TemporalPooling", "TimeDistributed", "get_yolov3_postprocess",
+           "YOLOV3_noback", "YOLOV3T", "YOLOV3Temporal", "YOLOV3TNeck", "YOLODetectionBlockV3", "Conv", "Conv1D", "TemporalPooling", "TimeDistributed", "get_yolov3_postprocess",
            "ANCHORS", "STRIDES", "ops", "parallel"]

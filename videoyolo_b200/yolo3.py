@@ -194,6 +194,33 @@ class YOLOV3(torch.nn.Module):
 YOLOV3_noback = YOLOV3
 
 
+class YOLOV3Temporal(YOLOV3):
+    """Inference tail of ``YOLOV3Temporal`` with ``t_out`` (yolo3_temporal.py:447-468, 540-555): the output layers run
+    ``TimeDistributed`` over the window (:468), the detections of the scales are concatenated on axis -2 (:540) and
+    ``box_nms`` runs over ``(B, T, R, 6)`` -- MXNet's operator treats every leading dimension as batch (:543-545) -- then
+    ``slice_axis(axis=-2, 0, post_nms)`` (:548) and the split (:550-552).
+
+    ``net(x1, x2, x3)`` takes the three inputs of the output layers, each (B, T, C_i, H_i, W_i) (head maps, or tip
+    features with ``in_channels``; a 4-D input is T = 1 and behaves like ``YOLOV3``), and returns
+    ``ids (B, T, post_nms, 1), scores (B, T, post_nms, 1), bboxes (B, T, post_nms, 4)``.  TimeDistributed folds T into
+    the batch (layers.py:241-250), so this is the fused decode + box_nms of ``YOLOV3`` on B*T frames; ``last_kept_rows``
+    is (B, T, post_nms)."""
+
+    def forward(self, *xs):
+        if xs[0].dim() != 5:
+            return super().forward(*xs)
+        B, T = xs[0].shape[0], xs[0].shape[1]
+        for x in xs:
+            if x.dim() != 5 or x.shape[0] != B or x.shape[1] != T:
+                raise ValueError("every input must be (B=%d, T=%d, C, H, W)" % (B, T))
+        flat = [x.reshape((B * T,) + tuple(x.shape[2:])) for x in xs]            # TimeDistributed: reshape (-3, -2)
+        ids, scores, bboxes = super().forward(*flat)
+        if self.last_kept_rows is not None:
+            self.last_kept_rows = self.last_kept_rows.reshape(B, T, -1)
+        unfold = lambda t: t.reshape((B, T) + tuple(t.shape[1:]))
+        return unfold(ids), unfold(scores), unfold(bboxes)
+
+
 class YOLOV3T(torch.nn.Module):
     """Post-backbone tail of the temporal detector YOLOV3T with a late join (yolo3.py:915-1302; the loop
     :1126-1177 and the NMS tail :1195-1206), i.e. BASELINE configs[2]: per scale
@@ -215,15 +242,24 @@ class YOLOV3T(torch.nn.Module):
 
     def __init__(self, classes: Sequence[str], k: int = 3, k_join_type: str = "max", block_conv_type: str = "3",
                  channels: Sequence[int] = (512, 256, 128), anchors=None, strides=None,
-                 nms_thresh=0.45, nms_topk=400, post_nms=100, agnostic=False, **kwargs):
+                 nms_thresh=0.45, nms_topk=400, post_nms=100, agnostic=False, k_join_pos: str = "late", **kwargs):
         super().__init__()
         from .layers import Conv, TemporalPooling
-        assert k > 1, "3-D and 2+1-D convolutions need a temporal window (yolo3.py:981-983)"
+        assert k_join_pos in ("late", "early")                            # yolo3.py:984
         assert k_join_type in ("max", "mean", "cat")                      # yolo3.py:984
-        assert block_conv_type in ("3", "21")
+        self._late = k_join_pos == "late"
+        if self._late:
+            assert k > 1, "3-D and 2+1-D convolutions need a temporal window (yolo3.py:981-983)"
+            assert block_conv_type in ("3", "21")
+        else:
+            # early join (yolo3.py:1107-1123): the window is joined right behind the backbone stages, everything after
+            # it is the 2-D detector on one frame's worth of activations
+            assert block_conv_type == "2", "after an early join the blocks are 2-D (yolo3.py:979-985)"
+            k = 1
         self._k, self._join = k, k_join_type
         self.tips = torch.nn.ModuleList([Conv(block_conv_type, 2 * c, 3, 1, 1, in_channels=c) for c in channels])
-        self.pools = torch.nn.ModuleList([TemporalPooling(k, k_join_type) for _ in channels]) if k_join_type != "cat" else None
+        self.pools = (torch.nn.ModuleList([TemporalPooling(k, k_join_type) for _ in channels])
+                      if k_join_type != "cat" and self._late else None)
         mult = k if k_join_type == "cat" else 1
         self.tail = YOLOV3(anchors, strides, classes=classes, nms_thresh=nms_thresh, nms_topk=nms_topk,
                            post_nms=post_nms, agnostic=agnostic, in_channels=[2 * c * mult for c in channels])
@@ -254,7 +290,7 @@ class YOLOV3T(torch.nn.Module):
         """the three joined tip feature maps (B, C', H, W) fp32 that feed the output layers"""
         feats = []
         for i, tip in enumerate(self._tips(xs)):
-            if self._join == "cat":
+            if self._join == "cat" or not self._late:
                 t = ops.unpack_p(tip, "NTCHW")                                  # (B, K, C, H, W)
                 feats.append(t.reshape(t.shape[0], -1, t.shape[3], t.shape[4]))  # reshape (0,-3,-2): yolo3.py:1136
             else:
@@ -267,7 +303,7 @@ class YOLOV3T(torch.nn.Module):
         side in the channels); only the head map is converted to NCHW."""
         heads = []
         for i, tip in enumerate(self._tips(xs)):
-            joined = tip if self._join == "cat" else self.pools[i](tip)
+            joined = tip if self._join == "cat" or not self._late else self.pools[i](tip)
             heads.append(self.tail.yolo_outputs[i].prediction(joined))
         return heads
 
@@ -280,7 +316,8 @@ class YOLOV3T(torch.nn.Module):
 
 
 class YOLOV3TNeck(torch.nn.Module):
-    """Everything of ``YOLOV3T.hybrid_forward`` after the backbone stages, late join (yolo3.py:1126-1206): per scale the
+    """Everything of ``YOLOV3T.hybrid_forward`` after the backbone stages (yolo3.py:1104-1206), late join (default) or,
+    with ``k_join_pos='early'`` and ``block_conv_type='2'``, the early join of :1107-1123 followed by the 2-D neck: per scale the
     detection block (:1131-1132), the late join of its tip (:1134-1138), the output layer (:1159); between scales the
     1x1 transition (:1167, a TimeDistributed 2-D cell :1050), ``_upsample`` x2 + ``slice_like`` + channel concat with the
     backbone's route of the next scale (:1170-1175); then concat -> box_nms -> slice (:1195-1206).
@@ -291,11 +328,20 @@ class YOLOV3TNeck(torch.nn.Module):
     are the ``YOLOV3T`` tail above."""
 
     def __init__(self, classes: Sequence[str], k: int = 3, k_join_type: str = "max", block_conv_type: str = "3",
-                 stage_channels: Sequence[int] = (1024, 512, 256), channels: Sequence[int] = (512, 256, 128), **kwargs):
+                 stage_channels: Sequence[int] = (1024, 512, 256), channels: Sequence[int] = (512, 256, 128),
+                 k_join_pos: str = "late", **kwargs):
         super().__init__()
-        from .layers import Conv, TimeDistributed, YOLODetectionBlockV3
+        from .layers import Conv, TemporalPooling, TimeDistributed, YOLODetectionBlockV3
         assert len(stage_channels) == len(channels)
-        self.head = YOLOV3T(classes, k=k, k_join_type=k_join_type, block_conv_type=block_conv_type, channels=channels, **kwargs)
+        assert k_join_pos in ("late", "early")
+        self._k, self._early, self._join = k, k_join_pos == "early", k_join_type
+        if self._early:
+            # early join (yolo3.py:1107-1123): every stage output is joined over the window first -- 'cat': reshape
+            # (0,-3,-2) = K*C channels (:1110), 'max' / 'mean': TemporalPooling (:1112) -- and the rest is the 2-D neck
+            self.join_pool = TemporalPooling(k, k_join_type) if k_join_type != "cat" else None
+            stage_channels = [c * (k if k_join_type == "cat" else 1) for c in stage_channels]
+        self.head = YOLOV3T(classes, k=k, k_join_type=k_join_type, block_conv_type=block_conv_type, channels=channels,
+                            k_join_pos=k_join_pos, **kwargs)
         blocks, transitions, cin = [], [], stage_channels[0]
         for i, c in enumerate(channels):
             blocks.append(YOLODetectionBlockV3(c, block_conv_type, in_channels=cin))
@@ -319,14 +365,23 @@ class YOLOV3TNeck(torch.nn.Module):
         if len(rs) != len(self.blocks):
             raise ValueError("expected %d stage outputs (deep to shallow)" % len(self.blocks))
         outs = []
-        x = ops.pack_p(rs[0], "NTCHW")
+        x = self._stage(rs[0])
         for i, block in enumerate(self.blocks):
             for cell in block.body:
                 x = cell(x)
             outs.append(x)
             if i + 1 < len(self.blocks):
-                x = ops.upsample_concat(self.transitions[i](x), ops.pack_p(rs[i + 1], "NTCHW"))
+                x = ops.upsample_concat(self.transitions[i](x), self._stage(rs[i + 1]))
         return outs
+
+    def _stage(self, r):
+        """a stage output (B, K, C, H, W) as a P-layout activation; with an early join, joined over the window"""
+        if r.dim() != 5 or r.shape[1] != self._k:
+            raise ValueError("stage outputs must be (B, K=%d, C, H, W)" % self._k)
+        x = ops.pack_p(r, "NTCHW")
+        if not self._early:
+            return x
+        return ops.cat_repeat(x, 1) if self._join == "cat" else self.join_pool(x)
 
     def forward(self, *rs):
         return self.head(*self.routes(*rs))
