@@ -1385,33 +1385,52 @@ __device__ __forceinline__ void fin_for_each_key(const VyHeads &hd, const SelPla
         const int a = rel / pl.items_per_plane[s];
         const int pos0 = (rel - a * pl.items_per_plane[s]) * 4;
         const int nv = min(4, sc.HW - pos0);
+        const bool vec = sc.vec == 4;                      // (then nv == 4: HW is a multiple of 4)
+        const int o1 = min(1, nv - 1), o2 = min(2, nv - 1), o3 = min(3, nv - 1);
         const float *p = sc.head + ((size_t)(b * hd.A + a) * hd.P) * (size_t)sc.HW + pos0;
         const u32 row0 = (u32)(sc.row_off + (long long)pos0 * hd.A + a);
+        auto load4 = [&](const float *q, float (&t)[4]) {
+            if (vec) { const float4 w = vy_ldg128(q); t[0] = w.x; t[1] = w.y; t[2] = w.z; t[3] = w.w; }
+            else { t[0] = vy_ldg32(q); t[1] = vy_ldg32(q + o1); t[2] = vy_ldg32(q + o2); t[3] = vy_ldg32(q + o3); }
+        };
         float conf[4];
+        load4(p + 4 * (size_t)sc.HW, conf);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) conf[v] = v < nv ? vy_sigmoid(vy_ldg32(p + 4 * (size_t)sc.HW + v)) : 0.0f;
-        for (int c = 0; c < hd.C; ++c) {
-            const float *q = p + (size_t)(5 + c) * (size_t)sc.HW;
+        for (int v = 0; v < 4; ++v) conf[v] = v < nv ? vy_sigmoid(conf[v]) : 0.0f;
+        // four class planes at a time: the loads first (the pass is a chain of L2 round trips otherwise)
+        for (int c0 = 0; c0 < hd.C; c0 += 4) {
+            float t[4][4];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                if (v < nv) {
-                    const float sv = vy_score(vy_ldg32(q + v), conf[v]);
-                    if (sv > pl.valid_thresh) f(vy_make_key(sv, row0 + (u32)c * (u32)sc.n_s + (u32)v * (u32)hd.A));
+            for (int u = 0; u < 4; ++u)
+                if (c0 + u < hd.C) load4(p + (size_t)(5 + c0 + u) * (size_t)sc.HW, t[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (c0 + u >= hd.C) break;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    if (v < nv) {
+                        const float sv = vy_score(t[u][v], conf[v]);
+                        if (sv > pl.valid_thresh) f(vy_make_key(sv, row0 + (u32)(c0 + u) * (u32)sc.n_s + (u32)v * (u32)hd.A));
+                    }
                 }
             }
         }
     }
 }
-// returns the number of keys written to out[0 .. cap); *lower = a lower bound of the image's K-th largest key (0: none)
-static __device__ __noinline__ int fin_rescue_heads(const VyHeads &hd, const SelPlan &pl, int b, int K, u64 *out, int cap,
-                                                    u32 *hist /* 256 + 4 words of shared memory */, u64 *lower) {
+// returns the number of keys written to out[0 .. cap); *lower = a lower bound of the image's K-th largest key (0: none).
+// priv: 16 x 256 words of shared memory -- a histogram per warp (two warps share one in a 1024-thread CTA): in the
+// degenerate case every key of the image matches the prefix in every pass, and 1.8 M atomics on ONE histogram were the
+// pass (1 ms); the CTA-wide histogram is S.hist.
+static __device__ __noinline__ int fin_rescue_heads(FinBuf &S, const VyHeads &hd, const SelPlan &pl, int b, int K, u64 *out,
+                                                    int cap, u32 *priv, u64 *lower) {
     const int tid = threadIdx.x;
+    u32 *mine = priv + (((tid >> 5) & 15) << 8);
     const int limit = cap < 4096 ? cap : 4096;           // (<= 4096 keys keep the finalize on its bucket-sort front end)
     u64 prefix = 0;
     int kk = K;
     int shift = 56;
     for (;; shift -= 8) {
-        for (int i = tid; i < 260; i += blockDim.x) hist[i] = 0u;
+        for (int i = tid; i < 16 * 256; i += blockDim.x) priv[i] = 0u;
         __syncthreads();
         {
             // run-length aggregation: neighbouring keys of a thread mostly share the leading digits
@@ -1421,26 +1440,33 @@ static __device__ __noinline__ int fin_rescue_heads(const VyHeads &hd, const Sel
             fin_for_each_key(hd, pl, b, [&](u64 key) {
                 if (sh == 56 || ((key ^ pf) >> (sh + 8)) == 0ull) {
                     const u32 d = (u32)(key >> sh) & 255u;
-                    if (d != cur) { if (run) atomicAdd(&hist[cur], run); cur = d; run = 0; }
+                    if (d != cur) { if (run) atomicAdd(&mine[cur], run); cur = d; run = 0; }
                     ++run;
                 }
             });
-            if (run) atomicAdd(&hist[cur], run);
+            if (run) atomicAdd(&mine[cur], run);
+        }
+        __syncthreads();
+        if (tid < 256) {
+            u32 sum = 0;
+#pragma unroll
+            for (int h = 0; h < 16; ++h) sum += priv[(h << 8) + tid];
+            S.hist[tid] = sum;
         }
         __syncthreads();
         if (tid == 0) {
             u32 above = 0;
             int dig = -1;
             for (int d = 255; d >= 0; --d) {
-                if (above + hist[d] >= (u32)kk) { dig = d; break; }
-                above += hist[d];
+                if (above + S.hist[d] >= (u32)kk) { dig = d; break; }
+                above += S.hist[d];
             }
-            hist[256] = (u32)dig; hist[257] = above; hist[258] = dig >= 0 ? hist[dig] : 0u;
+            S.sel_digit = dig; S.sel_above = (int)above; S.sel_in = dig >= 0 ? (int)S.hist[dig] : 0;
         }
         __syncthreads();
-        const int dig = (int)hist[256];
+        const int dig = S.sel_digit;
         if (dig < 0) { prefix = 0; break; }              // (first pass only) fewer than K valid keys in the image: take them all
-        const u32 above = hist[257], inb = hist[258];
+        const u32 above = (u32)S.sel_above, inb = (u32)S.sel_in;
         prefix |= (u64)dig << shift;
         kk -= (int)above;
         const long long ge = (long long)(K - kk) + inb;  // keys at or above the prefix (its lower bits zero)
@@ -1448,19 +1474,20 @@ static __device__ __noinline__ int fin_rescue_heads(const VyHeads &hd, const Sel
         if (ge <= limit || shift == 0) break;
     }
     // collect
-    if (tid == 0) hist[259] = 0u;
+    if (tid == 0) S.count = 0;
     __syncthreads();
     {
         const u64 pf = prefix;
         fin_for_each_key(hd, pl, b, [&](u64 key) {
             if (key >= pf) {
-                const u32 at = atomicAdd(&hist[259], 1u);
+                const u32 at = (u32)atomicAdd(&S.count, 1);
                 if (at < (u32)cap) out[at] = key;
             }
         });
     }
     __syncthreads();
-    const u32 n = hist[259];
+    const u32 n = (u32)S.count;
+    __syncthreads();
     *lower = prefix;
     return (int)(n < (u32)cap ? n : (u32)cap);
 }
@@ -1508,7 +1535,7 @@ vy_nms_finalize_kernel(const __grid_constant__ VyHeads hd, const __grid_constant
     u64 thr0 = use_s ? ~stream_bound_compl(g, b) : g.thr[b];
     if (SRC == 0 && use_s && !stream_list_ok(g, b, K)) {
         // unusable streamed list: this CTA redoes the image's selection exactly (fin_rescue_heads), into the same list
-        n_list = fin_rescue_heads(hd, pl, b, K, g.slist + (size_t)b * g.slist_cap, g.slist_cap, (u32 *)lbuf, &thr0);
+        n_list = fin_rescue_heads(S, hd, pl, b, K, g.slist + (size_t)b * g.slist_cap, g.slist_cap, (u32 *)lbuf, &thr0);
         __syncthreads();
     }
     if (tid == 0) { S.count = 0; S.flag = 0; S.thr = thr0; }
