@@ -1432,6 +1432,7 @@ static __device__ __noinline__ int fin_rescue_heads(FinBuf &S, const VyHeads &hd
     for (;; shift -= 8) {
         for (int i = tid; i < 16 * 256; i += blockDim.x) priv[i] = 0u;
         __syncthreads();
+        u64 kmin = ~0ull, kmax = 0ull;                     // of the keys that match the prefix
         {
             // run-length aggregation: neighbouring keys of a thread mostly share the leading digits
             u32 cur = 0xffffffffu, run = 0;
@@ -1442,10 +1443,21 @@ static __device__ __noinline__ int fin_rescue_heads(FinBuf &S, const VyHeads &hd
                     const u32 d = (u32)(key >> sh) & 255u;
                     if (d != cur) { if (run) atomicAdd(&mine[cur], run); cur = d; run = 0; }
                     ++run;
+                    kmin = key < kmin ? key : kmin;
+                    kmax = key > kmax ? key : kmax;
                 }
             });
             if (run) atomicAdd(&mine[cur], run);
         }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const u64 lo = sel_shfl_xor_u64(kmin, off), hi = sel_shfl_xor_u64(kmax, off);
+            kmin = lo < kmin ? lo : kmin;
+            kmax = hi > kmax ? hi : kmax;
+        }
+        if (tid == 0) { S.mm[0] = ~0ull; S.mm[1] = 0ull; }
+        __syncthreads();
+        if ((tid & 31) == 0) { atomicMin((unsigned long long *)&S.mm[0], (unsigned long long)kmin); atomicMax((unsigned long long *)&S.mm[1], (unsigned long long)kmax); }
         __syncthreads();
         if (tid < 256) {
             u32 sum = 0;
@@ -1470,8 +1482,23 @@ static __device__ __noinline__ int fin_rescue_heads(FinBuf &S, const VyHeads &hd
         prefix |= (u64)dig << shift;
         kk -= (int)above;
         const long long ge = (long long)(K - kk) + inb;  // keys at or above the prefix (its lower bits zero)
+        // every matching key in this one bin (all-equal scores: the keys differ only in their row bits): the bytes the
+        // smallest and the largest of them share tell nothing either -- go straight to the first byte that differs
+        const u64 diff = S.mm[0] ^ S.mm[1];
         __syncthreads();
         if (ge <= limit || shift == 0) break;
+        if (above == 0 && diff != 0ull && S.hist[dig] == inb) {
+            u32 total = 0;                                // (CTA-uniform: every thread reads the same histogram)
+            for (int d = 0; d < 256; ++d) total += S.hist[d];
+            const int top = 63 - __clzll((long long)diff);                 // highest differing bit
+            const int next = (top >> 3) << 3;
+            if (total == inb && next < shift - 8) {
+                const u64 keep = next + 8 >= 64 ? 0ull : ~((1ull << (next + 8)) - 1ull);
+                prefix = S.mm[0] & keep;
+                shift = next + 8;                         // (the loop's decrement lands on `next`)
+            }
+        }
+        __syncthreads();
     }
     // collect
     if (tid == 0) S.count = 0;
