@@ -486,7 +486,8 @@ vy_decode_sample_kernel(const __grid_constant__ VyHeads hd, const __grid_constan
     // a thread's two best keys stand for its <= 16 (the Ksq-th largest of a subset is <= that of the whole set, so the
     // bound can only come out lower = more careful, and it does only when one thread holds three of the CTA's Ksq
     // best: ~0.5 % of the threads at Ksq = 145).  The radix passes then walk 2 keys per thread instead of 16.
-    const bool full = pl.Ksq > SAMP_NT / 2;            // (CTA-uniform) large Ksq: every key takes part
+    // (CTA-uniform) every key takes part when Ksq is not small against the threads that hold keys (share > 1/2 per thread)
+    const bool full = 2 * pl.Ksq > pl.samp_ipj * min(pl.samp_pls, SAMP_NT / max(pl.samp_ipj, 1));
     if (full) {
 #pragma unroll
         for (int k = 0; k < SAMP_MAXK; ++k) skey[k][tid] = 0u;
