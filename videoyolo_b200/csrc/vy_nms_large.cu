@@ -315,92 +315,95 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
                             if (nms_suppresses_fast(sb[j], sa[j], bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT)) { alive = false; break; }
                 }
             }
-            if (GRID && m > 0) {                         // CTA-uniform; every lane of a warp walks the same loops
-                // The lanes of a warp hold 32 different candidates.  To keep them in step the probe loops run
-                // to the warp's largest trip count and only COLLECT non-empty chain heads; the chains are walked
-                // afterwards, one kept box per lane and iteration, until every lane has drained its heads.
-                const LgGeom gc = lg_geom<FMT>(bx);
-                bool fallback = alive && gc.kind == 2;       // irregular candidate: scans the whole kept list
-                const bool probing = alive && gc.kind == 0;  // inert candidates cannot be suppressed
-                int l_lo = 0, l_hi = -1;
-                if (probing) {
-                    const float mc = fmaxf(gc.w, gc.h);
-                    // sizes a suppressor can have: (t*mc, mc/t), with slack; thr >= 0.05 on this path
-                    l_lo = lg_level(p.thr * mc * 0.999f);
-                    l_hi = lg_level(mc / p.thr * 1.001f);
-                    if (l_hi - l_lo > 12) { fallback = true; l_hi = l_lo - 1; }
-                }
-                u32 hb[16];
-                int hn = 0;
-                u32 cur = LG_EMPTY;
-                if (probing && !fallback) cur = sh_irr;      // irregular kept boxes: everyone checks them
-                int budget = 8 * m + 256;                    // chain-walk steps (a corrupted table cannot hang the GPU)
-                // (the walk is a chain of dependent loads -- an L2 round trip per kept box -- and the tile waits for its
-                // longest walk: four chains are followed side by side, so four round trips overlap)
-                auto drain = [&]() {
-                    u32 c0 = cur, c1 = LG_EMPTY, c2 = LG_EMPTY, c3 = LG_EMPTY;
-                    for (;;) {
-                        if (c0 == LG_EMPTY && hn > 0) c0 = hb[--hn];
-                        if (c1 == LG_EMPTY && hn > 0) c1 = hb[--hn];
-                        if (c2 == LG_EMPTY && hn > 0) c2 = hb[--hn];
-                        if (c3 == LG_EMPTY && hn > 0) c3 = hb[--hn];
-                        const bool busy = alive && !fallback && budget > 0 &&
-                                          (c0 != LG_EMPTY || c1 != LG_EMPTY || c2 != LG_EMPTY || c3 != LG_EMPTY);
-                        if (!__any_sync(0xffffffffu, busy)) break;
-                        if (busy) {
-                            budget -= 4;
-                            // all the loads first
-                            const u32 q0 = c0 != LG_EMPTY ? c0 : 0u, q1 = c1 != LG_EMPTY ? c1 : 0u;
-                            const u32 q2 = c2 != LG_EMPTY ? c2 : 0u, q3 = c3 != LG_EMPTY ? c3 : 0u;
-                            const u32 n0 = p.next[q0], n1 = p.next[q1], n2 = p.next[q2], n3 = p.next[q3];
-                            const float4 b0 = p.kept_box[q0], b1 = p.kept_box[q1], b2 = p.kept_box[q2], b3 = p.kept_box[q3];
-                            const float a0 = p.kept_area[q0], a1 = p.kept_area[q1], a2 = p.kept_area[q2], a3 = p.kept_area[q3];
-                            bool hit = c0 != LG_EMPTY && nms_suppresses_fast(b0, a0, bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT);
-                            hit |= c1 != LG_EMPTY && nms_suppresses_fast(b1, a1, bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT);
-                            hit |= c2 != LG_EMPTY && nms_suppresses_fast(b2, a2, bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT);
-                            hit |= c3 != LG_EMPTY && nms_suppresses_fast(b3, a3, bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT);
-                            if (hit) alive = false;
-                            c0 = c0 != LG_EMPTY ? n0 : LG_EMPTY; c1 = c1 != LG_EMPTY ? n1 : LG_EMPTY;
-                            c2 = c2 != LG_EMPTY ? n2 : LG_EMPTY; c3 = c3 != LG_EMPTY ? n3 : LG_EMPTY;
+            if (GRID && m > 0) {                         // CTA-uniform
+                // One candidate at a time per warp, the 32 lanes side by side on ITS probes: every lane takes a cell of
+                // the candidate's windows and walks that cell's chain (oldest = highest-ranked kept box first), and the
+                // warp stops at the first suppressor any lane finds.  (With a candidate per lane the warp ran to the
+                // longest of its 32 walks -- a chain of dependent L2 round trips -- although 99 % of the candidates
+                // of a force_suppress tile are suppressed by one of the first kept boxes they meet.)
+                for (int c = 0; c < 32; ++c) {
+                    if (!__shfl_sync(0xffffffffu, alive ? 1 : 0, c)) continue;         // (warp-uniform)
+                    const float4 cb = make_float4(__shfl_sync(0xffffffffu, bx.x, c), __shfl_sync(0xffffffffu, bx.y, c),
+                                                  __shfl_sync(0xffffffffu, bx.z, c), __shfl_sync(0xffffffffu, bx.w, c));
+                    const float ca = __shfl_sync(0xffffffffu, ar, c);
+                    const LgGeom gc = lg_geom<FMT>(cb);
+                    if (gc.kind == 1) continue;                                        // inert: cannot be suppressed
+                    bool dead = false;
+                    bool scan_all = gc.kind == 2;                                      // irregular candidate: the whole kept list
+                    int my_x0 = 0, my_y0 = 0, my_nx = 1, my_n = 0, l_lo = 0;
+                    if (!scan_all) {
+                        const float mc = fmaxf(gc.w, gc.h);
+                        // sizes a suppressor can have: (t*mc, mc/t), with slack; thr >= 0.05 on this path
+                        l_lo = lg_level(p.thr * mc * 0.999f);
+                        const int nlev = lg_level(mc / p.thr * 1.001f) - l_lo + 1;
+                        bool bad = false;
+                        if (lane < nlev && nlev <= 8) {                                // lane i: the window at level l_lo + i
+                            const int L = l_lo + lane;
+                            // centres of two boxes with IoU > t are closer than reach * (own extent) per axis (derivation
+                            // at lg_adj_kernel); kept boxes are registered by centre in cells of 2^(L - sh)
+                            const float cs = lg_pow2(L - sh), inv = lg_pow2(sh - L);
+                            const float rx = gc.w * reach, ry = gc.h * reach;
+                            const float mx = rx + cs * 1e-3f + (fabsf(gc.cx) + rx) * 1e-6f;
+                            const float my = ry + cs * 1e-3f + (fabsf(gc.cy) + ry) * 1e-6f;
+                            const float fx0 = floorf((gc.cx - mx) * inv), fx1 = floorf((gc.cx + mx) * inv);
+                            const float fy0 = floorf((gc.cy - my) * inv), fy1 = floorf((gc.cy + my) * inv);
+                            if (!(fabsf(fx0) < 1.0e9f && fabsf(fx1) < 1.0e9f && fabsf(fy0) < 1.0e9f && fabsf(fy1) < 1.0e9f) ||
+                                fx1 - fx0 > 31.0f || fy1 - fy0 > 31.0f) bad = true;
+                            else {
+                                my_x0 = (int)fx0; my_y0 = (int)fy0; my_nx = (int)fx1 - (int)fx0 + 1;
+                                my_n = my_nx * ((int)fy1 - (int)fy0 + 1);
+                            }
+                        }
+                        scan_all = nlev > 8 || __any_sync(0xffffffffu, bad);
+                    }
+                    if (scan_all) {                                                    // awkward geometry: every kept box, 32 at a time
+                        for (int j0 = 0; j0 < m && !dead; j0 += 32) {
+                            const int j = j0 + lane;
+                            const bool hit = j < m && nms_suppresses_fast(p.kept_box[seg0 + j], p.kept_area[seg0 + j], cb, ca,
+                                                                          p.thr, p.thr_lo, p.thr_hi, FMT);
+                            dead = __any_sync(0xffffffffu, hit);
+                        }
+                    } else {
+                        int my_end = my_n;                                             // inclusive prefix over the levels (lanes 0..7)
+#pragma unroll
+                        for (int off = 1; off < 8; off <<= 1) {
+                            const int v = __shfl_up_sync(0xffffffffu, my_end, off);
+                            if (lane >= off) my_end += v;
+                        }
+                        const int total = __shfl_sync(0xffffffffu, my_end, 7);
+                        // cell `total` stands for the chain of irregular kept boxes: everyone checks them
+                        for (int q0 = 0; q0 <= total && !dead; q0 += 32) {
+                            const int q = q0 + lane;
+                            int i = 0;
+#pragma unroll
+                            for (int j = 0; j < 7; ++j) {
+                                const int e = __shfl_sync(0xffffffffu, my_end, j);
+                                if (q >= e) i = j + 1;
+                            }
+                            const int lv_end = __shfl_sync(0xffffffffu, my_end, i), lv_n = __shfl_sync(0xffffffffu, my_n, i);
+                            const int nx = __shfl_sync(0xffffffffu, my_nx, i), x0 = __shfl_sync(0xffffffffu, my_x0, i);
+                            const int y0 = __shfl_sync(0xffffffffu, my_y0, i);
+                            u32 cur = LG_EMPTY;
+                            if (q < total) {
+                                const int qq = q - (lv_end - lv_n);
+                                const int iy = qq / nx, ix = qq - iy * nx;
+                                cur = hhead[lg_hash(l_lo + i, x0 + ix, y0 + iy) & hmask];
+                            } else if (q == total) {
+                                cur = sh_irr;
+                            }
+                            for (int budget = m + 1; budget > 0; --budget) {           // (a corrupted table cannot hang the GPU)
+                                bool hit = false;
+                                if (cur != LG_EMPTY) {
+                                    const u32 nx_ = p.next[cur];
+                                    hit = nms_suppresses_fast(p.kept_box[cur], p.kept_area[cur], cb, ca, p.thr, p.thr_lo, p.thr_hi, FMT);
+                                    cur = nx_;
+                                }
+                                if (__any_sync(0xffffffffu, hit)) { dead = true; break; }
+                                if (!__any_sync(0xffffffffu, cur != LG_EMPTY)) break;
+                            }
                         }
                     }
-                    hn = 0; cur = LG_EMPTY;
-                };
-                const int wl_lo = __reduce_min_sync(0xffffffffu, probing && !fallback ? l_lo : 0x7fffffff);
-                const int wl_hi = __reduce_max_sync(0xffffffffu, probing && !fallback ? l_hi : (int)0x80000000);
-                for (int L = wl_lo; L <= wl_hi; ++L) {
-                    int x0 = 0, y0 = 0, nx = 0, ncell = 0;
-                    if (probing && !fallback && alive && L >= l_lo && L <= l_hi) {
-                        // centres of two boxes with IoU > t are closer than reach * (own extent) per axis (derivation at
-                        // lg_adj_kernel); kept boxes are registered by centre in cells of 2^(L - sh)
-                        const float cs = lg_pow2(L - sh), inv = lg_pow2(sh - L);
-                        const float rx = gc.w * reach, ry = gc.h * reach;
-                        const float mx = rx + cs * 1e-3f + (fabsf(gc.cx) + rx) * 1e-6f;
-                        const float my = ry + cs * 1e-3f + (fabsf(gc.cy) + ry) * 1e-6f;
-                        const float fx0 = floorf((gc.cx - mx) * inv), fx1 = floorf((gc.cx + mx) * inv);
-                        const float fy0 = floorf((gc.cy - my) * inv), fy1 = floorf((gc.cy + my) * inv);
-                        if (!(fabsf(fx0) < 1.0e9f && fabsf(fx1) < 1.0e9f && fabsf(fy0) < 1.0e9f && fabsf(fy1) < 1.0e9f) ||
-                            fx1 - fx0 > 31.0f || fy1 - fy0 > 31.0f) {
-                            fallback = true;
-                        } else {
-                            x0 = (int)fx0; y0 = (int)fy0; nx = (int)fx1 - x0 + 1;
-                            ncell = nx * ((int)fy1 - y0 + 1);
-                        }
-                    }
-                    const int wn = __reduce_max_sync(0xffffffffu, ncell);
-                    for (int q = 0; q < wn; ++q) {
-                        if (q < ncell && alive && !fallback) {
-                            const int iy = y0 + q / nx, ix = x0 + q % nx;
-                            const u32 k = hhead[lg_hash(L, ix, iy) & hmask];
-                            if (k != LG_EMPTY) hb[hn++] = k;
-                        }
-                        if (__any_sync(0xffffffffu, hn >= 15)) drain();
-                    }
-                }
-                drain();
-                if (fallback && alive) {
-                    for (int j = 0; j < m && alive; ++j)
-                        if (nms_suppresses_fast(p.kept_box[seg0 + j], p.kept_area[seg0 + j], bx, ar, p.thr, p.thr_lo, p.thr_hi, FMT)) alive = false;
+                    if (dead && lane == c) alive = false;
                 }
             }
             // ---- b. the tile's live candidates, compacted in order
