@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
     __shared__ int wcount[LG_WORDS], woff[LG_WORDS + 1], kpre[LG_WORDS + 1];
     __shared__ long long sh_len;
     __shared__ u32 sh_irr;                           // head of the segment's chain of irregular kept boxes
+    __shared__ int sh_next;                          // next candidate of the tile to be probed (GRID)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 lt_mask = (1u << lane) - 1u;
     const long long R = p.rp.R, N = (long long)p.B * R;
@@ -320,12 +321,22 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
                 // the candidate's windows and walks that cell's chain (oldest = highest-ranked kept box first), and the
                 // warp stops at the first suppressor any lane finds.  (With a candidate per lane the warp ran to the
                 // longest of its 32 walks -- a chain of dependent L2 round trips -- although 99 % of the candidates
-                // of a force_suppress tile are suppressed by one of the first kept boxes they meet.)
-                for (int c = 0; c < 32; ++c) {
-                    if (!__shfl_sync(0xffffffffu, alive ? 1 : 0, c)) continue;         // (warp-uniform)
-                    const float4 cb = make_float4(__shfl_sync(0xffffffffu, bx.x, c), __shfl_sync(0xffffffffu, bx.y, c),
-                                                  __shfl_sync(0xffffffffu, bx.z, c), __shfl_sync(0xffffffffu, bx.w, c));
-                    const float ca = __shfl_sync(0xffffffffu, ar, c);
+                // of a force_suppress tile are suppressed by one of the first kept boxes they meet.)  The warps take
+                // the tile's candidates from a shared counter: a survivor walks all its chains, and a warp that
+                // draws several of them would keep the other 31 waiting at the barrier.
+                __syncthreads();
+                sb[tid] = bx; sa[tid] = ar;                                            // (the staging buffers of the other path)
+                trank[tid] = have ? 1u : 0u;                                           // alive flags (trank is filled below)
+                if (tid == 0) sh_next = 0;
+                __syncthreads();
+                for (;;) {
+                    int c = 0;
+                    if (lane == 0) c = atomicAdd(&sh_next, 1);
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                    if (c >= LG_TILE) break;
+                    if (!trank[c]) continue;                                           // (warp-uniform)
+                    const float4 cb = sb[c];
+                    const float ca = sa[c];
                     const LgGeom gc = lg_geom<FMT>(cb);
                     if (gc.kind == 1) continue;                                        // inert: cannot be suppressed
                     bool dead = false;
@@ -403,8 +414,11 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
                             }
                         }
                     }
-                    if (dead && lane == c) alive = false;
+                    if (dead && lane == 0) trank[c] = 0u;
                 }
+                __syncthreads();
+                alive = trank[tid] != 0u;
+                __syncthreads();
             }
             // ---- b. the tile's live candidates, compacted in order
             const u32 bal = __ballot_sync(0xffffffffu, alive);
