@@ -442,7 +442,10 @@ __device__ __forceinline__ float samp_sigmoid(float x) {
 constexpr int SAMP_NT = 512;
 constexpr int SAMP_MAXK = 16;      // class planes per thread
 constexpr int SAMP_BATCH = 8;      // of which this many are loaded together
-constexpr int SAMP_RUN = 8;        // adjacent items sampled together: 8 x 16 B = one 128-byte line per plane
+#ifndef VY_SAMP_RUN
+#define VY_SAMP_RUN 8
+#endif
+constexpr int SAMP_RUN = VY_SAMP_RUN;   // adjacent items sampled together: 8 x 16 B = one 128-byte line per plane
 
 // sampled item j of image b -> where it lives (item = 4 consecutive positions of one (scale, anchor))
 struct ItemRef { const float *p; int HW, nv, o1, o2, o3; bool vec; };
@@ -1994,7 +1997,8 @@ static void plan_stream(const VyHeads &hd, SelPlan *pl) {
     // is below the K-th largest score except with negligible probability (rank std ~ S*sqrt(j) << 3K), and
     // an image where it is not (fewer than K candidates found under a non-trivial bound) is redone exactly
     // by the rescue pass (stream_list_ok).
-    long long j = (4LL * pl->K + pl->samp_stride - 1) / pl->samp_stride;
+    static const double aim = getenv("VY_SAMP_AIM") ? atof(getenv("VY_SAMP_AIM")) : 4.0;      // (A/B) rank aimed at, in units of K
+    long long j = (long long)((aim * pl->K + pl->samp_stride - 1) / pl->samp_stride);
     if (j > pl->K) j = pl->K;
     long long ksq = (j + pl->Gs - 1) / pl->Gs;
     if (ksq < 8) ksq = 8;
