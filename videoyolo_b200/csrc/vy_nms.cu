@@ -16,6 +16,7 @@
 #include "vy_nms_math.cuh"
 #include <math_constants.h>
 #include <stdlib.h>
+#include <math.h>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------
@@ -1050,6 +1051,7 @@ struct FinParams {
     int W;                       // output row width (6 for heads)
     int fill_rest;               // 1: this kernel writes the -1 padding rows itself
     int lcap;                    // candidate lists up to this length are staged in shared memory (0: never)
+    int force_rescue;            // (tools/rescue_time.py, VY_FORCE_RESCUE) treat every streamed list as unusable
     float *out;
     int *kept_rows;
 };
@@ -1421,6 +1423,53 @@ __device__ __forceinline__ void fin_for_each_key(const VyHeads &hd, const SelPla
         }
     }
 }
+// the same walk with the streaming pass's logit-domain test in front: f(key) for every element whose score can exceed
+// `smin` (t_c >= vy_tcmin(smin, conf): one compare per element, the sigmoids only for what passes)
+template <class F>
+__device__ __forceinline__ void fin_for_each_key_above(const VyHeads &hd, const SelPlan &pl, int b, float smin, F f) {
+    for (int idx = threadIdx.x; idx < pl.items_per_frame; idx += blockDim.x) {
+        int s = 0;
+        while (s + 1 < hd.n_scales && idx >= pl.item_begin[s + 1]) ++s;
+        const VyScale &sc = hd.sc[s];
+        const int rel = idx - pl.item_begin[s];
+        const int a = rel / pl.items_per_plane[s];
+        const int pos0 = (rel - a * pl.items_per_plane[s]) * 4;
+        const int nv = min(4, sc.HW - pos0);
+        const bool vec = sc.vec == 4;
+        const int o1 = min(1, nv - 1), o2 = min(2, nv - 1), o3 = min(3, nv - 1);
+        const float *p = sc.head + ((size_t)(b * hd.A + a) * hd.P) * (size_t)sc.HW + pos0;
+        const u32 row0 = (u32)(sc.row_off + (long long)pos0 * hd.A + a);
+        auto load4 = [&](const float *q, float (&t)[4]) {
+            if (vec) { const float4 w = vy_ldg128(q); t[0] = w.x; t[1] = w.y; t[2] = w.z; t[3] = w.w; }
+            else { t[0] = vy_ldg32(q); t[1] = vy_ldg32(q + o1); t[2] = vy_ldg32(q + o2); t[3] = vy_ldg32(q + o3); }
+        };
+        float conf[4], tcm[4];
+        load4(p + 4 * (size_t)sc.HW, conf);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            conf[v] = v < nv ? vy_sigmoid(conf[v]) : 0.0f;
+            tcm[v] = v < nv ? vy_tcmin(smin, conf[v]) : CUDART_INF_F;
+        }
+        for (int c0 = 0; c0 < hd.C; c0 += 4) {
+            float t[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (c0 + u < hd.C) load4(p + (size_t)(5 + c0 + u) * (size_t)sc.HW, t[u]);
+                else t[u][0] = t[u][1] = t[u][2] = t[u][3] = CUDART_NAN_F;
+            }
+            if (!vy_any_ge16(t, tcm)) continue;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    if (t[u][v] >= tcm[v]) {
+                        const float sv = vy_score(t[u][v], conf[v]);
+                        if (sv > pl.valid_thresh) f(vy_make_key(sv, row0 + (u32)(c0 + u) * (u32)sc.n_s + (u32)v * (u32)hd.A));
+                    }
+        }
+    }
+}
+
 // returns the number of keys written to out[0 .. cap); *lower = a lower bound of the image's K-th largest key (0: none).
 // priv: 16 x 256 words of shared memory -- a histogram per warp (two warps share one in a 1024-thread CTA): in the
 // degenerate case every key of the image matches the prefix in every pass, and 1.8 M atomics on ONE histogram were the
@@ -1430,6 +1479,23 @@ static __device__ __noinline__ int fin_rescue_heads(FinBuf &S, const VyHeads &hd
     const int tid = threadIdx.x;
     u32 *mine = priv + (((tid >> 5) & 15) << 8);
     const int limit = cap < 4096 ? cap : 4096;           // (<= 4096 keys keep the finalize on its bucket-sort front end)
+    // First try: every VALID key of the image (score > valid_thresh) in one pass, found with the streaming pass's cheap
+    // logit-domain test.  With trained-like logits -- where a bound that was too high is met in practice -- that is a few
+    // thousand keys and the rescue ends here; random-init logits overflow the list at once and take the radix passes.
+    if (tid == 0) S.count = 0;
+    __syncthreads();
+    fin_for_each_key_above(hd, pl, b, pl.valid_thresh, [&](u64 key) {
+        if (*(volatile int *)&S.count <= cap) {
+            const int at = atomicAdd(&S.count, 1);
+            if (at < cap) out[at] = key;
+        }
+    });
+    __syncthreads();
+    {
+        const int n_valid = S.count;
+        __syncthreads();
+        if (n_valid <= cap) { *lower = 0ull; return n_valid; }
+    }
     u64 prefix = 0;
     int kk = K;
     int shift = 56;
@@ -1564,7 +1630,7 @@ vy_nms_finalize_kernel(const __grid_constant__ VyHeads hd, const __grid_constant
     int n_list = use_s ? g.scount[b] : min(g.count[b], pl.list_cap);
     const u64 *list = use_s ? g.slist + (size_t)b * g.slist_cap : g.list + (size_t)b * pl.list_cap;
     u64 thr0 = use_s ? ~stream_bound_compl(g, b) : g.thr[b];
-    if (SRC == 0 && use_s && !stream_list_ok(g, b, K)) {
+    if (SRC == 0 && use_s && (fp.force_rescue || !stream_list_ok(g, b, K))) {
         // unusable streamed list: this CTA redoes the image's selection exactly (fin_rescue_heads), into the same list
         n_list = fin_rescue_heads(S, hd, pl, b, K, g.slist + (size_t)b * g.slist_cap, g.slist_cap, (u32 *)lbuf, &thr0);
         __syncthreads();
@@ -1997,7 +2063,16 @@ static void plan_stream(const VyHeads &hd, SelPlan *pl) {
     // is below the K-th largest score except with negligible probability (rank std ~ S*sqrt(j) << 3K), and
     // an image where it is not (fewer than K candidates found under a non-trivial bound) is redone exactly
     // by the rescue pass (stream_list_ok).
-    static const double aim = getenv("VY_SAMP_AIM") ? atof(getenv("VY_SAMP_AIM")) : 4.0;      // (A/B) rank aimed at, in units of K
+    // How far above K?  The estimate's rank has a relative spread ~ 1/sqrt(j) (j sampled scores above the bound, times a
+    // burstiness factor for clustered logits), so the margin in standard deviations is (1 - 1/aim) * sqrt(aim * K / S):
+    // 5.3 at the aim this path was tuned with (4K at S = 32, K = 400: no rescue in any measured config).  Where the
+    // sampling rate is higher the same margin needs a lower aim -- 2.4K at VID 320^2 (S = 11): 43 % shorter lists, the call
+    // 6 % faster, shortest list of 1 536 images 1.5 K (tools/aim_test.py).  VY_SAMP_AIM overrides (A/B).
+    static const double aim_env = getenv("VY_SAMP_AIM") ? atof(getenv("VY_SAMP_AIM")) : 0.0;
+    double aim = 4.0;
+    for (double a = 1.5; a < 4.0; a += 0.1)
+        if ((1.0 - 1.0 / a) * sqrt(a * pl->K / (double)pl->samp_stride) >= 5.3) { aim = a; break; }
+    if (aim_env > 0.0) aim = aim_env;
     long long j = (long long)((aim * pl->K + pl->samp_stride - 1) / pl->samp_stride);
     if (j > pl->K) j = pl->K;
     long long ksq = (j + pl->Gs - 1) / pl->Gs;
@@ -2234,6 +2309,8 @@ static int plan_launch(const vy_decode_nms_plan *P, const float *const *head, fl
     fp.overlap_thresh = P->overlap_thresh; fp.force_suppress = P->force_suppress;
     fp.in_format = VY_FMT_CORNER; fp.out_format = VY_FMT_CORNER; fp.W = 6; fp.fill_rest = 1;
     fp.out = out; fp.kept_rows = kept_rows;
+    static const bool force_rescue = getenv("VY_FORCE_RESCUE") != nullptr;
+    fp.force_rescue = force_rescue ? 1 : 0;
     RowParams rp;
     memset(&rp, 0, sizeof(rp));
     int rc = launch_finalize<0>(hd, rp, pl, g, fp, B, st);
@@ -2359,6 +2436,7 @@ extern "C" int vy_box_nms_f32(const float *data, int B, long R, int W_elem, floa
     VY_KERNEL(VY_K_SELECT_ROWS, st, (vy_rows_select_kernel<<<select_grid(pl.n_jobs), SEL_NT, 0, st>>>(rp, pl, g)));
     VY_LAUNCH_CHECK("vy_rows_select_kernel");
     FinParams fp;
+    fp.force_rescue = 0;
     fp.K = pl.K; fp.post_rows = (int)(out_rows < pl.K ? out_rows : pl.K); fp.out_stride_rows = out_rows;
     fp.overlap_thresh = overlap_thresh; fp.force_suppress = force_suppress;
     fp.in_format = in_format; fp.out_format = out_format; fp.W = W_elem;
