@@ -123,6 +123,60 @@ struct TapIter {
     }
 };
 
+// epilogue of one accumulator tile: 32 rows of the tile per warp (thread = TMEM lane = output row), BN columns in
+// chunks of 32: folded BN scale/shift, LeakyReLU, border rows zeroed, bf16 / fp32 P layout or fp32 NCHW store
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_tile(const ConvParams &cp, u32 tmem_acc, int quarter, int r, int n0, int t) {
+    const int plane = cp.Hp * cp.Wp;
+    const bool in_range = r < cp.rows;
+    const int rr = r % plane, hp = rr / cp.Wp, wp = rr % cp.Wp;
+    const bool interior = hp > 0 && hp < cp.Hp - 1 && wp > 0 && wp < cp.Wp - 1;
+    const size_t out_off = ((size_t)t * cp.rows + (size_t)r) * cp.Cout + n0;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+        u32 v[32];
+        tc_ld32(tmem_acc + ((u32)(quarter * 32) << 16) + (u32)(ch * 32), v);
+        if (in_range) {
+            float o[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int n = n0 + ch * 32 + i;
+                float x = fmaf(__uint_as_float(v[i]), __ldg(cp.scale + n), __ldg(cp.shift + n));   // layers.py:68,77
+                x = x > 0.0f ? x : x * cp.slope;                                                   // layers.py:69,78
+                o[i] = interior ? x : 0.0f;
+            }
+            if (cp.nchw_C > 0) {
+                // the head maps of YOLOOutputV3 leave the GEMM in the reference's own layout (yolo3.py:157-158):
+                // consecutive lanes hold consecutive pixels, so every channel is one 128-byte run per warp
+                if (interior) {
+                    const int bimg = r / plane;
+                    float *dst = (float *)cp.y + ((size_t)bimg * cp.nchw_C * cp.nchw_H + (size_t)(hp - 1)) * cp.nchw_W + (wp - 1);
+                    const size_t cstride = (size_t)cp.nchw_H * cp.nchw_W;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int n = n0 + ch * 32 + i;
+                        if (n < cp.nchw_C) dst[(size_t)n * cstride] = o[i];
+                    }
+                }
+            } else if (cp.y_is_f32) {
+                float4 *dst = (float4 *)((float *)cp.y + out_off + ch * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            } else {
+                uint4 *dst = (uint4 *)((__nv_bfloat16 *)cp.y + out_off + ch * 32);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(o[8 * i], o[8 * i + 1]);
+                    __nv_bfloat162 p1 = __floats2bfloat162_rn(o[8 * i + 2], o[8 * i + 3]);
+                    __nv_bfloat162 p2 = __floats2bfloat162_rn(o[8 * i + 4], o[8 * i + 5]);
+                    __nv_bfloat162 p3 = __floats2bfloat162_rn(o[8 * i + 6], o[8 * i + 7]);
+                    dst[i] = make_uint4(*(u32 *)&p0, *(u32 *)&p1, *(u32 *)&p2, *(u32 *)&p3);
+                }
+            }
+        }
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(CV_NT, 1)
 vy_fusion_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -210,62 +264,15 @@ vy_fusion_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;                                  // TMEM lanes 32*quarter .. +31
-        const int plane = cp.Hp * cp.Wp;
         int acc = 0; u32 acc_phase = 0;
         for (long long tile = blockIdx.x; tile < cp.n_tiles_total; tile += gridDim.x) {
             const int n_t = (int)(tile % cp.n_tiles);
             const long long rest = tile / cp.n_tiles;
             const int m_t = (int)(rest % cp.m_tiles), t = (int)(rest / cp.m_tiles);
             const int r = m_t * CV_BM + quarter * 32 + lane, n0 = n_t * BN;
-            const bool in_range = r < cp.rows;
-            const int rr = r % plane, hp = rr / cp.Wp, wp = rr % cp.Wp;
-            const bool interior = hp > 0 && hp < cp.Hp - 1 && wp > 0 && wp < cp.Wp - 1;
             mbar_wait(&bar_acc_full[acc], acc_phase);
             tc_fence_after();
-            const size_t out_off = ((size_t)t * cp.rows + (size_t)r) * cp.Cout + n0;
-#pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                u32 v[32];
-                tc_ld32(tmem_base + ((u32)(quarter * 32) << 16) + (u32)(acc * BN + ch * 32), v);
-                if (in_range) {
-                    float o[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int n = n0 + ch * 32 + i;
-                        float x = fmaf(__uint_as_float(v[i]), __ldg(cp.scale + n), __ldg(cp.shift + n));   // layers.py:68,77
-                        x = x > 0.0f ? x : x * cp.slope;                                                   // layers.py:69,78
-                        o[i] = interior ? x : 0.0f;
-                    }
-                    if (cp.nchw_C > 0) {
-                        // the head maps of YOLOOutputV3 leave the GEMM in the reference's own layout (yolo3.py:157-158):
-                        // consecutive lanes hold consecutive pixels, so every channel is one 128-byte run per warp
-                        if (interior) {
-                            const int bimg = r / plane;
-                            float *dst = (float *)cp.y + ((size_t)bimg * cp.nchw_C * cp.nchw_H + (size_t)(hp - 1)) * cp.nchw_W + (wp - 1);
-                            const size_t cstride = (size_t)cp.nchw_H * cp.nchw_W;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int n = n0 + ch * 32 + i;
-                                if (n < cp.nchw_C) dst[(size_t)n * cstride] = o[i];
-                            }
-                        }
-                    } else if (cp.y_is_f32) {
-                        float4 *dst = (float4 *)((float *)cp.y + out_off + ch * 32);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-                    } else {
-                        uint4 *dst = (uint4 *)((__nv_bfloat16 *)cp.y + out_off + ch * 32);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[8 * i], o[8 * i + 1]);
-                            __nv_bfloat162 p1 = __floats2bfloat162_rn(o[8 * i + 2], o[8 * i + 3]);
-                            __nv_bfloat162 p2 = __floats2bfloat162_rn(o[8 * i + 4], o[8 * i + 5]);
-                            __nv_bfloat162 p3 = __floats2bfloat162_rn(o[8 * i + 6], o[8 * i + 7]);
-                            dst[i] = make_uint4(*(u32 *)&p0, *(u32 *)&p1, *(u32 *)&p2, *(u32 *)&p3);
-                        }
-                    }
-                }
-            }
+            conv_epilogue_tile<BN>(cp, tmem_base + (u32)(acc * BN), quarter, r, n0, t);
             tc_fence_before();
             mbar_arrive(&bar_acc_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -276,6 +283,170 @@ vy_fusion_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ CTA-pair variant (tcgen05 cta_group::2)
+// Two CTAs of one cluster (the two SMs of a TPC) compute ONE 256 x BN tile: CTA r fetches its own 128 rows of A and
+// HALF of the weight tile (rows n0 + r*BN/2 ..), and a single tcgen05.mma.cta_group::2 issued by the leader reads A
+// from both CTAs and the two halves of B from both shared memories: per k-block a CTA receives 16 KB + BN*64 B
+// instead of 16 KB + BN*128 B -- the operand traffic from L2, which bounds the one-CTA kernel in full waves, drops by
+// a third at BN = 256, and the freed shared memory holds 6 stages instead of 4.  Accumulators: CTA r's TMEM lanes
+// hold rows 128 r .. of the tile, double-buffered (2 x BN columns), each CTA runs its own epilogue.
+//   barriers   full[s]      leader's; the leader's producer expects the bytes of BOTH CTAs, both CTAs' TMA loads
+//                           complete on it (cp.async.bulk.tensor ... cta_group::2, barrier address with the peer bit cleared)
+//              empty[s]     one per CTA; tcgen05.commit.cta_group::2 multicast from the leader frees the slot in both
+//              acc_full[a]  one per CTA, same multicast commit after the tile's last k-block
+//              acc_empty[a] leader's; 2 x 128 epilogue threads arrive (the peer's through mapa)
+__device__ __forceinline__ u32 cluster_ctarank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr u32 PEER_BIT_MASK = 0xFEFFFFFFu;     // shared::cluster address of the same offset in the pair's even CTA
+__device__ __forceinline__ void tma2_load_3d(void *dst, const CUtensorMap *map, u64 *bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void *dst, const CUtensorMap *map, u64 *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc2_commit(u64 *bar) {     // arrives on `bar` of BOTH CTAs when all MMAs issued so far are done
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void tc2_mma(u32 d_tmem, u64 desc_a, u64 desc_b, u32 idesc, u32 accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(u64 *bar, u32 cta) {      // arrive on the barrier at this offset in CTA `cta`
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        :: "r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+
+constexpr int CV2_BM = 2 * CV_BM;
+template <int BN> struct Conv2Cfg {
+    static constexpr u32 A_BYTES = CV_BM * CV_BK * 2, B_BYTES = (BN / 2) * CV_BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CV_NT, 1)
+vy_fusion_conv2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                       const __grid_constant__ ConvParams cp) {
+    using Cfg = Conv2Cfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr u32 A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
+    constexpr u32 TMEM_COLS = 2 * BN;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) u64 bar_full[STAGES], bar_empty[STAGES], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ u32 tmem_base_sh;
+    unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 rank = cluster_ctarank();
+    const long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {          // the same warp of both CTAs, same shared-memory offset for the result
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(&tmem_base_sh)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();       // barriers of the peer initialised, TMEM of both CTAs allocated
+    tc_fence_after();
+    const u32 tmem_base = tmem_base_sh;
+
+    const int khw = cp.kh * cp.kw;
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0; u32 phase = 0;
+            for (long long tile = pair; tile < cp.n_tiles_total; tile += n_pairs) {
+                const int n_t = (int)(tile % cp.n_tiles);
+                const long long rest = tile / cp.n_tiles;
+                const int m_t = (int)(rest % cp.m_tiles), t = (int)(rest / cp.m_tiles);
+                const int r0 = m_t * CV2_BM + (int)rank * CV_BM, n0 = n_t * BN + (int)rank * (BN / 2);
+                for (int a = 0; a < cp.kt; ++a) {
+                    const int tt = t + a - cp.kt / 2;
+                    if (tt < 0 || tt >= cp.T) continue;
+                    for (int hw = 0; hw < khw; ++hw) {
+                        const int dh = hw / cp.kw - cp.kh / 2, dw = hw % cp.kw - cp.kw / 2;
+                        const int row = r0 + dh * cp.Wp + dw;
+                        const int kbase = (a * khw + hw) * cp.Cin;
+                        for (int cb = 0; cb < cp.cin_blocks; ++cb) {
+                            mbar_wait(&bar_empty[stage], phase ^ 1u);
+                            unsigned char *sa = tiles + (size_t)stage * STAGE_BYTES, *sb = sa + A_BYTES;
+                            if (rank == 0) mbar_expect_tx(&bar_full[stage], 2 * STAGE_BYTES);
+                            tma2_load_3d(sa, &map_x, &bar_full[stage], cb * CV_BK, row, tt);
+                            tma2_load_2d(sb, &map_w, &bar_full[stage], kbase + cb * CV_BK, n0);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (rank == 0 && lane == 0) {
+            constexpr u32 idesc = umma_idesc(CV2_BM, BN);
+            int stage = 0; u32 phase = 0;
+            int acc = 0; u32 acc_phase = 0;
+            for (long long tile = pair; tile < cp.n_tiles_total; tile += n_pairs) {
+                const int t = (int)((tile / cp.n_tiles) / cp.m_tiles);
+                TapIter ti{cp.kt, cp.kh, cp.kw, cp.T, t};
+                const int n_kb = ti.count() * cp.cin_blocks;
+                mbar_wait(&bar_acc_empty[acc], acc_phase ^ 1u);       // both epilogues have drained this accumulator
+                tc_fence_after();
+                const u32 d_tmem = tmem_base + (u32)(acc * BN);
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&bar_full[stage], phase);
+                    tc_fence_after();
+                    const u32 sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES), sb = sa + A_BYTES;
+                    const u64 da = umma_desc(sa), db = umma_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < CV_BK / 16; ++k)
+                        tc2_mma(d_tmem, da + (u64)(2 * k), db + (u64)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc2_commit(&bar_empty[stage]);                    // the slot is free in both CTAs once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                tc2_commit(&bar_acc_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5 of both CTAs) =====================
+        const int quarter = warp & 3;
+        int acc = 0; u32 acc_phase = 0;
+        for (long long tile = pair; tile < cp.n_tiles_total; tile += n_pairs) {
+            const int n_t = (int)(tile % cp.n_tiles);
+            const long long rest = tile / cp.n_tiles;
+            const int m_t = (int)(rest % cp.m_tiles), t = (int)(rest / cp.m_tiles);
+            const int r = m_t * CV2_BM + (int)rank * CV_BM + quarter * 32 + lane, n0 = n_t * BN;
+            mbar_wait(&bar_acc_full[acc], acc_phase);
+            tc_fence_after();
+            conv_epilogue_tile<BN>(cp, tmem_base + (u32)(acc * BN), quarter, r, n0, t);
+            tc_fence_before();
+            mbar_arrive_cta(&bar_acc_empty[acc], 0u);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();       // nobody leaves (shared memory, barriers, TMEM) while the pair still works
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -496,6 +667,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 #ifndef CV_REL128
 #define CV_REL128 1.43     // time per output column of a 128-wide tile relative to a 256-wide one (measured at equal wave
 #define CV_REL64 2.36      // counts, tools/conv_bench.py with VY_CONV_BN: 0.112 / 0.185 ms against 0.078 ms at 26^2 256->512)
+#define CV_REL_PAIR256 0.88   // CTA pairs, per column and per 128 rows of a CTA, relative to the one-CTA 256-wide tile (equal wave
+#define CV_REL_PAIR128 1.24   // counts at 52^2 128->256, VY_CONV_CTA2: 0.074 / 0.104 ms against 0.084 ms)
 #endif
 
 EncodeTiledFn encode_fn() {
@@ -517,6 +690,16 @@ int launch_conv(const CUtensorMap &mx, const CUtensorMap &mw, const ConvParams &
     long long grid = cp.n_tiles_total < vy_sm_count() ? cp.n_tiles_total : vy_sm_count();
     VY_KERNEL(VY_K_FUSION_CONV, st, (vy_fusion_conv_kernel<BN><<<(unsigned)grid, CV_NT, smem, st>>>(mx, mw, cp)));
     VY_LAUNCH_CHECK("vy_fusion_conv_kernel");
+    return VY_OK;
+}
+
+template <int BN>
+int launch_conv2(const CUtensorMap &mx, const CUtensorMap &mw, const ConvParams &cp, cudaStream_t st) {
+    VY_CUDA_CHECK(cudaFuncSetAttribute(vy_fusion_conv2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Conv2Cfg<BN>::SMEM));
+    const long long pairs_max = vy_sm_count() / 2;
+    const long long pairs = cp.n_tiles_total < pairs_max ? cp.n_tiles_total : pairs_max;
+    VY_KERNEL(VY_K_FUSION_CONV, st, (vy_fusion_conv2_kernel<BN><<<(unsigned)(2 * pairs), CV_NT, Conv2Cfg<BN>::SMEM, st>>>(mx, mw, cp)));
+    VY_LAUNCH_CHECK("vy_fusion_conv2_kernel");
     return VY_OK;
 }
 
@@ -631,29 +814,41 @@ static int conv_launch(const void *x, const void *w, const float *scale, const f
     const int Hp = H + 2, Wp = W + 2;
     const long long rows = (long long)B * Hp * Wp;
     if (rows > 0x7fffff00LL) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16: B*Hp*Wp too large");
-    // N tile: the widest one wastes the least operand traffic, but the persistent grid runs ceil(tiles / SMs) waves of
-    // whole tiles -- 180 tiles of 128 x 256 at 13^2 x 8 windows are two waves, the second 22 % full.  Pick the width
-    // with the lowest estimated time = waves x width x (measured relative cost per column of the narrower tiles).  With
-    // the measured costs (a 128 x 128 MMA tile re-reads A twice as often: 1.43x per column) the widest width that divides
-    // Cout wins at every benchmarked shape, 13^2 included (0.114 ms against 0.148 ms); the estimate only moves to a narrower
-    // tile when it saves more than a third of the waves.
-    int BN = 64;
+    // Tile shape.  The widest N tile wastes the least operand traffic, and a CTA pair (256 rows, the weight tile split
+    // over the two CTAs) less still -- but the persistent grid runs ceil(tiles / units) waves of whole tiles, units = SMs
+    // or SM pairs: 180 tiles of 128 x 256 at 13^2 x 8 windows are two waves, the second 22 % full; 150 pair tiles at
+    // 26^2 x 8 windows are three waves on 74 pairs where 294 one-CTA tiles are two on 148 SMs.  Pick the shape with the
+    // lowest estimated time = waves x width x measured relative cost per column (one CTA: 128 wide re-reads A twice as
+    // often, 1.43x; pairs: 0.88x at 256, 1.24x at 128 -- DESIGN.md section 4.5).
+    // VY_CONV_BN = one-CTA width, VY_CONV_CTA2 = 0 (never pairs) | 128 | 256 (that pair width): A/B runs.
+    int BN = 64, pairBN = 0;
     {
-        static const char *force = getenv("VY_CONV_BN");          // (A/B runs)
-        const long long mt = (long long)T * ((rows + CV_BM - 1) / CV_BM);
+        static const char *force = getenv("VY_CONV_BN");
+        static const char *pe = getenv("VY_CONV_CTA2");
+        const int want_pair = pe ? atoi(pe) : -1;
         const int sms = vy_sm_count();
         double best = 1e300;
-        const int cand[3] = {256, 128, 64};
-        const double rel[3] = {1.0, CV_REL128, CV_REL64};
-        for (int i = 0; i < 3; ++i) {
+        const int cand[5] = {256, 128, 64, 256, 128};
+        const double rel[5] = {1.0, CV_REL128, CV_REL64, CV_REL_PAIR256, CV_REL_PAIR128};
+        for (int i = 0; i < 5; ++i) {
+            const bool is_pair = i >= 3;
             if (Cout % cand[i] != 0) continue;
-            if (force && atoi(force) != cand[i] && Cout % atoi(force) == 0) continue;
-            const long long tiles = mt * (Cout / cand[i]);
-            const long long waves = (tiles + sms - 1) / sms;
+            if (is_pair) {
+                if (want_pair == 0 || sms < 2) continue;
+                if (want_pair > 0 && want_pair != cand[i] && Cout % want_pair == 0) continue;
+            } else {
+                if (want_pair > 0 && Cout % want_pair == 0) continue;
+                if (force && atoi(force) != cand[i] && Cout % atoi(force) == 0) continue;
+            }
+            const int bm = is_pair ? CV2_BM : CV_BM;
+            const long long units = is_pair ? sms / 2 : sms;
+            const long long tiles = (long long)T * ((rows + bm - 1) / bm) * (Cout / cand[i]);
+            const long long waves = (tiles + units - 1) / units;
             const double cost = (double)waves * cand[i] * rel[i];
-            if (cost < best) { best = cost; BN = cand[i]; }
+            if (cost < best) { best = cost; BN = cand[i]; pairBN = is_pair ? cand[i] : 0; }
         }
     }
+    const int BM = pairBN ? CV2_BM : CV_BM;
     const long long Ktot = (long long)kt * kh * kw * Cin;
 
     CUtensorMap mx, mw;
@@ -669,7 +864,7 @@ static int conv_launch(const void *x, const void *w, const float *scale, const f
     {   // W: (Ktot, Cout) bf16, box (64, BN)
         cuuint64_t dim[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
         cuuint64_t str[1] = {(cuuint64_t)Ktot * 2};
-        cuuint32_t box[2] = {CV_BK, (cuuint32_t)BN}, es[2] = {1, 1};
+        cuuint32_t box[2] = {CV_BK, (cuuint32_t)(pairBN ? BN / 2 : BN)}, es[2] = {1, 1};
         const CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(w), dim, str, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -679,12 +874,14 @@ static int conv_launch(const void *x, const void *w, const float *scale, const f
     memset(&cp, 0, sizeof(cp));
     cp.T = T; cp.rows = (int)rows; cp.Hp = Hp; cp.Wp = Wp; cp.Cin = Cin; cp.Cout = Cout;
     cp.kt = kt; cp.kh = kh; cp.kw = kw;
-    cp.m_tiles = (int)((rows + CV_BM - 1) / CV_BM);
+    cp.m_tiles = (int)((rows + BM - 1) / BM);
     cp.n_tiles = Cout / BN;
     cp.cin_blocks = Cin / CV_BK;
     cp.n_tiles_total = (long long)T * cp.m_tiles * cp.n_tiles;
     cp.slope = leaky_slope; cp.scale = scale; cp.shift = shift; cp.y = y; cp.y_is_f32 = y_is_f32;
     cp.nchw_C = nchw_C; cp.nchw_H = H; cp.nchw_W = W;
+    if (pairBN == 256) return launch_conv2<256>(mx, mw, cp, st);
+    if (pairBN == 128) return launch_conv2<128>(mx, mw, cp, st);
     if (BN == 256) return launch_conv<256>(mx, mw, cp, st);
     if (BN == 128) return launch_conv<128>(mx, mw, cp, st);
     return launch_conv<64>(mx, mw, cp, st);
