@@ -153,6 +153,30 @@ def test_pack_unpack_roundtrip_and_pool(vy):
         np.testing.assert_allclose(got, ref, rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize("B,K,C,H,W", [(2, 3, 128, 26, 26), (1, 3, 72, 20, 12), (2, 1, 64, 13, 13), (1, 2, 30, 10, 10),
+                                       (3, 3, 256, 52, 52)])
+def test_pack_layout_and_zero_border(vy, B, K, C, H, W):
+    """The P layout bit for bit -- [T][B][H+2][W+2][C] bf16 with a ZERO one-pixel border -- written into a buffer that
+    held garbage: even grids take the 16-byte load path, channel counts that are multiples of 8 write the border from
+    the pack kernel itself, the others through the border kernel (yolo3.py:256-262 swapaxes view, layers.py:76 padding)."""
+    ops = vy.ops
+    rng = np.random.RandomState(B * 1000 + C)
+    x = bf16_round(rng.normal(size=(B, K, C, H, W)).astype(np.float32))
+    junk = [torch.full((K * B * (H + 2) * (W + 2) * C,), float("nan"), dtype=torch.bfloat16, device="cuda") for _ in range(4)]
+    del junk                                                    # the allocator hands the same memory back to pack_p
+    xt = torch.from_numpy(x).cuda()
+    for view, layout in ((xt, "NTCHW"), (xt.transpose(1, 2), "NCDHW-strided")):
+        if layout == "NTCHW":
+            xp = ops.pack_p(view, "NTCHW")
+        else:
+            xp = ops.pack_p(view.contiguous(), "NCDHW")
+        d = xp.data.float().cpu().numpy()                       # (T, B, H+2, W+2, C)
+        assert d.shape == (K, B, H + 2, W + 2, C)
+        np.testing.assert_array_equal(d[:, :, 1:-1, 1:-1], x.transpose(1, 0, 3, 4, 2))
+        for edge in (d[:, :, 0], d[:, :, -1], d[:, :, :, 0], d[:, :, :, -1]):
+            assert np.all(edge == 0.0)
+
+
 def test_temporal_dwconv_matches_oracle(vy):
     """_conv1d temporal merge (layers.py:50-60, h_darknet.py:97-119): window of 3 frames, C=32."""
     rng = np.random.RandomState(21)

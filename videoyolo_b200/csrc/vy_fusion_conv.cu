@@ -203,6 +203,10 @@ vy_fusion_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     __syncthreads();
     tc_fence_after();
     const u32 tmem_base = tmem_base_sh;
+    // programmatic dependent launch: everything above ran beside the tail of the kernel before this one in the stream;
+    // nothing below touches global memory before that kernel has completed, and the next conv of the chain may set up now
+    vy_grid_dep_wait();
+    vy_grid_dep_trigger();
 
     const int khw = cp.kh * cp.kw;
     if (warp == 0) {
@@ -367,6 +371,8 @@ vy_fusion_conv2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     cluster_sync_all();       // barriers of the peer initialised, TMEM of both CTAs allocated
     tc_fence_after();
     const u32 tmem_base = tmem_base_sh;
+    vy_grid_dep_wait();       // (programmatic dependent launch, as in the one-CTA kernel)
+    vy_grid_dep_trigger();
 
     const int khw = cp.kh * cp.kw;
     if (warp == 0) {
@@ -459,7 +465,7 @@ constexpr int LY_C = 64, LY_P = 128, LY_NT = 256;
 
 __global__ void __launch_bounds__(LY_NT)
 vy_pack_kernel(const float *__restrict__ x, long long sb, long long sc, long long st, int B, int C,
-               int T, int H, int W, __nv_bfloat16 *__restrict__ y, int Ctot, int split) {
+               int T, int H, int W, __nv_bfloat16 *__restrict__ y, int Ctot, int split, int vec, int border) {
     // split > 0 (vy_pack_f32_split_to_p_bf16): every value v goes out as hi = bf16(v) at channel c and split + c and as
     // lo = bf16(v - hi) at 2*split + c of a pixel of Ctot = 3*split channels
     __shared__ float tile[LY_C][LY_P + 1];
@@ -467,6 +473,25 @@ vy_pack_kernel(const float *__restrict__ x, long long sb, long long sc, long lon
     const int p0 = blockIdx.x * LY_P, c0 = blockIdx.y * LY_C;
     const int b = blockIdx.z % B, t = blockIdx.z / B;
     const float *src = x + (size_t)b * sb + (size_t)t * st;
+    if (vec) {
+        // even grids (H*W, the strides and the base are multiples of 4 floats): the whole tile in one round of eight
+        // 16-byte loads per thread.  A warp takes 4 channels x 32 positions at a time: four full 128-byte runs on the
+        // global side, and on the shared side (row stride 129 words) lane l writes bank (c + 4 (l % 8) + u + l / 8) % 32
+        // -- no conflicts.
+        const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        float4 v[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int task = it * 8 + wq, c = 4 * (task >> 2) + (lane >> 3), p = 32 * (task & 3) + 4 * (lane & 7);
+            v[it] = (c0 + c < C && p0 + p < HW) ? __ldg((const float4 *)(src + (size_t)(c0 + c) * sc + p0 + p))
+                                                 : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int task = it * 8 + wq, c = 4 * (task >> 2) + (lane >> 3), p = 32 * (task & 3) + 4 * (lane & 7);
+            tile[c][p] = v[it].x; tile[c][p + 1] = v[it].y; tile[c][p + 2] = v[it].z; tile[c][p + 3] = v[it].w;
+        }
+    } else
     // 8 independent 4-byte loads per thread and round: the fp32 side has no alignment to vectorise on
     // (H*W is odd at 13x13), so memory-level parallelism comes from unrolling
     for (int i0 = threadIdx.x; i0 < LY_C * LY_P; i0 += 8 * LY_NT) {
@@ -509,6 +534,19 @@ vy_pack_kernel(const float *__restrict__ x, long long sb, long long sc, long lon
 #pragma unroll
             for (int k = 0; k < 4; ++k) oh[k] = __floats2bfloat162_rn(tile[c + 2 * k][p], tile[c + 2 * k + 1][p]);
             *(uint4 *)(dst + ((size_t)(h + 1) * Wp + (w + 1)) * C + c0 + c) = o;
+        }
+        if (border && blockIdx.x == 0) {
+            // the frame's one-pixel zero border, this CTA's channel block of it (no separate launch)
+            const int Hp = H + 2, nb = 2 * Wp + 2 * H;
+            for (int i = threadIdx.x; i < nb * (LY_C / 8); i += LY_NT) {
+                const int q = i / (LY_C / 8), c = (i % (LY_C / 8)) * 8;
+                if (c0 + c >= C) continue;
+                int hp, wp;
+                if (q < Wp) { hp = 0; wp = q; }
+                else if (q < 2 * Wp) { hp = Hp - 1; wp = q - Wp; }
+                else { const int r = q - 2 * Wp; hp = 1 + (r >> 1); wp = (r & 1) ? Wp - 1 : 0; }
+                *(uint4 *)(dst + ((size_t)hp * Wp + wp) * C + c0 + c) = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
         return;
     }
@@ -688,8 +726,9 @@ int launch_conv(const CUtensorMap &mx, const CUtensorMap &mw, const ConvParams &
     const size_t smem = (size_t)CV_STAGES * (CV_BM * CV_BK * 2 + BN * CV_BK * 2) + 1024;
     VY_CUDA_CHECK(cudaFuncSetAttribute(vy_fusion_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = cp.n_tiles_total < vy_sm_count() ? cp.n_tiles_total : vy_sm_count();
-    VY_KERNEL(VY_K_FUSION_CONV, st, (vy_fusion_conv_kernel<BN><<<(unsigned)grid, CV_NT, smem, st>>>(mx, mw, cp)));
-    VY_LAUNCH_CHECK("vy_fusion_conv_kernel");
+    cudaError_t le = cudaSuccess;
+    VY_KERNEL(VY_K_FUSION_CONV, st, (le = vy_launch(vy_fusion_conv_kernel<BN>, dim3((unsigned)grid), dim3(CV_NT), smem, st, true, mx, mw, cp)));
+    if (le != cudaSuccess) VY_FAIL(VY_ECUDA, "launch of vy_fusion_conv_kernel failed: %s", cudaGetErrorString(le));
     return VY_OK;
 }
 
@@ -698,8 +737,10 @@ int launch_conv2(const CUtensorMap &mx, const CUtensorMap &mw, const ConvParams 
     VY_CUDA_CHECK(cudaFuncSetAttribute(vy_fusion_conv2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Conv2Cfg<BN>::SMEM));
     const long long pairs_max = vy_sm_count() / 2;
     const long long pairs = cp.n_tiles_total < pairs_max ? cp.n_tiles_total : pairs_max;
-    VY_KERNEL(VY_K_FUSION_CONV, st, (vy_fusion_conv2_kernel<BN><<<(unsigned)(2 * pairs), CV_NT, Conv2Cfg<BN>::SMEM, st>>>(mx, mw, cp)));
-    VY_LAUNCH_CHECK("vy_fusion_conv2_kernel");
+    cudaError_t le = cudaSuccess;
+    VY_KERNEL(VY_K_FUSION_CONV, st, (le = vy_launch(vy_fusion_conv2_kernel<BN>, dim3((unsigned)(2 * pairs)), dim3(CV_NT),
+                                                    Conv2Cfg<BN>::SMEM, st, true, mx, mw, cp)));
+    if (le != cudaSuccess) VY_FAIL(VY_ECUDA, "launch of vy_fusion_conv2_kernel failed: %s", cudaGetErrorString(le));
     return VY_OK;
 }
 
@@ -714,11 +755,16 @@ extern "C" int vy_pack_f32_to_p_bf16(const float *x, long long stride_b, long lo
     cudaStream_t st = (cudaStream_t)stream;
     if (!x || !y_p || B < 1 || C < 1 || T < 1 || H < 1 || W < 1) VY_FAIL(VY_EINVAL, "vy_pack_f32_to_p_bf16: bad arguments");
     if ((long long)T * B > 65535) VY_FAIL(VY_EUNSUPPORTED, "vy_pack_f32_to_p_bf16: T*B must be <= 65535");
-    VY_KERNEL(VY_K_LAYOUT, st, (vy_zero_border_kernel<<<dim3(64, T * B), 128, 0, st>>>((__nv_bfloat16 *)y_p, H, W, C)));
-    VY_LAUNCH_CHECK("vy_zero_border_kernel");
+    if (((uintptr_t)y_p & 15) != 0) VY_FAIL(VY_EALIGN, "vy_pack_f32_to_p_bf16: y_p must be 16-byte aligned");
+    const int fused_border = (C & 7) == 0;          // the pack kernel's 16-byte path also writes the zero border
+    if (!fused_border) {
+        VY_KERNEL(VY_K_LAYOUT, st, (vy_zero_border_kernel<<<dim3(64, T * B), 128, 0, st>>>((__nv_bfloat16 *)y_p, H, W, C)));
+        VY_LAUNCH_CHECK("vy_zero_border_kernel");
+    }
+    const int vec = ((H * W) % 4 == 0) && (stride_b % 4 == 0) && (stride_c % 4 == 0) && (stride_t % 4 == 0) && (((uintptr_t)x & 15) == 0);
     const dim3 grid((H * W + LY_P - 1) / LY_P, (C + LY_C - 1) / LY_C, T * B);
     VY_KERNEL(VY_K_LAYOUT, st, (vy_pack_kernel<<<grid, LY_NT, 0, st>>>(x, stride_b, stride_c, stride_t, B, C, T, H, W,
-                                                                     (__nv_bfloat16 *)y_p, C, 0)));
+                                                                     (__nv_bfloat16 *)y_p, C, 0, vec, fused_border)));
     VY_LAUNCH_CHECK("vy_pack_kernel");
     return VY_OK;
 }
@@ -732,7 +778,7 @@ extern "C" int vy_pack_f32_split_to_p_bf16(const float *x, long long stride_b, l
     VY_CUDA_CHECK(cudaMemsetAsync(y_p, 0, (size_t)T * B * (H + 2) * (W + 2) * 3 * Cpad * sizeof(__nv_bfloat16), st));
     const dim3 grid((H * W + LY_P - 1) / LY_P, (C + LY_C - 1) / LY_C, T * B);
     VY_KERNEL(VY_K_LAYOUT, st, (vy_pack_kernel<<<grid, LY_NT, 0, st>>>(x, stride_b, stride_c, stride_t, B, C, T, H, W,
-                                                                     (__nv_bfloat16 *)y_p, 3 * Cpad, Cpad)));
+                                                                     (__nv_bfloat16 *)y_p, 3 * Cpad, Cpad, 0, 0)));
     VY_LAUNCH_CHECK("vy_pack_kernel");
     return VY_OK;
 }
