@@ -1,6 +1,6 @@
 """Scratch timing of the temporal fusion conv (tcgen05 implicit GEMM) at the canonical K=3 tip-conv
 shapes of BASELINE configs[2].  CUDA events, L2 flushed.  Not the bench contract.
-usage: conv_bench.py [B] [one]      (one: a single launch of the 52x52 shape, for ncu)"""
+usage: conv_bench.py [B] [one]      (one: a single launch of each of the three tip shapes, for ncu)"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -19,7 +19,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 shapes = [(13, 512, 1024, (3, 3, 3)), (26, 256, 512, (3, 3, 3)), (52, 128, 256, (3, 3, 3)),
           (26, 256, 512, (1, 3, 3)), (26, 512, 512, (3, 1, 1)), (26, 768, 256, (1, 1, 1))]
 if one:
-    shapes = [shapes[2]]
+    shapes = shapes[:3]
 T = 3
 for g, Cin, Cout, k3 in shapes:
     x = ops.PTensor(torch.zeros((T, B, g + 2, g + 2, Cin), dtype=torch.bfloat16, device=dev), B, T, g, g, Cin)
