@@ -12,3 +12,4 @@ for B in (8, 32):
     print("tips B=%d" % B, json.dumps(leg), flush=True)
 print("tail", json.dumps(bench.temporal_tail_leg(dev)), flush=True)
 print("neck", json.dumps(bench.temporal_neck_leg(dev)), flush=True)
+print("neck, constructor BN", json.dumps(bench.temporal_neck_leg(dev, calibrated_bn=False)), flush=True)

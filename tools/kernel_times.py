@@ -9,7 +9,7 @@ from videoyolo_b200.synth import random_heads_cuda
 AN, ST = vy.ANCHORS[::-1], vy.STRIDES[::-1]
 dev = torch.device("cuda:0")
 cfgs = [("coco608_b64", 64, 80, 608), ("stress416_b128", 128, 80, 416), ("vid320_b256", 256, 30, 320), ("vid416_b32", 32, 30, 416),
-        ("voc416_b1", 1, 20, 416)]
+        ("vid416_b8", 8, 30, 416), ("voc416_b1", 1, 20, 416)]
 only = sys.argv[1:] or None
 for name, B, C, size in cfgs:
     if only and name not in only: continue

@@ -2101,6 +2101,18 @@ static void plan_stream(const VyHeads &hd, SelPlan *pl) {
             if (score > best) { best = score; best_g = ng; }
         }
         pl->n_groups = best_g;
+        // Small batches leave most warp slots empty (VID 416^2 x 8 windows: 720 units for 4736 slots) and the pass is as
+        // long as its busiest unit -- all hits of an (anchor, class) plane whose logits sit above the others, a
+        // confident region -- so the planes are cut further, down to groups of 4 (one round of the ring), as long as
+        // every unit still gets a warp of its own: the prologue (objectness + bounds) is repeated per group, in parallel.
+        static const int min_pu = getenv("VY_STR_MIN_PU") ? atoi(getenv("VY_STR_MIN_PU")) : 4;     // 0: off (A/B)
+        if (min_pu > 0 && (double)chunks_total * hd.A * g_min * hd.B < warps) {
+            for (int pu = min_pu; pu < hd.C; pu += 4) {
+                const int ng = (hd.C + pu - 1) / pu;
+                if (ng <= g_min) break;
+                if ((double)chunks_total * hd.A * ng * hd.B <= warps) { pl->n_groups = ng; break; }
+            }
+        }
     }
     pl->PU = (hd.C + pl->n_groups - 1) / pl->n_groups;
     int units = 0;
