@@ -2104,13 +2104,16 @@ static void plan_stream(const VyHeads &hd, SelPlan *pl) {
         // Small batches leave most warp slots empty (VID 416^2 x 8 windows: 720 units for 4736 slots) and the pass is as
         // long as its busiest unit -- all hits of an (anchor, class) plane whose logits sit above the others, a
         // confident region -- so the planes are cut further, down to groups of 4 (one round of the ring), as long as
-        // every unit still gets a warp of its own: the prologue (objectness + bounds) is repeated per group, in parallel.
+        // (nearly) every unit still gets a warp of its own: the prologue (objectness + bounds) is repeated per group, in
+        // parallel.  Up to 1.3 units per warp slot: VID 416^2 x 32 with two groups (1.22) 29.3 -> 22.2 us trained-like,
+        // 19.0 -> 18.9 us random-init; 2.0 units per slot: 23.0 / 21.1 us.
         static const int min_pu = getenv("VY_STR_MIN_PU") ? atoi(getenv("VY_STR_MIN_PU")) : 4;     // 0: off (A/B)
+        static const double split_waves = getenv("VY_STR_SPLIT_WAVES") ? atof(getenv("VY_STR_SPLIT_WAVES")) : 1.3;
         if (min_pu > 0 && (double)chunks_total * hd.A * g_min * hd.B < warps) {
             for (int pu = min_pu; pu < hd.C; pu += 4) {
                 const int ng = (hd.C + pu - 1) / pu;
                 if (ng <= g_min) break;
-                if ((double)chunks_total * hd.A * ng * hd.B <= warps) { pl->n_groups = ng; break; }
+                if ((double)chunks_total * hd.A * ng * hd.B <= warps * split_waves) { pl->n_groups = ng; break; }
             }
         }
     }
