@@ -11,9 +11,10 @@ dev = torch.device("cuda:0")
 os.environ["VY_DEBUG_LISTS"] = "1"
 n_seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 only = sys.argv[2:]
-for name, B, C, size in (("vid320_b256", 256, 30, 320), ("coco608_b64", 64, 80, 608), ("stress416_b128", 128, 80, 416)):
+for name, B, C, size in (("vid320_b256", 256, 30, 320), ("coco608_b64", 64, 80, 608), ("stress416_b128", 128, 80, 416),
+                          ("coco416_b320", 320, 80, 416)):          # (one sample job per image)
     if only and name not in only: continue
-    for kind in ("R", "T"):
+    for kind in (os.environ.get("AIM_REGIMES", "R,T").split(",")):
         for seed in range(1, n_seeds + 1):
             heads = random_heads_cuda(B, C, size, seed, dev, regime=kind)
             print(name, kind, seed, end=" ", flush=True)

@@ -55,5 +55,14 @@ def random_heads_cuda(B, C, size, seed, device, A=3, regime="R"):
             boost = torch.rand((B, 1, 1, s, s), generator=g, device=device) < 0.004
             h[:, :, 4:5] += boost * 12.0
             h[:, :, 5:6] += boost * 6.0
+        elif regime == "S":
+            # sparse: what a trained detector gives on a frame with one or two objects -- objectness ~ 1e-4 everywhere but
+            # in a few cells (all anchors of the cell confident), so tens to a few hundred scores pass valid_thresh
+            h[:, :, 2:4] *= 0.5
+            h[:, :, 4] = h[:, :, 4] - 9
+            h[:, :, 5:] = h[:, :, 5:] * 1.5 - 3
+            boost = torch.rand((B, 1, 1, s, s), generator=g, device=device) < 0.0005
+            h[:, :, 4:5] += boost * 15.0
+            h[:, :, 5:6] += boost * 6.0
         heads.append(h.reshape(B, A * (5 + C), s, s).contiguous())
     return heads
