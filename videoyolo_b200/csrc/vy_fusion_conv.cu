@@ -629,21 +629,31 @@ vy_unpack_kernel(const TIn *__restrict__ y, int B, int Cp, int C, int T, int H, 
 }
 
 // TemporalPooling 'direct' (layers.py:201-205) on P layout: y[i] = max / mean over t of x[t][i]
+__device__ __forceinline__ void pool_accumulate(const uint4 &q, bool first, int mode, float (&acc)[8]) {
+    const __nv_bfloat162 *h = (const __nv_bfloat162 *)&q;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        if (first) { acc[2 * k] = f.x; acc[2 * k + 1] = f.y; }
+        else if (mode == 0) { acc[2 * k] = fmaxf(acc[2 * k], f.x); acc[2 * k + 1] = fmaxf(acc[2 * k + 1], f.y); }
+        else { acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+    }
+}
 __global__ void vy_temporal_pool_kernel(const uint4 *__restrict__ x, int T, long long inner8, int mode, uint4 *__restrict__ y) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < inner8; i += stride) {
         float acc[8];
-        for (int t = 0; t < T; ++t) {
-            const uint4 q = x[(size_t)t * inner8 + i];
-            const __nv_bfloat162 *h = (const __nv_bfloat162 *)&q;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 f = __bfloat1622float2(h[k]);
-                if (t == 0) { acc[2 * k] = f.x; acc[2 * k + 1] = f.y; }
-                else if (mode == 0) { acc[2 * k] = fmaxf(acc[2 * k], f.x); acc[2 * k + 1] = fmaxf(acc[2 * k + 1], f.y); }
-                else { acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
-            }
-        }
+        // the first four frames are fetched together (one 16-byte load in flight per thread reaches 2/3 of the HBM rate)
+        uint4 q0, q1, q2, q3;
+        q0 = __ldg(x + i);
+        if (T > 1) q1 = __ldg(x + (size_t)inner8 + i);
+        if (T > 2) q2 = __ldg(x + (size_t)2 * inner8 + i);
+        if (T > 3) q3 = __ldg(x + (size_t)3 * inner8 + i);
+        pool_accumulate(q0, true, mode, acc);
+        if (T > 1) pool_accumulate(q1, false, mode, acc);
+        if (T > 2) pool_accumulate(q2, false, mode, acc);
+        if (T > 3) pool_accumulate(q3, false, mode, acc);
+        for (int t = 4; t < T; ++t) pool_accumulate(__ldg(x + (size_t)t * inner8 + i), false, mode, acc);
         uint4 o;
         __nv_bfloat162 *oh = (__nv_bfloat162 *)&o;
 #pragma unroll
