@@ -228,6 +228,8 @@ int vy_voc_match_f32(const float *dets, const float *gt_boxes, const float *gt_l
  *                 (scale = gamma/sqrt(var+eps), shift = beta - mean*scale; layers.py:68,77)
  *   y        P layout, Cout channels, bf16 (y_is_f32 = 0) or fp32 (1); 'same' padding p = k/2
  *   requires Cin % 64 == 0, Cout % 64 == 0, kt,kh,kw in {1,3}; needs no workspace.
+ * The tile shape is chosen per call: 128 x {64,128,256} tiles on one CTA, or 256 x {128,256} tiles on a CTA pair
+ * (tcgen05 cta_group::2, cluster of 2) where that does not cost whole extra rounds of tiles.
  */
 size_t vy_p_layout_elems(int B, int T, int H, int W, int C);
 size_t vy_fusion_conv_workspace_bytes(int B, int T, int H, int W, int Cin, int Cout,

@@ -331,10 +331,12 @@ __global__ void __launch_bounds__(LG_NT, 1) lg_nms_kernel(const __grid_constant_
                 __syncthreads();
                 for (;;) {
                     int c = 0;
-                    if (lane == 0) c = atomicAdd(&sh_next, 1);
+                    u32 alive_c = 0u;
+                    if (lane == 0) { c = atomicAdd(&sh_next, 1); alive_c = c < LG_TILE ? trank[c] : 0u; }   // only lane 0 touches trank[c] in this loop
                     c = __shfl_sync(0xffffffffu, c, 0);
+                    alive_c = __shfl_sync(0xffffffffu, alive_c, 0);
                     if (c >= LG_TILE) break;
-                    if (!trank[c]) continue;                                           // (warp-uniform)
+                    if (!alive_c) continue;                                            // (warp-uniform)
                     const float4 cb = sb[c];
                     const float ca = sa[c];
                     const LgGeom gc = lg_geom<FMT>(cb);
