@@ -80,6 +80,44 @@ def test_fusion_conv_matches_oracle(vy, B, T, H, W, Cin, Cout, k3):
     check(got, ref, str((B, T, H, W, Cin, Cout, k3)))
 
 
+_HASH_SCRIPT = r"""
+import hashlib, json, sys, torch
+import videoyolo_b200 as vy
+ops = vy.ops
+out = {}
+for B, g, Cin, Cout, k3 in [(8, 13, 512, 1024, (3, 3, 3)), (8, 26, 256, 512, (3, 3, 3)), (8, 52, 128, 256, (3, 3, 3)),
+                             (32, 13, 512, 1024, (3, 3, 3)), (8, 26, 768, 256, (1, 1, 1)), (5, 13, 64, 128, (3, 3, 3))]:
+    gen = torch.Generator(device="cuda").manual_seed(B * 1000 + g + Cout)
+    x = torch.randn((B, 3, Cin, g, g), generator=gen, device="cuda")
+    w = (torch.rand((Cout, Cin) + k3, generator=gen, device="cuda") * 0.14 - 0.07)
+    scale = torch.rand(Cout, generator=gen, device="cuda") + 0.5
+    shift = torch.randn(Cout, generator=gen, device="cuda") * 0.2
+    y = ops.fusion_conv(ops.pack_p(x, "NTCHW"), ops.conv_weight(w), scale, shift, 0.1)
+    torch.cuda.synchronize()
+    out["%d_%d_%d_%d_%s" % (B, g, Cin, Cout, k3)] = hashlib.sha256(y.data.view(torch.int16).cpu().numpy().tobytes()).hexdigest()
+print(json.dumps(out))
+"""
+
+
+def test_fusion_conv_pair_kernel_is_bit_identical_to_one_cta_kernel(vy):
+    """The CTA-pair kernel (tcgen05 cta_group::2, 256-row tiles) and the one-CTA kernel accumulate every output in the
+    same k order in fp32 TMEM, so at the benchmarked shapes (batch 8 and 32 windows: the plan picks pairs at 13 x 13 and
+    52 x 52) the whole P-layout output must be bit-identical with pairs switched off (VY_CONV_CTA2=0; the library reads
+    the switch once, hence two processes)."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = []
+    for env_extra in ({"VY_CONV_CTA2": "0"}, {}):
+        env = dict(os.environ, PYTHONPATH=root, **env_extra)
+        env.pop("VY_CONV_BN", None)
+        if not env_extra:
+            env.pop("VY_CONV_CTA2", None)
+        p = subprocess.run([sys.executable, "-c", _HASH_SCRIPT], env=env, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        res.append(json.loads(p.stdout.strip().splitlines()[-1]))
+    assert res[0] == res[1]
+
+
 def test_fusion_conv_fp32_output_and_chain(vy):
     """conv21d = two chained cells without repacking (layers.py:82-89); last output in fp32."""
     rng = np.random.RandomState(5)
