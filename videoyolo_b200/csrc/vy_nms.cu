@@ -2065,15 +2065,17 @@ static void plan_stream(const VyHeads &hd, SelPlan *pl) {
     // by the rescue pass (stream_list_ok).
     // How far above K?  The estimate's rank has a relative spread ~ 1/sqrt(j) (j sampled scores above the bound, times a
     // burstiness factor for clustered logits), so the margin in standard deviations is (1 - 1/aim) * sqrt(aim * K / S):
-    // 5.3 at 4K, S = 32, K = 400 -- where trained-like (clustered) logits at 416^2 x 80 classes still sent 4 of 3 072
-    // images to the rescue (0.4 ms each); at 5.8 = aim 4.5K there: 0 of 3 072 (shortest list 427), the call 0.5 % longer
-    // with random-init logits, 1.2 % with trained-like ones.  Where the sampling rate is higher the same margin needs a
-    // lower aim -- 2.6K at VID 320^2 (S = 11): 40 % shorter lists than at 4K, the call 5 % faster (tools/aim_test.py).
-    // VY_SAMP_AIM overrides (A/B).
+    // 5.3 at the aim this path was tuned with (4K at S = 32, K = 400).  Where the sampling rate is higher the same margin
+    // needs a lower aim -- 2.4K at VID 320^2 (S = 11): 43 % shorter lists, the call 6 % faster (tools/aim_test.py).
+    // The margin is a trade: at 5.3 trained-like (clustered) logits at 416^2 x 80 classes x 128 send 4 of 3 072 images to
+    // the rescue (0.4 ms each; no other measured configuration rescues any); at 5.8 (aim 4.5K / 2.6K) none of 9 216 images
+    // per regime, for 1.5-2.7 % of the 4-stream throughput at every configuration.  VY_SAMP_SIGMA sets the margin,
+    // VY_SAMP_AIM the aim itself (A/B).
     static const double aim_env = getenv("VY_SAMP_AIM") ? atof(getenv("VY_SAMP_AIM")) : 0.0;
-    double aim = 4.5;
-    for (double a = 1.5; a < 4.5; a += 0.1)
-        if ((1.0 - 1.0 / a) * sqrt(a * pl->K / (double)pl->samp_stride) >= 5.8) { aim = a; break; }
+    static const double sigma = getenv("VY_SAMP_SIGMA") ? atof(getenv("VY_SAMP_SIGMA")) : 5.3;
+    double aim = 6.0;
+    for (double a = 1.5; a < 6.0; a += 0.1)
+        if ((1.0 - 1.0 / a) * sqrt(a * pl->K / (double)pl->samp_stride) >= sigma) { aim = a; break; }
     if (aim_env > 0.0) aim = aim_env;
     long long j = (long long)((aim * pl->K + pl->samp_stride - 1) / pl->samp_stride);
     if (j > pl->K) j = pl->K;
