@@ -2065,14 +2065,16 @@ static void plan_stream(const VyHeads &hd, SelPlan *pl) {
     // by the rescue pass (stream_list_ok).
     // How far above K?  The estimate's rank has a relative spread ~ 1/sqrt(j) (j sampled scores above the bound, times a
     // burstiness factor for clustered logits), so the margin in standard deviations is (1 - 1/aim) * sqrt(aim * K / S):
-    // 5.8 = aim 4.5K at S = 32, K = 400.  Where the sampling rate is higher the same margin needs a lower aim -- 2.6K at
-    // VID 320^2 (S = 11): 40 % shorter lists than at 4K, the call 5 % faster (tools/aim_test.py).
-    // The margin is a trade: at 5.3 (aim 4K / 2.4K) trained-like (clustered) logits at 416^2 x 80 classes x 128 send 4 of
-    // 3 072 images to the rescue (0.4 ms each; no other measured configuration rescues any); at 5.8 none of 9 216 images
-    // per regime, for 0.1-0.9 % of the throughput (two full bench runs on the same pool).  VY_SAMP_SIGMA sets the
-    // margin, VY_SAMP_AIM the aim itself (A/B).
+    // 5.3 = aim 4K at S = 32, K = 400.  Where the sampling rate is higher the same margin needs a lower aim -- 2.4K at VID
+    // 320^2 (S = 11): 43 % shorter lists, the call 6 % faster (tools/aim_test.py).
+    // Clustered (trained-like) logits make the sample burstier than Poisson, the more so the fewer 128-byte runs of a
+    // plane it holds: 416^2 images (11 sampled runs; 608^2: 23, VID 320^2: 18) x 80 classes x 128 sent 4 of 3 072 images
+    // to the rescue at 5.3 (0.4 ms each; no other measured configuration rescued any) and none at 5.8 (aim 4.5K) -- which
+    // costs every configuration 1-2 % (longer lists, more hits), so only images with fewer than 16 sampled runs pay it.
+    // VY_SAMP_SIGMA sets the margin for all, VY_SAMP_AIM the aim itself (A/B).
     static const double aim_env = getenv("VY_SAMP_AIM") ? atof(getenv("VY_SAMP_AIM")) : 0.0;
-    static const double sigma = getenv("VY_SAMP_SIGMA") ? atof(getenv("VY_SAMP_SIGMA")) : 5.8;
+    static const double sigma_env = getenv("VY_SAMP_SIGMA") ? atof(getenv("VY_SAMP_SIGMA")) : 0.0;
+    const double sigma = sigma_env > 0.0 ? sigma_env : (pl->samp_items / SAMP_RUN < 16 ? 5.8 : 5.3);
     double aim = 6.0;
     for (double a = 1.5; a < 6.0; a += 0.1)
         if ((1.0 - 1.0 / a) * sqrt(a * pl->K / (double)pl->samp_stride) >= sigma) { aim = a; break; }
