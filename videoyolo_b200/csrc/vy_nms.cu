@@ -1181,7 +1181,8 @@ extern "C" int vy_debug_fin_front_clocks(long long *out) {
 #define FIN_TB(k) do { } while (0)
 #endif
 constexpr int FIN_BK_BINS = 2048;
-constexpr int FIN_BK_KPT = 8;         // keys per thread
+constexpr int FIN_BK_KPT_MAX = 16;    // keys per thread: 8 (lists <= 4096 at 512 threads) or 16
+template <int FIN_BK_KPT>
 static __device__ __noinline__ int fin_front_buckets(FinBuf &S, const u64 *list, int n, int K,
                                                      u32 *hist, u32 *excl, u64 *out, u64 *keyr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = (int)blockDim.x;   // nt = 512 or 1024
@@ -1639,8 +1640,11 @@ vy_nms_finalize_kernel(const __grid_constant__ VyHeads hd, const __grid_constant
     if (tid < 32) keeps[tid] = 0u;
     u64 *keyr = S.keys;                                 // the K best by rank (K <= FIN_NT_MAX)
     int m1 = -1;
-    if (n_list <= FIN_BK_KPT * FIN_NT && fp.lcap >= FIN_BK_BINS)
-        m1 = fin_front_buckets(S, list, n_list, K, (u32 *)cand, (u32 *)lbuf, lbuf + FIN_BK_BINS / 2, keyr);
+    if (fp.lcap >= FIN_BK_BINS) {
+        if (n_list <= 8 * FIN_NT) m1 = fin_front_buckets<8>(S, list, n_list, K, (u32 *)cand, (u32 *)lbuf, lbuf + FIN_BK_BINS / 2, keyr);
+        else if (n_list <= FIN_BK_KPT_MAX * FIN_NT)      // trained-like logits: lists of 4-8 K keys are common
+            m1 = fin_front_buckets<16>(S, list, n_list, K, (u32 *)cand, (u32 *)lbuf, lbuf + FIN_BK_BINS / 2, keyr);
+    }
     FIN_T(1);
     u64 mykey = 0ull;
     if (m1 < 0) {
