@@ -734,7 +734,7 @@ EncodeTiledFn encode_fn() {
 template <int BN>
 int launch_conv(const CUtensorMap &mx, const CUtensorMap &mw, const ConvParams &cp, cudaStream_t st) {
     const size_t smem = (size_t)CV_STAGES * (CV_BM * CV_BK * 2 + BN * CV_BK * 2) + 1024;
-    VY_CUDA_CHECK(cudaFuncSetAttribute(vy_fusion_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VY_CUDA_CHECK(vy_ensure_dyn_smem((const void *)vy_fusion_conv_kernel<BN>, smem));
     long long grid = cp.n_tiles_total < vy_sm_count() ? cp.n_tiles_total : vy_sm_count();
     cudaError_t le = cudaSuccess;
     VY_KERNEL(VY_K_FUSION_CONV, st, (le = vy_launch(vy_fusion_conv_kernel<BN>, dim3((unsigned)grid), dim3(CV_NT), smem, st, true, mx, mw, cp)));
@@ -744,7 +744,7 @@ int launch_conv(const CUtensorMap &mx, const CUtensorMap &mw, const ConvParams &
 
 template <int BN>
 int launch_conv2(const CUtensorMap &mx, const CUtensorMap &mw, const ConvParams &cp, cudaStream_t st) {
-    VY_CUDA_CHECK(cudaFuncSetAttribute(vy_fusion_conv2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Conv2Cfg<BN>::SMEM));
+    VY_CUDA_CHECK(vy_ensure_dyn_smem((const void *)vy_fusion_conv2_kernel<BN>, Conv2Cfg<BN>::SMEM));
     const long long pairs_max = vy_sm_count() / 2;
     const long long pairs = cp.n_tiles_total < pairs_max ? cp.n_tiles_total : pairs_max;
     cudaError_t le = cudaSuccess;
