@@ -13,8 +13,8 @@ cfgs = [("coco608_b64", 64, 80, 608), ("stress416_b128", 128, 80, 416), ("vid320
 only = sys.argv[1:] or None
 for name, B, C, size in cfgs:
     if only and name not in only: continue
-    for kind in ("R", "T", "nohits"):
-        heads = random_heads_cuda(B, C, size, 1234, dev, regime="T" if kind == "T" else "R")
+    for kind in ("R", "T", "S", "nohits"):
+        heads = random_heads_cuda(B, C, size, 1234, dev, regime=kind if kind in ("T", "S") else "R")
         if kind == "nohits":
             for h in heads: h.fill_(-30.0)
         for _ in range(5): vy.yolo3_decode_nms(heads, C, AN, ST)
