@@ -239,6 +239,13 @@ int vy_fusion_conv_bf16(const void *x, const void *w, const float *scale, const 
                         int kt, int kh, int kw, void *y, int y_is_f32,
                         void *workspace, size_t workspace_bytes, vy_stream_t stream);
 
+/* The same cell with the late 'max' join over the window (TemporalPooling(k, 'max'), layers.py:201-205, as used at
+ * yolo3.py:1134-1138) done in its epilogue: y is ONE P-layout frame (T = 1, Cout channels, bf16) = max over the T
+ * output frames; the un-pooled tip is never written.  Bit-identical to vy_fusion_conv_bf16 + vy_temporal_pool_bf16. */
+int vy_fusion_conv_bf16_maxpool(const void *x, const void *w, const float *scale, const float *shift,
+                                float leaky_slope, int B, int T, int H, int W, int Cin, int Cout,
+                                int kt, int kh, int kw, void *y, vy_stream_t stream);
+
 /* The same cell for T = 1 with the result written in the reference's own layout: y is the fp32 (B, out_channels, H, W)
  * tensor (NCHW), the first out_channels <= Cout channels, interior pixels only -- the 1x1 `prediction` conv of
  * YOLOOutputV3 (yolo3.py:62,157; Cout = all_pred padded to a multiple of 64, leaky_slope = 1, bias as shift) hands its

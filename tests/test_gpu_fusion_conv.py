@@ -215,6 +215,29 @@ def test_pack_layout_and_zero_border(vy, B, K, C, H, W):
             assert np.all(edge == 0.0)
 
 
+@pytest.mark.parametrize("B,T,H,W,Cin,Cout,k3", [(2, 3, 13, 13, 64, 128, (3, 3, 3)), (8, 3, 13, 13, 128, 1024, (3, 3, 3)),
+                                                 (3, 3, 26, 26, 64, 256, (3, 1, 1)), (2, 5, 10, 10, 64, 64, (3, 3, 3)),
+                                                 (32, 3, 52, 52, 64, 256, (1, 1, 1))])
+def test_fusion_conv_max_join_in_the_epilogue(vy, B, T, H, W, Cin, Cout, k3):
+    """Conv + TemporalPooling(k, 'max') (layers.py:201-205; the late join of yolo3.py:1134-1138) in one call: the pooled
+    frame comes out of the conv's epilogue (bf16x2 max reductions into a frame that starts at -inf) and must be
+    bit-identical to the conv followed by the pool kernel -- border zero, every tile shape (one CTA and CTA pairs)."""
+    ops = vy.ops
+    gen = torch.Generator(device="cuda").manual_seed(B * 100 + H + Cout)
+    x = torch.randn((B, T, Cin, H, W), generator=gen, device="cuda")
+    w = ops.conv_weight(torch.rand((Cout, Cin) + k3, generator=gen, device="cuda") * 0.14 - 0.07)
+    scale = torch.rand(Cout, generator=gen, device="cuda") + 0.5
+    shift = torch.randn(Cout, generator=gen, device="cuda") * 0.2
+    xp = ops.pack_p(x, "NTCHW")
+    ref = ops.temporal_pool(ops.fusion_conv(xp, w, scale, shift, 0.1), "max")
+    for _ in range(2):                                            # (twice: the -inf fill is part of every call)
+        got = ops.fusion_conv(xp, w, scale, shift, 0.1, pool_max=True)
+        assert got.T == 1 and got.data.shape == ref.data.shape
+        assert torch.equal(got.data.view(torch.int16), ref.data.view(torch.int16))
+    d = got.data.float()
+    assert float(d[:, :, 0].abs().max()) == 0 and float(d[:, :, :, -1].abs().max()) == 0
+
+
 def test_temporal_dwconv_matches_oracle(vy):
     """_conv1d temporal merge (layers.py:50-60, h_darknet.py:97-119): window of 3 frames, C=32."""
     rng = np.random.RandomState(21)

@@ -290,3 +290,33 @@ def test_graphed_module_equals_eager(vy):
         torch.cuda.synchronize()
         for a, b in zip(out, ref):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("ctype", ["3", "21"])
+def test_fused_max_join_equals_conv_then_pool(vy, ctype):
+    """YOLOV3T / YOLOV3TNeck with the late 'max' join done in the tip conv's epilogue (the default) give exactly the
+    detections, head maps and tip features of the same network with TemporalPooling as its own kernel."""
+    torch.manual_seed(11)
+    for net, chans in ((vy.YOLOV3T(["c%d" % i for i in range(20)], k=3, k_join_type="max", block_conv_type=ctype,
+                                   channels=(128, 64, 64)).cuda().eval(), (128, 64, 64)),
+                       (vy.YOLOV3TNeck(["c%d" % i for i in range(20)], k=3, k_join_type="max", block_conv_type=ctype,
+                                       stage_channels=(128, 64, 64), channels=(64, 64, 64)).cuda().eval(), (128, 64, 64))):
+        xs = [torch.randn((3, 3, c, g, g), device="cuda") for c, g in zip(chans, oracle.grid_sizes(96))]
+        head = net.head if hasattr(net, "head") else net
+        assert head.fuse_max_join
+        with torch.no_grad():
+            fused = [t.clone() for t in net(*xs)]
+            head.fuse_max_join = False
+            plain = [t.clone() for t in net(*xs)]
+            head.fuse_max_join = True
+        for a, b in zip(fused, plain):
+            assert torch.equal(a, b)
+    # head maps and tip features of the tail itself
+    net = vy.YOLOV3T(["c%d" % i for i in range(20)], k=3, k_join_type="max", block_conv_type=ctype, channels=(128, 64, 64)).cuda().eval()
+    xs = [torch.randn((2, 3, c, g, g), device="cuda") for c, g in zip((128, 64, 64), oracle.grid_sizes(96))]
+    with torch.no_grad():
+        h1, f1 = net.head_maps(*xs), net.tip_features(*xs)
+        net.fuse_max_join = False
+        h0, f0 = net.head_maps(*xs), net.tip_features(*xs)
+    for a, b in zip(h1 + f1, h0 + f0):
+        assert torch.equal(a, b)

@@ -43,6 +43,7 @@ struct ConvParams {
     void *y;
     int y_is_f32;
     int nchw_C, nchw_H, nchw_W;  // nchw_C > 0: y is the reference's fp32 (B, nchw_C, H, W) tensor (T == 1): interior pixels, first nchw_C channels
+    int pool_max;                // y is ONE P-layout frame [rows][Cout] bf16 pre-filled with -inf: max over the T frames (TemporalPooling 'max')
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -131,7 +132,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams &cp, u32 tme
     const bool in_range = r < cp.rows;
     const int rr = r % plane, hp = rr / cp.Wp, wp = rr % cp.Wp;
     const bool interior = hp > 0 && hp < cp.Hp - 1 && wp > 0 && wp < cp.Wp - 1;
-    const size_t out_off = ((size_t)t * cp.rows + (size_t)r) * cp.Cout + n0;
+    const size_t out_off = ((size_t)(cp.pool_max ? 0 : t) * cp.rows + (size_t)r) * cp.Cout + n0;
 #pragma unroll 1
     for (int ch = 0; ch < BN / 32; ++ch) {
         u32 v[32];
@@ -157,6 +158,20 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams &cp, u32 tme
                         const int n = n0 + ch * 32 + i;
                         if (n < cp.nchw_C) dst[(size_t)n * cstride] = o[i];
                     }
+                }
+            } else if (cp.pool_max) {
+                // the late 'max' join over the window (TemporalPooling, layers.py:201-205; yolo3.py:1134-1138) in the
+                // epilogue: the K frames' tiles meet in the one pooled frame through 16-byte bf16x2 max reductions at
+                // L2 (order-independent, so still deterministic); the un-pooled tip is never written
+                unsigned *dst = (unsigned *)((__nv_bfloat16 *)cp.y + out_off + ch * 32);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(o[8 * i], o[8 * i + 1]);
+                    __nv_bfloat162 p1 = __floats2bfloat162_rn(o[8 * i + 2], o[8 * i + 3]);
+                    __nv_bfloat162 p2 = __floats2bfloat162_rn(o[8 * i + 4], o[8 * i + 5]);
+                    __nv_bfloat162 p3 = __floats2bfloat162_rn(o[8 * i + 6], o[8 * i + 7]);
+                    asm volatile("red.global.max.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};"
+                                 :: "l"(dst + 4 * i), "r"(*(u32 *)&p0), "r"(*(u32 *)&p1), "r"(*(u32 *)&p2), "r"(*(u32 *)&p3) : "memory");
                 }
             } else if (cp.y_is_f32) {
                 float4 *dst = (float4 *)((float *)cp.y + out_off + ch * 32);
@@ -707,6 +722,11 @@ __global__ void vy_temporal_dwconv_kernel(const uint4 *__restrict__ x, int T, lo
     }
 }
 
+__global__ void vy_fill_u32x4_kernel(uint4 *__restrict__ y, long long n16, unsigned v) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) y[i] = make_uint4(v, v, v, v);
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -854,7 +874,7 @@ extern "C" size_t vy_fusion_conv_workspace_bytes(int B, int T, int H, int W, int
 
 static int conv_launch(const void *x, const void *w, const float *scale, const float *shift,
                        float leaky_slope, int B, int T, int H, int W, int Cin, int Cout,
-                       int kt, int kh, int kw, void *y, int y_is_f32, int nchw_C, vy_stream_t stream) {
+                       int kt, int kh, int kw, void *y, int y_is_f32, int nchw_C, int pool_max, vy_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!x || !w || !scale || !shift || !y) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16: null pointer");
     if (B < 1 || T < 1 || H < 1 || W < 1) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16: bad shape");
@@ -936,6 +956,7 @@ static int conv_launch(const void *x, const void *w, const float *scale, const f
     cp.n_tiles_total = (long long)T * cp.m_tiles * cp.n_tiles;
     cp.slope = leaky_slope; cp.scale = scale; cp.shift = shift; cp.y = y; cp.y_is_f32 = y_is_f32;
     cp.nchw_C = nchw_C; cp.nchw_H = H; cp.nchw_W = W;
+    cp.pool_max = pool_max;
     if (pairBN == 256) return launch_conv2<256>(mx, mw, cp, st);
     if (pairBN == 128) return launch_conv2<128>(mx, mw, cp, st);
     if (BN == 256) return launch_conv<256>(mx, mw, cp, st);
@@ -948,7 +969,23 @@ extern "C" int vy_fusion_conv_bf16(const void *x, const void *w, const float *sc
                                    int kt, int kh, int kw, void *y, int y_is_f32, void *workspace,
                                    size_t workspace_bytes, vy_stream_t stream) {
     (void)workspace; (void)workspace_bytes;
-    return conv_launch(x, w, scale, shift, leaky_slope, B, T, H, W, Cin, Cout, kt, kh, kw, y, y_is_f32, 0, stream);
+    return conv_launch(x, w, scale, shift, leaky_slope, B, T, H, W, Cin, Cout, kt, kh, kw, y, y_is_f32, 0, 0, stream);
+}
+
+extern "C" int vy_fusion_conv_bf16_maxpool(const void *x, const void *w, const float *scale, const float *shift,
+                                           float leaky_slope, int B, int T, int H, int W, int Cin, int Cout,
+                                           int kt, int kh, int kw, void *y, vy_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!y || B < 1 || T < 1 || H < 1 || W < 1 || Cout < 64 || Cout % 64 != 0) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16_maxpool: bad arguments");
+    if (((uintptr_t)y & 15) != 0) VY_FAIL(VY_EALIGN, "vy_fusion_conv_bf16_maxpool: y must be 16-byte aligned");
+    // the pooled frame starts at -inf (bf16 0xFF80); the conv's epilogue raises it
+    const long long n16 = (long long)B * (H + 2) * (W + 2) * Cout * 2 / 16;
+    long long blocks = (n16 + 255) / 256;
+    const long long cap = (long long)vy_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    VY_KERNEL(VY_K_LAYOUT, st, (vy_fill_u32x4_kernel<<<(unsigned)blocks, 256, 0, st>>>((uint4 *)y, n16, 0xFF80FF80u)));
+    VY_LAUNCH_CHECK("vy_fill_u32x4_kernel");
+    return conv_launch(x, w, scale, shift, leaky_slope, B, T, H, W, Cin, Cout, kt, kh, kw, y, 0, 0, 1, stream);
 }
 
 extern "C" int vy_fusion_conv_bf16_nchw(const void *x, const void *w, const float *scale, const float *shift,
@@ -956,7 +993,7 @@ extern "C" int vy_fusion_conv_bf16_nchw(const void *x, const void *w, const floa
                                         float *y, int out_channels, vy_stream_t stream) {
     if (out_channels < 1 || out_channels > Cout) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16_nchw: out_channels must be in [1, Cout]");
     if (((uintptr_t)y & 3) != 0) VY_FAIL(VY_EALIGN, "vy_fusion_conv_bf16_nchw: y must be 4-byte aligned");
-    return conv_launch(x, w, scale, shift, leaky_slope, B, 1, H, W, Cin, Cout, 1, kh, kw, y, 1, out_channels, stream);
+    return conv_launch(x, w, scale, shift, leaky_slope, B, 1, H, W, Cin, Cout, 1, kh, kw, y, 1, out_channels, 0, stream);
 }
 
 extern "C" int vy_temporal_pool_bf16(const void *x, int T, long inner, int mode, void *y, vy_stream_t stream) {

@@ -45,9 +45,9 @@ class _Cell(torch.nn.Module):
             self._packed = (key, w, scale, shift)
         return self._packed[1:]
 
-    def forward(self, x: ops.PTensor, out_f32: bool = False) -> ops.PTensor:
+    def forward(self, x: ops.PTensor, out_f32: bool = False, pool_max: bool = False) -> ops.PTensor:
         w, scale, shift = self.packed()
-        return ops.fusion_conv(x, w, scale, shift, self.slope, out_f32=out_f32)
+        return ops.fusion_conv(x, w, scale, shift, self.slope, out_f32=out_f32, pool_max=pool_max)
 
 
 class Conv(torch.nn.Module):
@@ -75,11 +75,13 @@ class Conv(torch.nn.Module):
         else:
             self.cells = torch.nn.ModuleList([_Cell(in_channels, channel, (1, k, k)), _Cell(channel, channel, (k, 1, 1))])
 
-    def forward(self, x: ops.PTensor, out_f32: bool = False) -> ops.PTensor:
+    def forward(self, x: ops.PTensor, out_f32: bool = False, pool_max: bool = False) -> ops.PTensor:
+        """``pool_max``: the conv followed by ``TemporalPooling(k, 'max')`` -- the last cell's epilogue does the join."""
         if self._type == "2" and x.T != 1:
             raise ValueError("Conv('2') takes a 2-D activation (T == 1); fold time first (TimeDistributed / 'cat')")
         for i, cell in enumerate(self.cells):
-            x = cell(x, out_f32=out_f32 and i == len(self.cells) - 1)
+            last = i == len(self.cells) - 1
+            x = cell(x, out_f32=out_f32 and last, pool_max=pool_max and last)
         return x
 
 

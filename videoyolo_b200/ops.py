@@ -497,11 +497,13 @@ def unpack_p(p: PTensor, layout: str = "NCDHW", channels: Optional[int] = None) 
 
 
 def fusion_conv(x: PTensor, weight: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
-                slope: float = 0.1, out_f32: bool = False) -> PTensor:
+                slope: float = 0.1, out_f32: bool = False, pool_max: bool = False) -> PTensor:
     """One Conv+BN+LeakyReLU cell (layers.py:63-79) on a P-layout activation.
 
     weight: (Cout, kt, kh, kw, Cin) bf16 CUDA (see ``conv_weight``); scale/shift: folded inference
-    BatchNorm per output channel, fp32 CUDA.  'same' padding, stride 1."""
+    BatchNorm per output channel, fp32 CUDA.  'same' padding, stride 1.
+    ``pool_max``: the cell followed by ``TemporalPooling(k, 'max')`` (the late join, yolo3.py:1134-1138) in one call:
+    returns the pooled frame (T = 1); the un-pooled output is never written."""
     if not isinstance(x, PTensor):
         raise TypeError("fusion_conv takes a PTensor (ops.pack_p)")
     w = _need_cuda(weight, "weight", torch.bfloat16)
@@ -512,6 +514,15 @@ def fusion_conv(x: PTensor, weight: torch.Tensor, scale: torch.Tensor, shift: to
         raise ValueError("weight has %d input channels, activation has %d" % (Cin, x.C))
     if scale.numel() != Cout or shift.numel() != Cout:
         raise ValueError("scale/shift must have Cout elements")
+    if pool_max:
+        if out_f32:
+            raise ValueError("pool_max writes bf16")
+        y = torch.empty((1, x.B, x.H + 2, x.W + 2, Cout), dtype=torch.bfloat16, device=x.data.device)
+        with torch.cuda.device(x.data.device):
+            _lib.check(_lib.lib().vy_fusion_conv_bf16_maxpool(x.data.data_ptr(), w.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                                              float(slope), x.B, x.T, x.H, x.W, Cin, Cout, kt, kh, kw,
+                                                              y.data_ptr(), _stream()))
+        return PTensor(y, x.B, 1, x.H, x.W, Cout)
     y = torch.empty((x.T, x.B, x.H + 2, x.W + 2, Cout), dtype=torch.float32 if out_f32 else torch.bfloat16,
                     device=x.data.device)
     with torch.cuda.device(x.data.device):

@@ -271,30 +271,39 @@ class YOLOV3T(torch.nn.Module):
     def set_nms(self, nms_thresh=0.45, nms_topk=400, post_nms=100):
         self.tail.set_nms(nms_thresh, nms_topk, post_nms)
 
-    def _tips(self, xs):
+    #: the late 'max' join runs in the tip conv's epilogue (ops.fusion_conv(pool_max=True)): the un-pooled tip is never
+    #: written and the TemporalPooling kernel does not run; False = conv, then TemporalPooling (same bits)
+    fuse_max_join = True
+
+    def _fused_join(self):
+        return self.fuse_max_join and self._late and self._join == "max"
+
+    def _tips(self, xs, joined=False):
+        """tip conv outputs; with ``joined`` and a late 'max' join, the already joined frame (T = 1)"""
         if len(xs) != len(self.tips):
             raise ValueError("expected %d inputs (stride 32,16,8 order)" % len(self.tips))
+        pool = joined and self._fused_join()
         tips = []
         for i, x in enumerate(xs):
             if isinstance(x, ops.PTensor):                 # already in the library's layout (YOLOV3TNeck)
                 if x.T != self._k:
                     raise ValueError("input %d must hold K=%d frames" % (i, self._k))
-                tips.append(self.tips[i](x))
+                tips.append(self.tips[i](x, pool_max=pool))
                 continue
             if x.dim() != 5 or x.shape[1] != self._k:
                 raise ValueError("input %d must be (B, K=%d, C, H, W)" % (i, self._k))
-            tips.append(self.tips[i](ops.pack_p(x, "NTCHW")))
+            tips.append(self.tips[i](ops.pack_p(x, "NTCHW"), pool_max=pool))
         return tips
 
     def tip_features(self, *xs):
         """the three joined tip feature maps (B, C', H, W) fp32 that feed the output layers"""
         feats = []
-        for i, tip in enumerate(self._tips(xs)):
+        for i, tip in enumerate(self._tips(xs, joined=True)):
             if self._join == "cat" or not self._late:
                 t = ops.unpack_p(tip, "NTCHW")                                  # (B, K, C, H, W)
                 feats.append(t.reshape(t.shape[0], -1, t.shape[3], t.shape[4]))  # reshape (0,-3,-2): yolo3.py:1136
             else:
-                feats.append(ops.unpack_p(self.pools[i](tip), "NCHW"))
+                feats.append(ops.unpack_p(tip if self._fused_join() else self.pools[i](tip), "NCHW"))
         return feats
 
     def head_maps(self, *xs):
@@ -302,8 +311,8 @@ class YOLOV3T(torch.nn.Module):
         by ``Prediction`` directly on the joined bf16 tip ('max' / 'mean': the pooled frame; 'cat': the K frames side by
         side in the channels); only the head map is converted to NCHW."""
         heads = []
-        for i, tip in enumerate(self._tips(xs)):
-            joined = tip if self._join == "cat" or not self._late else self.pools[i](tip)
+        for i, tip in enumerate(self._tips(xs, joined=True)):
+            joined = tip if self._join == "cat" or not self._late or self._fused_join() else self.pools[i](tip)
             heads.append(self.tail.yolo_outputs[i].prediction(joined))
         return heads
 
