@@ -239,6 +239,14 @@ int vy_fusion_conv_bf16(const void *x, const void *w, const float *scale, const 
                         int kt, int kh, int kw, void *y, int y_is_f32,
                         void *workspace, size_t workspace_bytes, vy_stream_t stream);
 
+/* The 1x1 prediction conv over the 'cat'-joined window (reshape (0,-3,-2), yolo3.py:1135-1136) without materialising
+ * the join: x is a P-layout tensor of T frames x C channels, the GEMM's K runs over rep*T*C channels -- k-block cb reads
+ * channels (cb % (C/64))*64 of frame (cb / (C/64)) % T; rep > 1 walks the window again (weights split into bf16 hi | lo
+ * parts: w is (Cout, rep*T*C)).  T = 1, rep = 2 serves the 'max' / 'mean' joins.  Output as vy_fusion_conv_bf16_nchw. */
+int vy_fusion_conv_bf16_nchw_joined(const void *x, const void *w, const float *scale, const float *shift,
+                                    float leaky_slope, int B, int T, int H, int W, int C, int rep, int Cout,
+                                    float *y, int out_channels, vy_stream_t stream);
+
 /* The same cell with the late 'max' join over the window (TemporalPooling(k, 'max'), layers.py:201-205, as used at
  * yolo3.py:1134-1138) done in its epilogue: y is ONE P-layout frame (T = 1, Cout channels, bf16) = max over the T
  * output frames; the un-pooled tip is never written.  Bit-identical to vy_fusion_conv_bf16 + vy_temporal_pool_bf16. */

@@ -238,6 +238,24 @@ def test_fusion_conv_max_join_in_the_epilogue(vy, B, T, H, W, Cin, Cout, k3):
     assert float(d[:, :, 0].abs().max()) == 0 and float(d[:, :, :, -1].abs().max()) == 0
 
 
+@pytest.mark.parametrize("B,T,H,W,C,n", [(2, 1, 13, 13, 128, 75), (3, 3, 13, 13, 64, 105), (8, 1, 52, 52, 256, 105),
+                                         (2, 3, 26, 26, 512, 255)])
+def test_prediction_conv_over_the_joined_window_without_materialising_it(vy, B, T, H, W, C, n):
+    """The 1x1 prediction conv on a bf16 tip (yolo3.py:62,157; 'cat' join :1135-1136; weight split hi | lo against the
+    activation walked twice): addressing frame t / channel block c of the tip from the conv's k loop gives exactly the
+    head map of the conv on the materialised ``cat_repeat(x, 2)``."""
+    ops = vy.ops
+    gen = torch.Generator(device="cuda").manual_seed(B + T + C + n)
+    x = ops.pack_p(torch.randn((B, T, C, H, W), generator=gen, device="cuda"), "NTCHW")
+    w = ops.split_weight(torch.rand((n, T * C, 1, 1), generator=gen, device="cuda") * 0.14 - 0.07, 2)
+    scale = torch.ones(w.shape[0], device="cuda")
+    shift = torch.randn(w.shape[0], generator=gen, device="cuda")
+    ref = ops.fusion_conv_nchw(ops.cat_repeat(x, 2), w, scale, shift, slope=1.0, channels=n)
+    got = ops.fusion_conv_nchw_joined(x, w, scale, shift, rep=2, slope=1.0, channels=n)
+    assert got.shape == (B, n, H, W)
+    assert torch.equal(got, ref)
+
+
 def test_temporal_dwconv_matches_oracle(vy):
     """_conv1d temporal merge (layers.py:50-60, h_darknet.py:97-119): window of 3 frames, C=32."""
     rng = np.random.RandomState(21)

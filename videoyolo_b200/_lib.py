@@ -53,6 +53,8 @@ SIGNATURES = {
     "vy_fusion_conv_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 9),
     "vy_fusion_conv_bf16": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_float] + [ctypes.c_int] * 9 +
                             [c_vp, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp]),
+    "vy_fusion_conv_bf16_nchw_joined": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_float] + [ctypes.c_int] * 7 +
+                                        [c_vp, ctypes.c_int, c_vp]),
     "vy_fusion_conv_bf16_maxpool": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_float] + [ctypes.c_int] * 9 + [c_vp, c_vp]),
     "vy_fusion_conv_bf16_nchw": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_float] + [ctypes.c_int] * 7 +
                                  [c_vp, ctypes.c_int, c_vp]),

@@ -44,6 +44,10 @@ struct ConvParams {
     int y_is_f32;
     int nchw_C, nchw_H, nchw_W;  // nchw_C > 0: y is the reference's fp32 (B, nchw_C, H, W) tensor (T == 1): interior pixels, first nchw_C channels
     int pool_max;                // y is ONE P-layout frame [rows][Cout] bf16 pre-filled with -inf: max over the T frames (TemporalPooling 'max')
+    // a_cpb > 0: 1 x 1 conv over the 'cat'-joined window WITHOUT materialising the join (yolo3.py:1135-1136): k-block cb
+    // reads channels (cb % a_cpb) * 64 of frame (cb / a_cpb) % a_frames of x; the k range beyond a_frames * a_cpb blocks
+    // wraps around (the activation repeated for split weights)
+    int a_cpb, a_frames;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -244,7 +248,8 @@ vy_fusion_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                             mbar_wait(&bar_empty[stage], phase ^ 1u);
                             unsigned char *sa = tiles + (size_t)stage * STAGE_BYTES, *sb = sa + A_BYTES;
                             mbar_expect_tx(&bar_full[stage], STAGE_BYTES);
-                            tma_load_3d(sa, &map_x, &bar_full[stage], cb * CV_BK, row, tt);
+                            tma_load_3d(sa, &map_x, &bar_full[stage], cp.a_cpb ? (cb % cp.a_cpb) * CV_BK : cb * CV_BK, row,
+                                        cp.a_cpb ? (cb / cp.a_cpb) % cp.a_frames : tt);
                             tma_load_2d(sb, &map_w, &bar_full[stage], kbase + cb * CV_BK, n0);
                             if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
                         }
@@ -410,7 +415,8 @@ vy_fusion_conv2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                             mbar_wait(&bar_empty[stage], phase ^ 1u);
                             unsigned char *sa = tiles + (size_t)stage * STAGE_BYTES, *sb = sa + A_BYTES;
                             if (rank == 0) mbar_expect_tx(&bar_full[stage], 2 * STAGE_BYTES);
-                            tma2_load_3d(sa, &map_x, &bar_full[stage], cb * CV_BK, row, tt);
+                            tma2_load_3d(sa, &map_x, &bar_full[stage], cp.a_cpb ? (cb % cp.a_cpb) * CV_BK : cb * CV_BK, row,
+                                         cp.a_cpb ? (cb / cp.a_cpb) % cp.a_frames : tt);
                             tma2_load_2d(sb, &map_w, &bar_full[stage], kbase + cb * CV_BK, n0);
                             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                         }
@@ -874,7 +880,8 @@ extern "C" size_t vy_fusion_conv_workspace_bytes(int B, int T, int H, int W, int
 
 static int conv_launch(const void *x, const void *w, const float *scale, const float *shift,
                        float leaky_slope, int B, int T, int H, int W, int Cin, int Cout,
-                       int kt, int kh, int kw, void *y, int y_is_f32, int nchw_C, int pool_max, vy_stream_t stream) {
+                       int kt, int kh, int kw, void *y, int y_is_f32, int nchw_C, int pool_max, vy_stream_t stream,
+                       int x_C = 0, int x_T = 0) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!x || !w || !scale || !shift || !y) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16: null pointer");
     if (B < 1 || T < 1 || H < 1 || W < 1) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16: bad shape");
@@ -929,8 +936,10 @@ static int conv_launch(const void *x, const void *w, const float *scale, const f
 
     CUtensorMap mx, mw;
     {   // X: (C, rows, T) bf16, box (64, 128, 1)
-        cuuint64_t dim[3] = {(cuuint64_t)Cin, (cuuint64_t)rows, (cuuint64_t)T};
-        cuuint64_t str[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)rows * Cin * 2};
+        // (x_C > 0: the joined 1 x 1 conv -- x holds x_T frames of x_C channels, Cin = the joined, possibly repeated, K)
+        const int xc = x_C > 0 ? x_C : Cin, xt = x_C > 0 ? x_T : T;
+        cuuint64_t dim[3] = {(cuuint64_t)xc, (cuuint64_t)rows, (cuuint64_t)xt};
+        cuuint64_t str[2] = {(cuuint64_t)xc * 2, (cuuint64_t)rows * xc * 2};
         cuuint32_t box[3] = {CV_BK, CV_BM, 1}, es[3] = {1, 1, 1};
         const CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(x), dim, str, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -957,6 +966,7 @@ static int conv_launch(const void *x, const void *w, const float *scale, const f
     cp.slope = leaky_slope; cp.scale = scale; cp.shift = shift; cp.y = y; cp.y_is_f32 = y_is_f32;
     cp.nchw_C = nchw_C; cp.nchw_H = H; cp.nchw_W = W;
     cp.pool_max = pool_max;
+    if (x_C > 0) { cp.a_cpb = x_C / CV_BK; cp.a_frames = x_T; }
     if (pairBN == 256) return launch_conv2<256>(mx, mw, cp, st);
     if (pairBN == 128) return launch_conv2<128>(mx, mw, cp, st);
     if (BN == 256) return launch_conv<256>(mx, mw, cp, st);
@@ -994,6 +1004,15 @@ extern "C" int vy_fusion_conv_bf16_nchw(const void *x, const void *w, const floa
     if (out_channels < 1 || out_channels > Cout) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16_nchw: out_channels must be in [1, Cout]");
     if (((uintptr_t)y & 3) != 0) VY_FAIL(VY_EALIGN, "vy_fusion_conv_bf16_nchw: y must be 4-byte aligned");
     return conv_launch(x, w, scale, shift, leaky_slope, B, 1, H, W, Cin, Cout, 1, kh, kw, y, 1, out_channels, 0, stream);
+}
+
+extern "C" int vy_fusion_conv_bf16_nchw_joined(const void *x, const void *w, const float *scale, const float *shift,
+                                               float leaky_slope, int B, int T, int H, int W, int C, int rep, int Cout,
+                                               float *y, int out_channels, vy_stream_t stream) {
+    if (T < 1 || rep < 1 || C < 64 || C % 64 != 0) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16_nchw_joined: C must be a multiple of 64, T, rep >= 1");
+    if (out_channels < 1 || out_channels > Cout) VY_FAIL(VY_EINVAL, "vy_fusion_conv_bf16_nchw_joined: out_channels must be in [1, Cout]");
+    if (((uintptr_t)y & 3) != 0) VY_FAIL(VY_EALIGN, "vy_fusion_conv_bf16_nchw_joined: y must be 4-byte aligned");
+    return conv_launch(x, w, scale, shift, leaky_slope, B, 1, H, W, rep * T * C, Cout, 1, 1, 1, y, 1, out_channels, 0, stream, C, T);
 }
 
 extern "C" int vy_temporal_pool_bf16(const void *x, int T, long inner, int mode, void *y, vy_stream_t stream) {

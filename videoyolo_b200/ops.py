@@ -562,6 +562,31 @@ def fusion_conv_nchw(x: PTensor, weight: torch.Tensor, scale: torch.Tensor, shif
     return y
 
 
+def fusion_conv_nchw_joined(x: PTensor, weight: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
+                            rep: int = 1, slope: float = 1.0, channels: Optional[int] = None) -> torch.Tensor:
+    """``fusion_conv_nchw(cat_repeat(x, rep), ...)`` without materialising the joined / repeated activation: the 1x1 conv
+    reads frame t, channel block c of ``x`` for k-block (r, t, c) of the (Cout, 1, 1, 1, rep*T*C) weight."""
+    if not isinstance(x, PTensor) or x.data.dtype != torch.bfloat16:
+        raise TypeError("fusion_conv_nchw_joined takes a bf16 PTensor")
+    w = _need_cuda(weight, "weight", torch.bfloat16)
+    scale = _need_cuda(scale, "scale")
+    shift = _need_cuda(shift, "shift")
+    Cout, kt, kh, kw, Cin = w.shape
+    if (kt, kh, kw) != (1, 1, 1) or Cin != rep * x.T * x.C:
+        raise ValueError("weight must be (Cout, 1, 1, 1, rep*T*C = %d), got %s" % (rep * x.T * x.C, tuple(w.shape)))
+    if scale.numel() != Cout or shift.numel() != Cout:
+        raise ValueError("scale/shift must have Cout elements")
+    C = Cout if channels is None else int(channels)
+    if not 1 <= C <= Cout:
+        raise ValueError("channels must be in [1, %d]" % Cout)
+    y = torch.empty((x.B, C, x.H, x.W), dtype=torch.float32, device=x.data.device)
+    with torch.cuda.device(x.data.device):
+        _lib.check(_lib.lib().vy_fusion_conv_bf16_nchw_joined(x.data.data_ptr(), w.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                                              float(slope), x.B, x.T, x.H, x.W, x.C, int(rep), Cout,
+                                                              y.data_ptr(), C, _stream()))
+    return y
+
+
 def conv_weight(w_ref: torch.Tensor) -> torch.Tensor:
     """The reference's conv weight (Cout, Cin, [kt,] kh, kw) fp32 -> (Cout, kt, kh, kw, Cin) bf16 CUDA."""
     if w_ref.dim() == 4:

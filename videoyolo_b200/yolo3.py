@@ -55,6 +55,10 @@ class Prediction(torch.nn.Module):
             if x.T * x.C != cin:
                 raise ValueError("prediction conv expects %d input channels, got %d x %d frames" % (cin, x.C, x.T))
             w, scale, shift = self._operands(2)
+            if x.C % 64 == 0:
+                # the join ('cat': K frames side by side in the channels) and the repeat for the split weight happen in
+                # the conv's operand addressing: nothing is materialised
+                return ops.fusion_conv_nchw_joined(x, w, scale, shift, rep=2, slope=1.0, channels=n)
             xp = ops.cat_repeat(x, 2)
         else:
             if x.dim() != 4 or x.shape[1] != cin:
