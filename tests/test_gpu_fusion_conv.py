@@ -192,11 +192,12 @@ def test_pack_unpack_roundtrip_and_pool(vy):
 
 
 @pytest.mark.parametrize("B,K,C,H,W", [(2, 3, 128, 26, 26), (1, 3, 72, 20, 12), (2, 1, 64, 13, 13), (1, 2, 30, 10, 10),
-                                       (3, 3, 256, 52, 52)])
+                                       (3, 3, 256, 52, 52), (2, 3, 128, 13, 13), (3, 2, 192, 11, 15), (1, 3, 64, 7, 9)])
 def test_pack_layout_and_zero_border(vy, B, K, C, H, W):
     """The P layout bit for bit -- [T][B][H+2][W+2][C] bf16 with a ZERO one-pixel border -- written into a buffer that
-    held garbage: even grids take the 16-byte load path, channel counts that are multiples of 8 write the border from
-    the pack kernel itself, the others through the border kernel (yolo3.py:256-262 swapaxes view, layers.py:76 padding)."""
+    held garbage: even grids take the 16-byte load path, small odd planes of contiguous channels (13 x 13) the flat
+    path, channel counts that are multiples of 8 write the border from the pack kernel itself, the others through the
+    border kernel (yolo3.py:256-262 swapaxes view, layers.py:76 padding)."""
     ops = vy.ops
     rng = np.random.RandomState(B * 1000 + C)
     x = bf16_round(rng.normal(size=(B, K, C, H, W)).astype(np.float32))

@@ -581,6 +581,62 @@ vy_pack_kernel(const float *__restrict__ x, long long sb, long long sc, long lon
 }
 
 // the one-pixel zero border of every (t, b) frame of a P-layout tensor (2*Wp + 2*H pixels x C channels)
+// Small planes whose channels lie back to back in memory (sc == H*W: the reference's contiguous (.., C, H, W) tensors; 13 x 13
+// = 169 floats, no alignment per plane to vectorise on): 64 channels x H*W positions are ONE contiguous run of 64*H*W floats,
+// read with 16-byte loads and scattered into the shared tile by flat index.  Writes the P-layout pixels and the zero border.
+constexpr int LYF_MAX_HW = 176;
+__global__ void __launch_bounds__(LY_NT)
+vy_pack_flat_kernel(const float *__restrict__ x, long long sb, long long st, int B, int C, int H, int W, __nv_bfloat16 *__restrict__ y) {
+    __shared__ float tile[LY_C * (LYF_MAX_HW + 1)];
+    const int HW = H * W, Wp = W + 2, Hp = H + 2;
+    const int S = HW | 1;                                  // odd row stride: the transposed read below is 2-way conflicted at worst
+    const int c0 = blockIdx.x * LY_C;
+    const int b = blockIdx.y % B, t = blockIdx.y / B;
+    const float4 *src = (const float4 *)(x + (size_t)b * sb + (size_t)t * st + (size_t)c0 * HW);
+    const int n4 = LY_C * HW / 4;
+    for (int i0 = threadIdx.x; i0 < n4; i0 += 8 * LY_NT) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * LY_NT;
+            v[u] = i < n4 ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * LY_NT;
+            if (i < n4) {
+                int c = (4 * i) / HW, p = 4 * i - c * HW;
+                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    tile[c * S + p] = e[k];
+                    if (++p == HW) { p = 0; ++c; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    __nv_bfloat16 *dst = y + ((size_t)t * B + b) * (size_t)Hp * Wp * C;
+    for (int i = threadIdx.x; i < HW * (LY_C / 8); i += LY_NT) {
+        const int p = i / (LY_C / 8), c = (i % (LY_C / 8)) * 8;
+        const int h = p / W, w = p % W;
+        uint4 o;
+        __nv_bfloat162 *oh = (__nv_bfloat162 *)&o;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh[k] = __floats2bfloat162_rn(tile[(c + 2 * k) * S + p], tile[(c + 2 * k + 1) * S + p]);
+        *(uint4 *)(dst + ((size_t)(h + 1) * Wp + (w + 1)) * C + c0 + c) = o;
+    }
+    const int nb = 2 * Wp + 2 * H;
+    for (int i = threadIdx.x; i < nb * (LY_C / 8); i += LY_NT) {
+        const int q = i / (LY_C / 8), c = (i % (LY_C / 8)) * 8;
+        int hp, wp;
+        if (q < Wp) { hp = 0; wp = q; }
+        else if (q < 2 * Wp) { hp = Hp - 1; wp = q - Wp; }
+        else { const int r = q - 2 * Wp; hp = 1 + (r >> 1); wp = (r & 1) ? Wp - 1 : 0; }
+        *(uint4 *)(dst + ((size_t)hp * Wp + wp) * C + c0 + c) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 __global__ void vy_zero_border_kernel(__nv_bfloat16 *__restrict__ y, int H, int W, int C) {
     const int Hp = H + 2, Wp = W + 2;
     const int nb = 2 * Wp + 2 * H;
@@ -792,6 +848,14 @@ extern "C" int vy_pack_f32_to_p_bf16(const float *x, long long stride_b, long lo
     if (!x || !y_p || B < 1 || C < 1 || T < 1 || H < 1 || W < 1) VY_FAIL(VY_EINVAL, "vy_pack_f32_to_p_bf16: bad arguments");
     if ((long long)T * B > 65535) VY_FAIL(VY_EUNSUPPORTED, "vy_pack_f32_to_p_bf16: T*B must be <= 65535");
     if (((uintptr_t)y_p & 15) != 0) VY_FAIL(VY_EALIGN, "vy_pack_f32_to_p_bf16: y_p must be 16-byte aligned");
+    if (C % LY_C == 0 && stride_c == (long long)H * W && H * W <= LYF_MAX_HW && (H * W) % 4 != 0 && stride_b % 4 == 0 &&
+        stride_t % 4 == 0 && ((uintptr_t)x & 15) == 0) {
+        // (even planes take the 16-byte path of the general kernel)
+        VY_KERNEL(VY_K_LAYOUT, st, (vy_pack_flat_kernel<<<dim3(C / LY_C, T * B), LY_NT, 0, st>>>(x, stride_b, stride_t, B, C, H, W,
+                                                                                              (__nv_bfloat16 *)y_p)));
+        VY_LAUNCH_CHECK("vy_pack_flat_kernel");
+        return VY_OK;
+    }
     const int fused_border = (C & 7) == 0;          // the pack kernel's 16-byte path also writes the zero border
     if (!fused_border) {
         VY_KERNEL(VY_K_LAYOUT, st, (vy_zero_border_kernel<<<dim3(64, T * B), 128, 0, st>>>((__nv_bfloat16 *)y_p, H, W, C)));
